@@ -1,0 +1,422 @@
+#!/usr/bin/env python
+"""Benchmark of the hard-sphere MC hot path (BASELINE.json: trial moves/s and % of the
+cell-list HBM roofline).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path
+
+Workload (config.workload): NVT hard spheres, fcc start, rho = 0.9, N = 16 777 216
+(fcc 256 x 128 x 128 unit cells; the long axis is x, the slab axis), i.e. BASELINE.json
+configs[3] -- the configuration the headline metric is quoted on; it fits one B200, and
+the same total system is slab-decomposed over N GPUs ("scaling": "strong").
+
+A step = one hsmc_gpu_sweep_nvt() call of --sweeps-per-step sweeps (each sweep = N trial
+moves = 8 checkerboard colour phases + one grid shift / cell-list rebuild).  `value` is
+timed on the device (CUDA events on the handle's stream) with the configuration resident
+in HBM; `e2e` is the same call driven from pinned HOST buffers: upload of the {id,x,y,z}
+table, the sweeps, download of the table and the move counters, wall-clock.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+RHO = 0.9
+DR_MAX = 0.1
+FALLBACK_HBM_GBS = 6650.0
+L2_BYTES = 126e6
+
+
+# --------------------------------------------------------------------------------------
+# synthetic input: the reference's own lattice generator (sim_info.c:125-166), vectorised
+# --------------------------------------------------------------------------------------
+def fcc_lattice(nx, ny, nz, rho, out=None):
+    a = (4.0 / rho) ** (1.0 / 3.0)   # pow(cell_vol, 1./3.)
+    n = 4 * nx * ny * nz
+    conf = out if out is not None else np.empty((n, 4))
+    ii, jj, kk = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    ii, jj, kk = ii.ravel().astype(np.float64), jj.ravel().astype(np.float64), kk.ravel().astype(np.float64)
+    v = conf.reshape(nx * ny * nz, 4, 4)
+    for b, (ox, oy, oz) in enumerate(((0, 0, 0), (0.5, 0.5, 0), (0.5, 0, 0.5), (0, 0.5, 0.5))):
+        v[:, b, 1] = (ii + ox) * a
+        v[:, b, 2] = (jj + oy) * a
+        v[:, b, 3] = (kk + oz) * a
+    conf[:, 0] = np.arange(n)
+    return np.array([nx * a, ny * a, nz * a]), conf
+
+
+# --------------------------------------------------------------------------------------
+# clocks during the timed region (B200_PROFILING.md recipe)
+# --------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """dram bytes per sweep-phase launch from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "sweep_phase_dram_bytes.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
+
+
+# --------------------------------------------------------------------------------------
+# CPU arm: the reference's own sweep_nvt()/part_move() on host cores
+# --------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    """One replica: reference lattice of `cells`^3 fcc cells, `sweeps` sweeps per step."""
+    kind, cells, seed, steps, warmup, sweeps, conn = args
+    from oracle import pyoracle
+    if kind == "reference":
+        r = pyoracle.Ref(lattice=(2, cells, cells, cells, RHO), neigh_dr=1.0, max_part=10, seed=seed)
+        r.set_moves(dr_max=DR_MAX)
+        run = lambda: r.sweep_nvt(sweeps)
+        n = r.N
+    else:
+        box, conf = pyoracle.Port.lattice(2, cells, cells, cells, RHO)
+        p = pyoracle.Port(conf, box, neigh_dr=1.0, max_part=10)
+        state = {"k": 0}
+
+        def run():
+            p.sweep_nvt(sweeps, DR_MAX, seed + state["k"])
+            state["k"] += 1
+        n = conf.shape[0]
+    times = []
+    for s in range(warmup + steps):
+        conn.send("ready")
+        conn.recv()               # lock-step start so replicas overlap
+        t0 = time.perf_counter()
+        run()
+        times.append(time.perf_counter() - t0)
+    conn.send(("done", n, times[warmup:]))
+
+
+def cpu_reference_arm(steps, warmup, cells, sweeps, cores):
+    """K steps, each = every replica (one per host core) runs `sweeps` sweeps of a
+    `cells`^3 fcc box at rho 0.9 through the reference's own sweep_nvt()."""
+    import multiprocessing as mp
+    from oracle import pyoracle
+    kind = "reference" if pyoracle.have_ref() else "port"
+    if kind == "port":
+        pyoracle.build()
+    ctx = mp.get_context("spawn")
+    procs, conns = [], []
+    for c in range(cores):
+        a, b = ctx.Pipe()
+        p = ctx.Process(target=_cpu_worker, args=((kind, cells, 1000 + c, steps, warmup, sweeps, b),))
+        p.start()
+        procs.append(p); conns.append(a)
+    step_times = []
+    for s in range(warmup + steps):
+        for c in conns:
+            assert c.recv() == "ready"
+        t0 = time.perf_counter()
+        for c in conns:
+            c.send("go")
+        # next "ready" (or "done") arrives when the replica finished this step
+        if s < warmup + steps - 1:
+            pass
+        step_times.append(t0)
+    results = [c.recv() for c in conns]
+    for p in procs:
+        p.join()
+    n = results[0][1]
+    per_step = np.max(np.array([r[2] for r in results]), axis=0)   # slowest replica per step
+    moves_per_step = n * sweeps * cores
+    total = float(per_step.sum())
+    return {
+        "value": moves_per_step * steps / total, "ms_per_step": 1e3 * total / steps, "kind": kind, "cores": cores,
+        "sample": (f"{cores} independent replicas (one per host core) x {sweeps} sweep(s) of a cubic fcc {cells}^3 "
+                   f"box, N={n}, rho={RHO}, dr_max={DR_MAX}, neigh_list 1.0, through the reference's own "
+                   f"sweep_nvt()/part_move() ({'unmodified sources, oracle/_ref' if kind == 'reference' else 'oracle C restatement'}); "
+                   "the reference cannot index the non-cubic 16.8M box (SURVEY 0.6) and a smaller box is cache-friendlier, "
+                   "so this over-states the CPU"),
+    }
+
+
+# --------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--sweeps-per-step", type=int, default=10)
+    ap.add_argument("--cells", type=int, nargs=3, default=[256, 128, 128], help="fcc unit cells (x is the slab axis)")
+    ap.add_argument("--regrid", type=int, default=1)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-cells", type=int, default=64)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sweep-impl", type=int, default=0)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    nx, ny, nz = args.cells
+    N = 4 * nx * ny * nz
+    workload = {
+        "workload": f"NVT hard spheres, fcc {nx}x{ny}x{nz} start, N={N}, rho={RHO}, dr_max={DR_MAX}",
+        "N": N, "rho": RHO, "dr_max": DR_MAX, "sweeps_per_step": args.sweeps_per_step,
+        "regrid_interval": args.regrid, "positions": "double4 {x,y,z,id}, cell-ordered",
+    }
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cores = len(os.sched_getaffinity(0))
+        res = cpu_reference_arm(args.steps, args.warmup, args.cpu_cells, 1, cores)
+        line = {
+            "impl": "reference", "metric": "hard_sphere_trial_moves_per_sec", "value": res["value"], "unit": "moves/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload,
+            "cpu_baseline": {"value": res["value"], "unit": "moves/s", "cores": res["cores"], "kind": res["kind"],
+                             "sample": res["sample"]},
+            "e2e": {"value": res["value"], "unit": "moves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import hsmc_b200
+    from hsmc_b200 import gpu as G
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("cpu:gloo,cuda:nccl", rank=rank, world_size=world,
+                                device_id=torch.device("cuda", local_rank))
+        ids = [G.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        nccl_id = ids[0]
+    else:
+        nccl_id = None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def allmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    def allsum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t[0])
+
+    box, conf = fcc_lattice(nx, ny, nz, RHO)
+    h = hsmc_b200.HsmcGpu(N, box, seed=20261017, device=local_rank, rank=rank, world=world, nccl_id=nccl_id,
+                          cell_min=1.0, regrid_interval=args.regrid, sweep_impl=args.sweep_impl)
+    h.upload(conf)
+    info = h.info()
+    del conf
+    n_owned0 = info["n_owned"]
+    # pinned host mirror of this rank's rows, used by the end-to-end leg
+    cap_rows = int(n_owned0 * 1.3) + 4096 if world > 1 else N
+    host = torch.empty((cap_rows, 4), dtype=torch.float64, pin_memory=True)
+    stream = torch.cuda.ExternalStream(h.stream_ptr(), device=torch.device("cuda", local_rank))
+    S = args.sweeps_per_step
+
+    # ---- warm-up ----
+    for _ in range(args.warmup):
+        h.sweep_nvt(S, DR_MAX)
+    h.sync()
+    h.reset_counters()
+    h.profile(True)
+    h.profile_read()
+    l0 = h.info()["kernel_launches"]
+
+    # ---- timed region: K steps, device-timed per step on the handle's stream ----
+    resident = 2 * info["n_local"] * 32
+    flush = None
+    if resident < 2 * L2_BYTES:
+        flush = torch.empty(int(3 * L2_BYTES), dtype=torch.uint8, device=f"cuda:{local_rank}")
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    torch.cuda.synchronize()
+    ev = []
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        if flush is not None:
+            with torch.cuda.stream(stream):
+                flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        h.sweep_nvt(S, DR_MAX)
+        b.record(stream)
+        ev.append((a, b))
+    h.sync()
+    torch.cuda.synchronize()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    ms_local = sum(a.elapsed_time(b) for a, b in ev)
+    ms_total = allmax(ms_local)
+    prof = h.profile_read()
+    h.profile(False)
+    launches = allsum(h.info()["kernel_launches"] - l0)
+    cnt = h.counters()           # all-reduced over ranks by the library
+    moves = int(cnt[0])
+    assert moves == N * S * args.steps, (moves, N * S * args.steps)
+    value = moves / (ms_total * 1e-3)
+
+    # ---- roofline of the dominant kernel (sweep colour phase) ----
+    ncell = info["cells"][0] * info["cells"][1] * info["cells"][2]
+    nbar = N / ncell
+    b_move = 32.0 * (27.0 * nbar + 2.0)               # double4 slots: 32 B, SURVEY 8(d) with 16 -> 32
+    sweep_ms, sweep_groups = prof["sweep"]
+    moves_local = info["n_owned"] * S * args.steps     # this rank's trial moves (N/world up to migration)
+    per_launch_s = (sweep_ms * 1e-3) / max(sweep_groups, 1)
+    achieved = (moves_local / max(sweep_groups, 1)) * b_move / per_launch_s / 1e9
+    peak, peak_src = measured_peak()
+    traffic = ncu_traffic()
+    roofline = {
+        "bound": "hbm", "kernel": "k_sweep_phase", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "peak_source": peak_src,
+        "algorithmic_bytes_per_move": b_move, "nbar": nbar, "moves_per_launch": moves_local / max(sweep_groups, 1),
+        "avg_launch_ms": per_launch_s * 1e3, "launches_timed": sweep_groups,
+        "kernel_share_of_step": sweep_ms / ms_local if ms_local > 0 else None,
+        "build_share_of_step": prof["build"][0] / ms_local if ms_local > 0 else None,
+        "halo_share_of_step": prof["halo"][0] / ms_local if ms_local > 0 else None,
+        "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+        "traffic_source": (traffic or {}).get("source"),
+    }
+
+    # ---- end to end: host buffers in, host buffers out, every step ----
+    def pull():
+        if world > 1:
+            return h.download_owned_ptr(host.data_ptr(), cap_rows)
+        h.download_ptr(host.data_ptr())
+        return N
+    n_rows = pull()
+    h2d = d2h = 0
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        h.upload_ptr(host.data_ptr(), n_rows)
+        h2d += n_rows * 32
+        h.sweep_nvt(S, DR_MAX)
+        n_rows = pull()
+        d2h += n_rows * 32 + 48
+        c2 = h.counters()
+    h.sync()
+    barrier()
+    t_e2e = allmax(time.perf_counter() - t0)
+    e2e_val = N * S * args.e2e_steps / t_e2e
+    e2e = {"value": e2e_val, "unit": "moves/s", "h2d_bytes_per_step": int(allsum(h2d) / args.e2e_steps),
+           "d2h_bytes_per_step": int(allsum(d2h) / args.e2e_steps), "steps": args.e2e_steps,
+           "ms_per_step": 1e3 * t_e2e / args.e2e_steps,
+           "what": "hsmc_gpu_upload(pinned host rows) + hsmc_gpu_sweep_nvt + hsmc_gpu_download + hsmc_gpu_counters per step"}
+    acc = float(cnt[1]) / float(cnt[0])
+    min_r2 = h.min_dist2()
+    assert min_r2 >= 1.0, f"overlap after benchmark: min r^2 = {min_r2}"
+    h.close()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = len(os.sched_getaffinity(0))
+        # bounded sample: ~cpu_seconds of CPU work per replica (about 1.1 us per move per core)
+        ncpu = 4 * args.cpu_cells ** 3
+        steps_cpu = max(1, int(args.cpu_seconds / (ncpu * 1.2e-6)))
+        try:
+            r = cpu_reference_arm(steps_cpu, 1, args.cpu_cells, 1, cores)
+            cpu = {"value": r["value"], "unit": "moves/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+        except Exception as e:   # the baseline is reported, never required
+            cpu = {"value": None, "unit": "moves/s", "cores": cores, "kind": "unavailable", "sample": repr(e)}
+
+    if rank == 0:
+        line = {
+            "metric": "hard_sphere_trial_moves_per_sec", "value": value, "unit": "moves/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": dict(workload, cells=list(info["cells"]), cell_size=list(info["cell_size"]),
+                           acceptance=acc, l2="inputs larger than L2" if flush is None else "L2 flushed between steps",
+                           resident_bytes_per_rank=resident, wall_s_timed_region=t_wall, min_r2_after=min_r2),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,78 @@
+"""Build recipe for the native parts (in-tree, explicit nvcc / gcc; nothing is JIT-cached).
+
+  csrc/libhsmc_gpu.so   CUDA kernels + C ABI (include/hsmc_gpu.h), sm_100a only
+  host/hsmc_b200        C host driver (drop-in for the reference's `hsmc` executable)
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+HOST = os.path.join(PKG, "host")
+LIB = os.path.join(CSRC, "libhsmc_gpu.so")
+EXE = os.path.join(HOST, "hsmc_b200")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-fmad=false",            # bit-exact with the reference's unfused gcc -O2 arithmetic
+    "--extended-lambda",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(s) <= t for s in sources)
+
+
+def nvcc_path():
+    for c in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if c and os.path.exists(c):
+            return c
+    raise RuntimeError("nvcc not found")
+
+
+def build_lib(force=False, verbose=False):
+    srcs = [os.path.join(CSRC, f) for f in ("hsmc_gpu.cu", "geom.cuh", "philox.cuh")]
+    srcs.append(os.path.join(ROOT, "include", "hsmc_gpu.h"))
+    if not force and _newer(LIB, srcs):
+        return LIB
+    cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", LIB, os.path.join(CSRC, "hsmc_gpu.cu"), "-lnccl"]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+        print(" ".join(cmd))
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or out.returncode != 0:
+        sys.stderr.write(out.stdout + out.stderr)
+    if out.returncode != 0:
+        raise RuntimeError("nvcc failed building libhsmc_gpu.so")
+    return LIB
+
+
+def build_host(force=False, verbose=False):
+    if not os.path.isdir(HOST) or not os.path.exists(os.path.join(HOST, "Makefile")):
+        return None
+    cmd = ["make", "-C", HOST] + (["-B"] if force else [])
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or out.returncode != 0:
+        sys.stderr.write(out.stdout + out.stderr)
+    if out.returncode != 0:
+        raise RuntimeError("host driver build failed")
+    return EXE
+
+
+def build_all(force=False, verbose=False):
+    build_lib(force, verbose)
+    build_host(force, verbose)
+
+
+if __name__ == "__main__":
+    build_all(force="-f" in sys.argv, verbose=True)

@@ -1,0 +1,1500 @@
+// hsmc_gpu.cu -- B200 (sm_100a) hard-sphere Monte Carlo hot path behind the C ABI of
+// include/hsmc_gpu.h.  Hand-written CUDA, no CPU fallback, no library kernels.
+//
+// Data layout in HBM (per rank):
+//   pos[2][cap]   double4 {x, y, z, id}, cell-ordered (counting sort), ping-pong
+//   cell_start    int[ncell_local + 1]   CSR offsets into pos
+//   key, rnk      int[cap]               scratch of the counting sort
+// Kernels ("new kernel" table):
+//   K1  k_cell_count / k_scan_* / k_cell_scatter   cell_list_new   (cell_list.c:142-175)
+//   K2  k_sweep_phase        part_move + check_overlap             (moves.c:27-80,157-212)
+//   K3  k_overlap_scaled     vol_move / presst verdict             (moves.c:106-112)
+//   K4  k_widom              widom_insertion                       (compute_widom_chem_pot.c:44-71)
+//   K5  k_rdf_pairs          rdf_hist_compute                      (compute_rdf.c:110-128)
+//   K6  k_contact_hist       pressv_compute_hist                   (compute_press.c:123-165)
+//   K7  k_rescale            accepted volume move                  (moves.c:135-142)
+#include <cuda_runtime.h>
+#include <nccl.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "../../include/hsmc_gpu.h"
+#include "geom.cuh"
+#include "philox.cuh"
+
+// ----------------------------------------------------------------------------------
+// error plumbing
+// ----------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(const std::string& m) {
+  g_err = m;
+  return 1;
+}
+
+#define CU(call)                                                                       \
+  do {                                                                                 \
+    cudaError_t e__ = (call);                                                          \
+    if (e__ != cudaSuccess)                                                            \
+      return fail(std::string("CUDA: ") + cudaGetErrorString(e__) + " at " #call);     \
+  } while (0)
+
+#define NC(call)                                                                       \
+  do {                                                                                 \
+    ncclResult_t r__ = (call);                                                         \
+    if (r__ != ncclSuccess)                                                            \
+      return fail(std::string("NCCL: ") + ncclGetErrorString(r__) + " at " #call);     \
+  } while (0)
+
+#define TRY(call)            \
+  do {                       \
+    int rc__ = (call);       \
+    if (rc__) return rc__;   \
+  } while (0)
+
+extern "C" const char* hsmc_gpu_last_error(void) { return g_err.c_str(); }
+
+// ----------------------------------------------------------------------------------
+// handle
+// ----------------------------------------------------------------------------------
+enum { CNT_TRIALS = 0, CNT_ACC = 1, CNT_REJ_OVERLAP = 2, CNT_REJ_CELL = 3, CNT_N = 8 };
+
+struct hsmc_gpu {
+  hsmc_gpu_config cfg;
+  int64_t N = 0;           // global particle count
+  int64_t n_local = 0;     // resident particles (owned + ghosts)
+  int64_t n_owned = 0;
+  int64_t own_first = 0;   // slot of the first owned particle
+  int64_t cap = 0;         // slots in pos[*]
+  double box[3];
+  Grid g;
+  int64_t ncell = 0;       // local cells
+  int64_t cap_cells = 0;
+  cudaStream_t st = nullptr;
+  double4* pos[2] = {nullptr, nullptr};
+  int cur = 0;
+  int *key = nullptr, *rnk = nullptr;    // [cap + 2*cap_halo]
+  int *cell_count = nullptr, *cell_start = nullptr, *bsum = nullptr;
+  unsigned long long* d_cnt = nullptr;       // CNT_N counters
+  unsigned long long* d_scratch = nullptr;   // SCRATCH_N x u64 general scratch (flags, hist, min)
+  int* d_slot_of_id = nullptr;           // parity entry points only
+  void* h_stage = nullptr;               // pinned staging for small results
+  double* d_io = nullptr;                // staging for upload/download
+  int64_t cap_io = 0;
+  uint64_t sweeps_done = 0;
+  uint64_t launches = 0, nccl_calls = 0;
+  int64_t vol_cnt[3] = {0, 0, 0};
+  bool have_conf = false;
+  int since_regrid = 0;
+  ncclComm_t comm = nullptr;
+  // slab mode
+  double4 *send_l = nullptr, *send_r = nullptr, *recv_l = nullptr, *recv_r = nullptr;
+  int64_t cap_halo = 0;                  // slots per halo buffer, slot 0 = header
+  int* d_halo_cnt = nullptr;             // [0]=send_l count [1]=send_r count [2]=error flags
+  int lay[6] = {0, 0, 0, 0, 0, 0};       // slot offsets of layers 0,1,2,nlx-2,nlx-1,nlx
+  void* d_sfargs = nullptr;
+  hsmc_gpu_trial* d_log = nullptr;
+  int64_t cap_log = 0;
+  // optional event timing
+  bool prof = false;
+  std::vector<cudaEvent_t> ev_pool;
+  struct Span { cudaEvent_t a, b; int bucket; };
+  std::vector<Span> spans;
+  double prof_ms[HSMC_GPU_PROFILE_BUCKETS] = {0, 0, 0, 0};
+  int64_t prof_n[HSMC_GPU_PROFILE_BUCKETS] = {0, 0, 0, 0};
+};
+
+static cudaEvent_t prof_event(hsmc_gpu* h) {
+  cudaEvent_t e;
+  if (!h->ev_pool.empty()) { e = h->ev_pool.back(); h->ev_pool.pop_back(); }
+  else cudaEventCreate(&e);
+  return e;
+}
+struct ProfSpan {
+  hsmc_gpu* h; cudaEvent_t a; int bucket; bool on;
+  ProfSpan(hsmc_gpu* h_, int bucket_) : h(h_), bucket(bucket_), on(h_->prof) {
+    if (on) { a = prof_event(h); cudaEventRecord(a, h->st); }
+  }
+  ~ProfSpan() {
+    if (on) { cudaEvent_t b = prof_event(h); cudaEventRecord(b, h->st); h->spans.push_back({a, b, bucket}); }
+  }
+};
+
+#define SCRATCH_N 16384
+
+static inline int nblk(int64_t n, int t) { return (int)((n + t - 1) / t); }
+
+// ----------------------------------------------------------------------------------
+// K1: cell list = counting sort
+// ----------------------------------------------------------------------------------
+// pass 1: cell key of every particle, rank inside its cell by atomic counter
+__global__ void k_cell_count(Grid g, const double4* __restrict__ in, int n, int* __restrict__ key,
+                             int* __restrict__ rnk, int* __restrict__ count) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double4 p = in[i];
+  long long c = local_cell(g, p.x, p.y, p.z);
+  key[i] = (int)c;
+  if (c >= 0) rnk[i] = atomicAdd(&count[c], 1);
+}
+
+// exclusive scan of count[0..n) into out[0..n], out[n] = total: three small kernels
+#define SCAN_T 512
+#define SCAN_V 8
+#define SCAN_CHUNK (SCAN_T * SCAN_V)
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* total) {
+  __shared__ int wsum[SCAN_T / 32];
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) wsum[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    int s = (lane < SCAN_T / 32) ? wsum[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += t;
+    }
+    if (lane < SCAN_T / 32) wsum[lane] = s;
+  }
+  __syncthreads();
+  int base = (w > 0) ? wsum[w - 1] : 0;
+  *total = wsum[SCAN_T / 32 - 1];
+  __syncthreads();
+  return base + inc - v;
+}
+
+__global__ void k_scan_blocksum(const int* __restrict__ in, long long n, int* __restrict__ bsum) {
+  long long base = (long long)blockIdx.x * SCAN_CHUNK;
+  int s = 0;
+#pragma unroll
+  for (int j = 0; j < SCAN_V; j++) {
+    long long i = base + (long long)j * SCAN_T + threadIdx.x;
+    if (i < n) s += in[i];
+  }
+  int tot;
+  block_exclusive_scan(s, &tot);
+  if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
+}
+
+__global__ void k_scan_top(int* bsum, int nb) {
+  // single block; sequential over chunks of SCAN_T with a running carry
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < nb; b0 += SCAN_T) {
+    int i = b0 + threadIdx.x;
+    int v = (i < nb) ? bsum[i] : 0;
+    int tot;
+    int ex = block_exclusive_scan(v, &tot);
+    if (i < nb) bsum[i] = carry + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += tot;
+    __syncthreads();
+  }
+}
+
+__global__ void k_scan_final(const int* __restrict__ in, long long n, const int* __restrict__ bsum,
+                             int* __restrict__ out) {
+  long long base = (long long)blockIdx.x * SCAN_CHUNK + (long long)threadIdx.x * SCAN_V;
+  int v[SCAN_V];
+  int s = 0;
+#pragma unroll
+  for (int j = 0; j < SCAN_V; j++) {
+    long long i = base + j;
+    v[j] = (i < n) ? in[i] : 0;
+    s += v[j];
+  }
+  int tot;
+  int ex = block_exclusive_scan(s, &tot) + bsum[blockIdx.x];
+#pragma unroll
+  for (int j = 0; j < SCAN_V; j++) {
+    long long i = base + j;
+    if (i < n) out[i] = ex;
+    ex += v[j];
+    if (i == n - 1) out[n] = ex;
+  }
+}
+
+// pass 3: scatter into cell order
+__global__ void k_cell_scatter(const double4* __restrict__ in, int n, const int* __restrict__ key,
+                               const int* __restrict__ rnk, const int* __restrict__ cs,
+                               double4* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int c = key[i];
+  if (c < 0) return;
+  out[cs[c] + rnk[i]] = in[i];
+}
+
+// ----------------------------------------------------------------------------------
+// host <-> device table conversion ({id,x,y,z} rows <-> {x,y,z,id} slots)
+// ----------------------------------------------------------------------------------
+__global__ void k_unpack_rows(const double* __restrict__ rows, int n, double4* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double4 r = reinterpret_cast<const double4*>(rows)[i];
+  out[i] = make_double4(r.y, r.z, r.w, r.x);
+}
+
+__global__ void k_pack_by_id(const double4* __restrict__ pos, int first, int n, double* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double4 p = pos[first + i];
+  long long id = (long long)p.w;
+  reinterpret_cast<double4*>(out)[id] = make_double4(p.w, p.x, p.y, p.z);
+}
+
+__global__ void k_pack_rows(const double4* __restrict__ pos, int first, int n, double* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double4 p = pos[first + i];
+  reinterpret_cast<double4*>(out)[i] = make_double4(p.w, p.x, p.y, p.z);
+}
+
+__global__ void k_slot_of_id(const double4* __restrict__ pos, int n, int* __restrict__ slot) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  slot[(long long)pos[i].w] = i;
+}
+
+// ----------------------------------------------------------------------------------
+// K2: one colour phase of the checkerboard sweep.
+//
+// Cells are coloured by the parity of their (global) indices, 2x2x2 = 8 colours.  Two
+// cells of one colour are separated by a full cell (edge >= 1.0 = sigma), so particles
+// in different active cells can never overlap whatever moves they make inside their
+// cells: all active cells are independent and are processed concurrently, one thread
+// per active cell, the particles of a cell sequentially in ascending-id order.  A trial
+// that would leave its cell is rejected (membership is static within a sweep); the grid
+// origin is redrawn between sweeps so that walls move (Anderson et al., J. Comput. Phys.
+// 254 (2013) 27).  Each trial is the reference's part_move(): three uniforms,
+// x += (u - 0.5)*dr_max, apply_pbc, accept iff check_overlap is false.
+// ----------------------------------------------------------------------------------
+struct SweepArgs {
+  Grid g;
+  Box box;
+  double dr_max;
+  uint32_t key0, key1;
+  uint32_t sweep_lo, sweep_hi;
+  int cx, cy, cz, phase;
+};
+
+template <bool LOG>
+__global__ void __launch_bounds__(128)
+k_sweep_phase(SweepArgs a, double4* __restrict__ pos, const int* __restrict__ cs,
+              unsigned long long* __restrict__ cnt, hsmc_gpu_trial* __restrict__ log,
+              unsigned long long* __restrict__ nlog, long long logcap) {
+  const Grid& g = a.g;
+  const int hx = (g.own_hi - g.own_lo) >> 1, hy = g.ny >> 1, hz = g.nz >> 1;
+  const long long total = (long long)hx * hy * hz;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int n_acc = 0, n_ov = 0, n_cell = 0;
+  if (t < total) {
+    int az = (int)(t % hz);
+    long long r = t / hz;
+    int ay = (int)(r % hy), ax = (int)(r / hy);
+    int par0 = (g.gx0 + g.own_lo) & 1;
+    int l = g.own_lo + 2 * ax + ((a.cx - par0) & 1);
+    int iy = 2 * ay + a.cy, iz = 2 * az + a.cz;
+    long long c = ((long long)l * g.ny + iy) * g.nz + iz;
+    int beg = cs[c], end = cs[c + 1];
+    long long gcell = global_cell_of_local(g, l, iy, iz);
+    double last_id = -1.0;
+    for (int j = 0; j < end - beg; j++) {
+      // next particle of this cell in ascending-id order (order is then independent of
+      // how the counting sort happened to place them)
+      int sel = beg;
+      double best = 1e300;
+      for (int k = beg; k < end; k++) {
+        double id = pos[k].w;
+        if (id > last_id && id < best) { best = id; sel = k; }
+      }
+      last_id = best;
+      double4 p = pos[sel];
+      Philox4 rn = philox4x32_10((uint32_t)gcell, (HSMC_STREAM_MOVE << 24) | (uint32_t)j, a.sweep_lo,
+                                 a.sweep_hi, a.key0, a.key1);
+      // moves.c:52-54
+      double xn = p.x + (hsmc_u01(rn.v[0]) - 0.5) * a.dr_max;
+      double yn = p.y + (hsmc_u01(rn.v[1]) - 0.5) * a.dr_max;
+      double zn = p.z + (hsmc_u01(rn.v[2]) - 0.5) * a.dr_max;
+      // moves.c:215-226
+      if (xn > g.Lx) xn -= g.Lx; else if (xn < 0.0) xn += g.Lx;
+      if (yn > g.Ly) yn -= g.Ly; else if (yn < 0.0) yn += g.Ly;
+      if (zn > g.Lz) zn -= g.Lz; else if (zn < 0.0) zn += g.Lz;
+      int verdict;
+      if (axis_cell(xn, g.sx, g.iwx, g.nx) != ((g.gx0 + l >= g.nx) ? g.gx0 + l - g.nx : g.gx0 + l) ||
+          axis_cell(yn, g.sy, g.iwy, g.ny) != iy || axis_cell(zn, g.sz, g.iwz, g.nz) != iz) {
+        verdict = 2;
+        n_cell++;
+      } else {
+        const Box& b = a.box;
+        bool ov = stencil_any(g, cs, l, iy, iz, [&](int k) {
+          if (k == sel) return false;
+          double4 q = pos[k];
+          return pair_r2(xn, yn, zn, q.x, q.y, q.z, b) < 1.0;
+        });
+        if (ov) { verdict = 1; n_ov++; }
+        else {
+          verdict = 0; n_acc++;
+          pos[sel] = make_double4(xn, yn, zn, p.w);
+        }
+      }
+      if (LOG) {
+        unsigned long long s = atomicAdd(nlog, 1ull);
+        if ((long long)s < logcap) {
+          hsmc_gpu_trial tr;
+          tr.seq = ((unsigned long long)a.phase << 56) | ((unsigned long long)gcell << 8) | (unsigned)j;
+          tr.id = (int)p.w; tr.verdict = verdict;
+          tr.raw[0] = rn.v[0]; tr.raw[1] = rn.v[1]; tr.raw[2] = rn.v[2]; tr.pad = 0;
+          log[s] = tr;
+        }
+      }
+    }
+  }
+  // block-aggregated counters
+  __shared__ int s_cnt[3];
+  if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  if (n_acc) atomicAdd(&s_cnt[0], n_acc);
+  if (n_ov) atomicAdd(&s_cnt[1], n_ov);
+  if (n_cell) atomicAdd(&s_cnt[2], n_cell);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = s_cnt[0] + s_cnt[1] + s_cnt[2];
+    if (tot) {
+      atomicAdd(&cnt[CNT_TRIALS], (unsigned long long)tot);
+      if (s_cnt[0]) atomicAdd(&cnt[CNT_ACC], (unsigned long long)s_cnt[0]);
+      if (s_cnt[1]) atomicAdd(&cnt[CNT_REJ_OVERLAP], (unsigned long long)s_cnt[1]);
+      if (s_cnt[2]) atomicAdd(&cnt[CNT_REJ_CELL], (unsigned long long)s_cnt[2]);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------
+// K3: global scaled-overlap verdict for nsf scale factors in one pass over the pairs.
+// One thread per owned cell; each unordered pair is visited once (id_j > id_i).
+// A cheap unscaled pre-test skips pairs that cannot overlap under any of the factors
+// (threshold carries a 1e-6 relative margin, far above rounding); pairs that pass are
+// evaluated with the reference's exact scaled arithmetic for every factor.
+// ----------------------------------------------------------------------------------
+#define MAX_SF 64
+struct SfArgs {
+  int n;
+  double r2_skip;       // unscaled r2 above which no factor can give an overlap
+  double sf[MAX_SF];
+  Box box[MAX_SF];
+};
+
+__global__ void __launch_bounds__(128)
+k_overlap_scaled(Grid g, Box ubox, const SfArgs* __restrict__ sa, const double4* __restrict__ pos,
+                 const int* __restrict__ cs, int* __restrict__ flags) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)(g.own_hi - g.own_lo) * g.ny * g.nz;
+  if (t >= total) return;
+  int nsf = sa->n;
+  if (nsf == 1 && flags[0]) return;   // verdict already known
+  int iz = (int)(t % g.nz);
+  long long r = t / g.nz;
+  int iy = (int)(r % g.ny), l = g.own_lo + (int)(r / g.ny);
+  long long c = ((long long)l * g.ny + iy) * g.nz + iz;
+  int beg = cs[c], end = cs[c + 1];
+  double r2_skip = sa->r2_skip;
+  for (int s = beg; s < end; s++) {
+    double4 p = pos[s];
+    stencil_any(g, cs, l, iy, iz, [&](int k) {
+      double4 q = pos[k];
+      if (!(q.w > p.w)) return false;
+      if (pair_r2(p.x, p.y, p.z, q.x, q.y, q.z, ubox) > r2_skip) return false;
+      bool all = true;
+      for (int m = 0; m < nsf; m++) {
+        if (pair_r2_scaled(p.x, p.y, p.z, q.x, q.y, q.z, sa->sf[m], sa->box[m]) < 1.0) flags[m] = 1;
+        else all = false;
+      }
+      return nsf == 1 && all;
+    });
+  }
+}
+
+// ----------------------------------------------------------------------------------
+// K4: Widom insertions.  One thread per insertion point; the point is
+// r = u * L (compute_widom_chem_pot.c:73-80) with u from Philox(sample, index).
+// ----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_widom(Grid g, Box box, const double4* __restrict__ pos, const int* __restrict__ cs, uint32_t key0,
+        uint32_t key1, uint32_t sample_lo, uint32_t sample_hi, long long first, long long count,
+        unsigned long long* __restrict__ accepted) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int ok = 0;
+  if (t < count) {
+    unsigned long long m = (unsigned long long)(first + t);
+    Philox4 rn = philox4x32_10((uint32_t)m, (HSMC_STREAM_WIDOM << 24) | (uint32_t)(m >> 32), sample_lo,
+                               sample_hi, key0, key1);
+    double rx = hsmc_u01(rn.v[0]) * g.Lx, ry = hsmc_u01(rn.v[1]) * g.Ly, rz = hsmc_u01(rn.v[2]) * g.Lz;
+    int l = local_layer(g, axis_cell(rx, g.sx, g.iwx, g.nx));
+    if (l >= g.own_lo && l < g.own_hi) {
+      int iy = axis_cell(ry, g.sy, g.iwy, g.ny), iz = axis_cell(rz, g.sz, g.iwz, g.nz);
+      bool ov = stencil_any(g, cs, l, iy, iz, [&](int k) {
+        double4 q = pos[k];
+        return pair_r2(rx, ry, rz, q.x, q.y, q.z, box) < 1.0;
+      });
+      ok = ov ? 0 : 1;
+    }
+  }
+  unsigned m = __ballot_sync(0xffffffffu, ok);
+  __shared__ int s_ok;
+  if (threadIdx.x == 0) s_ok = 0;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(&s_ok, __popc(m));
+  __syncthreads();
+  if (threadIdx.x == 0 && s_ok) atomicAdd(accepted, (unsigned long long)s_ok);
+}
+
+// explicit points (parity entry point)
+__global__ void k_widom_points(Grid g, Box box, const double4* __restrict__ pos, const int* __restrict__ cs,
+                               const double* __restrict__ xyz, int n, int* __restrict__ flags) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  double rx = xyz[3 * t], ry = xyz[3 * t + 1], rz = xyz[3 * t + 2];
+  int l = local_layer(g, axis_cell(rx, g.sx, g.iwx, g.nx));
+  int iy = axis_cell(ry, g.sy, g.iwy, g.ny), iz = axis_cell(rz, g.sz, g.iwz, g.nz);
+  bool ov = stencil_any(g, cs, l, iy, iz, [&](int k) {
+    double4 q = pos[k];
+    return pair_r2(rx, ry, rz, q.x, q.y, q.z, box) < 1.0;
+  });
+  flags[t] = ov ? 1 : 0;
+}
+
+// explicit trial moves (parity entry point): verdict of check_overlap for particle
+// idx placed at xyz with everything else fixed
+__global__ void k_trial_points(Grid g, Box sbox, double sf, const double4* __restrict__ pos,
+                               const int* __restrict__ cs, const int* __restrict__ idx,
+                               const double* __restrict__ xyz, int n, int* __restrict__ flags) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  double rx = xyz[3 * t], ry = xyz[3 * t + 1], rz = xyz[3 * t + 2];
+  double id = (double)idx[t];
+  int l = local_layer(g, axis_cell(rx, g.sx, g.iwx, g.nx));
+  int iy = axis_cell(ry, g.sy, g.iwy, g.ny), iz = axis_cell(rz, g.sz, g.iwz, g.nz);
+  bool ov = stencil_any(g, cs, l, iy, iz, [&](int k) {
+    double4 q = pos[k];
+    if (q.w == id) return false;
+    return pair_r2_scaled(rx, ry, rz, q.x, q.y, q.z, sf, sbox) < 1.0;
+  });
+  flags[t] = ov ? 1 : 0;
+}
+
+// ----------------------------------------------------------------------------------
+// K5: RDF pair histogram, all pairs (compute_rdf.c:110-128), shared-memory privatised.
+// Tiles of RDF_T x RDF_T pairs; the j tile is staged in shared memory; the square root
+// and the division (needed for a bit-exact bin index) are only evaluated for pairs that
+// pass a conservative r2 pre-test.
+// ----------------------------------------------------------------------------------
+#define RDF_T 256
+#define RDF_MAX_SMEM_BINS 8192
+__global__ void __launch_bounds__(RDF_T)
+k_rdf_pairs(const double4* __restrict__ pos, int n, Box box, double rmax, double r2_pre, double dr_bin,
+            int nn, int ntile, unsigned long long* __restrict__ hist) {
+  // linear block index -> (ti, tj) with tj >= ti
+  long long b = blockIdx.x;
+  int ti = 0;
+  {
+    // rows of the upper triangle have ntile - ti entries
+    double nt = (double)ntile;
+    ti = (int)floor(((2.0 * nt + 1.0) - sqrt((2.0 * nt + 1.0) * (2.0 * nt + 1.0) - 8.0 * (double)b)) * 0.5);
+    while ((long long)ti * (2LL * ntile - ti + 1) / 2 > b) ti--;
+    while ((long long)(ti + 1) * (2LL * ntile - ti) / 2 <= b) ti++;
+  }
+  int tj = ti + (int)(b - (long long)ti * (2LL * ntile - ti + 1) / 2);
+  extern __shared__ unsigned char smem_raw[];
+  double* sx = reinterpret_cast<double*>(smem_raw);
+  double* sy = sx + RDF_T;
+  double* sz = sy + RDF_T;
+  unsigned int* sh = reinterpret_cast<unsigned int*>(sz + RDF_T);
+  bool use_sh = nn <= RDF_MAX_SMEM_BINS;
+  if (use_sh)
+    for (int k = threadIdx.x; k < nn; k += RDF_T) sh[k] = 0;
+  int j0 = tj * RDF_T;
+  int jn = min(RDF_T, n - j0);
+  if ((int)threadIdx.x < jn) {
+    double4 q = pos[j0 + threadIdx.x];
+    sx[threadIdx.x] = q.x; sy[threadIdx.x] = q.y; sz[threadIdx.x] = q.z;
+  }
+  __syncthreads();
+  int i = ti * RDF_T + threadIdx.x;
+  if (i < n) {
+    double4 p = pos[i];
+    int jb = (ti == tj) ? (int)threadIdx.x + 1 : 0;
+    for (int j = jb; j < jn; j++) {
+      double r2 = pair_r2(p.x, p.y, p.z, sx[j], sy[j], sz[j], box);
+      if (r2 < r2_pre) {
+        double dr = sqrt(r2);
+        if (dr < rmax) {
+          int bin = (int)((dr - 1.0) / dr_bin);
+          if (bin >= 0 && bin < nn) {
+            if (use_sh) atomicAdd(&sh[bin], 1u);
+            else atomicAdd(&hist[bin], 1ull);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (use_sh)
+    for (int k = threadIdx.x; k < nn; k += RDF_T)
+      if (sh[k]) atomicAdd(&hist[k], (unsigned long long)sh[k]);
+}
+
+// ----------------------------------------------------------------------------------
+// K6: near-contact pair histogram through the cell list (compute_press.c:123-165).
+// ----------------------------------------------------------------------------------
+#define CONTACT_MAX_BINS 1024
+__global__ void __launch_bounds__(128)
+k_contact_hist(Grid g, Box box, const double4* __restrict__ pos, const int* __restrict__ cs, double rmax,
+               double dr_bin, int nn, unsigned long long* __restrict__ hist) {
+  __shared__ unsigned int sh[CONTACT_MAX_BINS];
+  for (int k = threadIdx.x; k < nn; k += blockDim.x) sh[k] = 0;
+  __syncthreads();
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)(g.own_hi - g.own_lo) * g.ny * g.nz;
+  if (t < total) {
+    int iz = (int)(t % g.nz);
+    long long r = t / g.nz;
+    int iy = (int)(r % g.ny), l = g.own_lo + (int)(r / g.ny);
+    long long c = ((long long)l * g.ny + iy) * g.nz + iz;
+    int beg = cs[c], end = cs[c + 1];
+    double r2_pre = rmax * rmax * (1.0 + 1e-9);
+    for (int s = beg; s < end; s++) {
+      double4 p = pos[s];
+      stencil_any(g, cs, l, iy, iz, [&](int k) {
+        double4 q = pos[k];
+        if (!(q.w > p.w)) return false;
+        double r2 = pair_r2(p.x, p.y, p.z, q.x, q.y, q.z, box);
+        if (r2 < r2_pre) {
+          double dr = sqrt(r2);
+          if (dr < rmax) {
+            int bin = (int)((dr - 1.0) / dr_bin);
+            if (bin >= 0 && bin < nn) atomicAdd(&sh[bin], 1u);
+          }
+        }
+        return false;
+      });
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < nn; k += blockDim.x)
+    if (sh[k]) atomicAdd(&hist[k], (unsigned long long)sh[k]);
+}
+
+// min pair r2 over the stencil (invariant check: never below 1.0 in a valid run)
+__global__ void k_min_r2(Grid g, Box box, const double4* __restrict__ pos, const int* __restrict__ cs,
+                         unsigned long long* __restrict__ out) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)(g.own_hi - g.own_lo) * g.ny * g.nz;
+  if (t >= total) return;
+  int iz = (int)(t % g.nz);
+  long long r = t / g.nz;
+  int iy = (int)(r % g.ny), l = g.own_lo + (int)(r / g.ny);
+  long long c = ((long long)l * g.ny + iy) * g.nz + iz;
+  int beg = cs[c], end = cs[c + 1];
+  double best = 1e300;
+  for (int s = beg; s < end; s++) {
+    double4 p = pos[s];
+    stencil_any(g, cs, l, iy, iz, [&](int k) {
+      double4 q = pos[k];
+      if (q.w > p.w) best = fmin(best, pair_r2(p.x, p.y, p.z, q.x, q.y, q.z, box));
+      return false;
+    });
+  }
+  if (best < 1e299) atomicMin(out, (unsigned long long)__double_as_longlong(best));
+}
+
+// ----------------------------------------------------------------------------------
+// K7: accepted volume move (moves.c:135-141): x *= sf, then apply_pbc with the new box
+// ----------------------------------------------------------------------------------
+__global__ void k_rescale(double4* __restrict__ pos, int n, double sf, double lx, double ly, double lz) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double4 p = pos[i];
+  p.x *= sf; p.y *= sf; p.z *= sf;
+  if (p.x > lx) p.x -= lx; else if (p.x < 0.0) p.x += lx;
+  if (p.y > ly) p.y -= ly; else if (p.y < 0.0) p.y += ly;
+  if (p.z > lz) p.z -= lz; else if (p.z < 0.0) p.z += lz;
+  pos[i] = p;
+}
+
+// ----------------------------------------------------------------------------------
+// slab decomposition (world > 1): classify + halo buffers
+// ----------------------------------------------------------------------------------
+// Source particles are this rank's previously owned ones (or, for an upload, arbitrary
+// rows).  Each is keyed into the local cell grid and, when it lies in one of the two
+// layers at either end of the slab, also appended to the buffer bound for that
+// neighbour: layers {0,1} -> left, {nlx-2,nlx-1} -> right (migrants + fresh ghosts in one
+// message).  upload_mode keeps only owned layers and sends only boundary layers.
+__global__ void k_slab_classify(Grid g, const double4* __restrict__ in, int n, int rows_layout,
+                                int upload_mode, int* __restrict__ key, int* __restrict__ rnk,
+                                int* __restrict__ count, double4* __restrict__ send_l,
+                                double4* __restrict__ send_r, int* __restrict__ halo_cnt, int cap_halo) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double4 p = in[i];
+  if (rows_layout) p = make_double4(p.y, p.z, p.w, p.x);
+  long long c = local_cell(g, p.x, p.y, p.z);
+  int lyr = (c >= 0) ? (int)(c / ((long long)g.ny * g.nz)) : -1;
+  bool keep, to_l, to_r;
+  if (upload_mode) {
+    keep = lyr >= g.own_lo && lyr < g.own_hi;
+    to_l = lyr == g.own_lo;
+    to_r = lyr == g.own_hi - 1;
+  } else {
+    if (c < 0) atomicOr(&halo_cnt[2], 1);   // moved more than one layer: impossible by construction
+    keep = c >= 0;
+    to_l = keep && lyr <= 1;
+    to_r = keep && lyr >= g.nlx - 2;
+  }
+  key[i] = keep ? (int)c : -1;
+  if (keep) rnk[i] = atomicAdd(&count[c], 1);
+  if (to_l) {
+    int s = atomicAdd(&halo_cnt[0], 1);
+    if (s + 1 < cap_halo) send_l[s + 1] = p; else atomicOr(&halo_cnt[2], 2);
+  }
+  if (to_r) {
+    int s = atomicAdd(&halo_cnt[1], 1);
+    if (s + 1 < cap_halo) send_r[s + 1] = p; else atomicOr(&halo_cnt[2], 2);
+  }
+}
+
+__global__ void k_halo_headers(double4* send_l, double4* send_r, const int* halo_cnt) {
+  send_l[0] = make_double4((double)halo_cnt[0], 0, 0, 0);
+  send_r[0] = make_double4((double)halo_cnt[1], 0, 0, 0);
+}
+
+// key the received particles (count in the header slot)
+__global__ void k_recv_count(Grid g, const double4* __restrict__ buf, int cap_halo, int* __restrict__ key,
+                             int* __restrict__ rnk, int* __restrict__ count, int* __restrict__ halo_cnt) {
+  int n = (int)buf[0].x;
+  if (n > cap_halo - 1) n = cap_halo - 1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double4 p = buf[i + 1];
+    long long c = local_cell(g, p.x, p.y, p.z);
+    key[i] = (int)c;
+    if (c >= 0) rnk[i] = atomicAdd(&count[c], 1);
+    else atomicOr(&halo_cnt[2], 4);
+  }
+}
+
+__global__ void k_recv_scatter(const double4* __restrict__ buf, int cap_halo, const int* __restrict__ key,
+                               const int* __restrict__ rnk, const int* __restrict__ cs,
+                               double4* __restrict__ out) {
+  int n = (int)buf[0].x;
+  if (n > cap_halo - 1) n = cap_halo - 1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int c = key[i];
+    if (c >= 0) out[cs[c] + rnk[i]] = buf[i + 1];
+  }
+}
+
+__global__ void k_scatter_layout(const double4* __restrict__ in, int n, int rows_layout,
+                                 const int* __restrict__ key, const int* __restrict__ rnk,
+                                 const int* __restrict__ cs, double4* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int c = key[i];
+  if (c < 0) return;
+  double4 p = in[i];
+  if (rows_layout) p = make_double4(p.y, p.z, p.w, p.x);
+  out[cs[c] + rnk[i]] = p;
+}
+
+// canonical (ascending id) slot order inside every cell of the given layers, so that a
+// boundary layer and its ghost copy on the neighbour are slot-for-slot identical
+__global__ void k_sort_cells_by_id(Grid g, double4* __restrict__ pos, const int* __restrict__ cs,
+                                   int layer_a, int layer_b) {
+  long long per = (long long)g.ny * g.nz;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 2 * per) return;
+  long long c = (t < per) ? (long long)layer_a * per + t : (long long)layer_b * per + (t - per);
+  int beg = cs[c], end = cs[c + 1];
+  for (int i = beg + 1; i < end; i++) {
+    double4 v = pos[i];
+    int j = i - 1;
+    while (j >= beg && pos[j].w > v.w) { pos[j + 1] = pos[j]; j--; }
+    pos[j + 1] = v;
+  }
+}
+
+// ----------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------
+static int even_cells(double L, double cell_min) {
+  int n = (int)floor(L / cell_min);
+  n &= ~1;
+  // keep a rounding margin between the cell edge and the requested minimum
+  while (n >= 2 && L / n < cell_min * (1.0 + 1e-9)) n -= 2;
+  return n;
+}
+
+static int setup_grid(hsmc_gpu* h) {
+  double cm = h->cfg.cell_min;
+  Grid& g = h->g;
+  g.nx = even_cells(h->box[0], cm);
+  g.ny = even_cells(h->box[1], cm);
+  g.nz = even_cells(h->box[2], cm);
+  if (g.nx < 4 || g.ny < 4 || g.nz < 4)
+    return fail("simulation box too small for the checkerboard decomposition: every edge must hold at least 4 cells of size >= cell_min");
+  g.Lx = h->box[0]; g.Ly = h->box[1]; g.Lz = h->box[2];
+  g.wx = g.Lx / g.nx; g.wy = g.Ly / g.ny; g.wz = g.Lz / g.nz;
+  g.iwx = 1.0 / g.wx; g.iwy = 1.0 / g.wy; g.iwz = 1.0 / g.wz;
+  g.sx = g.sy = g.sz = 0.0;
+  int W = h->cfg.world;
+  if (W == 1) {
+    g.gx0 = 0; g.nlx = g.nx; g.own_lo = 0; g.own_hi = g.nx; g.wrap_x = 1;
+  } else {
+    int pairs = g.nx / 2;
+    if (pairs < 2 * W) return fail("too few cell layers along x for this many slabs (need >= 4 layers per rank)");
+    int x0 = 2 * (int)(((long long)pairs * h->cfg.rank) / W);
+    int x1 = 2 * (int)(((long long)pairs * (h->cfg.rank + 1)) / W);
+    g.gx0 = (x0 - 1 + g.nx) % g.nx;
+    g.nlx = (x1 - x0) + 2;
+    g.own_lo = 1; g.own_hi = 1 + (x1 - x0);
+    g.wrap_x = 0;
+  }
+  h->ncell = (int64_t)g.nlx * g.ny * g.nz;
+  if (h->ncell + 1 > (int64_t)INT32_MAX) return fail("too many cells for 32-bit cell indices");
+  return 0;
+}
+
+static int ensure_cell_arrays(hsmc_gpu* h) {
+  if (h->ncell + 1 <= h->cap_cells) return 0;
+  if (h->cell_start) cudaFree(h->cell_start);
+  if (h->cell_count) cudaFree(h->cell_count);
+  if (h->bsum) cudaFree(h->bsum);
+  h->cap_cells = h->ncell + 1 + h->ncell / 8;
+  CU(cudaMalloc(&h->cell_start, sizeof(int) * (size_t)h->cap_cells));
+  CU(cudaMalloc(&h->cell_count, sizeof(int) * (size_t)h->cap_cells));
+  CU(cudaMalloc(&h->bsum, sizeof(int) * (size_t)((h->cap_cells + SCAN_CHUNK - 1) / SCAN_CHUNK + 1)));
+  return 0;
+}
+
+static int ensure_io(hsmc_gpu* h, int64_t rows) {
+  if (rows <= h->cap_io) return 0;
+  if (h->d_io) cudaFree(h->d_io);
+  h->cap_io = rows;
+  CU(cudaMalloc(&h->d_io, sizeof(double) * 4 * (size_t)rows));
+  return 0;
+}
+
+// grid shift of the current sweep counter: same on every rank, no communication
+static void draw_shift(hsmc_gpu* h) {
+  Philox4 r = philox4x32_10(0u, HSMC_STREAM_SHIFT << 24, (uint32_t)h->sweeps_done,
+                            (uint32_t)(h->sweeps_done >> 32), (uint32_t)h->cfg.seed,
+                            (uint32_t)(h->cfg.seed >> 32));
+  Grid& g = h->g;
+  g.sx = ((double)r.v[0] / 4294967296.0) * g.wx;
+  g.sy = ((double)r.v[1] / 4294967296.0) * g.wy;
+  g.sz = ((double)r.v[2] / 4294967296.0) * g.wz;
+}
+
+static int exclusive_scan(hsmc_gpu* h, const int* in, int64_t n, int* out) {
+  int nb = (int)((n + SCAN_CHUNK - 1) / SCAN_CHUNK);
+  k_scan_blocksum<<<nb, SCAN_T, 0, h->st>>>(in, n, h->bsum);
+  k_scan_top<<<1, SCAN_T, 0, h->st>>>(h->bsum, nb);
+  k_scan_final<<<nb, SCAN_T, 0, h->st>>>(in, n, h->bsum, out);
+  h->launches += 3;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+static inline int left_of(const hsmc_gpu* h) { return (h->cfg.rank + h->cfg.world - 1) % h->cfg.world; }
+static inline int right_of(const hsmc_gpu* h) { return (h->cfg.rank + 1) % h->cfg.world; }
+
+// Rebuild the cell-ordered table from `src` (n_in particles; rows_layout: {id,x,y,z}
+// instead of {x,y,z,id}) under the current grid.  Output goes to pos[cur^1]; cur flips.
+static int rebuild(hsmc_gpu* h, const double4* src, int64_t n_in, int rows_layout, int upload_mode) {
+  ProfSpan span(h, 1);
+  TRY(ensure_cell_arrays(h));
+  Grid& g = h->g;
+  const int T = 256;
+  double4* dst = h->pos[h->cur ^ 1];
+  CU(cudaMemsetAsync(h->cell_count, 0, sizeof(int) * (size_t)h->ncell, h->st));
+  if (h->cfg.world == 1) {
+    if (n_in != h->N) return fail("internal: particle count mismatch in rebuild");
+    if (rows_layout) {
+      // host rows {id,x,y,z} -> slots {x,y,z,id} in the (free) current buffer first
+      k_unpack_rows<<<nblk(n_in, T), T, 0, h->st>>>(reinterpret_cast<const double*>(src), (int)n_in, h->pos[h->cur]);
+      h->launches++;
+      src = h->pos[h->cur];
+    }
+    k_cell_count<<<nblk(n_in, T), T, 0, h->st>>>(g, src, (int)n_in, h->key, h->rnk, h->cell_count);
+    h->launches++;
+    TRY(exclusive_scan(h, h->cell_count, h->ncell, h->cell_start));
+    k_cell_scatter<<<nblk(n_in, T), T, 0, h->st>>>(src, (int)n_in, h->key, h->rnk, h->cell_start, dst);
+    h->launches++;
+    CU(cudaGetLastError());
+    h->cur ^= 1;
+    h->n_local = h->n_owned = h->N;
+    h->own_first = 0;
+    return 0;
+  }
+  // ---- slab mode ----
+  CU(cudaMemsetAsync(h->d_halo_cnt, 0, sizeof(int) * 4, h->st));
+  if (n_in > 0) {
+    k_slab_classify<<<nblk(n_in, T), T, 0, h->st>>>(g, src, (int)n_in, rows_layout, upload_mode, h->key,
+                                                     h->rnk, h->cell_count, h->send_l, h->send_r,
+                                                     h->d_halo_cnt, (int)h->cap_halo);
+    h->launches++;
+  }
+  k_halo_headers<<<1, 1, 0, h->st>>>(h->send_l, h->send_r, h->d_halo_cnt);
+  h->launches++;
+  size_t cnt = (size_t)h->cap_halo * 4;
+  NC(ncclGroupStart());
+  NC(ncclSend(h->send_l, cnt, ncclDouble, left_of(h), h->comm, h->st));
+  NC(ncclRecv(h->recv_r, cnt, ncclDouble, right_of(h), h->comm, h->st));
+  NC(ncclSend(h->send_r, cnt, ncclDouble, right_of(h), h->comm, h->st));
+  NC(ncclRecv(h->recv_l, cnt, ncclDouble, left_of(h), h->comm, h->st));
+  NC(ncclGroupEnd());
+  h->nccl_calls += 4;
+  int* key_l = h->key + h->cap;
+  int* rnk_l = h->rnk + h->cap;
+  int* key_r = key_l + h->cap_halo;
+  int* rnk_r = rnk_l + h->cap_halo;
+  int gb = 148 * 4;
+  k_recv_count<<<gb, T, 0, h->st>>>(g, h->recv_l, (int)h->cap_halo, key_l, rnk_l, h->cell_count, h->d_halo_cnt);
+  k_recv_count<<<gb, T, 0, h->st>>>(g, h->recv_r, (int)h->cap_halo, key_r, rnk_r, h->cell_count, h->d_halo_cnt);
+  h->launches += 2;
+  TRY(exclusive_scan(h, h->cell_count, h->ncell, h->cell_start));
+  if (n_in > 0) {
+    k_scatter_layout<<<nblk(n_in, T), T, 0, h->st>>>(src, (int)n_in, rows_layout, h->key, h->rnk,
+                                                      h->cell_start, dst);
+    h->launches++;
+  }
+  k_recv_scatter<<<gb, T, 0, h->st>>>(h->recv_l, (int)h->cap_halo, key_l, rnk_l, h->cell_start, dst);
+  k_recv_scatter<<<gb, T, 0, h->st>>>(h->recv_r, (int)h->cap_halo, key_r, rnk_r, h->cell_start, dst);
+  h->launches += 2;
+  long long per = (long long)g.ny * g.nz;
+  k_sort_cells_by_id<<<nblk(2 * per, 128), 128, 0, h->st>>>(g, dst, h->cell_start, 0, 1);
+  k_sort_cells_by_id<<<nblk(2 * per, 128), 128, 0, h->st>>>(g, dst, h->cell_start, g.nlx - 2, g.nlx - 1);
+  h->launches += 2;
+  CU(cudaGetLastError());
+  // layer offsets + error flags back to the host (one small sync per rebuild)
+  int* hs = (int*)h->h_stage;
+  long long offs[6] = {0, per, 2 * per, (long long)(g.nlx - 2) * per, (long long)(g.nlx - 1) * per,
+                       (long long)g.nlx * per};
+  for (int k = 0; k < 6; k++)
+    CU(cudaMemcpyAsync(&hs[k], h->cell_start + offs[k], sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  CU(cudaMemcpyAsync(&hs[6], h->d_halo_cnt, sizeof(int) * 3, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  for (int k = 0; k < 6; k++) h->lay[k] = hs[k];
+  if (hs[8] & 1) return fail("slab decomposition: a particle moved more than one cell layer between regrids");
+  if (hs[8] & 2) return fail("slab decomposition: halo buffer overflow");
+  if (hs[8] & 4) return fail("slab decomposition: received a particle outside the local layers");
+  if (hs[5] > h->cap) return fail("slab decomposition: local particle capacity exceeded");
+  h->cur ^= 1;
+  h->n_local = h->lay[5];
+  h->own_first = h->lay[1];
+  h->n_owned = h->lay[4] - h->lay[1];
+  return 0;
+}
+
+extern "C" int hsmc_gpu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+extern "C" int hsmc_gpu_nccl_id(void* out_id) {
+  ncclUniqueId id;
+  NC(ncclGetUniqueId(&id));
+  static_assert(sizeof(ncclUniqueId) == HSMC_GPU_NCCL_ID_BYTES, "nccl id size");
+  memcpy(out_id, &id, sizeof(id));
+  return 0;
+}
+
+extern "C" int hsmc_gpu_destroy(hsmc_gpu* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->cfg.device);
+  if (h->st) cudaStreamSynchronize(h->st);
+  if (h->comm) ncclCommDestroy(h->comm);
+  void* ptrs[] = {h->pos[0], h->pos[1], h->key, h->rnk, h->cell_count, h->cell_start, h->bsum, h->d_cnt,
+                  h->d_scratch, h->d_slot_of_id, h->d_io, h->send_l, h->send_r, h->recv_l, h->recv_r,
+                  h->d_halo_cnt, h->d_sfargs, h->d_log};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (h->h_stage) cudaFreeHost(h->h_stage);
+  for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+  for (auto e : h->ev_pool) cudaEventDestroy(e);
+  if (h->st) cudaStreamDestroy(h->st);
+  delete h;
+  return 0;
+}
+
+extern "C" int hsmc_gpu_create(hsmc_gpu** out, const hsmc_gpu_config* cfg, int64_t n_particles,
+                               const double box[3]) {
+  if (!out || !cfg || !box) return fail("null argument");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    return fail("no CUDA device: the B200 path has no CPU fallback");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail("invalid CUDA device ordinal");
+  if (cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world) return fail("invalid rank/world");
+  if (cfg->world > 1 && !cfg->nccl_id) return fail("world > 1 needs an NCCL unique id");
+  if (n_particles <= 0 || n_particles >= (int64_t)INT32_MAX) return fail("invalid particle count");
+  hsmc_gpu* h = new hsmc_gpu();
+  h->cfg = *cfg;
+  if (h->cfg.cell_min == 0.0) h->cfg.cell_min = 1.0;
+  if (h->cfg.cell_min < 1.0) { delete h; return fail("cell_min must be >= 1.0 (the particle diameter)"); }
+  if (h->cfg.regrid_interval <= 0) h->cfg.regrid_interval = 1;
+  h->N = n_particles;
+  h->box[0] = box[0]; h->box[1] = box[1]; h->box[2] = box[2];
+#define CUD(call)                                                                              \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess) {                                                                  \
+      fail(std::string("CUDA: ") + cudaGetErrorString(e__) + " at " #call);                    \
+      hsmc_gpu_destroy(h);                                                                     \
+      return 1;                                                                                \
+    }                                                                                          \
+  } while (0)
+  CUD(cudaSetDevice(cfg->device));
+  CUD(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+  if (setup_grid(h)) { hsmc_gpu_destroy(h); return 1; }
+  int W = cfg->world;
+  if (W == 1) {
+    h->cap = h->N;
+    h->cap_halo = 0;
+  } else {
+    // owned share + two ghost layers, with head-room for density fluctuations
+    double own_frac = (double)(h->g.own_hi - h->g.own_lo) / h->g.nx;
+    double lay_frac = 1.0 / h->g.nx;
+    h->cap = (int64_t)((own_frac + 2 * lay_frac) * h->N * 1.25) + 4096;
+    h->cap_halo = (int64_t)(2 * lay_frac * h->N * 1.5) + 4096;
+  }
+  CUD(cudaMalloc(&h->pos[0], sizeof(double4) * (size_t)h->cap));
+  CUD(cudaMalloc(&h->pos[1], sizeof(double4) * (size_t)h->cap));
+  CUD(cudaMalloc(&h->key, sizeof(int) * (size_t)(h->cap + 2 * h->cap_halo)));
+  CUD(cudaMalloc(&h->rnk, sizeof(int) * (size_t)(h->cap + 2 * h->cap_halo)));
+  CUD(cudaMalloc(&h->d_cnt, sizeof(unsigned long long) * CNT_N));
+  CUD(cudaMemset(h->d_cnt, 0, sizeof(unsigned long long) * CNT_N));
+  CUD(cudaMalloc(&h->d_scratch, sizeof(unsigned long long) * SCRATCH_N));
+  CUD(cudaMalloc(&h->d_halo_cnt, sizeof(int) * 4));
+  CUD(cudaMemset(h->d_halo_cnt, 0, sizeof(int) * 4));
+  CUD(cudaMalloc(&h->d_sfargs, sizeof(SfArgs)));
+  CUD(cudaMallocHost(&h->h_stage, sizeof(unsigned long long) * SCRATCH_N));
+  if (ensure_cell_arrays(h)) { hsmc_gpu_destroy(h); return 1; }
+  if (W > 1) {
+    CUD(cudaMalloc(&h->send_l, sizeof(double4) * (size_t)h->cap_halo));
+    CUD(cudaMalloc(&h->send_r, sizeof(double4) * (size_t)h->cap_halo));
+    CUD(cudaMalloc(&h->recv_l, sizeof(double4) * (size_t)h->cap_halo));
+    CUD(cudaMalloc(&h->recv_r, sizeof(double4) * (size_t)h->cap_halo));
+    ncclUniqueId id;
+    memcpy(&id, cfg->nccl_id, sizeof(id));
+    ncclResult_t r = ncclCommInitRank(&h->comm, W, id, cfg->rank);
+    if (r != ncclSuccess) {
+      fail(std::string("NCCL: ") + ncclGetErrorString(r) + " at ncclCommInitRank");
+      h->comm = nullptr;
+      hsmc_gpu_destroy(h);
+      return 1;
+    }
+  }
+#undef CUD
+  *out = h;
+  return 0;
+}
+
+extern "C" int hsmc_gpu_get_info(hsmc_gpu* h, hsmc_gpu_info* o) {
+  if (!h || !o) return fail("null argument");
+  memset(o, 0, sizeof(*o));
+  o->abi_version = HSMC_GPU_ABI_VERSION;
+  o->rank = h->cfg.rank; o->world = h->cfg.world;
+  o->n_total = h->N; o->n_owned = h->n_owned; o->n_local = h->n_local;
+  o->cells[0] = h->g.nx; o->cells[1] = h->g.ny; o->cells[2] = h->g.nz;
+  int x0 = (h->g.gx0 + h->g.own_lo) % h->g.nx;
+  o->own_x0 = x0; o->own_x1 = x0 + (h->g.own_hi - h->g.own_lo);
+  o->cell_size[0] = h->g.wx; o->cell_size[1] = h->g.wy; o->cell_size[2] = h->g.wz;
+  o->box[0] = h->box[0]; o->box[1] = h->box[1]; o->box[2] = h->box[2];
+  o->sweeps_done = h->sweeps_done;
+  o->kernel_launches = h->launches;
+  o->nccl_calls = h->nccl_calls;
+  return 0;
+}
+
+extern "C" void* hsmc_gpu_stream(hsmc_gpu* h) { return h ? (void*)h->st : nullptr; }
+
+extern "C" int hsmc_gpu_sync(hsmc_gpu* h) {
+  if (!h) return fail("null handle");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaStreamSynchronize(h->st));
+  return 0;
+}
+
+extern "C" int hsmc_gpu_upload(hsmc_gpu* h, const double* rows, int64_t n_rows) {
+  if (!h || !rows) return fail("null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  if (h->cfg.world == 1 && n_rows != h->N) return fail("upload: n_rows must equal the particle count");
+  if (n_rows < 0 || n_rows > h->N) return fail("upload: bad row count");
+  TRY(ensure_io(h, std::max<int64_t>(n_rows, 1)));
+  CU(cudaMemcpyAsync(h->d_io, rows, sizeof(double) * 4 * (size_t)n_rows, cudaMemcpyHostToDevice, h->st));
+  TRY(rebuild(h, reinterpret_cast<const double4*>(h->d_io), n_rows, 1, 1));
+  h->have_conf = true;
+  h->since_regrid = 0;
+  return 0;
+}
+
+extern "C" int hsmc_gpu_download(hsmc_gpu* h, double* conf) {
+  if (!h || !conf) return fail("null argument");
+  if (!h->have_conf) return fail("download: no configuration uploaded");
+  if (h->cfg.world != 1) return fail("download: full-table download needs world == 1; use download_owned");
+  CU(cudaSetDevice(h->cfg.device));
+  TRY(ensure_io(h, h->N));
+  k_pack_by_id<<<nblk(h->N, 256), 256, 0, h->st>>>(h->pos[h->cur], 0, (int)h->N, h->d_io);
+  h->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(conf, h->d_io, sizeof(double) * 4 * (size_t)h->N, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  return 0;
+}
+
+extern "C" int hsmc_gpu_download_owned(hsmc_gpu* h, double* rows, int64_t capacity_rows, int64_t* n_rows) {
+  if (!h || !rows || !n_rows) return fail("null argument");
+  if (!h->have_conf) return fail("download: no configuration uploaded");
+  CU(cudaSetDevice(h->cfg.device));
+  if (capacity_rows < h->n_owned) return fail("download_owned: buffer too small");
+  TRY(ensure_io(h, std::max<int64_t>(h->n_owned, 1)));
+  if (h->n_owned > 0) {
+    k_pack_rows<<<nblk(h->n_owned, 256), 256, 0, h->st>>>(h->pos[h->cur], (int)h->own_first, (int)h->n_owned, h->d_io);
+    h->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(rows, h->d_io, sizeof(double) * 4 * (size_t)h->n_owned, cudaMemcpyDeviceToHost, h->st));
+  }
+  CU(cudaStreamSynchronize(h->st));
+  *n_rows = h->n_owned;
+  return 0;
+}
+
+// boundary-layer refresh after the colour phases of x-parity `cx` (slab mode):
+// the layer of that parity at the slab edge was updated; its ghost copy lives on the
+// neighbour, slot-for-slot in the same order.
+static int halo_refresh(hsmc_gpu* h, int cx) {
+  ProfSpan span(h, 2);
+  double4* p = h->pos[h->cur];
+  NC(ncclGroupStart());
+  if (cx == 0) {
+    // first owned layer (even global index) -> left neighbour's right ghost
+    size_t ns = (size_t)(h->lay[2] - h->lay[1]) * 4, nr = (size_t)(h->lay[5] - h->lay[4]) * 4;
+    NC(ncclSend(p + h->lay[1], ns, ncclDouble, left_of(h), h->comm, h->st));
+    NC(ncclRecv(p + h->lay[4], nr, ncclDouble, right_of(h), h->comm, h->st));
+  } else {
+    // last owned layer (odd) -> right neighbour's left ghost
+    size_t ns = (size_t)(h->lay[4] - h->lay[3]) * 4, nr = (size_t)(h->lay[1] - h->lay[0]) * 4;
+    NC(ncclSend(p + h->lay[3], ns, ncclDouble, right_of(h), h->comm, h->st));
+    NC(ncclRecv(p + h->lay[0], nr, ncclDouble, left_of(h), h->comm, h->st));
+  }
+  NC(ncclGroupEnd());
+  h->nccl_calls += 2;
+  return 0;
+}
+
+static int do_regrid(hsmc_gpu* h) {
+  draw_shift(h);
+  const double4* src = h->pos[h->cur] + h->own_first;
+  return rebuild(h, src, h->n_owned, 0, 0);
+}
+
+static int sweep_once(hsmc_gpu* h, double dr_max, bool logged) {
+  if (h->since_regrid % h->cfg.regrid_interval == 0) TRY(do_regrid(h));
+  h->since_regrid++;
+  Grid& g = h->g;
+  SweepArgs a;
+  a.g = g;
+  a.box = make_box(g.Lx, g.Ly, g.Lz, 1.0);
+  a.dr_max = dr_max;
+  a.key0 = (uint32_t)h->cfg.seed; a.key1 = (uint32_t)(h->cfg.seed >> 32);
+  a.sweep_lo = (uint32_t)h->sweeps_done; a.sweep_hi = (uint32_t)(h->sweeps_done >> 32);
+  long long total = (long long)((g.own_hi - g.own_lo) / 2) * (g.ny / 2) * (g.nz / 2);
+  const int T = 128;
+  for (int ph = 0; ph < 8; ph++) {
+    a.cx = (ph >> 2) & 1; a.cy = (ph >> 1) & 1; a.cz = ph & 1; a.phase = ph;
+    {
+    ProfSpan span(h, 0);
+    if (logged)
+      k_sweep_phase<true><<<nblk(total, T), T, 0, h->st>>>(a, h->pos[h->cur], h->cell_start, h->d_cnt, h->d_log,
+                                                            h->d_scratch, (long long)h->cap_log);
+    else
+      k_sweep_phase<false><<<nblk(total, T), T, 0, h->st>>>(a, h->pos[h->cur], h->cell_start, h->d_cnt, nullptr,
+                                                             nullptr, 0);
+    }
+    h->launches++;
+    if (h->cfg.world > 1) {
+      // ghosts of parity cx are read only by phases of the other parity: one refresh
+      // after the last phase of each parity is enough
+      if (ph == 3) TRY(halo_refresh(h, 0));
+      if (ph == 7) TRY(halo_refresh(h, 1));
+    }
+  }
+  CU(cudaGetLastError());
+  h->sweeps_done++;
+  return 0;
+}
+
+extern "C" int hsmc_gpu_sweep_nvt(hsmc_gpu* h, int n_sweeps, double dr_max) {
+  if (!h) return fail("null handle");
+  if (!h->have_conf) return fail("sweep: no configuration uploaded");
+  if (!(dr_max > 0.0) || dr_max > 2.0 * std::min(h->g.wx, std::min(h->g.wy, h->g.wz)))
+    return fail("sweep: dr_max out of range");
+  CU(cudaSetDevice(h->cfg.device));
+  for (int s = 0; s < n_sweeps; s++) TRY(sweep_once(h, dr_max, false));
+  return 0;
+}
+
+extern "C" int hsmc_gpu_sweep_nvt_logged(hsmc_gpu* h, double dr_max, hsmc_gpu_trial* log, int64_t capacity,
+                                         int64_t* n_logged) {
+  if (!h || !log || !n_logged) return fail("null argument");
+  if (!h->have_conf) return fail("sweep: no configuration uploaded");
+  CU(cudaSetDevice(h->cfg.device));
+  if (capacity > h->cap_log) {
+    if (h->d_log) cudaFree(h->d_log);
+    h->cap_log = capacity;
+    CU(cudaMalloc(&h->d_log, sizeof(hsmc_gpu_trial) * (size_t)capacity));
+  }
+  CU(cudaMemsetAsync(h->d_scratch, 0, sizeof(unsigned long long), h->st));
+  TRY(sweep_once(h, dr_max, true));
+  unsigned long long* hs = (unsigned long long*)h->h_stage;
+  CU(cudaMemcpyAsync(hs, h->d_scratch, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  int64_t n = (int64_t)hs[0];
+  if (n > capacity) return fail("sweep log capacity exceeded");
+  CU(cudaMemcpyAsync(log, h->d_log, sizeof(hsmc_gpu_trial) * (size_t)n, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  *n_logged = n;
+  return 0;
+}
+
+// ---- scaled overlap verdicts -----------------------------------------------------
+static int overlap_flags(hsmc_gpu* h, const double* sf, int nn, int* flags_out) {
+  if (nn < 1 || nn > MAX_SF) return fail("scaled overlap: number of scale factors must be in [1, 64]");
+  Grid& g = h->g;
+  SfArgs sa;
+  memset(&sa, 0, sizeof(sa));
+  sa.n = nn;
+  double sfmin = sf[0];
+  for (int k = 0; k < nn; k++) {
+    if (!(sf[k] > 0.0)) return fail("scaled overlap: scale factor must be positive");
+    sa.sf[k] = sf[k];
+    sa.box[k] = make_box(g.Lx, g.Ly, g.Lz, sf[k]);
+    sfmin = std::min(sfmin, sf[k]);
+  }
+  double wmin = std::min(g.wx, std::min(g.wy, g.wz));
+  if (wmin * sfmin < 1.0)
+    return fail("scaled overlap: cell size too small for this compression (cell*sf < 1); increase neigh_list");
+  sa.r2_skip = (1.0 / (sfmin * sfmin)) * (1.0 + 1e-6);
+  SfArgs* hsa = (SfArgs*)h->h_stage;
+  *hsa = sa;
+  CU(cudaMemcpyAsync(h->d_sfargs, hsa, sizeof(SfArgs), cudaMemcpyHostToDevice, h->st));
+  int* d_flags = (int*)h->d_scratch;
+  CU(cudaMemsetAsync(d_flags, 0, sizeof(int) * MAX_SF, h->st));
+  long long total = (long long)(g.own_hi - g.own_lo) * g.ny * g.nz;
+  k_overlap_scaled<<<nblk(total, 128), 128, 0, h->st>>>(g, make_box(g.Lx, g.Ly, g.Lz, 1.0), (const SfArgs*)h->d_sfargs,
+                                                         h->pos[h->cur], h->cell_start, d_flags);
+  h->launches++;
+  CU(cudaGetLastError());
+  if (h->cfg.world > 1) {
+    NC(ncclAllReduce(d_flags, d_flags, nn, ncclInt, ncclMax, h->comm, h->st));
+    h->nccl_calls++;
+  }
+  // h_stage currently holds the SfArgs copy source; wait for it before reuse
+  CU(cudaStreamSynchronize(h->st));
+  int* hf = (int*)h->h_stage;
+  CU(cudaMemcpyAsync(hf, d_flags, sizeof(int) * nn, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  for (int k = 0; k < nn; k++) flags_out[k] = hf[k];
+  return 0;
+}
+
+extern "C" int hsmc_gpu_overlap_scaled(hsmc_gpu* h, double sf, int* overlap) {
+  if (!h || !overlap) return fail("null argument");
+  if (!h->have_conf) return fail("no configuration uploaded");
+  CU(cudaSetDevice(h->cfg.device));
+  int f = 0;
+  TRY(overlap_flags(h, &sf, 1, &f));
+  *overlap = f;
+  return 0;
+}
+
+extern "C" int hsmc_gpu_presst_flags(hsmc_gpu* h, const double* sf, int nn, int* no_overlap) {
+  if (!h || !sf || !no_overlap) return fail("null argument");
+  if (!h->have_conf) return fail("no configuration uploaded");
+  CU(cudaSetDevice(h->cfg.device));
+  for (int k0 = 0; k0 < nn; k0 += MAX_SF) {
+    int m = std::min(MAX_SF, nn - k0);
+    int f[MAX_SF];
+    TRY(overlap_flags(h, sf + k0, m, f));
+    for (int k = 0; k < m; k++) no_overlap[k0 + k] = f[k] ? 0 : 1;
+  }
+  return 0;
+}
+
+extern "C" int hsmc_gpu_rescale(hsmc_gpu* h, double sf, const double new_box[3]) {
+  if (!h || !new_box) return fail("null argument");
+  if (!h->have_conf) return fail("no configuration uploaded");
+  CU(cudaSetDevice(h->cfg.device));
+  if (h->cfg.world > 1) return fail("rescale: NpT volume moves are not supported in slab mode yet");
+  k_rescale<<<nblk(h->n_local, 256), 256, 0, h->st>>>(h->pos[h->cur], (int)h->n_local, sf, new_box[0],
+                                                       new_box[1], new_box[2]);
+  h->launches++;
+  CU(cudaGetLastError());
+  h->box[0] = new_box[0]; h->box[1] = new_box[1]; h->box[2] = new_box[2];
+  double sx = h->g.sx / h->g.wx, sy = h->g.sy / h->g.wy, sz = h->g.sz / h->g.wz;
+  TRY(setup_grid(h));
+  h->g.sx = sx * h->g.wx; h->g.sy = sy * h->g.wy; h->g.sz = sz * h->g.wz;
+  TRY(rebuild(h, h->pos[h->cur], h->n_local, 0, 0));
+  return 0;
+}
+
+// ---- observables ------------------------------------------------------------------
+extern "C" int hsmc_gpu_widom(hsmc_gpu* h, uint64_t sample_id, int64_t first, int64_t count, int reduce,
+                              int64_t* accepted) {
+  if (!h || !accepted) return fail("null argument");
+  if (!h->have_conf) return fail("no configuration uploaded");
+  if (count < 0 || first < 0) return fail("widom: bad range");
+  CU(cudaSetDevice(h->cfg.device));
+  Grid& g = h->g;
+  unsigned long long* d_acc = h->d_scratch;
+  CU(cudaMemsetAsync(d_acc, 0, sizeof(unsigned long long), h->st));
+  const long long chunk = 1LL << 30;
+  for (long long off = 0; off < count; off += chunk) {
+    long long c = std::min<long long>(chunk, count - off);
+    k_widom<<<nblk(c, 256), 256, 0, h->st>>>(g, make_box(g.Lx, g.Ly, g.Lz, 1.0), h->pos[h->cur], h->cell_start,
+                                             (uint32_t)h->cfg.seed, (uint32_t)(h->cfg.seed >> 32),
+                                             (uint32_t)sample_id, (uint32_t)(sample_id >> 32), first + off, c, d_acc);
+    h->launches++;
+  }
+  CU(cudaGetLastError());
+  if (h->cfg.world > 1 && reduce) {
+    NC(ncclAllReduce(d_acc, d_acc, 1, ncclUint64, ncclSum, h->comm, h->st));
+    h->nccl_calls++;
+  }
+  unsigned long long* hs = (unsigned long long*)h->h_stage;
+  CU(cudaMemcpyAsync(hs, d_acc, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  *accepted = (int64_t)hs[0];
+  return 0;
+}
+
+extern "C" int hsmc_gpu_rdf_counts(hsmc_gpu* h, double dr_bin, int nn, uint64_t* counts) {
+  if (!h || !counts) return fail("null argument");
+  if (!h->have_conf) return fail("no configuration uploaded");
+  if (h->cfg.world > 1) return fail("rdf: the all-pairs histogram needs the whole configuration on one GPU (world == 1)");
+  if (nn < 1 || nn > SCRATCH_N) return fail("rdf: bin count out of range");
+  if (!(dr_bin > 0.0)) return fail("rdf: bin width must be positive");
+  CU(cudaSetDevice(h->cfg.device));
+  Grid& g = h->g;
+  double rmax = dr_bin * nn + 1.0;   // compute_rdf.c:104
+  double r2_pre = rmax * rmax * (1.0 + 1e-9);
+  CU(cudaMemsetAsync(h->d_scratch, 0, sizeof(unsigned long long) * nn, h->st));
+  int ntile = (int)((h->N + RDF_T - 1) / RDF_T);
+  long long nblocks = (long long)ntile * (ntile + 1) / 2;
+  if (nblocks > 0x7fffffffLL) return fail("rdf: system too large for the all-pairs histogram");
+  size_t smem = sizeof(double) * 3 * RDF_T + sizeof(unsigned int) * (nn <= RDF_MAX_SMEM_BINS ? nn : 0);
+  k_rdf_pairs<<<(unsigned)nblocks, RDF_T, smem, h->st>>>(h->pos[h->cur], (int)h->N, make_box(g.Lx, g.Ly, g.Lz, 1.0),
+                                                         rmax, r2_pre, dr_bin, nn, ntile, h->d_scratch);
+  h->launches++;
+  CU(cudaGetLastError());
+  unsigned long long* hs = (unsigned long long*)h->h_stage;
+  CU(cudaMemcpyAsync(hs, h->d_scratch, sizeof(unsigned long long) * nn, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  for (int k = 0; k < nn; k++) counts[k] = hs[k];
+  return 0;
+}
+
+extern "C" int hsmc_gpu_contact_counts(hsmc_gpu* h, double dr_bin, int nn, uint64_t* counts) {
+  if (!h || !counts) return fail("null argument");
+  if (!h->have_conf) return fail("no configuration uploaded");
+  if (nn < 1 || nn > CONTACT_MAX_BINS) return fail("contact histogram: bin count out of range");
+  if (!(dr_bin > 0.0)) return fail("contact histogram: bin width must be positive");
+  CU(cudaSetDevice(h->cfg.device));
+  Grid& g = h->g;
+  double rmax = dr_bin * nn + 1.0;   // compute_press.c:116
+  if (std::min(g.wx, std::min(g.wy, g.wz)) < rmax)
+    return fail("The size of the cells in the neighbor list does not allow a correct calculation of the pressure, increase neigh_list");
+  CU(cudaMemsetAsync(h->d_scratch, 0, sizeof(unsigned long long) * nn, h->st));
+  long long total = (long long)(g.own_hi - g.own_lo) * g.ny * g.nz;
+  k_contact_hist<<<nblk(total, 128), 128, 0, h->st>>>(g, make_box(g.Lx, g.Ly, g.Lz, 1.0), h->pos[h->cur],
+                                                       h->cell_start, rmax, dr_bin, nn, h->d_scratch);
+  h->launches++;
+  CU(cudaGetLastError());
+  if (h->cfg.world > 1) {
+    NC(ncclAllReduce(h->d_scratch, h->d_scratch, nn, ncclUint64, ncclSum, h->comm, h->st));
+    h->nccl_calls++;
+  }
+  unsigned long long* hs = (unsigned long long*)h->h_stage;
+  CU(cudaMemcpyAsync(hs, h->d_scratch, sizeof(unsigned long long) * nn, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  for (int k = 0; k < nn; k++) counts[k] = hs[k];
+  return 0;
+}
+
+extern "C" int hsmc_gpu_min_dist2(hsmc_gpu* h, double* out) {
+  if (!h || !out) return fail("null argument");
+  if (!h->have_conf) return fail("no configuration uploaded");
+  CU(cudaSetDevice(h->cfg.device));
+  Grid& g = h->g;
+  unsigned long long* hs = (unsigned long long*)h->h_stage;
+  double big = 1e300;
+  memcpy(&hs[0], &big, 8);
+  CU(cudaMemcpyAsync(h->d_scratch, hs, 8, cudaMemcpyHostToDevice, h->st));
+  long long total = (long long)(g.own_hi - g.own_lo) * g.ny * g.nz;
+  k_min_r2<<<nblk(total, 128), 128, 0, h->st>>>(g, make_box(g.Lx, g.Ly, g.Lz, 1.0), h->pos[h->cur], h->cell_start,
+                                                 h->d_scratch);
+  h->launches++;
+  CU(cudaGetLastError());
+  if (h->cfg.world > 1) {
+    NC(ncclAllReduce(h->d_scratch, h->d_scratch, 1, ncclDouble, ncclMin, h->comm, h->st));
+    h->nccl_calls++;
+  }
+  CU(cudaStreamSynchronize(h->st));
+  CU(cudaMemcpyAsync(hs, h->d_scratch, 8, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  memcpy(out, &hs[0], 8);
+  return 0;
+}
+
+// ---- counters ----------------------------------------------------------------------
+static int read_counters(hsmc_gpu* h, unsigned long long* c) {
+  unsigned long long* hs = (unsigned long long*)h->h_stage;
+  if (h->cfg.world > 1) {
+    unsigned long long* tmp = h->d_scratch;
+    NC(ncclAllReduce(h->d_cnt, tmp, CNT_N, ncclUint64, ncclSum, h->comm, h->st));
+    h->nccl_calls++;
+    CU(cudaMemcpyAsync(hs, tmp, sizeof(unsigned long long) * CNT_N, cudaMemcpyDeviceToHost, h->st));
+  } else {
+    CU(cudaMemcpyAsync(hs, h->d_cnt, sizeof(unsigned long long) * CNT_N, cudaMemcpyDeviceToHost, h->st));
+  }
+  CU(cudaStreamSynchronize(h->st));
+  for (int k = 0; k < CNT_N; k++) c[k] = hs[k];
+  return 0;
+}
+
+extern "C" int hsmc_gpu_counters(hsmc_gpu* h, int64_t out[6]) {
+  if (!h || !out) return fail("null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  unsigned long long c[CNT_N];
+  TRY(read_counters(h, c));
+  out[0] = (int64_t)c[CNT_TRIALS];
+  out[1] = (int64_t)c[CNT_ACC];
+  out[2] = (int64_t)(c[CNT_REJ_OVERLAP] + c[CNT_REJ_CELL]);
+  out[3] = h->vol_cnt[0]; out[4] = h->vol_cnt[1]; out[5] = h->vol_cnt[2];
+  return 0;
+}
+
+extern "C" int hsmc_gpu_cell_rejects(hsmc_gpu* h, int64_t* out) {
+  if (!h || !out) return fail("null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  unsigned long long c[CNT_N];
+  TRY(read_counters(h, c));
+  *out = (int64_t)c[CNT_REJ_CELL];
+  return 0;
+}
+
+extern "C" int hsmc_gpu_reset_counters(hsmc_gpu* h) {
+  if (!h) return fail("null handle");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaMemsetAsync(h->d_cnt, 0, sizeof(unsigned long long) * CNT_N, h->st));
+  h->vol_cnt[0] = h->vol_cnt[1] = h->vol_cnt[2] = 0;
+  return 0;
+}
+
+extern "C" int hsmc_gpu_add_vol_move(hsmc_gpu* h, int accepted) {
+  if (!h) return fail("null handle");
+  h->vol_cnt[0]++;
+  if (accepted) h->vol_cnt[1]++; else h->vol_cnt[2]++;
+  return 0;
+}
+
+extern "C" int hsmc_gpu_profile(hsmc_gpu* h, int enable) {
+  if (!h) return fail("null handle");
+  h->prof = enable != 0;
+  return 0;
+}
+
+extern "C" int hsmc_gpu_profile_read(hsmc_gpu* h, double ms[HSMC_GPU_PROFILE_BUCKETS],
+                                     int64_t groups[HSMC_GPU_PROFILE_BUCKETS]) {
+  if (!h || !ms || !groups) return fail("null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaStreamSynchronize(h->st));
+  for (auto& sp : h->spans) {
+    float t = 0.f;
+    CU(cudaEventElapsedTime(&t, sp.a, sp.b));
+    h->prof_ms[sp.bucket] += t;
+    h->prof_n[sp.bucket] += 1;
+    h->ev_pool.push_back(sp.a);
+    h->ev_pool.push_back(sp.b);
+  }
+  h->spans.clear();
+  for (int k = 0; k < HSMC_GPU_PROFILE_BUCKETS; k++) {
+    ms[k] = h->prof_ms[k]; groups[k] = h->prof_n[k];
+    h->prof_ms[k] = 0; h->prof_n[k] = 0;
+  }
+  return 0;
+}
+
+extern "C" int hsmc_gpu_set_sweep_counter(hsmc_gpu* h, uint64_t sweeps_done) {
+  if (!h) return fail("null handle");
+  h->sweeps_done = sweeps_done;
+  return 0;
+}
+
+// ---- parity entry points ---------------------------------------------------------
+extern "C" int hsmc_gpu_trial_verdicts(hsmc_gpu* h, int n, const int* idx, const double* xyz, double sf, int* flags) {
+  if (!h || !idx || !xyz || !flags) return fail("null argument");
+  if (!h->have_conf) return fail("no configuration uploaded");
+  if (h->cfg.world != 1) return fail("trial_verdicts: world == 1 only");
+  CU(cudaSetDevice(h->cfg.device));
+  Grid& g = h->g;
+  if (sf < 1.0 && std::min(g.wx, std::min(g.wy, g.wz)) * sf < 1.0)
+    return fail("scaled overlap: cell size too small for this compression (cell*sf < 1); increase neigh_list");
+  double* d_xyz; int *d_idx, *d_fl;
+  CU(cudaMalloc(&d_xyz, sizeof(double) * 3 * (size_t)n));
+  CU(cudaMalloc(&d_idx, sizeof(int) * (size_t)n));
+  CU(cudaMalloc(&d_fl, sizeof(int) * (size_t)n));
+  CU(cudaMemcpyAsync(d_xyz, xyz, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, h->st));
+  CU(cudaMemcpyAsync(d_idx, idx, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, h->st));
+  k_trial_points<<<nblk(n, 128), 128, 0, h->st>>>(g, make_box(g.Lx, g.Ly, g.Lz, sf), sf, h->pos[h->cur],
+                                                   h->cell_start, d_idx, d_xyz, n, d_fl);
+  h->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(flags, d_fl, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  cudaFree(d_xyz); cudaFree(d_idx); cudaFree(d_fl);
+  return 0;
+}
+
+extern "C" int hsmc_gpu_widom_verdicts(hsmc_gpu* h, int n, const double* xyz, int* flags) {
+  if (!h || !xyz || !flags) return fail("null argument");
+  if (!h->have_conf) return fail("no configuration uploaded");
+  if (h->cfg.world != 1) return fail("widom_verdicts: world == 1 only");
+  CU(cudaSetDevice(h->cfg.device));
+  Grid& g = h->g;
+  double* d_xyz; int* d_fl;
+  CU(cudaMalloc(&d_xyz, sizeof(double) * 3 * (size_t)n));
+  CU(cudaMalloc(&d_fl, sizeof(int) * (size_t)n));
+  CU(cudaMemcpyAsync(d_xyz, xyz, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, h->st));
+  k_widom_points<<<nblk(n, 128), 128, 0, h->st>>>(g, make_box(g.Lx, g.Ly, g.Lz, 1.0), h->pos[h->cur],
+                                                   h->cell_start, d_xyz, n, d_fl);
+  h->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(flags, d_fl, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  cudaFree(d_xyz); cudaFree(d_fl);
+  return 0;
+}

@@ -1,0 +1,173 @@
+"""GPU parity tests (run with -m gpu on the B200 box), all through the C ABI.
+
+Checker: the CPU oracle (oracle/liboracle_port.so, validated against the unmodified
+reference in test_oracle_cpu.py) and the golden fixtures produced by the reference itself.
+Bar: bit-exact -- overlap verdicts, accept/reject decisions, Widom counts and integer
+histogram counts are integers; coordinates are compared as raw doubles."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN_FILES = sorted(glob.glob(os.path.join(GOLDEN, "*.npz")))
+IDS = [os.path.basename(p)[:-4] for p in GOLDEN_FILES]
+
+
+@pytest.fixture(scope="module")
+def hs(lib_built):
+    import hsmc_b200
+    if hsmc_b200.load_library().hsmc_gpu_device_count() < 1:
+        pytest.fail("no CUDA device visible: GPU tests cannot run (there is no CPU fallback)")
+    return hsmc_b200
+
+
+def _gpu(hs, g, **kw):
+    h = hs.HsmcGpu(g["conf"].shape[0], g["box"][:3], **kw)
+    h.upload(g["conf"])
+    return h
+
+
+def _philox_widom_raw(oracle, seed, sample, first, count):
+    out = np.zeros((count, 3), dtype=np.uint32)
+    key = [seed & 0xFFFFFFFF, seed >> 32]
+    for i in range(count):
+        m = first + i
+        r = oracle.Port.philox([m & 0xFFFFFFFF, (1 << 24) | (m >> 32), sample & 0xFFFFFFFF, sample >> 32], key)
+        out[i] = r[:3]
+    return out
+
+
+@pytest.mark.parametrize("path", GOLDEN_FILES, ids=IDS)
+def test_upload_download_roundtrip(hs, path):
+    g = dict(np.load(path))
+    with _gpu(hs, g) as h:
+        back = h.download()
+        assert np.array_equal(back, g["conf"])
+        info = h.info()
+        assert all(c % 2 == 0 and c >= 4 for c in info["cells"])
+        assert all(s >= 1.0 for s in info["cell_size"])
+
+
+@pytest.mark.parametrize("path", GOLDEN_FILES, ids=IDS)
+def test_trial_verdicts_match_reference_golden(hs, path):
+    g = dict(np.load(path))
+    with _gpu(hs, g) as h:
+        f = h.trial_verdicts(g["trial_idx"], g["trial_xyz"], 1.0)
+        assert np.array_equal(f, g["trial_flags"])
+        fs = h.trial_verdicts(g["trial_idx"], g["trial_xyz"], float(g["sf"]))
+        assert np.array_equal(fs, g["trial_flags_sf"])
+
+
+def test_adversarial_tail_exercises_both_verdicts():
+    """The last 1000 trial points of each fixture sit at |r-1| <= 4 ulp from a particle;
+    across the fixtures (dilute ones in particular) both verdicts must occur there."""
+    tails = np.concatenate([np.load(p)["trial_flags"][-1000:] for p in GOLDEN_FILES])
+    assert 0 < tails.sum() < tails.size
+    dilute = np.load(os.path.join(GOLDEN, "fcc5_rho03.npz"))["trial_flags"][-1000:]
+    assert 100 < dilute.sum() < 900
+
+
+@pytest.mark.parametrize("path", GOLDEN_FILES, ids=IDS)
+def test_global_overlap_verdict(hs, path, oracle_built):
+    g = dict(np.load(path))
+    with _gpu(hs, g) as h:
+        assert h.overlap_scaled(1.0) == int(g["overlap_all_1"].any()) == 0
+        assert h.overlap_scaled(float(g["sf"])) == int(g["overlap_all_sf"].any())
+        if "presst_hist" in g:
+            xi = g["presst_xi"]
+            sf = np.array([pow(1 - x, 1.0 / 3.0) for x in xi])
+            p = oracle_built.Port(g["conf"], g["box"], neigh_dr=float(g["neigh_dr"]), max_part=12)
+            _, sf_o = p.presst_flags(0.0001, 0.002)
+            assert np.array_equal(sf, sf_o)
+            f = h.presst_flags(sf)
+            assert np.array_equal(f.astype(float), g["presst_hist"])
+        assert h.min_dist2() >= 1.0
+
+
+@pytest.mark.parametrize("path", GOLDEN_FILES, ids=IDS)
+def test_widom_verdicts_and_counts(hs, path, oracle_built):
+    g = dict(np.load(path))
+    box = g["box"]
+    with _gpu(hs, g, seed=0xC0FFEE1234) as h:
+        raw = g["widom_raw"]
+        xyz = (raw.astype(np.float64) / 4294967295.0) * box[None, :3]
+        assert np.array_equal(h.widom_verdicts(xyz), g["widom_flags"])
+        # device-generated points: regenerate the same Philox draws on the host and count
+        # with the oracle
+        M = 20000
+        n_gpu = h.widom(sample_id=7, count=M)
+        raw_d = _philox_widom_raw(oracle_built, 0xC0FFEE1234, 7, 0, M)
+        p = oracle_built.Port(g["conf"], box, neigh_dr=float(g["neigh_dr"]), max_part=12)
+        assert n_gpu == p.widom_count_raw(raw_d)
+        # range splitting is additive (multi-GPU sharding of insertions)
+        assert h.widom(7, 5000, first=0) + h.widom(7, M - 5000, first=5000) == n_gpu
+
+
+@pytest.mark.parametrize("path", GOLDEN_FILES, ids=IDS)
+def test_rdf_counts(hs, path):
+    g = dict(np.load(path))
+    with _gpu(hs, g) as h:
+        dr = float(g["rdf_dr"])
+        nn = int((float(g["rdf_rmax_eff"]) - 1.0) / dr)
+        c = h.rdf_counts(dr, nn)
+        assert np.array_equal(2.0 * c.astype(np.float64), g["rdf_hist"])
+
+
+@pytest.mark.parametrize("path", GOLDEN_FILES, ids=IDS)
+def test_contact_counts(hs, path, oracle_built):
+    g = dict(np.load(path))
+    with _gpu(hs, g) as h:
+        info = h.info()
+        if min(info["cell_size"]) < 1.05:
+            with pytest.raises(hs.HsmcError, match="size of the cells"):
+                h.contact_counts(0.002, 25)
+            # a narrower histogram that fits the cells still has to agree with the oracle
+            nn = int((min(info["cell_size"]) - 1.0) / 0.002)
+            if nn < 1:
+                return
+        else:
+            nn = int((1.05 - 1.0) / 0.002)
+            if "pressv_hist" in g:
+                assert np.array_equal(2.0 * h.contact_counts(0.002, nn).astype(float), g["pressv_hist"])
+        # oracle all-pairs histogram restricted to the first nn bins is the same quantity
+        p = oracle_built.Port(g["conf"], g["box"], neigh_dr=float(g["neigh_dr"]), max_part=12)
+        full = p.rdf_counts(0.002, 1.0 + 0.002 * nn)
+        assert np.array_equal(h.contact_counts(0.002, nn), full[:nn])
+
+
+def test_random_fluid_against_oracle(hs, oracle_built):
+    """Seeded non-lattice input: dilute random configuration, larger box, ragged cells."""
+    rng = np.random.default_rng(11)
+    L = 14.3
+    pts = []
+    while len(pts) < 700:
+        c = rng.random(3) * L
+        if all(np.linalg.norm((c - q + L / 2) % L - L / 2) >= 1.0 for q in pts):
+            pts.append(c)
+    conf = oracle_built.conf_from_xyz(np.array(pts))
+    box = [L, L, L]
+    p = oracle_built.Port(conf, box, neigh_dr=1.0, max_part=12)
+    with hs.HsmcGpu(700, box, seed=3) as h:
+        h.upload(conf)
+        idx = rng.integers(0, 700, 5000).astype(np.int32)
+        xyz = (conf[idx, 1:] + (rng.random((5000, 3)) - 0.5) * 0.8) % L
+        assert np.array_equal(h.trial_verdicts(idx, xyz), p.trial_verdicts(idx, xyz))
+        w = rng.random((5000, 3)) * L
+        assert np.array_equal(h.widom_verdicts(w), p.widom_verdicts(w))
+        nn = int((L / 2 - 1.0) / 0.05)
+        assert np.array_equal(h.rdf_counts(0.05, nn), p.rdf_counts(0.05, L / 2))
+
+
+def test_errors_follow_reference_convention(hs):
+    with pytest.raises(hs.HsmcError, match="too small"):
+        hs.HsmcGpu(10, [3.0, 3.0, 3.0])
+    with hs.HsmcGpu(500, [8.5, 8.5, 8.5]) as h:
+        with pytest.raises(hs.HsmcError, match="no configuration"):
+            h.sweep_nvt(1, 0.1)
+        with pytest.raises(hs.HsmcError, match="n_rows"):
+            h.upload(np.zeros((10, 4)))

@@ -1,0 +1,137 @@
+"""GPU tests of the checkerboard sweep (K2): every trial move's verdict replayed through
+the reference's part_move arithmetic, invariants, determinism, counters."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN_FILES = sorted(glob.glob(os.path.join(GOLDEN, "*.npz")))
+IDS = [os.path.basename(p)[:-4] for p in GOLDEN_FILES]
+
+
+@pytest.fixture(scope="module")
+def hs(lib_built):
+    import hsmc_b200
+    if hsmc_b200.load_library().hsmc_gpu_device_count() < 1:
+        pytest.fail("no CUDA device visible: GPU tests cannot run (there is no CPU fallback)")
+    return hsmc_b200
+
+
+def _replay(checker, log, dr_max):
+    """Feed the GPU's trial log, in its serial order, to part_move() of the checker.
+
+    Trials the checkerboard chain rejected for leaving their cell (verdict 2) never reach
+    check_overlap on the GPU and are skipped; every other trial must get the same verdict
+    from the reference arithmetic, and the final coordinates must agree bit for bit."""
+    keep = log[log["verdict"] != 2]
+    acc = checker.replay_moves(keep["id"], keep["raw"], dr_max)
+    return keep, acc
+
+
+@pytest.mark.parametrize("path", GOLDEN_FILES, ids=IDS)
+def test_every_trial_verdict_replays_through_oracle(hs, path, oracle_built):
+    g = dict(np.load(path))
+    dr_max = float(g["dr_max"])
+    N = g["conf"].shape[0]
+    p = oracle_built.Port(g["conf"], g["box"], neigh_dr=float(g["neigh_dr"]), max_part=12)
+    with hs.HsmcGpu(N, g["box"][:3], seed=2024) as h:
+        h.upload(g["conf"])
+        for sweep in range(3):
+            log = h.sweep_nvt_logged(dr_max)
+            assert len(log) == N                                  # one trial per particle
+            assert np.array_equal(np.sort(log["id"]), np.arange(N))
+            keep, acc = _replay(p, log, dr_max)
+            assert np.array_equal(acc, (keep["verdict"] == 0).astype(np.int32))
+            assert np.array_equal(h.download(), p.get_conf())
+        c = h.counters()
+        assert c[0] == 3 * N and c[1] + c[2] == c[0]
+        assert c[1] == p.counters()[1]
+        assert h.cell_rejects() == c[0] - p.counters()[0]
+
+
+def test_replay_through_unmodified_reference(hs, oracle_built):
+    """Same replay, but through the reference's own part_move() (oracle/_ref)."""
+    if not oracle_built.have_ref():
+        pytest.skip("oracle/_ref not present")
+    g = dict(np.load(os.path.join(GOLDEN, "fcc6_rho09.npz")))
+    dr_max = float(g["dr_max"])
+    N = g["conf"].shape[0]
+    with oracle_built.Ref(conf=g["conf"], box=g["box"], neigh_dr=float(g["neigh_dr"]), max_part=12) as r, \
+            hs.HsmcGpu(N, g["box"][:3], seed=99) as h:
+        h.upload(g["conf"])
+        for sweep in range(2):
+            log = h.sweep_nvt_logged(dr_max)
+            keep = log[log["verdict"] != 2]
+            cnt = r.replay_moves(keep["id"], keep["raw"], dr_max)
+            assert cnt[0] == len(keep)
+            assert cnt[1] == int((keep["verdict"] == 0).sum())
+            assert cnt[2] == int((keep["verdict"] == 1).sum())
+            assert np.array_equal(h.download(), r.get_conf())
+
+
+def test_logged_and_plain_sweeps_are_the_same_chain(hs):
+    g = dict(np.load(os.path.join(GOLDEN, "sc10_rho05.npz")))
+    N = g["conf"].shape[0]
+    with hs.HsmcGpu(N, g["box"][:3], seed=5) as a, hs.HsmcGpu(N, g["box"][:3], seed=5) as b:
+        a.upload(g["conf"])
+        b.upload(g["conf"])
+        for _ in range(4):
+            a.sweep_nvt_logged(0.2)
+        b.sweep_nvt(4, 0.2)
+        assert np.array_equal(a.download(), b.download())
+        assert np.array_equal(a.counters(), b.counters())
+
+
+def test_sweeps_keep_hard_sphere_invariants(hs, oracle_built):
+    """Config-2 shape scaled down: fcc start, rho 0.9, many sweeps: no pair < 1, N conserved,
+    acceptance in a sane band, ids a permutation, coordinates inside the closed box."""
+    box, conf = oracle_built.Port.lattice(2, 10, 10, 10, 0.9)
+    N = conf.shape[0]
+    with hs.HsmcGpu(N, box[:3], seed=1) as h:
+        h.upload(conf)
+        h.sweep_nvt(200, 0.1)
+        out = h.download()
+        assert np.array_equal(out[:, 0], np.arange(N))
+        assert (out[:, 1:] >= 0).all() and (out[:, 1:] <= box[None, :3]).all()
+        assert h.min_dist2() >= 1.0
+        assert h.overlap_scaled(1.0) == 0
+        p = oracle_built.Port(out, box, neigh_dr=1.0, max_part=12)
+        assert p.any_overlap(1.0) == 0
+        c = h.counters()
+        assert c[0] == 200 * N
+        assert 0.3 < c[1] / c[0] < 0.9
+        assert not np.array_equal(out, conf)
+        # particles do cross cell walls thanks to the per-sweep grid shift
+        assert np.abs(out[:, 1:] - conf[:, 1:]).max() > 0.5
+
+
+def test_determinism_and_seed_sensitivity(hs, oracle_built):
+    box, conf = oracle_built.Port.lattice(2, 6, 6, 6, 0.7)
+    N = conf.shape[0]
+    outs = []
+    for seed in (42, 42, 43):
+        with hs.HsmcGpu(N, box[:3], seed=seed) as h:
+            h.upload(conf)
+            h.sweep_nvt(25, 0.2)
+            outs.append(h.download())
+    assert np.array_equal(outs[0], outs[1])
+    assert not np.array_equal(outs[0], outs[2])
+
+
+def test_counters_reset_and_64bit(hs, oracle_built):
+    box, conf = oracle_built.Port.lattice(1, 8, 8, 8, 0.4)
+    with hs.HsmcGpu(512, box[:3], seed=1) as h:
+        h.upload(conf)
+        h.sweep_nvt(3, 0.3)
+        assert h.counters()[0] == 3 * 512
+        h.add_vol_move(True)
+        h.add_vol_move(False)
+        assert list(h.counters()[3:]) == [2, 1, 1]
+        h.reset_counters()
+        assert not h.counters().any()
+        assert h.counters().dtype == np.int64

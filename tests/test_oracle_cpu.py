@@ -1,0 +1,186 @@
+"""CPU tests of the oracle: known answers, golden fixtures, and (where the compiled
+reference is present) bit-for-bit agreement of the C restatement with the unmodified
+reference routines.  Nothing here touches the GPU path."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+GOLDEN_FILES = sorted(glob.glob(os.path.join(GOLDEN, "*.npz")))
+
+
+def _load(path):
+    return dict(np.load(path))
+
+
+# ---- known answers ---------------------------------------------------------------
+def test_mt19937_gsl_known_answer(oracle_built):
+    # GSL rng/test.c: mt19937, seed 4357, 1000th output
+    m = oracle_built.MT(4357)
+    v = [m.raw() for _ in range(1000)]
+    assert v[-1] == 1186927261
+    # independent implementation
+    from numpy.random import MT19937
+    ref = MT19937()
+    ref._legacy_seeding(4357)
+    assert np.array_equal(np.array(v, dtype=np.uint64), ref.random_raw(1000))
+
+
+def test_mt19937_seed_zero_is_4357(oracle_built):
+    a, b = oracle_built.MT(0), oracle_built.MT(4357)
+    assert [a.raw() for _ in range(10)] == [b.raw() for _ in range(10)]
+
+
+def test_mt_uniform_int_matches_gsl_rule(oracle_built):
+    m, m2 = oracle_built.MT(5), oracle_built.MT(5)
+    n = 1000
+    scale = 0xFFFFFFFF // n
+    for _ in range(2000):
+        k = m.int(n)
+        while True:
+            r = m2.raw() // scale
+            if r < n:
+                break
+        assert k == r
+
+
+def test_philox_known_answers(oracle_built):
+    # Random123 kat_vectors, philox4x32-10
+    P = oracle_built.Port.philox
+    assert [hex(x) for x in P([0] * 4, [0] * 2)] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
+    assert [hex(x) for x in P([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2)] == \
+        ["0x408f276d", "0x41c83b0e", "0xa20bc7c6", "0x6d5451fd"]
+    assert [hex(x) for x in P([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0])] == \
+        ["0xd16cfe09", "0x94fdcceb", "0x5001e420", "0x24126ea1"]
+
+
+def test_lattice_matches_reference_formulae(oracle_built):
+    box, conf = oracle_built.Port.lattice(2, 5, 5, 5, 0.8)
+    assert conf.shape == (500, 4)
+    a = (4 / 0.8) ** (1 / 3)
+    assert np.allclose(box[:3], 5 * a) and np.isclose(box[3], 625.0)
+    assert np.array_equal(conf[:, 0], np.arange(500))
+    assert np.allclose(conf[1, 1:], [0.5 * a, 0.5 * a, 0.0])
+
+
+# ---- golden fixtures (outputs of the reference itself) ---------------------------------
+@pytest.mark.parametrize("path", GOLDEN_FILES, ids=[os.path.basename(p) for p in GOLDEN_FILES])
+def test_port_against_golden(oracle_built, path):
+    g = _load(path)
+    conf, box = g["conf"], g["box"]
+    p = oracle_built.Port(conf, box, neigh_dr=float(g["neigh_dr"]), max_part=12)
+    assert np.array_equal(p.cells()[0], g["cells"])
+    assert np.array_equal(p.trial_verdicts(g["trial_idx"], g["trial_xyz"], 1.0), g["trial_flags"])
+    sf = float(g["sf"])
+    assert np.array_equal(p.trial_verdicts(g["trial_idx"], g["trial_xyz"], sf), g["trial_flags_sf"])
+    assert np.array_equal(p.overlap_all(sf), g["overlap_all_sf"])
+    assert np.array_equal(p.overlap_all(1.0), g["overlap_all_1"])
+    assert p.any_overlap(1.0) == int(g["overlap_all_1"].any())
+    # widom
+    raw = g["widom_raw"]
+    xyz = (raw.astype(np.float64) / 4294967295.0) * box[None, :3]
+    assert np.array_equal(p.widom_verdicts(xyz), g["widom_flags"])
+    assert p.widom_count_raw(raw) == int((g["widom_flags"] == 0).sum())
+    # histograms: the reference stores 2.0 per pair
+    assert np.array_equal(2.0 * p.rdf_counts(float(g["rdf_dr"]), float(g["rdf_rmax_eff"])), g["rdf_hist"])
+    if "pressv_hist" in g:
+        assert np.array_equal(2.0 * p.pressv_counts(float(g["pressv_dr"])), g["pressv_hist"])
+    if "presst_hist" in g:
+        f, _ = p.presst_flags(0.0001, 0.002)
+        assert np.array_equal(f.astype(float), g["presst_hist"])
+    # scripted part_move replay
+    acc = p.replay_moves(g["replay_ids"], g["replay_raw"], float(g["dr_max"]))
+    c = p.counters()
+    assert np.array_equal(c[:3], g["replay_counters"][:3]) and acc.sum() == c[1]
+    assert np.array_equal(p.get_conf(), g["replay_conf"])
+
+
+def test_golden_files_present():
+    assert len(GOLDEN_FILES) >= 4
+
+
+# ---- port vs the compiled reference (only where oracle/_ref exists) ------------------------
+@pytest.fixture()
+def ref_mod(oracle_built):
+    if not oracle_built.have_ref():
+        pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
+    return oracle_built
+
+
+@pytest.mark.parametrize("lat", [(2, 4, 4, 4, 0.7), (1, 7, 7, 7, 0.45), (2, 6, 6, 6, 0.95)])
+def test_port_trajectory_equals_reference(ref_mod, lat):
+    """Same MT19937 stream, same moves, same final configuration -- bit for bit."""
+    box, conf = ref_mod.Port.lattice(*lat)
+    with ref_mod.Ref(lattice=lat, neigh_dr=1.0, max_part=10, seed=12345) as r:
+        r.set_moves(dr_max=0.15)
+        r.sweep_nvt(30)
+        rc, rconf = r.counters(), r.get_conf()
+        d_ref = [r.compute_dist(0, j, 0.999) for j in range(1, 20)]
+    p = ref_mod.Port(conf, box, neigh_dr=1.0, max_part=10)
+    p.sweep_nvt(30, 0.15, 12345)
+    assert np.array_equal(p.counters()[:3], rc[:3])
+    assert np.array_equal(p.get_conf(), rconf)
+    assert d_ref == [p.compute_dist(0, j, 0.999) for j in range(1, 20)]
+
+
+def test_port_observables_equal_reference(ref_mod):
+    lat = (2, 5, 5, 5, 0.85)
+    rng = np.random.default_rng(3)
+    with ref_mod.Ref(lattice=lat, neigh_dr=1.05, max_part=12, seed=77) as r:
+        r.set_moves(dr_max=0.1)
+        r.sweep_nvt(80)
+        conf, box = r.get_conf(), r.box4()
+        raw = rng.integers(0, 2**32, (3000, 3), dtype=np.uint64).astype(np.uint32)
+        wf = r.widom_verdicts_raw(raw)
+        rdf = r.rdf_hist(0.02, box[0] / 2)
+        pv = r.pressv_hist(0.002)
+        pt, xi = r.presst_hist(0.0001, 0.002)
+        oa = r.overlap_all(0.9992)
+    p = ref_mod.Port(conf, box, neigh_dr=1.05, max_part=12)
+    assert np.array_equal(p.widom_verdicts((raw / 4294967295.0) * box[None, :3]), wf)
+    assert np.array_equal(2.0 * p.rdf_counts(0.02, box[0] / 2), rdf)
+    assert np.array_equal(2.0 * p.pressv_counts(0.002), pv)
+    f, sf = p.presst_flags(0.0001, 0.002)
+    assert np.array_equal(f.astype(float), pt)
+    assert np.array_equal(p.overlap_all(0.9992), oa)
+
+
+def test_port_volume_rescale_equals_reference(ref_mod):
+    """An accepted vol_move (moves.c:129-142) leaves the same coordinates in both."""
+    lat = (2, 5, 5, 5, 0.6)
+    box, conf = ref_mod.Port.lattice(*lat)
+    with ref_mod.Ref(lattice=lat, neigh_dr=1.0, max_part=10, seed=5) as r:
+        r.set_moves(dr_max=0.1, dv_max=0.01, press=3.0)
+        before = r.get_conf()
+        acc = 0
+        for _ in range(200):
+            c0 = r.counters()
+            b0 = r.box4()
+            r.vol_move()
+            if r.counters()[4] > c0[4]:
+                acc += 1
+                b1 = r.box4()
+                sf = (b1[3] / b0[3])
+                break
+        assert acc == 1
+        after = r.get_conf()
+        newbox = r.box4()
+    # recover the reference's sf exactly: sf = pow(vol_new/vol, 1/3); coordinates were x*sf
+    # so compare through the port with sf derived from a particle with a large coordinate
+    i = int(np.argmax(before[:, 1]))
+    p = ref_mod.Port(before, box, neigh_dr=1.0, max_part=10)
+    # scan candidate sf values around the ratio until the coordinates reproduce bit-exactly
+    ratio = after[i, 1] / before[i, 1]
+    cands = [np.nextafter(ratio, 0), ratio, np.nextafter(ratio, 2)]
+    ok = False
+    for sfc in cands:
+        q = ref_mod.Port(before, box, neigh_dr=1.0, max_part=10)
+        q.rescale(float(sfc), newbox)
+        if np.array_equal(q.get_conf(), after):
+            ok = True
+            break
+    assert ok
+    del p
