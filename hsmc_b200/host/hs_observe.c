@@ -1,0 +1,288 @@
+/* hs_observe.c -- observables of the drop-in host driver.
+ *
+ * The pair loops run on the device through the C ABI and come back as integer counts;
+ * this file turns them into the reference's histograms (hist = 2.0 * count, as the
+ * reference adds 2.0 per pair), normalises and writes the reference's file formats:
+ *   press_virial.dat  compute_press.c:277-307     press_thermo.dat / density.dat  :311-359
+ *   chem_pot.dat      compute_widom_chem_pot.c:164-182
+ *   rdf_%06d.dat.gz   compute_rdf.c:155-205       order_param.dat  compute_order_parameter.c:232-253
+ */
+#define _GNU_SOURCE
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <zlib.h>
+
+#include "hs_sim.h"
+
+static void hist_alloc(hs_hist *h, int nn) {
+  h->nn = nn;
+  h->x = malloc(sizeof(double) * (size_t)(nn > 0 ? nn : 1));
+  h->h = malloc(sizeof(double) * (size_t)(nn > 0 ? nn : 1));
+  if (!h->x || !h->h) hs_die("Failed histogram allocation");
+  h->live = true;
+}
+
+static void hist_free(hs_hist *h) {
+  if (!h->live) return;
+  free(h->x);
+  free(h->h);
+  h->live = false;
+}
+
+/* shell normalisation shared by the contact histogram and the rdf
+   (compute_press.c:170-187, compute_rdf.c:133-150) */
+static void shell_normalise(hs_hist *h, double rho, int N) {
+  double dr = h->x[1] - h->x[0];
+  for (int i = 0; i < h->nn; i++) {
+    double r1 = h->x[i] - dr / 2., r2 = h->x[i] + dr / 2.;
+    double bin_vol = (4. * M_PI / 3.) * (pow(r2, 3.) - pow(r1, 3.));
+    h->h[i] = h->h[i] / (bin_vol * rho * N);
+  }
+}
+
+static FILE *open_sample_file(const char *name, bool init, const char *what) {
+  FILE *f = fopen(name, init ? "w" : "a");
+  if (!f) {
+    char msg[128];
+    snprintf(msg, sizeof(msg), "Error while creating the file for the %s\n", what);
+    perror(msg);
+    exit(EXIT_FAILURE);
+  }
+  return f;
+}
+
+/* ---- pressure, virial route ---------------------------------------------------------- */
+void hs_compute_pressv(hs_sim *s, bool init) {
+  const hs_input *in = &s->in;
+  if (init) {
+    s->pressv_rmax = 1.05;   /* compute_press.c:36 */
+    hist_alloc(&s->pressv, (int)((s->pressv_rmax - 1.0) / in->pressv_dr));
+  }
+  hs_hist *h = &s->pressv;
+  for (int i = 0; i < h->nn; i++) h->x[i] = (i + 1. / 2.) * in->pressv_dr + 1.0;
+  s->pressv_rmax = in->pressv_dr * h->nn + 1.0;
+  uint64_t *cnt = calloc((size_t)(h->nn > 0 ? h->nn : 1), sizeof(uint64_t));
+  /* the device refuses, with the reference's message, when its cells are narrower than
+     the histogram range (compute_press.c:58-69) */
+  hs_gpu_check(hsmc_gpu_contact_counts(s->gpu, in->pressv_dr, h->nn, cnt));
+  for (int i = 0; i < h->nn; i++) h->h[i] = 2.0 * (double)cnt[i];
+  free(cnt);
+  shell_normalise(h, in->rho, s->part.NN);
+  FILE *f = open_sample_file("press_virial.dat", init, "virial pressure");
+  fprintf(f, "######################################\n");
+  fprintf(f, "# Bins, volume, number of particles\n");
+  fprintf(f, "######################################\n");
+  fprintf(f, "%d %.8e %d\n", h->nn, s->box.vol, s->part.NN);
+  fprintf(f, "###############################\n");
+  fprintf(f, "# rr, rdf\n");
+  fprintf(f, "###############################\n");
+  for (int i = 0; i < h->nn; i++) fprintf(f, "%.8e %.8e\n", h->x[i], h->h[i]);
+  fclose(f);
+}
+
+/* ---- pressure, thermodynamic route ------------------------------------------------------- */
+void hs_compute_presst(hs_sim *s, bool init) {
+  const hs_input *in = &s->in;
+  if (init) hist_alloc(&s->presst, (int)(in->presst_xi_max / in->presst_dxi));
+  hs_hist *h = &s->presst;
+  double *sf = malloc(sizeof(double) * (size_t)(h->nn > 0 ? h->nn : 1));
+  int *free_of_overlap = calloc((size_t)(h->nn > 0 ? h->nn : 1), sizeof(int));
+  for (int i = 0; i < h->nn; i++) {
+    h->x[i] = (i + 1) * in->presst_dxi;
+    sf[i] = pow(1 - h->x[i], 1. / 3.);   /* compute_press.c:253-256 */
+  }
+  if (h->nn > 0) hs_gpu_check(hsmc_gpu_presst_flags(s->gpu, sf, h->nn, free_of_overlap));
+  for (int i = 0; i < h->nn; i++) h->h[i] = free_of_overlap[i] ? 1.0 : 0.0;
+  free(sf);
+  free(free_of_overlap);
+  FILE *f = open_sample_file("press_thermo.dat", init, "thermo pressure");
+  fprintf(f, "######################################\n");
+  fprintf(f, "# Bins, volume, number of particles\n");
+  fprintf(f, "######################################\n");
+  fprintf(f, "%d %.8e %d\n", h->nn, s->box.vol, s->part.NN);
+  fprintf(f, "######################################\n");
+  fprintf(f, "# abs(xi), exp(-beta*U)\n");
+  fprintf(f, "######################################\n");
+  for (int i = 0; i < h->nn; i++) fprintf(f, "%.8e %.8e\n", h->x[i], h->h[i]);
+  fclose(f);
+  if (in->press > 0) {
+    f = open_sample_file("density.dat", init, "density");
+    if (init) {
+      fprintf(f, "######################################\n");
+      fprintf(f, "# Density (each line is one sample)\n");
+      fprintf(f, "######################################\n");
+    }
+    fprintf(f, "%.8e\n", in->rho);
+    fclose(f);
+  }
+}
+
+/* ---- chemical potential, Widom insertions -------------------------------------------------- */
+void hs_compute_mu(hs_sim *s, bool init) {
+  const hs_input *in = &s->in;
+  int64_t wtest = 0;
+  hs_gpu_check(hsmc_gpu_widom(s->gpu, s->mu_samples++, 0, in->mu_insertions, 1, &wtest));
+  double mu = (wtest > 0) ? -log((double)wtest / in->mu_insertions) : 0.0;
+  FILE *f = open_sample_file("chem_pot.dat", init, "chemical potential");
+  if (init) {
+    fprintf(f, "##################################################################################\n");
+    fprintf(f, "# Chemical potenital (average over %d insertions, Fraction of accepted insertions)\n", in->mu_insertions);
+    fprintf(f, "##################################################################################\n");
+  }
+  fprintf(f, "%.8e %.8e\n", mu, (double)wtest / in->mu_insertions);
+  fclose(f);
+}
+
+/* ---- radial distribution function -------------------------------------------------------------- */
+void hs_compute_rdf(hs_sim *s, bool init, int sweep) {
+  hs_input *in = &s->in;
+  if (init) {
+    /* compute_rdf.c:39-52 (the reference compares against the LARGEST edge) */
+    double lmax = s->box.lx;
+    if (lmax < s->box.ly) lmax = s->box.ly;
+    if (lmax < s->box.lz) lmax = s->box.lz;
+    if (lmax < 2.0 * in->rdf_rmax) {
+      in->rdf_rmax = lmax / 2.0;
+      printf("WARNING: Cutoff for the rdf extraction reduced to %f in order to be consistent with minimum image convention\n",
+             in->rdf_rmax);
+    }
+    hist_alloc(&s->rdf, (int)((in->rdf_rmax - 1.0) / in->rdf_dr));
+  }
+  hs_hist *h = &s->rdf;
+  for (int i = 0; i < h->nn; i++) h->x[i] = (i + 1. / 2.) * in->rdf_dr + 1.0;
+  in->rdf_rmax = in->rdf_dr * h->nn + 1.0;
+  uint64_t *cnt = calloc((size_t)(h->nn > 0 ? h->nn : 1), sizeof(uint64_t));
+  if (h->nn > 0) hs_gpu_check(hsmc_gpu_rdf_counts(s->gpu, in->rdf_dr, h->nn, cnt));
+  for (int i = 0; i < h->nn; i++) h->h[i] = 2.0 * (double)cnt[i];
+  free(cnt);
+  shell_normalise(h, in->rho, s->part.NN);
+  if (init && (double)(in->sweep_stat + in->sweep_eq) / (in->rdf_sample_int * in->rdf_samples) > 100000)
+    printf("ERROR: Too many (> 100000) rdf files will be produced. Consider increasing number of samples per file\n");
+  char name[32];
+  snprintf(name, sizeof(name), "rdf_%06d.dat.gz", s->rdf_file_id);
+  gzFile f = gzopen(name, s->rdf_samples_in_file == 0 ? "w" : "a");
+  if (f == Z_NULL) { perror("Error while creating rdf file"); exit(EXIT_FAILURE); }
+  gzprintf(f, "######################################\n");
+  gzprintf(f, "# Sweep, Bins, volume, number of particles\n");
+  gzprintf(f, "######################################\n");
+  gzprintf(f, "%d %d %.8e %d\n", sweep, h->nn, s->box.vol, s->part.NN);
+  gzprintf(f, "###############################\n");
+  gzprintf(f, "# rr, rdf\n");
+  gzprintf(f, "###############################\n");
+  for (int i = 0; i < h->nn; i++) gzprintf(f, "%.8e %.8e\n", h->x[i], h->h[i]);
+  gzclose(f);
+  if (++s->rdf_samples_in_file == in->rdf_samples) {
+    s->rdf_samples_in_file = 0;
+    s->rdf_file_id++;
+  }
+}
+
+/* ---- Steinhardt order parameter q_l (host; SURVEY.md section 8f "next" #1) -----------------
+ * q_l(i) = sqrt(4 pi/(2l+1) sum_m |<Y_lm>_bonds|^2), bonds = neighbours within ql_rmax
+ * (compute_order_parameter.c:99-229).  Evaluated on the host mirror with a private
+ * linked-cell search; normalised associated Legendre functions by recurrence. */
+static double sph_plm(int l, int m, double x) {
+  double pmm = 1.0;
+  if (m > 0) {
+    double s = sqrt((1.0 - x) * (1.0 + x)), f = 1.0;
+    for (int i = 1; i <= m; i++, f += 2.0) pmm *= -f * s;
+  }
+  double p = pmm;
+  if (l > m) {
+    double p1 = x * (2.0 * m + 1.0) * pmm;
+    p = p1;
+    for (int k = m + 2; k <= l; k++) {
+      double pk = (x * (2.0 * k - 1.0) * p1 - (k + m - 1.0) * pmm) / (double)(k - m);
+      pmm = p1; p1 = pk; p = pk;
+    }
+  }
+  double ratio = 1.0;
+  for (int k = l - m + 1; k <= l + m; k++) ratio /= (double)k;
+  return sqrt((2.0 * l + 1.0) / (4.0 * M_PI) * ratio) * p;
+}
+
+void hs_compute_op(hs_sim *s, bool init) {
+  hs_input *in = &s->in;
+  const int N = s->part.NN, l = in->ql_order;
+  const double L[3] = {s->box.lx, s->box.ly, s->box.lz};
+  if (init) {
+    /* compute_order_parameter.c:47-60: the cutoff may not exceed the cell size there;
+       here the search grid adapts instead, only the half-box bound remains */
+    double lmin = fmin(L[0], fmin(L[1], L[2]));
+    if (in->ql_rmax > lmin / 2.0) in->ql_rmax = lmin / 2.0;
+  }
+  hs_gpu_pull(s);
+  int nc[3];
+  for (int a = 0; a < 3; a++) { nc[a] = (int)floor(L[a] / in->ql_rmax); if (nc[a] < 1) nc[a] = 1; }
+  int ncell = nc[0] * nc[1] * nc[2];
+  int *head = malloc(sizeof(int) * (size_t)ncell), *next = malloc(sizeof(int) * (size_t)N);
+  for (int c = 0; c < ncell; c++) head[c] = -1;
+  int ci[3];
+  for (int i = 0; i < N; i++) {
+    for (int a = 0; a < 3; a++) {
+      ci[a] = (int)(s->conf[i][a + 1] / L[a] * nc[a]);
+      if (ci[a] >= nc[a]) ci[a] = nc[a] - 1;
+      if (ci[a] < 0) ci[a] = 0;
+    }
+    int c = (ci[0] * nc[1] + ci[1]) * nc[2] + ci[2];
+    next[i] = head[c]; head[c] = i;
+  }
+  double *re = malloc(sizeof(double) * (size_t)(l + 1)), *im = malloc(sizeof(double) * (size_t)(l + 1));
+  double ql_ave = 0.0;
+  for (int i = 0; i < N; i++) {
+    for (int m = 0; m <= l; m++) re[m] = im[m] = 0.0;
+    int bonds = 0;
+    for (int a = 0; a < 3; a++) {
+      ci[a] = (int)(s->conf[i][a + 1] / L[a] * nc[a]);
+      if (ci[a] >= nc[a]) ci[a] = nc[a] - 1;
+    }
+    int seen[27], nseen = 0;
+    for (int dx = -1; dx <= 1; dx++) for (int dy = -1; dy <= 1; dy++) for (int dz = -1; dz <= 1; dz++) {
+      int cx = (ci[0] + dx + nc[0]) % nc[0], cy = (ci[1] + dy + nc[1]) % nc[1], cz = (ci[2] + dz + nc[2]) % nc[2];
+      int c = (cx * nc[1] + cy) * nc[2] + cz, dup = 0;
+      for (int q = 0; q < nseen; q++) if (seen[q] == c) dup = 1;
+      if (dup) continue;
+      seen[nseen++] = c;
+      for (int j = head[c]; j >= 0; j = next[j]) {
+        if (j == i) continue;
+        double d[3];
+        for (int a = 0; a < 3; a++) {
+          d[a] = s->conf[i][a + 1] - s->conf[j][a + 1];
+          if (d[a] > L[a] / 2.0) d[a] -= L[a]; else if (d[a] < -L[a] / 2.0) d[a] += L[a];
+        }
+        double dr = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        if (dr > in->ql_rmax) continue;
+        double phi = atan2(d[1], d[0]);
+        if (phi < 0) phi += 2. * M_PI;
+        bonds++;
+        for (int m = 0; m <= l; m++) {
+          double plm = sph_plm(l, m, d[2] / dr);
+          re[m] += plm * cos(m * phi);
+          im[m] += plm * sin(m * phi);
+        }
+      }
+    }
+    double sum = 0.0;
+    for (int m = 0; m <= l; m++) {
+      double a = bonds ? re[m] / bonds : 0.0, b = bonds ? im[m] / bonds : 0.0;
+      sum += (m == 0 ? 1.0 : 2.0) * (a * a + b * b);   /* |Y_l,-m| = |Y_l,m| */
+    }
+    ql_ave += sqrt(sum * 4 * M_PI / (2 * l + 1)) / N;
+  }
+  free(re); free(im); free(head); free(next);
+  FILE *f = open_sample_file("order_param.dat", init, "order parameter");
+  if (init) {
+    fprintf(f, "###############################################################\n");
+    fprintf(f, "# Average order parameter of order %d (each line is one sample)\n", in->ql_order);
+    fprintf(f, "###############################################################\n");
+  }
+  fprintf(f, "%.8e\n", ql_ave);
+  fclose(f);
+}
+
+void hs_observables_free(hs_sim *s) {
+  hist_free(&s->pressv);
+  hist_free(&s->presst);
+  hist_free(&s->rdf);
+}
