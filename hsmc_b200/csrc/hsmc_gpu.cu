@@ -64,6 +64,19 @@ extern "C" const char* hsmc_gpu_last_error(void) { return g_err.c_str(); }
 // ----------------------------------------------------------------------------------
 enum { CNT_TRIALS = 0, CNT_ACC = 1, CNT_REJ_OVERLAP = 2, CNT_REJ_CELL = 3, CNT_N = 8 };
 
+#define TILE_MAX_A 4          // active cells per tile along x and y (max)
+#define TILE_MAX_AZ 16        // along z (max)
+#define TILE_THREADS 192
+#define TILE_MAX_ROWS ((2 * TILE_MAX_A + 1) * (2 * TILE_MAX_A + 1))
+#define TILE_MAX_CELLS (TILE_MAX_A * TILE_MAX_A * TILE_MAX_AZ)
+
+struct TileCfg {
+  int ax, ay, az;          // active cells per tile
+  int ntx, nty, ntz;       // tiles per axis of the active-cell lattice
+  int cap;                 // staged particle capacity (slots of 32 B)
+  int use_tma;
+};
+
 struct hsmc_gpu {
   hsmc_gpu_config cfg;
   int64_t N = 0;           // global particle count
@@ -77,8 +90,11 @@ struct hsmc_gpu {
   int64_t cap_cells = 0;
   cudaStream_t st = nullptr;
   double4* pos[2] = {nullptr, nullptr};
+  float4* rel = nullptr;                 // fp32 shadow {cell-relative offset, id} of pos[cur]
   int cur = 0;
-  int *key = nullptr, *rnk = nullptr;    // [cap + 2*cap_halo]
+  int *key = nullptr, *rnk = nullptr;    // [cap_keys]
+  int64_t cap_keys = 0;
+  int *key_halo = nullptr, *rnk_halo = nullptr;   // [2*cap_halo]
   int *cell_count = nullptr, *cell_start = nullptr, *bsum = nullptr;
   unsigned long long* d_cnt = nullptr;       // CNT_N counters
   unsigned long long* d_scratch = nullptr;   // SCRATCH_N x u64 general scratch (flags, hist, min)
@@ -98,6 +114,9 @@ struct hsmc_gpu {
   int* d_halo_cnt = nullptr;             // [0]=send_l count [1]=send_r count [2]=error flags
   int lay[6] = {0, 0, 0, 0, 0, 0};       // slot offsets of layers 0,1,2,nlx-2,nlx-1,nlx
   void* d_sfargs = nullptr;
+  TileCfg tile;
+  size_t tile_smem = 0;
+  bool tile_ok = false;
   hsmc_gpu_trial* d_log = nullptr;
   int64_t cap_log = 0;
   // optional event timing
@@ -228,14 +247,17 @@ __global__ void k_scan_final(const int* __restrict__ in, long long n, const int*
 }
 
 // pass 3: scatter into cell order
-__global__ void k_cell_scatter(const double4* __restrict__ in, int n, const int* __restrict__ key,
+__global__ void k_cell_scatter(Grid g, const double4* __restrict__ in, int n, const int* __restrict__ key,
                                const int* __restrict__ rnk, const int* __restrict__ cs,
-                               double4* __restrict__ out) {
+                               double4* __restrict__ out, float4* __restrict__ rel) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int c = key[i];
   if (c < 0) return;
-  out[cs[c] + rnk[i]] = in[i];
+  double4 p = in[i];
+  int d = cs[c] + rnk[i];
+  out[d] = p;
+  rel[d] = make_rel_cell(g, c, p);
 }
 
 // ----------------------------------------------------------------------------------
@@ -289,11 +311,81 @@ struct SweepArgs {
   uint32_t key0, key1;
   uint32_t sweep_lo, sweep_hi;
   int cx, cy, cz, phase;
+  float eps;   // half-width of the fp32 filter's uncertainty band around r^2 = 1
 };
 
+// all trials of one active cell straight from global memory (generic path: any grid,
+// minimum image always evaluated)
+template <bool LOG>
+__device__ __forceinline__ void cell_update_global(const SweepArgs& a, double4* __restrict__ pos,
+                                                   float4* __restrict__ rel, const int* __restrict__ cs, int l,
+                                                   int iy, int iz, int& n_acc,
+                                                   int& n_ov, int& n_cell, hsmc_gpu_trial* __restrict__ log,
+                                                   unsigned long long* __restrict__ nlog, long long logcap) {
+  const Grid& g = a.g;
+  long long c = ((long long)l * g.ny + iy) * g.nz + iz;
+  int beg = cs[c], end = cs[c + 1];
+  if (beg == end) return;
+  const int gx = (g.gx0 + l >= g.nx) ? g.gx0 + l - g.nx : g.gx0 + l;
+  long long gcell = ((long long)gx * g.ny + iy) * g.nz + iz;
+  double last_id = -1.0;
+  for (int j = 0; j < end - beg; j++) {
+    // next particle of this cell in ascending-id order (order is then independent of
+    // how the counting sort happened to place them)
+    int sel = beg;
+    double best = 1e300;
+    for (int k = beg; k < end; k++) {
+      double id = pos[k].w;
+      if (id > last_id && id < best) { best = id; sel = k; }
+    }
+    last_id = best;
+    double4 p = pos[sel];
+    Philox4 rn = philox4x32_10((uint32_t)gcell, (HSMC_STREAM_MOVE << 24) | (uint32_t)j, a.sweep_lo, a.sweep_hi,
+                               a.key0, a.key1);
+    // moves.c:52-54
+    double xn = p.x + (hsmc_u01(rn.v[0]) - 0.5) * a.dr_max;
+    double yn = p.y + (hsmc_u01(rn.v[1]) - 0.5) * a.dr_max;
+    double zn = p.z + (hsmc_u01(rn.v[2]) - 0.5) * a.dr_max;
+    // moves.c:215-226
+    if (xn > g.Lx) xn -= g.Lx; else if (xn < 0.0) xn += g.Lx;
+    if (yn > g.Ly) yn -= g.Ly; else if (yn < 0.0) yn += g.Ly;
+    if (zn > g.Lz) zn -= g.Lz; else if (zn < 0.0) zn += g.Lz;
+    int verdict;
+    if (axis_cell(xn, g.sx, g.iwx, g.nx) != gx || axis_cell(yn, g.sy, g.iwy, g.ny) != iy ||
+        axis_cell(zn, g.sz, g.iwz, g.nz) != iz) {
+      verdict = 2;
+      n_cell++;
+    } else {
+      const Box& b = a.box;
+      bool ov = stencil_any(g, cs, l, iy, iz, [&](int k) {
+        if (k == sel) return false;
+        double4 q = pos[k];
+        return pair_r2(xn, yn, zn, q.x, q.y, q.z, b) < 1.0;
+      });
+      if (ov) { verdict = 1; n_ov++; }
+      else {
+        verdict = 0; n_acc++;
+        pos[sel] = make_double4(xn, yn, zn, p.w);
+        rel[sel] = make_rel(g, gx, iy, iz, xn, yn, zn, p.w);
+      }
+    }
+    if (LOG) {
+      unsigned long long s = atomicAdd(nlog, 1ull);
+      if ((long long)s < logcap) {
+        hsmc_gpu_trial tr;
+        tr.seq = ((unsigned long long)a.phase << 56) | ((unsigned long long)gcell << 8) | (unsigned)j;
+        tr.id = (int)p.w; tr.verdict = verdict;
+        tr.raw[0] = rn.v[0]; tr.raw[1] = rn.v[1]; tr.raw[2] = rn.v[2]; tr.pad = 0;
+        log[s] = tr;
+      }
+    }
+  }
+}
+
+// generic kernel: one thread per active cell, everything from global memory
 template <bool LOG>
 __global__ void __launch_bounds__(128)
-k_sweep_phase(SweepArgs a, double4* __restrict__ pos, const int* __restrict__ cs,
+k_sweep_phase(SweepArgs a, double4* __restrict__ pos, float4* __restrict__ rel, const int* __restrict__ cs,
               unsigned long long* __restrict__ cnt, hsmc_gpu_trial* __restrict__ log,
               unsigned long long* __restrict__ nlog, long long logcap) {
   const Grid& g = a.g;
@@ -308,60 +400,7 @@ k_sweep_phase(SweepArgs a, double4* __restrict__ pos, const int* __restrict__ cs
     int par0 = (g.gx0 + g.own_lo) & 1;
     int l = g.own_lo + 2 * ax + ((a.cx - par0) & 1);
     int iy = 2 * ay + a.cy, iz = 2 * az + a.cz;
-    long long c = ((long long)l * g.ny + iy) * g.nz + iz;
-    int beg = cs[c], end = cs[c + 1];
-    long long gcell = global_cell_of_local(g, l, iy, iz);
-    double last_id = -1.0;
-    for (int j = 0; j < end - beg; j++) {
-      // next particle of this cell in ascending-id order (order is then independent of
-      // how the counting sort happened to place them)
-      int sel = beg;
-      double best = 1e300;
-      for (int k = beg; k < end; k++) {
-        double id = pos[k].w;
-        if (id > last_id && id < best) { best = id; sel = k; }
-      }
-      last_id = best;
-      double4 p = pos[sel];
-      Philox4 rn = philox4x32_10((uint32_t)gcell, (HSMC_STREAM_MOVE << 24) | (uint32_t)j, a.sweep_lo,
-                                 a.sweep_hi, a.key0, a.key1);
-      // moves.c:52-54
-      double xn = p.x + (hsmc_u01(rn.v[0]) - 0.5) * a.dr_max;
-      double yn = p.y + (hsmc_u01(rn.v[1]) - 0.5) * a.dr_max;
-      double zn = p.z + (hsmc_u01(rn.v[2]) - 0.5) * a.dr_max;
-      // moves.c:215-226
-      if (xn > g.Lx) xn -= g.Lx; else if (xn < 0.0) xn += g.Lx;
-      if (yn > g.Ly) yn -= g.Ly; else if (yn < 0.0) yn += g.Ly;
-      if (zn > g.Lz) zn -= g.Lz; else if (zn < 0.0) zn += g.Lz;
-      int verdict;
-      if (axis_cell(xn, g.sx, g.iwx, g.nx) != ((g.gx0 + l >= g.nx) ? g.gx0 + l - g.nx : g.gx0 + l) ||
-          axis_cell(yn, g.sy, g.iwy, g.ny) != iy || axis_cell(zn, g.sz, g.iwz, g.nz) != iz) {
-        verdict = 2;
-        n_cell++;
-      } else {
-        const Box& b = a.box;
-        bool ov = stencil_any(g, cs, l, iy, iz, [&](int k) {
-          if (k == sel) return false;
-          double4 q = pos[k];
-          return pair_r2(xn, yn, zn, q.x, q.y, q.z, b) < 1.0;
-        });
-        if (ov) { verdict = 1; n_ov++; }
-        else {
-          verdict = 0; n_acc++;
-          pos[sel] = make_double4(xn, yn, zn, p.w);
-        }
-      }
-      if (LOG) {
-        unsigned long long s = atomicAdd(nlog, 1ull);
-        if ((long long)s < logcap) {
-          hsmc_gpu_trial tr;
-          tr.seq = ((unsigned long long)a.phase << 56) | ((unsigned long long)gcell << 8) | (unsigned)j;
-          tr.id = (int)p.w; tr.verdict = verdict;
-          tr.raw[0] = rn.v[0]; tr.raw[1] = rn.v[1]; tr.raw[2] = rn.v[2]; tr.pad = 0;
-          log[s] = tr;
-        }
-      }
-    }
+    cell_update_global<LOG>(a, pos, rel, cs, l, iy, iz, n_acc, n_ov, n_cell, log, nlog, logcap);
   }
   // block-aggregated counters
   __shared__ int s_cnt[3];
@@ -381,6 +420,8 @@ k_sweep_phase(SweepArgs a, double4* __restrict__ pos, const int* __restrict__ cs
     }
   }
 }
+
+#include "sweep_tile.cuh"
 
 // ----------------------------------------------------------------------------------
 // K3: global scaled-overlap verdict for nsf scale factors in one pass over the pairs.
@@ -694,33 +735,40 @@ __global__ void k_recv_count(Grid g, const double4* __restrict__ buf, int cap_ha
   }
 }
 
-__global__ void k_recv_scatter(const double4* __restrict__ buf, int cap_halo, const int* __restrict__ key,
+__global__ void k_recv_scatter(Grid g, const double4* __restrict__ buf, int cap_halo, const int* __restrict__ key,
                                const int* __restrict__ rnk, const int* __restrict__ cs,
-                               double4* __restrict__ out) {
+                               double4* __restrict__ out, float4* __restrict__ rel) {
   int n = (int)buf[0].x;
   if (n > cap_halo - 1) n = cap_halo - 1;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     int c = key[i];
-    if (c >= 0) out[cs[c] + rnk[i]] = buf[i + 1];
+    if (c >= 0) {
+      double4 p = buf[i + 1];
+      int d = cs[c] + rnk[i];
+      out[d] = p;
+      rel[d] = make_rel_cell(g, c, p);
+    }
   }
 }
 
-__global__ void k_scatter_layout(const double4* __restrict__ in, int n, int rows_layout,
+__global__ void k_scatter_layout(Grid g, const double4* __restrict__ in, int n, int rows_layout,
                                  const int* __restrict__ key, const int* __restrict__ rnk,
-                                 const int* __restrict__ cs, double4* __restrict__ out) {
+                                 const int* __restrict__ cs, double4* __restrict__ out, float4* __restrict__ rel) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int c = key[i];
   if (c < 0) return;
   double4 p = in[i];
   if (rows_layout) p = make_double4(p.y, p.z, p.w, p.x);
-  out[cs[c] + rnk[i]] = p;
+  int d = cs[c] + rnk[i];
+  out[d] = p;
+  rel[d] = make_rel_cell(g, c, p);
 }
 
 // canonical (ascending id) slot order inside every cell of the given layers, so that a
 // boundary layer and its ghost copy on the neighbour are slot-for-slot identical
-__global__ void k_sort_cells_by_id(Grid g, double4* __restrict__ pos, const int* __restrict__ cs,
-                                   int layer_a, int layer_b) {
+__global__ void k_sort_cells_by_id(Grid g, double4* __restrict__ pos, float4* __restrict__ rel,
+                                   const int* __restrict__ cs, int layer_a, int layer_b) {
   long long per = (long long)g.ny * g.nz;
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= 2 * per) return;
@@ -732,6 +780,17 @@ __global__ void k_sort_cells_by_id(Grid g, double4* __restrict__ pos, const int*
     while (j >= beg && pos[j].w > v.w) { pos[j + 1] = pos[j]; j--; }
     pos[j + 1] = v;
   }
+  for (int i = beg; i < end; i++) rel[i] = make_rel_cell(g, c, pos[i]);
+}
+
+// shadow of one cell layer recomputed from the master table (ghost layers after a halo refresh)
+__global__ void k_rel_layer(Grid g, const double4* __restrict__ pos, float4* __restrict__ rel,
+                            const int* __restrict__ cs, int layer) {
+  long long per = (long long)g.ny * g.nz;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= per) return;
+  long long c = (long long)layer * per + t;
+  for (int i = cs[c]; i < cs[c + 1]; i++) rel[i] = make_rel_cell(g, c, pos[i]);
 }
 
 // ----------------------------------------------------------------------------------
@@ -744,6 +803,8 @@ static int even_cells(double L, double cell_min) {
   while (n >= 2 && L / n < cell_min * (1.0 + 1e-9)) n -= 2;
   return n;
 }
+
+static void setup_tiles(hsmc_gpu* h);
 
 static int setup_grid(hsmc_gpu* h) {
   double cm = h->cfg.cell_min;
@@ -772,6 +833,7 @@ static int setup_grid(hsmc_gpu* h) {
   }
   h->ncell = (int64_t)g.nlx * g.ny * g.nz;
   if (h->ncell + 1 > (int64_t)INT32_MAX) return fail("too many cells for 32-bit cell indices");
+  setup_tiles(h);
   return 0;
 }
 
@@ -784,6 +846,16 @@ static int ensure_cell_arrays(hsmc_gpu* h) {
   CU(cudaMalloc(&h->cell_start, sizeof(int) * (size_t)h->cap_cells));
   CU(cudaMalloc(&h->cell_count, sizeof(int) * (size_t)h->cap_cells));
   CU(cudaMalloc(&h->bsum, sizeof(int) * (size_t)((h->cap_cells + SCAN_CHUNK - 1) / SCAN_CHUNK + 1)));
+  return 0;
+}
+
+static int ensure_keys(hsmc_gpu* h, int64_t n) {
+  if (n <= h->cap_keys) return 0;
+  if (h->key) cudaFree(h->key);
+  if (h->rnk) cudaFree(h->rnk);
+  h->cap_keys = n;
+  CU(cudaMalloc(&h->key, sizeof(int) * (size_t)n));
+  CU(cudaMalloc(&h->rnk, sizeof(int) * (size_t)n));
   return 0;
 }
 
@@ -816,6 +888,33 @@ static int exclusive_scan(hsmc_gpu* h, const int* in, int64_t n, int* out) {
   return 0;
 }
 
+// tile shape of the staged sweep kernel for the current grid / density
+static void setup_tiles(hsmc_gpu* h) {
+  Grid& g = h->g;
+  TileCfg& t = h->tile;
+  int hx = (g.own_hi - g.own_lo) / 2, hy = g.ny / 2, hz = g.nz / 2;
+  auto fit = [](int amax, int n_cells, int half) {
+    int a = std::min(amax, std::max(1, (n_cells - 1) / 2));
+    return std::min(a, std::max(1, half));
+  };
+  t.ax = fit(TILE_MAX_A, g.wrap_x ? g.nx : g.nlx, hx);
+  t.ay = fit(TILE_MAX_A, g.ny, hy);
+  t.az = fit(TILE_MAX_AZ, g.nz, hz);
+  double nbar = (double)h->N / ((double)g.nx * g.ny * g.nz);
+  const int cap_max = 2944;   // 46 KB of staged shadow entries: four CTAs per SM
+  for (;;) {
+    double region = (2.0 * t.ax + 1) * (2.0 * t.ay + 1) * (2.0 * t.az + 1);
+    int want = (int)(region * nbar * 1.15) + 96;
+    if (want <= cap_max || t.az == 1) { t.cap = std::min(std::max(want, 256), cap_max); break; }
+    t.az = std::max(1, t.az / 2);
+  }
+  t.cap = (t.cap + 31) & ~31;
+  t.ntx = (hx + t.ax - 1) / t.ax; t.nty = (hy + t.ay - 1) / t.ay; t.ntz = (hz + t.az - 1) / t.az;
+  t.use_tma = (h->cfg.sweep_impl == 2) ? 0 : 1;
+  h->tile_smem = (size_t)t.cap * 16 + (size_t)TILE_MAX_ROWS * (2 * TILE_MAX_AZ + 2) * sizeof(unsigned short);
+  h->tile_ok = h->cfg.sweep_impl != 1 && t.cap * 1 <= 65535;
+}
+
 static inline int left_of(const hsmc_gpu* h) { return (h->cfg.rank + h->cfg.world - 1) % h->cfg.world; }
 static inline int right_of(const hsmc_gpu* h) { return (h->cfg.rank + 1) % h->cfg.world; }
 
@@ -824,6 +923,7 @@ static inline int right_of(const hsmc_gpu* h) { return (h->cfg.rank + 1) % h->cf
 static int rebuild(hsmc_gpu* h, const double4* src, int64_t n_in, int rows_layout, int upload_mode) {
   ProfSpan span(h, 1);
   TRY(ensure_cell_arrays(h));
+  TRY(ensure_keys(h, std::max<int64_t>(n_in, h->cap)));
   Grid& g = h->g;
   const int T = 256;
   double4* dst = h->pos[h->cur ^ 1];
@@ -839,7 +939,7 @@ static int rebuild(hsmc_gpu* h, const double4* src, int64_t n_in, int rows_layou
     k_cell_count<<<nblk(n_in, T), T, 0, h->st>>>(g, src, (int)n_in, h->key, h->rnk, h->cell_count);
     h->launches++;
     TRY(exclusive_scan(h, h->cell_count, h->ncell, h->cell_start));
-    k_cell_scatter<<<nblk(n_in, T), T, 0, h->st>>>(src, (int)n_in, h->key, h->rnk, h->cell_start, dst);
+    k_cell_scatter<<<nblk(n_in, T), T, 0, h->st>>>(g, src, (int)n_in, h->key, h->rnk, h->cell_start, dst, h->rel);
     h->launches++;
     CU(cudaGetLastError());
     h->cur ^= 1;
@@ -865,8 +965,8 @@ static int rebuild(hsmc_gpu* h, const double4* src, int64_t n_in, int rows_layou
   NC(ncclRecv(h->recv_l, cnt, ncclDouble, left_of(h), h->comm, h->st));
   NC(ncclGroupEnd());
   h->nccl_calls += 4;
-  int* key_l = h->key + h->cap;
-  int* rnk_l = h->rnk + h->cap;
+  int* key_l = h->key_halo;
+  int* rnk_l = h->rnk_halo;
   int* key_r = key_l + h->cap_halo;
   int* rnk_r = rnk_l + h->cap_halo;
   int gb = 148 * 4;
@@ -875,16 +975,16 @@ static int rebuild(hsmc_gpu* h, const double4* src, int64_t n_in, int rows_layou
   h->launches += 2;
   TRY(exclusive_scan(h, h->cell_count, h->ncell, h->cell_start));
   if (n_in > 0) {
-    k_scatter_layout<<<nblk(n_in, T), T, 0, h->st>>>(src, (int)n_in, rows_layout, h->key, h->rnk,
-                                                      h->cell_start, dst);
+    k_scatter_layout<<<nblk(n_in, T), T, 0, h->st>>>(g, src, (int)n_in, rows_layout, h->key, h->rnk,
+                                                      h->cell_start, dst, h->rel);
     h->launches++;
   }
-  k_recv_scatter<<<gb, T, 0, h->st>>>(h->recv_l, (int)h->cap_halo, key_l, rnk_l, h->cell_start, dst);
-  k_recv_scatter<<<gb, T, 0, h->st>>>(h->recv_r, (int)h->cap_halo, key_r, rnk_r, h->cell_start, dst);
+  k_recv_scatter<<<gb, T, 0, h->st>>>(g, h->recv_l, (int)h->cap_halo, key_l, rnk_l, h->cell_start, dst, h->rel);
+  k_recv_scatter<<<gb, T, 0, h->st>>>(g, h->recv_r, (int)h->cap_halo, key_r, rnk_r, h->cell_start, dst, h->rel);
   h->launches += 2;
   long long per = (long long)g.ny * g.nz;
-  k_sort_cells_by_id<<<nblk(2 * per, 128), 128, 0, h->st>>>(g, dst, h->cell_start, 0, 1);
-  k_sort_cells_by_id<<<nblk(2 * per, 128), 128, 0, h->st>>>(g, dst, h->cell_start, g.nlx - 2, g.nlx - 1);
+  k_sort_cells_by_id<<<nblk(2 * per, 128), 128, 0, h->st>>>(g, dst, h->rel, h->cell_start, 0, 1);
+  k_sort_cells_by_id<<<nblk(2 * per, 128), 128, 0, h->st>>>(g, dst, h->rel, h->cell_start, g.nlx - 2, g.nlx - 1);
   h->launches += 2;
   CU(cudaGetLastError());
   // layer offsets + error flags back to the host (one small sync per rebuild)
@@ -926,9 +1026,9 @@ extern "C" int hsmc_gpu_destroy(hsmc_gpu* h) {
   cudaSetDevice(h->cfg.device);
   if (h->st) cudaStreamSynchronize(h->st);
   if (h->comm) ncclCommDestroy(h->comm);
-  void* ptrs[] = {h->pos[0], h->pos[1], h->key, h->rnk, h->cell_count, h->cell_start, h->bsum, h->d_cnt,
+  void* ptrs[] = {h->pos[0], h->pos[1], h->rel, h->key, h->rnk, h->cell_count, h->cell_start, h->bsum, h->d_cnt,
                   h->d_scratch, h->d_slot_of_id, h->d_io, h->send_l, h->send_r, h->recv_l, h->recv_r,
-                  h->d_halo_cnt, h->d_sfargs, h->d_log};
+                  h->d_halo_cnt, h->d_sfargs, h->d_log, h->key_halo, h->rnk_halo};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -982,8 +1082,11 @@ extern "C" int hsmc_gpu_create(hsmc_gpu** out, const hsmc_gpu_config* cfg, int64
   }
   CUD(cudaMalloc(&h->pos[0], sizeof(double4) * (size_t)h->cap));
   CUD(cudaMalloc(&h->pos[1], sizeof(double4) * (size_t)h->cap));
-  CUD(cudaMalloc(&h->key, sizeof(int) * (size_t)(h->cap + 2 * h->cap_halo)));
-  CUD(cudaMalloc(&h->rnk, sizeof(int) * (size_t)(h->cap + 2 * h->cap_halo)));
+  CUD(cudaMalloc(&h->rel, sizeof(float4) * (size_t)h->cap));
+  if (h->cap_halo) {
+    CUD(cudaMalloc(&h->key_halo, sizeof(int) * (size_t)(2 * h->cap_halo)));
+    CUD(cudaMalloc(&h->rnk_halo, sizeof(int) * (size_t)(2 * h->cap_halo)));
+  }
   CUD(cudaMalloc(&h->d_cnt, sizeof(unsigned long long) * CNT_N));
   CUD(cudaMemset(h->d_cnt, 0, sizeof(unsigned long long) * CNT_N));
   CUD(cudaMalloc(&h->d_scratch, sizeof(unsigned long long) * SCRATCH_N));
@@ -992,6 +1095,8 @@ extern "C" int hsmc_gpu_create(hsmc_gpu** out, const hsmc_gpu_config* cfg, int64
   CUD(cudaMalloc(&h->d_sfargs, sizeof(SfArgs)));
   CUD(cudaMallocHost(&h->h_stage, sizeof(unsigned long long) * SCRATCH_N));
   if (ensure_cell_arrays(h)) { hsmc_gpu_destroy(h); return 1; }
+  CUD(cudaFuncSetAttribute(k_sweep_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+  CUD(cudaFuncSetAttribute(k_sweep_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
   if (W > 1) {
     CUD(cudaMalloc(&h->send_l, sizeof(double4) * (size_t)h->cap_halo));
     CUD(cudaMalloc(&h->send_r, sizeof(double4) * (size_t)h->cap_halo));
@@ -1102,6 +1207,13 @@ static int halo_refresh(hsmc_gpu* h, int cx) {
   }
   NC(ncclGroupEnd());
   h->nccl_calls += 2;
+  {
+    long long per = (long long)h->g.ny * h->g.nz;
+    int layer = (cx == 0) ? h->g.nlx - 1 : 0;
+    k_rel_layer<<<nblk(per, 128), 128, 0, h->st>>>(h->g, p, h->rel, h->cell_start, layer);
+    h->launches++;
+    CU(cudaGetLastError());
+  }
   return 0;
 }
 
@@ -1121,17 +1233,26 @@ static int sweep_once(hsmc_gpu* h, double dr_max, bool logged) {
   a.dr_max = dr_max;
   a.key0 = (uint32_t)h->cfg.seed; a.key1 = (uint32_t)(h->cfg.seed >> 32);
   a.sweep_lo = (uint32_t)h->sweeps_done; a.sweep_hi = (uint32_t)(h->sweeps_done >> 32);
+  a.eps = (h->cfg.sweep_impl == 3) ? 0.0f : 1.0e-5f * (float)std::max(1.0, std::max(g.wx, std::max(g.wy, g.wz)));
   long long total = (long long)((g.own_hi - g.own_lo) / 2) * (g.ny / 2) * (g.nz / 2);
   const int T = 128;
   for (int ph = 0; ph < 8; ph++) {
     a.cx = (ph >> 2) & 1; a.cy = (ph >> 1) & 1; a.cz = ph & 1; a.phase = ph;
     {
     ProfSpan span(h, 0);
-    if (logged)
-      k_sweep_phase<true><<<nblk(total, T), T, 0, h->st>>>(a, h->pos[h->cur], h->cell_start, h->d_cnt, h->d_log,
+    if (h->tile_ok) {
+      int nb = h->tile.ntx * h->tile.nty * h->tile.ntz;
+      if (logged)
+        k_sweep_tile<true><<<nb, TILE_THREADS, h->tile_smem, h->st>>>(a, h->tile, h->pos[h->cur], h->rel, h->cell_start, h->d_cnt,
+                                                                      h->d_log, h->d_scratch, (long long)h->cap_log);
+      else
+        k_sweep_tile<false><<<nb, TILE_THREADS, h->tile_smem, h->st>>>(a, h->tile, h->pos[h->cur], h->rel, h->cell_start, h->d_cnt,
+                                                                       nullptr, nullptr, 0);
+    } else if (logged)
+      k_sweep_phase<true><<<nblk(total, T), T, 0, h->st>>>(a, h->pos[h->cur], h->rel, h->cell_start, h->d_cnt, h->d_log,
                                                             h->d_scratch, (long long)h->cap_log);
     else
-      k_sweep_phase<false><<<nblk(total, T), T, 0, h->st>>>(a, h->pos[h->cur], h->cell_start, h->d_cnt, nullptr,
+      k_sweep_phase<false><<<nblk(total, T), T, 0, h->st>>>(a, h->pos[h->cur], h->rel, h->cell_start, h->d_cnt, nullptr,
                                                              nullptr, 0);
     }
     h->launches++;

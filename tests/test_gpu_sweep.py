@@ -33,13 +33,14 @@ def _replay(checker, log, dr_max):
     return keep, acc
 
 
+@pytest.mark.parametrize("impl", [0, 1, 2], ids=["tile_tma", "global", "tile_ldg"])
 @pytest.mark.parametrize("path", GOLDEN_FILES, ids=IDS)
-def test_every_trial_verdict_replays_through_oracle(hs, path, oracle_built):
+def test_every_trial_verdict_replays_through_oracle(hs, path, impl, oracle_built):
     g = dict(np.load(path))
     dr_max = float(g["dr_max"])
     N = g["conf"].shape[0]
     p = oracle_built.Port(g["conf"], g["box"], neigh_dr=float(g["neigh_dr"]), max_part=12)
-    with hs.HsmcGpu(N, g["box"][:3], seed=2024) as h:
+    with hs.HsmcGpu(N, g["box"][:3], seed=2024, sweep_impl=impl) as h:
         h.upload(g["conf"])
         for sweep in range(3):
             log = h.sweep_nvt_logged(dr_max)
@@ -135,3 +136,85 @@ def test_counters_reset_and_64bit(hs, oracle_built):
         h.reset_counters()
         assert not h.counters().any()
         assert h.counters().dtype == np.int64
+
+
+def test_kernel_variants_produce_the_same_chain(hs, oracle_built):
+    """The tile-staged kernel (TMA or plain-load staging) and the generic global-memory
+    kernel are the same Markov chain, bit for bit, on a box large enough to have interior
+    (no minimum image) cells, boundary cells and partial tiles."""
+    box, conf = oracle_built.Port.lattice(2, 14, 9, 11, 0.85)
+    N = conf.shape[0]
+    outs, cnts = [], []
+    for impl in (0, 1, 2):
+        with hs.HsmcGpu(N, box[:3], seed=77, sweep_impl=impl) as h:
+            h.upload(conf)
+            h.sweep_nvt(12, 0.15)
+            outs.append(h.download())
+            cnts.append(h.counters())
+            assert h.min_dist2() >= 1.0
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    assert np.array_equal(cnts[0], cnts[1]) and np.array_equal(cnts[0], cnts[2])
+
+
+def test_interior_fast_path_replays_through_oracle(hs, oracle_built):
+    """A 16^3-cell box has interior cells (no minimum-image branches evaluated on the GPU);
+    their verdicts must still equal the reference arithmetic, which always evaluates them."""
+    box, conf = oracle_built.Port.lattice(2, 10, 10, 10, 0.9)
+    N = conf.shape[0]
+    p = oracle_built.Port(conf, box, neigh_dr=1.0, max_part=12)
+    with hs.HsmcGpu(N, box[:3], seed=31337) as h:
+        assert min(h.info()["cells"]) >= 8
+        h.upload(conf)
+        for _ in range(4):
+            log = h.sweep_nvt_logged(0.12)
+            keep = log[log["verdict"] != 2]
+            acc = p.replay_moves(keep["id"], keep["raw"], 0.12)
+            assert np.array_equal(acc, (keep["verdict"] == 0).astype(np.int32))
+            assert np.array_equal(h.download(), p.get_conf())
+
+
+def _near_contact_system(oracle_built):
+    """Simple-cubic crystal with lattice constant 1 + 1e-7 and dr_max = 1e-6: every trial
+    lands within ~1e-6 of contact with its six neighbours, far below fp32 resolution, so
+    every verdict has to come from the exact double-precision re-evaluation."""
+    a = 1.0 + 1e-7
+    box, conf = oracle_built.Port.lattice(1, 8, 8, 8, 1.0 / a**3)
+    return box, conf, 1e-6
+
+
+def test_near_contact_trials_take_the_exact_path(hs, oracle_built):
+    box, conf, dr = _near_contact_system(oracle_built)
+    N = conf.shape[0]
+    p = oracle_built.Port(conf, box, neigh_dr=1.0, max_part=12)
+    with hs.HsmcGpu(N, box[:3], seed=8) as h:
+        h.upload(conf)
+        n_acc = n_rej = 0
+        for _ in range(6):
+            log = h.sweep_nvt_logged(dr)
+            keep = log[log["verdict"] != 2]
+            acc = p.replay_moves(keep["id"], keep["raw"], dr)
+            assert np.array_equal(acc, (keep["verdict"] == 0).astype(np.int32))
+            assert np.array_equal(h.download(), p.get_conf())
+            n_acc += int((keep["verdict"] == 0).sum()); n_rej += int((keep["verdict"] == 1).sum())
+        assert n_acc > 20 and n_rej > 20          # both verdicts, all decided inside the fp32 band
+        assert h.min_dist2() >= 1.0
+
+
+def test_fp32_filter_without_error_band_is_caught(hs, oracle_built):
+    """Negative control: with the uncertainty band forced to zero (sweep_impl=3) the fp32
+    filter decides near-contact pairs on its own and the replay through the oracle must
+    disagree -- i.e. the parity test really is sensitive to the last bits."""
+    box, conf, dr = _near_contact_system(oracle_built)
+    N = conf.shape[0]
+    p = oracle_built.Port(conf, box, neigh_dr=1.0, max_part=12)
+    with hs.HsmcGpu(N, box[:3], seed=8, sweep_impl=3) as h:
+        h.upload(conf)
+        mismatch = False
+        for _ in range(8):
+            log = h.sweep_nvt_logged(dr)
+            keep = log[log["verdict"] != 2]
+            acc = p.replay_moves(keep["id"], keep["raw"], dr)
+            if not np.array_equal(acc, (keep["verdict"] == 0).astype(np.int32)):
+                mismatch = True
+                break
+        assert mismatch
