@@ -65,16 +65,17 @@ extern "C" const char* hsmc_gpu_last_error(void) { return g_err.c_str(); }
 enum { CNT_TRIALS = 0, CNT_ACC = 1, CNT_REJ_OVERLAP = 2, CNT_REJ_CELL = 3, CNT_N = 8 };
 
 #define TILE_MAX_A 4          // active cells per tile along x and y (max)
-#define TILE_MAX_AZ 16        // along z (max)
-#define TILE_THREADS 192
+#define TILE_MAX_AZ 12        // along z (max)
+#define TILE_THREADS 96
 #define TILE_MAX_ROWS ((2 * TILE_MAX_A + 1) * (2 * TILE_MAX_A + 1))
 #define TILE_MAX_CELLS (TILE_MAX_A * TILE_MAX_A * TILE_MAX_AZ)
 
 struct TileCfg {
   int ax, ay, az;          // active cells per tile
   int ntx, nty, ntz;       // tiles per axis of the active-cell lattice
-  int cap;                 // staged particle capacity (slots of 32 B)
+  int cap;                 // staged shadow capacity (entries of 16 B)
   int use_tma;
+  int cs_stride;           // ints per staged CSR row
 };
 
 struct hsmc_gpu {
@@ -115,6 +116,9 @@ struct hsmc_gpu {
   int lay[6] = {0, 0, 0, 0, 0, 0};       // slot offsets of layers 0,1,2,nlx-2,nlx-1,nlx
   void* d_sfargs = nullptr;
   TileCfg tile;
+  int* deep_list = nullptr;              // [8][deep_stride] cells with >= 3 particles, per colour
+  int* deep_count = nullptr;             // [8]
+  int64_t deep_stride = 0;
   size_t tile_smem = 0;
   bool tile_ok = false;
   hsmc_gpu_trial* d_log = nullptr;
@@ -319,7 +323,7 @@ struct SweepArgs {
 template <bool LOG>
 __device__ __forceinline__ void cell_update_global(const SweepArgs& a, double4* __restrict__ pos,
                                                    float4* __restrict__ rel, const int* __restrict__ cs, int l,
-                                                   int iy, int iz, int& n_acc,
+                                                   int iy, int iz, int j0, int j1, int& n_acc,
                                                    int& n_ov, int& n_cell, hsmc_gpu_trial* __restrict__ log,
                                                    unsigned long long* __restrict__ nlog, long long logcap) {
   const Grid& g = a.g;
@@ -339,6 +343,8 @@ __device__ __forceinline__ void cell_update_global(const SweepArgs& a, double4* 
       if (id > last_id && id < best) { best = id; sel = k; }
     }
     last_id = best;
+    if (j < j0) continue;      // trials below j0 belong to the tile kernel
+    if (j >= j1) break;
     double4 p = pos[sel];
     Philox4 rn = philox4x32_10((uint32_t)gcell, (HSMC_STREAM_MOVE << 24) | (uint32_t)j, a.sweep_lo, a.sweep_hi,
                                a.key0, a.key1);
@@ -400,7 +406,7 @@ k_sweep_phase(SweepArgs a, double4* __restrict__ pos, float4* __restrict__ rel, 
     int par0 = (g.gx0 + g.own_lo) & 1;
     int l = g.own_lo + 2 * ax + ((a.cx - par0) & 1);
     int iy = 2 * ay + a.cy, iz = 2 * az + a.cz;
-    cell_update_global<LOG>(a, pos, rel, cs, l, iy, iz, n_acc, n_ov, n_cell, log, nlog, logcap);
+    cell_update_global<LOG>(a, pos, rel, cs, l, iy, iz, 0, 1 << 30, n_acc, n_ov, n_cell, log, nlog, logcap);
   }
   // block-aggregated counters
   __shared__ int s_cnt[3];
@@ -846,6 +852,10 @@ static int ensure_cell_arrays(hsmc_gpu* h) {
   CU(cudaMalloc(&h->cell_start, sizeof(int) * (size_t)h->cap_cells));
   CU(cudaMalloc(&h->cell_count, sizeof(int) * (size_t)h->cap_cells));
   CU(cudaMalloc(&h->bsum, sizeof(int) * (size_t)((h->cap_cells + SCAN_CHUNK - 1) / SCAN_CHUNK + 1)));
+  if (h->deep_list) cudaFree(h->deep_list);
+  h->deep_stride = h->cap_cells / 8 + 64;
+  CU(cudaMalloc(&h->deep_list, sizeof(int) * (size_t)(8 * h->deep_stride)));
+  if (!h->deep_count) CU(cudaMalloc(&h->deep_count, sizeof(int) * 8));
   return 0;
 }
 
@@ -901,7 +911,7 @@ static void setup_tiles(hsmc_gpu* h) {
   t.ay = fit(TILE_MAX_A, g.ny, hy);
   t.az = fit(TILE_MAX_AZ, g.nz, hz);
   double nbar = (double)h->N / ((double)g.nx * g.ny * g.nz);
-  const int cap_max = 2944;   // 46 KB of staged shadow entries: four CTAs per SM
+  const int cap_max = 2240;   // ~35 KB of staged shadow entries: four CTAs per SM
   for (;;) {
     double region = (2.0 * t.ax + 1) * (2.0 * t.ay + 1) * (2.0 * t.az + 1);
     int want = (int)(region * nbar * 1.15) + 96;
@@ -911,8 +921,20 @@ static void setup_tiles(hsmc_gpu* h) {
   t.cap = (t.cap + 31) & ~31;
   t.ntx = (hx + t.ax - 1) / t.ax; t.nty = (hy + t.ay - 1) / t.ay; t.ntz = (hz + t.az - 1) / t.az;
   t.use_tma = (h->cfg.sweep_impl == 2) ? 0 : 1;
-  h->tile_smem = (size_t)t.cap * 16 + (size_t)TILE_MAX_ROWS * (2 * TILE_MAX_AZ + 2) * sizeof(unsigned short);
+  t.cs_stride = (2 * t.az + 2 + 3 + 3) & ~3;
+  h->tile_smem = (size_t)t.cap * 16 + (size_t)TILE_MAX_ROWS * t.cs_stride * sizeof(int);
   h->tile_ok = h->cfg.sweep_impl != 1 && t.cap * 1 <= 65535;
+}
+
+static int build_deep_lists(hsmc_gpu* h) {
+  Grid& g = h->g;
+  CU(cudaMemsetAsync(h->deep_count, 0, sizeof(int) * 8, h->st));
+  long long total = (long long)(g.own_hi - g.own_lo) * g.ny * g.nz;
+  k_deep_lists<<<nblk(total, 256), 256, 0, h->st>>>(g, h->cell_start, h->deep_list, h->deep_count,
+                                                     (int)h->deep_stride, h->d_halo_cnt + 2);
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
 }
 
 static inline int left_of(const hsmc_gpu* h) { return (h->cfg.rank + h->cfg.world - 1) % h->cfg.world; }
@@ -942,6 +964,7 @@ static int rebuild(hsmc_gpu* h, const double4* src, int64_t n_in, int rows_layou
     k_cell_scatter<<<nblk(n_in, T), T, 0, h->st>>>(g, src, (int)n_in, h->key, h->rnk, h->cell_start, dst, h->rel);
     h->launches++;
     CU(cudaGetLastError());
+    TRY(build_deep_lists(h));
     h->cur ^= 1;
     h->n_local = h->n_owned = h->N;
     h->own_first = 0;
@@ -987,6 +1010,7 @@ static int rebuild(hsmc_gpu* h, const double4* src, int64_t n_in, int rows_layou
   k_sort_cells_by_id<<<nblk(2 * per, 128), 128, 0, h->st>>>(g, dst, h->rel, h->cell_start, g.nlx - 2, g.nlx - 1);
   h->launches += 2;
   CU(cudaGetLastError());
+  TRY(build_deep_lists(h));
   // layer offsets + error flags back to the host (one small sync per rebuild)
   int* hs = (int*)h->h_stage;
   long long offs[6] = {0, per, 2 * per, (long long)(g.nlx - 2) * per, (long long)(g.nlx - 1) * per,
@@ -1028,7 +1052,7 @@ extern "C" int hsmc_gpu_destroy(hsmc_gpu* h) {
   if (h->comm) ncclCommDestroy(h->comm);
   void* ptrs[] = {h->pos[0], h->pos[1], h->rel, h->key, h->rnk, h->cell_count, h->cell_start, h->bsum, h->d_cnt,
                   h->d_scratch, h->d_slot_of_id, h->d_io, h->send_l, h->send_r, h->recv_l, h->recv_r,
-                  h->d_halo_cnt, h->d_sfargs, h->d_log, h->key_halo, h->rnk_halo};
+                  h->d_halo_cnt, h->d_sfargs, h->d_log, h->key_halo, h->rnk_halo, h->deep_list, h->deep_count};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -1248,6 +1272,15 @@ static int sweep_once(hsmc_gpu* h, double dr_max, bool logged) {
       else
         k_sweep_tile<false><<<nb, TILE_THREADS, h->tile_smem, h->st>>>(a, h->tile, h->pos[h->cur], h->rel, h->cell_start, h->d_cnt,
                                                                        nullptr, nullptr, 0);
+      h->launches++;
+      int gb = 148 * 2;
+      if (logged)
+        k_sweep_deep<true><<<gb, 128, 0, h->st>>>(a, h->deep_list, h->deep_count, ph, (int)h->deep_stride, h->pos[h->cur],
+                                                  h->rel, h->cell_start, h->d_cnt, h->d_log, h->d_scratch,
+                                                  (long long)h->cap_log);
+      else
+        k_sweep_deep<false><<<gb, 128, 0, h->st>>>(a, h->deep_list, h->deep_count, ph, (int)h->deep_stride, h->pos[h->cur],
+                                                   h->rel, h->cell_start, h->d_cnt, nullptr, nullptr, 0);
     } else if (logged)
       k_sweep_phase<true><<<nblk(total, T), T, 0, h->st>>>(a, h->pos[h->cur], h->rel, h->cell_start, h->d_cnt, h->d_log,
                                                             h->d_scratch, (long long)h->cap_log);

@@ -50,41 +50,61 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
 template <bool LOG>
 __device__ __noinline__ void cell_update_global_noinline(const SweepArgs& a, double4* __restrict__ pos,
                                                          float4* __restrict__ rel, const int* __restrict__ cs, int l,
-                                                         int iy, int iz, int& n_acc, int& n_ov, int& n_cell,
-                                                         hsmc_gpu_trial* __restrict__ log,
+                                                         int iy, int iz, int j0, int j1, int& n_acc, int& n_ov,
+                                                         int& n_cell, hsmc_gpu_trial* __restrict__ log,
                                                          unsigned long long* __restrict__ nlog, long long logcap) {
-  cell_update_global<LOG>(a, pos, rel, cs, l, iy, iz, n_acc, n_ov, n_cell, log, nlog, logcap);
+  cell_update_global<LOG>(a, pos, rel, cs, l, iy, iz, j0, j1, n_acc, n_ov, n_cell, log, nlog, logcap);
 }
 
-// exact verdict for one pair inside the fp32 error band: staged index -> global slot ->
-// reference arithmetic on the master table (rare, kept out of line)
-__device__ __noinline__ bool tile_exact_overlap(const double4* __restrict__ pos, const int* s_gbA, const int* s_gbB,
-                                                const int* s_cntA, const int* s_off, int row, int k, double xn,
-                                                double yn, double zn, const Box& box) {
-  int o = k - s_off[row];
-  int gs = (o < s_cntA[row]) ? s_gbA[row] + o : s_gbB[row] + o - s_cntA[row];
-  double4 q = pos[gs];
-  return pair_r2(xn, yn, zn, q.x, q.y, q.z, box) < 1.0;
-}
+// per-row staging record
+struct TileRow {
+  int gbA, gbB;     // global slot of the first particle of piece A / B (B: wrapped part of the row)
+  int cntA;         // particles in piece A
+  int off;          // staged index of the row's first particle
+  int shift;        // alignment shift of the TMA'd CSR row
+  int delta;        // gbA - off: staged index = CSR value - delta
+};
 
-#define TILE_CS_STRIDE (2 * TILE_MAX_AZ + 2)
+// exact re-evaluation of a whole stencil from the master table with the reference's
+// arithmetic (moves.c:157-212, 400-431): taken only when some pair fell inside the fp32
+// error band and no certain overlap was found (~3e-4 of the trials), kept out of line
+__device__ __noinline__ bool tile_exact_rescan(const double4* __restrict__ pos, const TileRow* s_row,
+                                               const int* s_cs, int cs_stride, int nry, int rxc, int ryc, int rz,
+                                               int sel, double xn, double yn, double zn, const Box& box) {
+  for (int dx = -1; dx <= 1; dx++)
+    for (int dy = -1; dy <= 1; dy++) {
+      int row = (rxc + dx) * nry + ryc + dy;
+      TileRow rw = s_row[row];
+      const int* cp = s_cs + row * cs_stride + rw.shift + rz;
+      int b = cp[-1] - rw.delta, e = cp[2] - rw.delta;
+      for (int k = b; k < e; k++) {
+        if (k == sel) continue;
+        int o = k - rw.off;
+        int gs = (o < rw.cntA) ? rw.gbA + o : rw.gbB + o - rw.cntA;
+        double4 q = pos[gs];
+        if (pair_r2(xn, yn, zn, q.x, q.y, q.z, box) < 1.0) return true;
+      }
+    }
+  return false;
+}
 
 template <bool LOG>
-__global__ void __launch_bounds__(TILE_THREADS, 4)
+__global__ void __launch_bounds__(TILE_THREADS, 5)
 k_sweep_tile(SweepArgs a, TileCfg tc, double4* __restrict__ pos, float4* __restrict__ rel,
              const int* __restrict__ cs, unsigned long long* __restrict__ cnt, hsmc_gpu_trial* __restrict__ log,
              unsigned long long* __restrict__ nlog, long long logcap) {
   const Grid& g = a.g;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float4* s_rel = reinterpret_cast<float4*>(smem_raw);
-  unsigned short* s_cs = reinterpret_cast<unsigned short*>(s_rel + tc.cap);   // [rows][TILE_CS_STRIDE]
-  __shared__ int s_gbA[TILE_MAX_ROWS], s_gbB[TILE_MAX_ROWS], s_cntA[TILE_MAX_ROWS];
-  __shared__ int s_off[TILE_MAX_ROWS + 1];
-  __shared__ int s_items[TILE_MAX_CELLS];
-  __shared__ int s_ccnt[8], s_coff[8];
+  int* s_cs = reinterpret_cast<int*>(s_rel + tc.cap);        // [rows][cs_stride] raw CSR values
+  __shared__ TileRow s_row[TILE_MAX_ROWS];
+  __shared__ int s_cnt[TILE_MAX_ROWS + 1];
+  __shared__ unsigned short s_items[TILE_MAX_CELLS];
+  __shared__ int s_n[4];                                   // [0] cells with >= 2, [1] cells with 1
   __shared__ int s_acc[3];
   __shared__ __align__(8) uint64_t s_bar;
   const int tid = threadIdx.x;
+  const int cs_stride = tc.cs_stride;
 
   // ---- which tile -------------------------------------------------------------------
   const int tz = blockIdx.x % tc.ntz;
@@ -101,15 +121,17 @@ k_sweep_tile(SweepArgs a, TileCfg tc, double4* __restrict__ pos, float4* __restr
   const int nry = 2 * nay + 1, lenz = 2 * naz + 1;
   const int nrows = (2 * nax + 1) * nry;
   const int zs = (z0 < 0) ? z0 + g.nz : z0;
+  const bool zwrap = zs + lenz > g.nz;     // tile-uniform: the region crosses the periodic z edge
 
   if (tid == 0) {
     mbar_init(&s_bar, TILE_THREADS);
     s_acc[0] = s_acc[1] = s_acc[2] = 0;
+    s_n[0] = s_n[1] = 0;
   }
-  if (tid < 8) s_ccnt[tid] = 0;
 
-  // ---- one round trip to the CSR offsets: row pieces + every staged cell's offset ----
-  // each (x,y) row of the region is one contiguous slot range, or two when it wraps in z
+  // ---- row pieces: each (x,y) row of the region is one contiguous slot range, or two
+  //      when it wraps in z
+  long long my_rbase = 0;
   int my_cntB = 0;
   if (tid < nrows) {
     int rx = tid / nry, ry = tid - rx * nry;
@@ -117,32 +139,13 @@ k_sweep_tile(SweepArgs a, TileCfg tc, double4* __restrict__ pos, float4* __restr
     if (g.wrap_x) { if (lx < 0) lx += g.nlx; else if (lx >= g.nlx) lx -= g.nlx; }
     int y = y0 + ry;
     if (y < 0) y += g.ny; else if (y >= g.ny) y -= g.ny;
-    long long rbase = ((long long)lx * g.ny + y) * g.nz;
-    int gbA = cs[rbase + zs], geA = cs[rbase + min(zs + lenz, g.nz)];
+    my_rbase = ((long long)lx * g.ny + y) * g.nz;
+    int gbA = cs[my_rbase + zs], geA = cs[my_rbase + min(zs + lenz, g.nz)];
     int gbB = 0, geB = 0;
-    if (zs + lenz > g.nz) { gbB = cs[rbase]; geB = cs[rbase + (zs + lenz - g.nz)]; }
-    s_gbA[tid] = gbA; s_cntA[tid] = geA - gbA;
-    s_gbB[tid] = gbB; my_cntB = geB - gbB;
-    s_off[tid] = (geA - gbA) + my_cntB;   // row count, scanned in place below
-  }
-  constexpr int RAW_PER_THREAD = (TILE_MAX_ROWS * TILE_CS_STRIDE + TILE_THREADS - 1) / TILE_THREADS;
-  int raw[RAW_PER_THREAD];
-  const int ncs = nrows * (lenz + 1);
-#pragma unroll
-  for (int m = 0; m < RAW_PER_THREAD; m++) {
-    int idx = tid + m * TILE_THREADS;
-    raw[m] = 0;
-    if (idx < ncs) {
-      int r = idx / (lenz + 1), zi = idx - r * (lenz + 1);
-      int rx = r / nry, ry = r - rx * nry;
-      int lx = x0 + rx;
-      if (g.wrap_x) { if (lx < 0) lx += g.nlx; else if (lx >= g.nlx) lx -= g.nlx; }
-      int y = y0 + ry;
-      if (y < 0) y += g.ny; else if (y >= g.ny) y -= g.ny;
-      long long rbase = ((long long)lx * g.ny + y) * g.nz;
-      int z = zs + zi;
-      raw[m] = cs[rbase + (z <= g.nz ? z : z - g.nz)];
-    }
+    if (zwrap) { gbB = cs[my_rbase]; geB = cs[my_rbase + (zs + lenz - g.nz)]; }
+    my_cntB = geB - gbB;
+    s_row[tid].gbA = gbA; s_row[tid].gbB = gbB; s_row[tid].cntA = geA - gbA;
+    s_cnt[tid] = (geA - gbA) + my_cntB;
   }
   __syncthreads();
   // ---- exclusive scan of the row counts (<= 81 rows) by warp 0 ----------------------
@@ -150,105 +153,130 @@ k_sweep_tile(SweepArgs a, TileCfg tc, double4* __restrict__ pos, float4* __restr
     int carry = 0;
     for (int base = 0; base < nrows; base += 32) {
       int r = base + tid;
-      int v = (r < nrows) ? s_off[r] : 0;
+      int v = (r < nrows) ? s_cnt[r] : 0;
       int inc = v;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         int t = __shfl_up_sync(0xffffffffu, inc, o);
         if (tid >= o) inc += t;
       }
-      if (r < nrows) s_off[r] = carry + inc - v;
+      if (r < nrows) s_cnt[r] = carry + inc - v;
       carry += __shfl_sync(0xffffffffu, inc, 31);
     }
-    if (tid == 0) s_off[nrows] = carry;
+    if (tid == 0) s_cnt[nrows] = carry;
   }
   __syncthreads();
-  const int total = s_off[nrows];
+  const int total = s_cnt[nrows];
   const bool staged = total <= tc.cap;
 
   int n_acc = 0, n_ov = 0, n_cell = 0;
 
   if (staged) {
-    // ---- stage the shadow rows: TMA bulk copies (or plain loads), completion on s_bar --
-    if (tc.use_tma) {
-      if (tid < nrows) {
-        int cA = s_cntA[tid], off = s_off[tid];
+    // ---- stage shadow rows and CSR rows: TMA bulk copies, completion on s_bar ----------
+    const bool tma_cs = tc.use_tma && !zwrap;
+    if (tid < nrows) {
+      TileRow& rw = s_row[tid];
+      const int off = s_cnt[tid], cA = rw.cntA;
+      const long long i0 = my_rbase + zs;
+      const int shift = tma_cs ? (int)(i0 & 3) : 0;
+      rw.off = off; rw.shift = shift; rw.delta = rw.gbA - off;
+      if (tc.use_tma) {
         uint32_t bytes = (uint32_t)(cA + my_cntB) * 16u;
-        if (bytes) mbar_arrive_tx(&s_bar, bytes); else mbar_arrive(&s_bar);
-        if (cA) tma_bulk_g2s(&s_rel[off], &rel[s_gbA[tid]], (uint32_t)cA * 16u, &s_bar);
-        if (my_cntB) tma_bulk_g2s(&s_rel[off + cA], &rel[s_gbB[tid]], (uint32_t)my_cntB * 16u, &s_bar);
-      } else {
-        mbar_arrive(&s_bar);
+        uint32_t cs_bytes = tma_cs ? (uint32_t)((shift + lenz + 1 + 3) & ~3) * 4u : 0u;
+        if (bytes + cs_bytes) mbar_arrive_tx(&s_bar, bytes + cs_bytes); else mbar_arrive(&s_bar);
+        if (cA) tma_bulk_g2s(&s_rel[off], &rel[rw.gbA], (uint32_t)cA * 16u, &s_bar);
+        if (my_cntB) tma_bulk_g2s(&s_rel[off + cA], &rel[rw.gbB], (uint32_t)my_cntB * 16u, &s_bar);
+        if (cs_bytes) tma_bulk_g2s(&s_cs[tid * cs_stride], &cs[i0 - shift], cs_bytes, &s_bar);
       }
-    } else {
-      for (int r = tid >> 5; r < nrows; r += TILE_THREADS / 32) {
-        int cA = s_cntA[r], cT = s_off[r + 1] - s_off[r], off = s_off[r], gA = s_gbA[r], gB = s_gbB[r];
-        for (int k = tid & 31; k < cA; k += 32) s_rel[off + k] = rel[gA + k];
-        for (int k = (tid & 31) + cA; k < cT; k += 32) s_rel[off + k] = rel[gB + k - cA];
-      }
-    }
-    // ---- rebase the CSR offsets held in registers to shared-memory indices -------------
-#pragma unroll
-    for (int m = 0; m < RAW_PER_THREAD; m++) {
-      int idx = tid + m * TILE_THREADS;
-      if (idx < ncs) {
-        int r = idx / (lenz + 1), zi = idx - r * (lenz + 1);
-        int o = (zs + zi <= g.nz) ? raw[m] - s_gbA[r] : s_cntA[r] + raw[m] - s_gbB[r];
-        s_cs[r * TILE_CS_STRIDE + zi] = (unsigned short)(s_off[r] + o);
-      }
+    } else if (tc.use_tma) {
+      mbar_arrive(&s_bar);
     }
     __syncthreads();
-    // ---- the tile's non-empty cells, sorted by occupancy (>=4, 3, 2, 1) ----------------
+    if (!tc.use_tma) {
+      for (int r = tid >> 5; r < nrows; r += TILE_THREADS / 32) {
+        TileRow rw = s_row[r];
+        int cT = s_cnt[r + 1] - s_cnt[r];
+        for (int k = tid & 31; k < rw.cntA; k += 32) s_rel[rw.off + k] = rel[rw.gbA + k];
+        for (int k = (tid & 31) + rw.cntA; k < cT; k += 32) s_rel[rw.off + k] = rel[rw.gbB + k - rw.cntA];
+      }
+    }
+    if (!tma_cs) {
+      // CSR rows by plain loads; entries of the wrapped part are renumbered so that
+      // (value - delta) is the staged index for every entry of the row
+#pragma unroll 1
+      for (int r = tid >> 5; r < nrows; r += TILE_THREADS / 32) {
+        int rx = r / nry, ry = r - rx * nry;
+        int lx = x0 + rx;
+        if (g.wrap_x) { if (lx < 0) lx += g.nlx; else if (lx >= g.nlx) lx -= g.nlx; }
+        int y = y0 + ry;
+        if (y < 0) y += g.ny; else if (y >= g.ny) y -= g.ny;
+        long long rbase = ((long long)lx * g.ny + y) * g.nz;
+        TileRow rw = s_row[r];
+        for (int zi = tid & 31; zi <= lenz; zi += 32) {
+          int z = zs + zi;
+          s_cs[r * cs_stride + zi] = (z <= g.nz) ? cs[rbase + z] : cs[rbase + z - g.nz] - rw.gbB + rw.gbA + rw.cntA;
+        }
+      }
+    }
+    if (tc.use_tma) mbar_wait(&s_bar, 0);
+    __syncthreads();
+
+    // ---- the tile's non-empty cells: those with >= 2 particles first, then singles -----
     const int ncell_t = nax * nay * naz;
     constexpr int CELLS_PER_THREAD = (TILE_MAX_CELLS + TILE_THREADS - 1) / TILE_THREADS;
-    int my_cls[CELLS_PER_THREAD], my_rank[CELLS_PER_THREAD];
+    int my_code[CELLS_PER_THREAD], my_rank[CELLS_PER_THREAD];
 #pragma unroll
     for (int m = 0; m < CELLS_PER_THREAD; m++) {
       int q = tid + m * TILE_THREADS;
-      my_cls[m] = -1;
+      my_code[m] = -1;
       my_rank[m] = 0;
       if (q < ncell_t) {
         int qz = q % naz, qy = (q / naz) % nay, qx = q / (naz * nay);
-        int row = (2 * qx + 1) * nry + (2 * qy + 1), rz = 2 * qz + 1;
-        int n = (int)s_cs[row * TILE_CS_STRIDE + rz + 1] - (int)s_cs[row * TILE_CS_STRIDE + rz];
+        int rxc = 2 * qx + 1, ryc = 2 * qy + 1, rz = 2 * qz + 1;
+        int row = rxc * nry + ryc;
+        const int* cp = s_cs + row * cs_stride + s_row[row].shift + rz;
+        int n = cp[1] - cp[0];
         if (n > 0) {
-          my_cls[m] = n >= 4 ? 0 : 4 - n;
-          my_rank[m] = atomicAdd(&s_ccnt[my_cls[m]], 1);
+          int cls = n >= 2 ? 0 : 1;
+          my_rank[m] = atomicAdd(&s_n[cls], 1);
+          my_code[m] = (cls << 15) | (rxc << 10) | (ryc << 6) | rz;      // rxc,ryc <= 9, rz <= 33
         }
       }
     }
     __syncthreads();
-    if (tid == 0) {
-      int o = 0;
-      for (int c = 0; c < 4; c++) { s_coff[c] = o; o += s_ccnt[c]; }
-      s_coff[4] = o;
-    }
-    __syncthreads();
+    const int nA = s_n[0], n_items = s_n[0] + s_n[1];
 #pragma unroll
     for (int m = 0; m < CELLS_PER_THREAD; m++)
-      if (my_cls[m] >= 0) s_items[s_coff[my_cls[m]] + my_rank[m]] = tid + m * TILE_THREADS;
-    const int n_items = s_coff[4];
-    if (tc.use_tma) mbar_wait(&s_bar, 0);
+      if (my_code[m] >= 0)
+        s_items[((my_code[m] >> 15) ? nA : 0) + my_rank[m]] = (unsigned short)(my_code[m] & 0x7fff);
     __syncthreads();
 
-    // ---- trials ----------------------------------------------------------------------
+    // ---- trials: at most two per cell here (deeper cells finish in k_sweep_deep) ---------
+    // lane t runs item t; lanes whose first item was a single take further singles, so
+    // every lane does about two trials
     const float wxf = (float)g.wx, wyf = (float)g.wy, wzf = (float)g.wz;
     const float lo = 1.0f - a.eps, hi = 1.0f + a.eps;
-    for (int it = tid; it < n_items; it += TILE_THREADS) {
-      const int q = s_items[it];
-      const int qz = q % naz, qy = (q / naz) % nay, qx = q / (naz * nay);
-      const int rxc = 2 * qx + 1, ryc = 2 * qy + 1, rz = 2 * qz + 1;
+    const int nB_lanes = TILE_THREADS - min(nA, TILE_THREADS);
+    int it = tid;
+    int pass = 0;
+    while (it < n_items) {
+      const int code = s_items[it];
+      const int rxc = code >> 10, ryc = (code >> 6) & 15, rz = code & 63;
       const int rowc = rxc * nry + ryc;
-      const int ob = s_cs[rowc * TILE_CS_STRIDE + rz], oe = s_cs[rowc * TILE_CS_STRIDE + rz + 1];
+      const TileRow rwc = s_row[rowc];
+      const int* cpc = s_cs + rowc * cs_stride + rwc.shift + rz;
+      const int ob = cpc[0] - rwc.delta, oe = cpc[1] - rwc.delta;
       const int n = oe - ob;
-      // cell coordinates (local layer, y, z), its origin, global slot of its first particle
+      // cell coordinates (local layer, y, z), global slot of its first particle
       const int l = x0 + rxc, iy = y0 + ryc, iz = z0 + rz;
       const int gx = (g.gx0 + l >= g.nx) ? g.gx0 + l - g.nx : g.gx0 + l;
       const long long gcell = ((long long)gx * g.ny + iy) * g.nz + iz;
-      const int ro = ob - s_off[rowc];
-      const int gslot0 = (ro < s_cntA[rowc]) ? s_gbA[rowc] + ro : s_gbB[rowc] + ro - s_cntA[rowc];
+      const int ro = ob - rwc.off;
+      const int gslot0 = (ro < rwc.cntA) ? rwc.gbA + ro : rwc.gbB + ro - rwc.cntA;
       int last_id = -1;
-      for (int j = 0; j < n; j++) {
+      const int depth = min(n, 2);
+#pragma unroll 1
+      for (int j = 0; j < depth; j++) {
         int sel = ob;
         if (n > 1) {
           int best = 0x7fffffff;
@@ -276,43 +304,35 @@ k_sweep_tile(SweepArgs a, TileCfg tc, double4* __restrict__ pos, float4* __restr
         } else {
           // offsets of the trial position from its cell origin (the cell may straddle the box edge)
           const float4 nrel = make_rel(g, gx, iy, iz, xn, yn, zn, p.w);
-          bool ov = false;
+          bool ov = false, inband = false;
 #pragma unroll 1
           for (int dx = -1; dx <= 1; dx++) {
-            const unsigned short* rowp = s_cs + ((rxc + dx) * nry + (ryc - 1)) * TILE_CS_STRIDE + rz;
             const float fx = nrel.x - (float)dx * wxf;
 #pragma unroll
-            for (int dy = 0; dy < 3; dy++) {
-              const int b = rowp[dy * TILE_CS_STRIDE - 1], m1 = rowp[dy * TILE_CS_STRIDE];
-              const int m2 = rowp[dy * TILE_CS_STRIDE + 1], e = rowp[dy * TILE_CS_STRIDE + 2];
-              const float fy = nrel.y - (float)(dy - 1) * wyf;
+            for (int dy = -1; dy <= 1; dy++) {
+              const int row = (rxc + dx) * nry + ryc + dy;
+              const int shift = s_row[row].shift, delta = s_row[row].delta;
+              const int* cp = s_cs + row * cs_stride + shift + rz;
+              const int b = cp[-1] - delta, m1 = cp[0] - delta, m2 = cp[1] - delta, e = cp[2] - delta;
+              const float fy = nrel.y - (float)dy * wyf;
+              for (int k0 = b; k0 < e; k0 += 4) {
 #pragma unroll
-              for (int s = 0; s < 4; s++) {
-                int k = b + s;
-                bool v = (k < e) && (k != sel);
-                int kk = v ? k : sel;
-                float4 qv = s_rel[kk];
-                float fz = nrel.z - (float)((k >= m1) + (k >= m2) - 1) * wzf;
-                float ddx = fx - qv.x, ddy = fy - qv.y, ddz = fz - qv.z;
-                float r2 = __fmaf_rn(ddz, ddz, __fmaf_rn(ddy, ddy, ddx * ddx));
-                ov |= v && (r2 < lo);
-                if (v && r2 >= lo && r2 <= hi)
-                  ov |= tile_exact_overlap(pos, s_gbA, s_gbB, s_cntA, s_off, (rxc + dx) * nry + ryc - 1 + dy, kk, xn,
-                                           yn, zn, a.box);
-              }
-              for (int k = b + 4; k < e; k++) {
-                if (k == sel) continue;
-                float4 qv = s_rel[k];
-                float fz = nrel.z - (float)((k >= m1) + (k >= m2) - 1) * wzf;
-                float ddx = fx - qv.x, ddy = fy - qv.y, ddz = fz - qv.z;
-                float r2 = __fmaf_rn(ddz, ddz, __fmaf_rn(ddy, ddy, ddx * ddx));
-                ov |= (r2 < lo);
-                if (r2 >= lo && r2 <= hi)
-                  ov |= tile_exact_overlap(pos, s_gbA, s_gbB, s_cntA, s_off, (rxc + dx) * nry + ryc - 1 + dy, k, xn,
-                                           yn, zn, a.box);
+                for (int s = 0; s < 4; s++) {
+                  int k = k0 + s;
+                  bool v = (k < e) && (k != sel);
+                  int kk = v ? k : sel;
+                  float4 qv = s_rel[kk];
+                  float fz = nrel.z - (float)((k >= m1) + (k >= m2) - 1) * wzf;
+                  float ddx = fx - qv.x, ddy = fy - qv.y, ddz = fz - qv.z;
+                  float r2 = __fmaf_rn(ddz, ddz, __fmaf_rn(ddy, ddy, ddx * ddx));
+                  ov |= v && (r2 < lo);
+                  inband |= v && (r2 <= hi);
+                }
               }
             }
           }
+          if (!ov && inband)
+            ov = tile_exact_rescan(pos, s_row, s_cs, cs_stride, nry, rxc, ryc, rz, sel, xn, yn, zn, a.box);
           if (ov) { verdict = 1; n_ov++; }
           else {
             verdict = 0; n_acc++;
@@ -332,6 +352,10 @@ k_sweep_tile(SweepArgs a, TileCfg tc, double4* __restrict__ pos, float4* __restr
           }
         }
       }
+      // next item of this lane
+      if (nB_lanes == 0) it += TILE_THREADS;
+      else if (tid < nA) break;
+      else { it = TILE_THREADS + pass * nB_lanes + (tid - nA); pass++; }
     }
   } else {
     // ---- staging capacity exceeded (unusually dense tile): global-memory path ---------
@@ -339,14 +363,19 @@ k_sweep_tile(SweepArgs a, TileCfg tc, double4* __restrict__ pos, float4* __restr
     for (int q = tid; q < ncell_t; q += TILE_THREADS) {
       int qz = q % naz, qy = (q / naz) % nay, qx = q / (naz * nay);
       int l = x0 + 2 * qx + 1, iy = y0 + 2 * qy + 1, iz = z0 + 2 * qz + 1;
-      cell_update_global_noinline<LOG>(a, pos, rel, cs, l, iy, iz, n_acc, n_ov, n_cell, log, nlog, logcap);
+      cell_update_global_noinline<LOG>(a, pos, rel, cs, l, iy, iz, 0, 2, n_acc, n_ov, n_cell, log, nlog, logcap);
     }
   }
 
-  __syncthreads();
-  if (n_acc) atomicAdd(&s_acc[0], n_acc);
-  if (n_ov) atomicAdd(&s_acc[1], n_ov);
-  if (n_cell) atomicAdd(&s_acc[2], n_cell);
+  // ---- counters: one shared-memory atomic per warp, one global atomic set per CTA -------
+  n_acc = __reduce_add_sync(0xffffffffu, n_acc);
+  n_ov = __reduce_add_sync(0xffffffffu, n_ov);
+  n_cell = __reduce_add_sync(0xffffffffu, n_cell);
+  if ((tid & 31) == 0) {
+    if (n_acc) atomicAdd(&s_acc[0], n_acc);
+    if (n_ov) atomicAdd(&s_acc[1], n_ov);
+    if (n_cell) atomicAdd(&s_acc[2], n_cell);
+  }
   __syncthreads();
   if (tid == 0) {
     int tot = s_acc[0] + s_acc[1] + s_acc[2];
@@ -357,4 +386,53 @@ k_sweep_tile(SweepArgs a, TileCfg tc, double4* __restrict__ pos, float4* __restr
       if (s_acc[2]) atomicAdd(&cnt[CNT_REJ_CELL], (unsigned long long)s_acc[2]);
     }
   }
+}
+
+// ---- trials beyond the second in cells holding three or more particles ----------------
+// (2-3 % of the cells at rho 0.9).  The per-colour lists are built with the cell list;
+// one thread per listed cell, global-memory path, trial index continues at j = 2.
+template <bool LOG>
+__global__ void __launch_bounds__(128)
+k_sweep_deep(SweepArgs a, const int* __restrict__ deep_list, const int* __restrict__ deep_count, int colour,
+             int list_stride, double4* __restrict__ pos, float4* __restrict__ rel, const int* __restrict__ cs,
+             unsigned long long* __restrict__ cnt, hsmc_gpu_trial* __restrict__ log,
+             unsigned long long* __restrict__ nlog, long long logcap) {
+  const Grid& g = a.g;
+  int n_acc = 0, n_ov = 0, n_cell = 0;
+  const int n = min(deep_count[colour], list_stride);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int c = deep_list[(long long)colour * list_stride + i];
+    int iz = c % g.nz;
+    int r = c / g.nz;
+    int iy = r % g.ny, l = r / g.ny;
+    cell_update_global<LOG>(a, pos, rel, cs, l, iy, iz, 2, 1 << 30, n_acc, n_ov, n_cell, log, nlog, logcap);
+  }
+  n_acc = __reduce_add_sync(0xffffffffu, n_acc);
+  n_ov = __reduce_add_sync(0xffffffffu, n_ov);
+  n_cell = __reduce_add_sync(0xffffffffu, n_cell);
+  if ((threadIdx.x & 31) == 0 && (n_acc | n_ov | n_cell)) {
+    atomicAdd(&cnt[CNT_TRIALS], (unsigned long long)(n_acc + n_ov + n_cell));
+    if (n_acc) atomicAdd(&cnt[CNT_ACC], (unsigned long long)n_acc);
+    if (n_ov) atomicAdd(&cnt[CNT_REJ_OVERLAP], (unsigned long long)n_ov);
+    if (n_cell) atomicAdd(&cnt[CNT_REJ_CELL], (unsigned long long)n_cell);
+  }
+}
+
+// cells with >= 3 particles, listed per colour (built right after the counting sort)
+__global__ void k_deep_lists(Grid g, const int* __restrict__ cs, int* __restrict__ deep_list,
+                             int* __restrict__ deep_count, int list_stride, int* __restrict__ flags) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long per = (long long)g.ny * g.nz;
+  long long total = (long long)(g.own_hi - g.own_lo) * per;
+  if (t >= total) return;
+  long long c = (long long)g.own_lo * per + t;
+  if (cs[c + 1] - cs[c] < 3) return;
+  int iz = (int)(c % g.nz);
+  long long r = c / g.nz;
+  int iy = (int)(r % g.ny), l = (int)(r / g.ny);
+  int gx = g.gx0 + l;
+  int colour = ((gx & 1) << 2) | ((iy & 1) << 1) | (iz & 1);
+  int s = atomicAdd(&deep_count[colour], 1);
+  if (s < list_stride) deep_list[(long long)colour * list_stride + s] = (int)c;
+  else atomicOr(flags, 8);
 }
