@@ -1273,13 +1273,13 @@ static int sweep_once(hsmc_gpu* h, double dr_max, bool logged) {
         k_sweep_tile<false><<<nb, TILE_THREADS, h->tile_smem, h->st>>>(a, h->tile, h->pos[h->cur], h->rel, h->cell_start, h->d_cnt,
                                                                        nullptr, nullptr, 0);
       h->launches++;
-      int gb = 148 * 2;
+      int gb = 148 * 4;
       if (logged)
-        k_sweep_deep<true><<<gb, 128, 0, h->st>>>(a, h->deep_list, h->deep_count, ph, (int)h->deep_stride, h->pos[h->cur],
+        k_sweep_deep<true><<<gb, 256, 0, h->st>>>(a, h->deep_list, h->deep_count, ph, (int)h->deep_stride, h->pos[h->cur],
                                                   h->rel, h->cell_start, h->d_cnt, h->d_log, h->d_scratch,
                                                   (long long)h->cap_log);
       else
-        k_sweep_deep<false><<<gb, 128, 0, h->st>>>(a, h->deep_list, h->deep_count, ph, (int)h->deep_stride, h->pos[h->cur],
+        k_sweep_deep<false><<<gb, 256, 0, h->st>>>(a, h->deep_list, h->deep_count, ph, (int)h->deep_stride, h->pos[h->cur],
                                                    h->rel, h->cell_start, h->d_cnt, nullptr, nullptr, 0);
     } else if (logged)
       k_sweep_phase<true><<<nblk(total, T), T, 0, h->st>>>(a, h->pos[h->cur], h->rel, h->cell_start, h->d_cnt, h->d_log,

@@ -56,6 +56,8 @@ __device__ __noinline__ void cell_update_global_noinline(const SweepArgs& a, dou
   cell_update_global<LOG>(a, pos, rel, cs, l, iy, iz, j0, j1, n_acc, n_ov, n_cell, log, nlog, logcap);
 }
 
+#define TILE_SLOTS 6     // padded stencil slots evaluated per row and pass (a z-column of 3 cells holds <= 6 in 99.7 %)
+
 // per-row staging record
 struct TileRow {
   int gbA, gbB;     // global slot of the first particle of piece A / B (B: wrapped part of the row)
@@ -257,8 +259,11 @@ k_sweep_tile(SweepArgs a, TileCfg tc, double4* __restrict__ pos, float4* __restr
     const float wxf = (float)g.wx, wyf = (float)g.wy, wzf = (float)g.wz;
     const float lo = 1.0f - a.eps, hi = 1.0f + a.eps;
     const int nB_lanes = TILE_THREADS - min(nA, TILE_THREADS);
-    int it = tid;
-    int pass = 0;
+    // One flat loop: every iteration is exactly one trial (item `it`, trial index `j`), so
+    // lanes on their second trial of a cell and lanes that moved on to another cell stay
+    // converged in the same code.
+    int it = tid, pass = 0, j = 0, last_id = -1;
+#pragma unroll 1
     while (it < n_items) {
       const int code = s_items[it];
       const int rxc = code >> 10, ryc = (code >> 6) & 15, rz = code & 63;
@@ -273,10 +278,7 @@ k_sweep_tile(SweepArgs a, TileCfg tc, double4* __restrict__ pos, float4* __restr
       const long long gcell = ((long long)gx * g.ny + iy) * g.nz + iz;
       const int ro = ob - rwc.off;
       const int gslot0 = (ro < rwc.cntA) ? rwc.gbA + ro : rwc.gbB + ro - rwc.cntA;
-      int last_id = -1;
-      const int depth = min(n, 2);
-#pragma unroll 1
-      for (int j = 0; j < depth; j++) {
+      {
         int sel = ob;
         if (n > 1) {
           int best = 0x7fffffff;
@@ -304,6 +306,7 @@ k_sweep_tile(SweepArgs a, TileCfg tc, double4* __restrict__ pos, float4* __restr
         } else {
           // offsets of the trial position from its cell origin (the cell may straddle the box edge)
           const float4 nrel = make_rel(g, gx, iy, iz, xn, yn, zn, p.w);
+          const float fzm = nrel.z + wzf, fzp = nrel.z - wzf;
           bool ov = false, inband = false;
 #pragma unroll 1
           for (int dx = -1; dx <= 1; dx++) {
@@ -315,14 +318,15 @@ k_sweep_tile(SweepArgs a, TileCfg tc, double4* __restrict__ pos, float4* __restr
               const int* cp = s_cs + row * cs_stride + shift + rz;
               const int b = cp[-1] - delta, m1 = cp[0] - delta, m2 = cp[1] - delta, e = cp[2] - delta;
               const float fy = nrel.y - (float)dy * wyf;
-              for (int k0 = b; k0 < e; k0 += 4) {
+#pragma unroll 1
+              for (int k0 = b; k0 < e; k0 += TILE_SLOTS) {
 #pragma unroll
-                for (int s = 0; s < 4; s++) {
+                for (int s = 0; s < TILE_SLOTS; s++) {
                   int k = k0 + s;
                   bool v = (k < e) && (k != sel);
                   int kk = v ? k : sel;
                   float4 qv = s_rel[kk];
-                  float fz = nrel.z - (float)((k >= m1) + (k >= m2) - 1) * wzf;
+                  float fz = (k < m1) ? fzm : ((k < m2) ? nrel.z : fzp);
                   float ddx = fx - qv.x, ddy = fy - qv.y, ddz = fz - qv.z;
                   float r2 = __fmaf_rn(ddz, ddz, __fmaf_rn(ddy, ddy, ddx * ddx));
                   ov |= v && (r2 < lo);
@@ -352,7 +356,9 @@ k_sweep_tile(SweepArgs a, TileCfg tc, double4* __restrict__ pos, float4* __restr
           }
         }
       }
-      // next item of this lane
+      // next trial of this lane: second particle of the cell, else the next item
+      if (++j < min(n, 2)) continue;
+      j = 0; last_id = -1;
       if (nB_lanes == 0) it += TILE_THREADS;
       else if (tid < nA) break;
       else { it = TILE_THREADS + pass * nB_lanes + (tid - nA); pass++; }
@@ -389,28 +395,97 @@ k_sweep_tile(SweepArgs a, TileCfg tc, double4* __restrict__ pos, float4* __restr
 }
 
 // ---- trials beyond the second in cells holding three or more particles ----------------
-// (2-3 % of the cells at rho 0.9).  The per-colour lists are built with the cell list;
-// one thread per listed cell, global-memory path, trial index continues at j = 2.
+// (2-3 % of the cells at rho 0.9).  The per-colour lists are built with the cell list.
+// One WARP per listed cell: the trial is generated redundantly by all lanes (uniform),
+// lanes 0..26 each test one stencil cell against the master table with the reference's
+// double arithmetic, the verdict is a ballot.  Trial index continues at j = 2.
 template <bool LOG>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_sweep_deep(SweepArgs a, const int* __restrict__ deep_list, const int* __restrict__ deep_count, int colour,
              int list_stride, double4* __restrict__ pos, float4* __restrict__ rel, const int* __restrict__ cs,
              unsigned long long* __restrict__ cnt, hsmc_gpu_trial* __restrict__ log,
              unsigned long long* __restrict__ nlog, long long logcap) {
   const Grid& g = a.g;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   int n_acc = 0, n_ov = 0, n_cell = 0;
-  const int n = min(deep_count[colour], list_stride);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    int c = deep_list[(long long)colour * list_stride + i];
-    int iz = c % g.nz;
-    int r = c / g.nz;
-    int iy = r % g.ny, l = r / g.ny;
-    cell_update_global<LOG>(a, pos, rel, cs, l, iy, iz, 2, 1 << 30, n_acc, n_ov, n_cell, log, nlog, logcap);
+  const int nlist = min(deep_count[colour], list_stride);
+  // this lane's stencil cell
+  const int ddx = lane / 9 - 1, ddy = (lane / 3) % 3 - 1, ddz = lane % 3 - 1;
+  for (int i = warp; i < nlist; i += nwarps) {
+    const int c = deep_list[(long long)colour * list_stride + i];
+    const int iz = c % g.nz;
+    const int r = c / g.nz;
+    const int iy = r % g.ny, l = r / g.ny;
+    const int gx = (g.gx0 + l >= g.nx) ? g.gx0 + l - g.nx : g.gx0 + l;
+    const long long gcell = ((long long)gx * g.ny + iy) * g.nz + iz;
+    const int beg = cs[c], end = cs[c + 1];
+    int nb = 0, ne = 0;
+    if (lane < 27) {
+      int ll = l + ddx, yy = iy + ddy, zz = iz + ddz;
+      if (g.wrap_x) { if (ll < 0) ll += g.nlx; else if (ll >= g.nlx) ll -= g.nlx; }
+      if (yy < 0) yy += g.ny; else if (yy >= g.ny) yy -= g.ny;
+      if (zz < 0) zz += g.nz; else if (zz >= g.nz) zz -= g.nz;
+      long long cc = ((long long)ll * g.ny + yy) * g.nz + zz;
+      nb = cs[cc]; ne = cs[cc + 1];
+    }
+    double last_id = -1.0;
+    for (int j = 0; j < end - beg; j++) {
+      int sel = beg;
+      double best = 1e300;
+      for (int k = beg; k < end; k++) {
+        double id = pos[k].w;
+        if (id > last_id && id < best) { best = id; sel = k; }
+      }
+      last_id = best;
+      if (j < 2) continue;     // trials 0 and 1 were done by the tile kernel
+      const double4 p = pos[sel];
+      Philox4 rn = philox4x32_10((uint32_t)gcell, (HSMC_STREAM_MOVE << 24) | (uint32_t)j, a.sweep_lo, a.sweep_hi,
+                                 a.key0, a.key1);
+      double xn = p.x + (hsmc_u01(rn.v[0]) - 0.5) * a.dr_max;
+      double yn = p.y + (hsmc_u01(rn.v[1]) - 0.5) * a.dr_max;
+      double zn = p.z + (hsmc_u01(rn.v[2]) - 0.5) * a.dr_max;
+      if (xn > g.Lx) xn -= g.Lx; else if (xn < 0.0) xn += g.Lx;
+      if (yn > g.Ly) yn -= g.Ly; else if (yn < 0.0) yn += g.Ly;
+      if (zn > g.Lz) zn -= g.Lz; else if (zn < 0.0) zn += g.Lz;
+      int verdict;
+      if (axis_cell(xn, g.sx, g.iwx, g.nx) != gx || axis_cell(yn, g.sy, g.iwy, g.ny) != iy ||
+          axis_cell(zn, g.sz, g.iwz, g.nz) != iz) {
+        verdict = 2;
+        if (lane == 0) n_cell++;
+      } else {
+        bool ov = false;
+        for (int k = nb; k < ne; k++) {
+          if (k == sel) continue;
+          double4 q = pos[k];
+          ov |= pair_r2(xn, yn, zn, q.x, q.y, q.z, a.box) < 1.0;
+        }
+        if (__any_sync(0xffffffffu, ov)) {
+          verdict = 1;
+          if (lane == 0) n_ov++;
+        } else {
+          verdict = 0;
+          if (lane == 0) {
+            n_acc++;
+            pos[sel] = make_double4(xn, yn, zn, p.w);
+            rel[sel] = make_rel(g, gx, iy, iz, xn, yn, zn, p.w);
+          }
+        }
+        __syncwarp();
+      }
+      if (LOG && lane == 0) {
+        unsigned long long s = atomicAdd(nlog, 1ull);
+        if ((long long)s < logcap) {
+          hsmc_gpu_trial tr;
+          tr.seq = ((unsigned long long)a.phase << 56) | ((unsigned long long)gcell << 8) | (unsigned)j;
+          tr.id = (int)p.w; tr.verdict = verdict;
+          tr.raw[0] = rn.v[0]; tr.raw[1] = rn.v[1]; tr.raw[2] = rn.v[2]; tr.pad = 0;
+          log[s] = tr;
+        }
+      }
+    }
   }
-  n_acc = __reduce_add_sync(0xffffffffu, n_acc);
-  n_ov = __reduce_add_sync(0xffffffffu, n_ov);
-  n_cell = __reduce_add_sync(0xffffffffu, n_cell);
-  if ((threadIdx.x & 31) == 0 && (n_acc | n_ov | n_cell)) {
+  if (lane == 0 && (n_acc | n_ov | n_cell)) {
     atomicAdd(&cnt[CNT_TRIALS], (unsigned long long)(n_acc + n_ov + n_cell));
     if (n_acc) atomicAdd(&cnt[CNT_ACC], (unsigned long long)n_acc);
     if (n_ov) atomicAdd(&cnt[CNT_REJ_OVERLAP], (unsigned long long)n_ov);
