@@ -294,6 +294,8 @@ def main():
     stream = torch.cuda.ExternalStream(h.stream_ptr(), device=torch.device("cuda", local_rank))
     S = args.sweeps_per_step
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     # ---- warm-up ----
     for _ in range(args.warmup):
         h.sweep_nvt(S, DR_MAX)
@@ -308,8 +310,6 @@ def main():
     flush = None
     if resident < 2 * L2_BYTES:
         flush = torch.empty(int(3 * L2_BYTES), dtype=torch.uint8, device=f"cuda:{local_rank}")
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
     torch.cuda.synchronize()
     ev = []

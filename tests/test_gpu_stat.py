@@ -1,0 +1,104 @@
+"""Statistical parity of equilibrium observables (the second correctness level of
+BASELINE.json's north_star): this repo's host driver (C, over the C ABI, on the GPU) against
+the reference executable's CPU run of the SAME input file, within 3 sigma of the combined
+blocking-analysis error (the reference's own hsmc_stat.blocking_std, restated in _stat.py).
+
+Reference series: tests/golden/stat/*_ref.npz (tests/golden/make_stat_golden.py).  The two
+chains differ (checkerboard vs random sequential updates), the stationary distribution does
+not -- which is what is being tested."""
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+from _outputs import collect
+from _stat import agree, std_error
+
+pytestmark = pytest.mark.gpu
+STAT = os.path.join(GOLDEN, "stat")
+EXE = os.path.join(ROOT, "hsmc_b200", "host", "hsmc_b200")
+
+
+@pytest.fixture(scope="module")
+def runs(lib_built):
+    if lib_built.load_library().hsmc_gpu_device_count() < 1:
+        pytest.fail("no CUDA device visible")
+    from hsmc_b200 import build
+    build.build_host()
+    out = {}
+    for case in ("S1_nvt_rho08", "S2_nvt_rho05", "S3_npt_p3471"):
+        d = tempfile.mkdtemp(prefix=f"hsmc_b200_{case}_")
+        r = subprocess.run([EXE, "-i", os.path.join(STAT, case + ".in"), "-o", "out.txt"], cwd=d,
+                           capture_output=True, text=True, timeout=1500)
+        log = open(os.path.join(d, "out.txt")).read() if os.path.exists(os.path.join(d, "out.txt")) else ""
+        assert r.returncode == 0 and "Simulation complete!" in log, (r.stdout + r.stderr + log)[-2000:]
+        out[case] = (collect(d), dict(np.load(os.path.join(STAT, case + "_ref.npz"))), log)
+    return out
+
+
+def _check(name, mine, ref, nsigma=3.0):
+    ok, ma, mb, se = agree(mine, ref, nsigma)
+    assert ok, f"{name}: gpu {ma:.6g} vs reference {mb:.6g}, combined standard error {se:.3g}"
+    return ma, mb, se
+
+
+def test_stdout_contract(runs):
+    for case, (_, _, log) in runs.items():
+        for needle in ("Reading input data from", "Done", "Simulation box size (x, y, z):", "Number of particles:",
+                       "Equilibration...", "Equilibration completed.", "Production...", "Production completed.",
+                       "-- Particle moves:", "   Acceptance percentage:", "Elapsed time:", "Simulation complete!"):
+            assert needle in log, (case, needle)
+    assert "Optimal maximum displacement:" in runs["S1_nvt_rho08"][2]
+    assert "-- Volume moves:" in runs["S3_npt_p3471"][2] and "Sweep number  Density" in runs["S3_npt_p3471"][2]
+
+
+def test_virial_pressure_rho08_and_rho05(runs):
+    for case, rho in (("S1_nvt_rho08", 0.8), ("S2_nvt_rho05", 0.5)):
+        mine, ref, _ = runs[case]
+        assert mine["pressv_rr"].shape == ref["pressv_rr"].shape and np.allclose(mine["pressv_rr"], ref["pressv_rr"])
+        assert mine["g_contact"].shape == ref["g_contact"].shape          # same sampling schedule
+        ma, mb, se = _check(f"{case} g(1+)", mine["g_contact"], ref["g_contact"])
+        # coarse physics anchor: Carnahan-Starling contact value
+        eta = np.pi * rho / 6
+        assert abs(ma - (1 - eta / 2) / (1 - eta) ** 3) < 0.1
+
+
+def test_thermodynamic_pressure_histogram(runs):
+    mine, ref, _ = runs["S1_nvt_rho08"]
+    assert np.allclose(mine["presst_xi"], ref["presst_xi"])
+    for k in (0, 4, 9, 19):
+        _check(f"presst xi[{k}]", mine["presst_h"][:, k], ref["presst_h"][:, k])
+
+
+def test_widom_chemical_potential(runs):
+    mine, ref, _ = runs["S2_nvt_rho05"]
+    ma, mb, se = _check("widom accepted fraction rho=0.5", mine["widom_frac"], ref["widom_frac"])
+    # README table / Adams: mu_ex(rho=0.5) = 3.83-3.86
+    assert abs(-np.log(ma) - 3.85) < 0.1
+    m1, r1, _ = runs["S1_nvt_rho08"]
+    _check("widom accepted fraction rho=0.8", m1["widom_frac"], r1["widom_frac"], nsigma=4.0)
+
+
+def test_radial_distribution_function(runs):
+    mine, ref, _ = runs["S1_nvt_rho08"]
+    assert np.allclose(mine["rdf_rr"], ref["rdf_rr"])
+    # per-bin 3 sigma near contact (8 bins with per-sample series on both sides)
+    for k in range(8):
+        _check(f"g(r) bin {k}", mine["rdf_g"][:, k], ref["rdf_g_samples_first8"][:, k], nsigma=3.5)
+    # the whole curve: mean absolute deviation of the sample means
+    assert np.abs(mine["rdf_g"].mean(axis=0) - ref["rdf_g_mean"]).mean() < 0.01
+
+
+def test_order_parameter(runs):
+    mine, ref, _ = runs["S1_nvt_rho08"]
+    _check("q6", mine["ql"], ref["ql"])
+
+
+def test_npt_density(runs):
+    mine, ref, _ = runs["S3_npt_p3471"]
+    ma, mb, se = _check("NpT density at P=3.471", mine["density"], ref["density"])
+    # README.md:151-158: packing fraction 0.35(10) at this pressure
+    assert abs(np.pi * ma / 6 - 0.349) < 0.01
