@@ -56,7 +56,7 @@ __device__ __noinline__ void cell_update_global_noinline(const SweepArgs& a, dou
   cell_update_global<LOG>(a, pos, rel, cs, l, iy, iz, j0, j1, n_acc, n_ov, n_cell, log, nlog, logcap);
 }
 
-#define TILE_SLOTS 6     // padded stencil slots evaluated per row and pass (a z-column of 3 cells holds <= 6 in 99.7 %)
+#define TILE_SLOTS 7     // padded stencil slots evaluated per row and pass (a z-column of 3 cells holds <= 6 in 99.7 %)
 
 // per-row staging record
 struct TileRow {
@@ -261,35 +261,61 @@ k_sweep_tile(SweepArgs a, TileCfg tc, double4* __restrict__ pos, float4* __restr
     const int nB_lanes = TILE_THREADS - min(nA, TILE_THREADS);
     // One flat loop: every iteration is exactly one trial (item `it`, trial index `j`), so
     // lanes on their second trial of a cell and lanes that moved on to another cell stay
-    // converged in the same code.
-    int it = tid, pass = 0, j = 0, last_id = -1;
+    // converged in the same code.  The master-table entry of the NEXT trial's particle is
+    // requested one iteration ahead (its HBM/L2 latency is as long as a whole stencil scan).
+    struct Cur {
+      int rxc, ryc, rz, ob, oe, n, sel, gslot, gx, iy, iz, last_id;
+      long long gcell;
+    };
+    auto decode = [&](int it, int j, int last_id) {
+      Cur c;
+      const int code = s_items[it];
+      c.rxc = code >> 10; c.ryc = (code >> 6) & 15; c.rz = code & 63;
+      const int rowc = c.rxc * nry + c.ryc;
+      const TileRow rwc = s_row[rowc];
+      const int* cpc = s_cs + rowc * cs_stride + rwc.shift + c.rz;
+      c.ob = cpc[0] - rwc.delta; c.oe = cpc[1] - rwc.delta;
+      c.n = c.oe - c.ob;
+      const int l = x0 + c.rxc;
+      c.iy = y0 + c.ryc; c.iz = z0 + c.rz;
+      c.gx = (g.gx0 + l >= g.nx) ? g.gx0 + l - g.nx : g.gx0 + l;
+      c.gcell = ((long long)c.gx * g.ny + c.iy) * g.nz + c.iz;
+      // particle of trial j: ascending id inside the cell
+      c.sel = c.ob;
+      c.last_id = last_id;
+      if (c.n > 1) {
+        int best = 0x7fffffff;
+        for (int k = c.ob; k < c.oe; k++) {
+          int id = __float_as_int(s_rel[k].w);
+          if (id > last_id && id < best) { best = id; c.sel = k; }
+        }
+        c.last_id = best;
+      }
+      const int ro = c.sel - rwc.off;
+      c.gslot = (ro < rwc.cntA) ? rwc.gbA + ro : rwc.gbB + ro - rwc.cntA;
+      return c;
+    };
+    int it = tid, pass = 0, j = 0;
+    Cur cur;
+    double4 p_next = make_double4(0, 0, 0, 0);
+    if (it < n_items) { cur = decode(it, 0, -1); p_next = pos[cur.gslot]; }
 #pragma unroll 1
     while (it < n_items) {
-      const int code = s_items[it];
-      const int rxc = code >> 10, ryc = (code >> 6) & 15, rz = code & 63;
-      const int rowc = rxc * nry + ryc;
-      const TileRow rwc = s_row[rowc];
-      const int* cpc = s_cs + rowc * cs_stride + rwc.shift + rz;
-      const int ob = cpc[0] - rwc.delta, oe = cpc[1] - rwc.delta;
-      const int n = oe - ob;
-      // cell coordinates (local layer, y, z), global slot of its first particle
-      const int l = x0 + rxc, iy = y0 + ryc, iz = z0 + rz;
-      const int gx = (g.gx0 + l >= g.nx) ? g.gx0 + l - g.nx : g.gx0 + l;
-      const long long gcell = ((long long)gx * g.ny + iy) * g.nz + iz;
-      const int ro = ob - rwc.off;
-      const int gslot0 = (ro < rwc.cntA) ? rwc.gbA + ro : rwc.gbB + ro - rwc.cntA;
+      const double4 p = p_next;
+      const Cur c = cur;
+      // where this lane goes next, and the early request for that particle
+      int it2 = it, j2 = j + 1, pass2 = pass;
+      if (j2 >= min(c.n, 2)) {
+        j2 = 0;
+        if (nB_lanes == 0) it2 = it + TILE_THREADS;
+        else if (tid < nA) it2 = n_items;
+        else { it2 = TILE_THREADS + pass * nB_lanes + (tid - nA); pass2 = pass + 1; }
+      }
+      if (it2 < n_items) { cur = decode(it2, j2, j2 ? c.last_id : -1); p_next = pos[cur.gslot]; }
       {
-        int sel = ob;
-        if (n > 1) {
-          int best = 0x7fffffff;
-          for (int k = ob; k < oe; k++) {
-            int id = __float_as_int(s_rel[k].w);
-            if (id > last_id && id < best) { best = id; sel = k; }
-          }
-          last_id = best;
-        }
-        const int gslot = gslot0 + (sel - ob);
-        const double4 p = pos[gslot];
+        const int rxc = c.rxc, ryc = c.ryc, rz = c.rz, sel = c.sel, gslot = c.gslot;
+        const int gx = c.gx, iy = c.iy, iz = c.iz;
+        const long long gcell = c.gcell;
         Philox4 rn = philox4x32_10((uint32_t)gcell, (HSMC_STREAM_MOVE << 24) | (uint32_t)j, a.sweep_lo, a.sweep_hi,
                                    a.key0, a.key1);
         double xn = p.x + (hsmc_u01(rn.v[0]) - 0.5) * a.dr_max;
@@ -356,12 +382,7 @@ k_sweep_tile(SweepArgs a, TileCfg tc, double4* __restrict__ pos, float4* __restr
           }
         }
       }
-      // next trial of this lane: second particle of the cell, else the next item
-      if (++j < min(n, 2)) continue;
-      j = 0; last_id = -1;
-      if (nB_lanes == 0) it += TILE_THREADS;
-      else if (tid < nA) break;
-      else { it = TILE_THREADS + pass * nB_lanes + (tid - nA); pass++; }
+      it = it2; j = j2; pass = pass2;
     }
   } else {
     // ---- staging capacity exceeded (unusually dense tile): global-memory path ---------
