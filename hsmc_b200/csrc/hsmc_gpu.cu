@@ -90,6 +90,8 @@ struct hsmc_gpu {
   int64_t ncell = 0;       // local cells
   int64_t cap_cells = 0;
   cudaStream_t st = nullptr;
+  cudaStream_t st2 = nullptr;            // deep-cell kernel runs beside the tile kernel
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   double4* pos[2] = {nullptr, nullptr};
   float4* rel = nullptr;                 // fp32 shadow {cell-relative offset, id} of pos[cur]
   int cur = 0;
@@ -330,6 +332,10 @@ __device__ __forceinline__ void cell_update_global(const SweepArgs& a, double4* 
   long long c = ((long long)l * g.ny + iy) * g.nz + iz;
   int beg = cs[c], end = cs[c + 1];
   if (beg == end) return;
+  if (j0 < 0) {                        // tile-kernel fallback: deep cells are not its business
+    if (end - beg > j1) return;
+    j0 = 0;
+  }
   const int gx = (g.gx0 + l >= g.nx) ? g.gx0 + l - g.nx : g.gx0 + l;
   long long gcell = ((long long)gx * g.ny + iy) * g.nz + iz;
   double last_id = -1.0;
@@ -1058,6 +1064,9 @@ extern "C" int hsmc_gpu_destroy(hsmc_gpu* h) {
   if (h->h_stage) cudaFreeHost(h->h_stage);
   for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
   for (auto e : h->ev_pool) cudaEventDestroy(e);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->st2) cudaStreamDestroy(h->st2);
   if (h->st) cudaStreamDestroy(h->st);
   delete h;
   return 0;
@@ -1092,6 +1101,9 @@ extern "C" int hsmc_gpu_create(hsmc_gpu** out, const hsmc_gpu_config* cfg, int64
   } while (0)
   CUD(cudaSetDevice(cfg->device));
   CUD(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+  CUD(cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking));
+  CUD(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  CUD(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   if (setup_grid(h)) { hsmc_gpu_destroy(h); return 1; }
   int W = cfg->world;
   if (W == 1) {
@@ -1155,6 +1167,27 @@ extern "C" int hsmc_gpu_get_info(hsmc_gpu* h, hsmc_gpu_info* o) {
   o->sweeps_done = h->sweeps_done;
   o->kernel_launches = h->launches;
   o->nccl_calls = h->nccl_calls;
+  return 0;
+}
+
+extern "C" int hsmc_gpu_plan(const double box[3], double cell_min, int world, int rank, hsmc_gpu_info* o) {
+  if (!box || !o) return fail("null argument");
+  if (world < 1 || rank < 0 || rank >= world) return fail("invalid rank/world");
+  hsmc_gpu tmp;
+  tmp.cfg.device = 0; tmp.cfg.rank = rank; tmp.cfg.world = world; tmp.cfg.nccl_id = nullptr; tmp.cfg.seed = 0;
+  tmp.cfg.cell_min = cell_min == 0.0 ? 1.0 : cell_min; tmp.cfg.regrid_interval = 1; tmp.cfg.sweep_impl = 0;
+  if (tmp.cfg.cell_min < 1.0) return fail("cell_min must be >= 1.0 (the particle diameter)");
+  tmp.N = 1;
+  tmp.box[0] = box[0]; tmp.box[1] = box[1]; tmp.box[2] = box[2];
+  TRY(setup_grid(&tmp));
+  memset(o, 0, sizeof(*o));
+  o->abi_version = HSMC_GPU_ABI_VERSION;
+  o->rank = rank; o->world = world;
+  o->cells[0] = tmp.g.nx; o->cells[1] = tmp.g.ny; o->cells[2] = tmp.g.nz;
+  int x0 = (tmp.g.gx0 + tmp.g.own_lo) % tmp.g.nx;
+  o->own_x0 = x0; o->own_x1 = x0 + (tmp.g.own_hi - tmp.g.own_lo);
+  o->cell_size[0] = tmp.g.wx; o->cell_size[1] = tmp.g.wy; o->cell_size[2] = tmp.g.wz;
+  o->box[0] = box[0]; o->box[1] = box[1]; o->box[2] = box[2];
   return 0;
 }
 
@@ -1266,21 +1299,26 @@ static int sweep_once(hsmc_gpu* h, double dr_max, bool logged) {
     ProfSpan span(h, 0);
     if (h->tile_ok) {
       int nb = h->tile.ntx * h->tile.nty * h->tile.ntz;
+      int gb = 148 * 4;
+      // cells with >= 3 particles (same colour, hence independent) on the second stream
+      CU(cudaEventRecord(h->ev_fork, h->st));
+      CU(cudaStreamWaitEvent(h->st2, h->ev_fork, 0));
+      if (logged)
+        k_sweep_deep<true><<<gb, 256, 0, h->st2>>>(a, h->deep_list, h->deep_count, ph, (int)h->deep_stride, h->pos[h->cur],
+                                                   h->rel, h->cell_start, h->d_cnt, h->d_log, h->d_scratch,
+                                                   (long long)h->cap_log);
+      else
+        k_sweep_deep<false><<<gb, 256, 0, h->st2>>>(a, h->deep_list, h->deep_count, ph, (int)h->deep_stride, h->pos[h->cur],
+                                                    h->rel, h->cell_start, h->d_cnt, nullptr, nullptr, 0);
+      CU(cudaEventRecord(h->ev_join, h->st2));
       if (logged)
         k_sweep_tile<true><<<nb, TILE_THREADS, h->tile_smem, h->st>>>(a, h->tile, h->pos[h->cur], h->rel, h->cell_start, h->d_cnt,
                                                                       h->d_log, h->d_scratch, (long long)h->cap_log);
       else
         k_sweep_tile<false><<<nb, TILE_THREADS, h->tile_smem, h->st>>>(a, h->tile, h->pos[h->cur], h->rel, h->cell_start, h->d_cnt,
                                                                        nullptr, nullptr, 0);
+      CU(cudaStreamWaitEvent(h->st, h->ev_join, 0));
       h->launches++;
-      int gb = 148 * 4;
-      if (logged)
-        k_sweep_deep<true><<<gb, 256, 0, h->st>>>(a, h->deep_list, h->deep_count, ph, (int)h->deep_stride, h->pos[h->cur],
-                                                  h->rel, h->cell_start, h->d_cnt, h->d_log, h->d_scratch,
-                                                  (long long)h->cap_log);
-      else
-        k_sweep_deep<false><<<gb, 256, 0, h->st>>>(a, h->deep_list, h->deep_count, ph, (int)h->deep_stride, h->pos[h->cur],
-                                                   h->rel, h->cell_start, h->d_cnt, nullptr, nullptr, 0);
     } else if (logged)
       k_sweep_phase<true><<<nblk(total, T), T, 0, h->st>>>(a, h->pos[h->cur], h->rel, h->cell_start, h->d_cnt, h->d_log,
                                                             h->d_scratch, (long long)h->cap_log);

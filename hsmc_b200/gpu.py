@@ -18,7 +18,7 @@ NCCL_ID_BYTES = 128
 # every symbol include/hsmc_gpu.h declares
 ABI_SYMBOLS = [
     "hsmc_gpu_last_error", "hsmc_gpu_device_count", "hsmc_gpu_nccl_id", "hsmc_gpu_create",
-    "hsmc_gpu_destroy", "hsmc_gpu_get_info", "hsmc_gpu_stream", "hsmc_gpu_sync", "hsmc_gpu_upload",
+    "hsmc_gpu_destroy", "hsmc_gpu_get_info", "hsmc_gpu_plan", "hsmc_gpu_stream", "hsmc_gpu_sync", "hsmc_gpu_upload",
     "hsmc_gpu_download", "hsmc_gpu_download_owned", "hsmc_gpu_sweep_nvt", "hsmc_gpu_overlap_scaled",
     "hsmc_gpu_rescale", "hsmc_gpu_widom", "hsmc_gpu_rdf_counts", "hsmc_gpu_contact_counts",
     "hsmc_gpu_presst_flags", "hsmc_gpu_counters", "hsmc_gpu_reset_counters", "hsmc_gpu_add_vol_move",
@@ -71,6 +71,7 @@ def load_library():
     L.hsmc_gpu_create.argtypes = [C.POINTER(vp), C.POINTER(_Config), C.c_int64, dp]
     L.hsmc_gpu_destroy.argtypes = [vp]
     L.hsmc_gpu_get_info.argtypes = [vp, C.POINTER(_Info)]
+    L.hsmc_gpu_plan.argtypes = [dp, C.c_double, C.c_int, C.c_int, C.POINTER(_Info)]
     L.hsmc_gpu_stream.restype = vp
     L.hsmc_gpu_stream.argtypes = [vp]
     L.hsmc_gpu_sync.argtypes = [vp]
@@ -105,6 +106,17 @@ def nccl_unique_id() -> bytes:
     if L.hsmc_gpu_nccl_id(buf):
         raise HsmcError(L.hsmc_gpu_last_error().decode())
     return buf.raw
+
+
+def plan(box, cell_min=1.0, world=1, rank=0):
+    """Cell grid and x-slab of `rank` for this box (host only, no GPU needed)."""
+    L = load_library()
+    b = (C.c_double * 3)(*[float(x) for x in box[:3]])
+    i = _Info()
+    if L.hsmc_gpu_plan(b, float(cell_min), int(world), int(rank), C.byref(i)):
+        raise HsmcError(L.hsmc_gpu_last_error().decode())
+    return {"cells": tuple(i.cells), "cell_size": tuple(i.cell_size), "own_x": (i.own_x0, i.own_x1),
+            "rank": i.rank, "world": i.world}
 
 
 def _ptr(a):

@@ -207,8 +207,21 @@ void hs_compute_op(hs_sim *s, bool init) {
   const int N = s->part.NN, l = in->ql_order;
   const double L[3] = {s->box.lx, s->box.ly, s->box.lz};
   if (init) {
-    /* compute_order_parameter.c:47-60: the cutoff may not exceed the cell size there;
-       here the search grid adapts instead, only the half-box bound remains */
+    /* compute_order_parameter.c:29-40: the reference limits the cutoff to the edge of ITS
+       neighbour-list cells, L/floor(L/neigh_dr) (it keeps the largest of the three edges),
+       and says so.  The drop-in reproduces value and message so q_l stays comparable. */
+    double size[3];
+    int num[3], tot = 1;
+    for (int a = 0; a < 3; a++) { num[a] = (int)floor(L[a] / in->neigh_dr); tot *= num[a]; }
+    if (tot < 27) num[0] = num[1] = num[2] = 3;          /* cell_list.c:108-113 */
+    for (int a = 0; a < 3; a++) size[a] = L[a] / num[a];
+    double nl_size = size[0];
+    if (nl_size < size[1]) nl_size = size[1];
+    if (nl_size < size[2]) nl_size = size[2];
+    if (nl_size < in->ql_rmax) {
+      printf("WARNING: The cutoff for the order parameter was reduced to %f in order to be consistent with the neighbor list size\n", nl_size);
+      in->ql_rmax = nl_size;
+    }
     double lmin = fmin(L[0], fmin(L[1], L[2]));
     if (in->ql_rmax > lmin / 2.0) in->ql_rmax = lmin / 2.0;
   }

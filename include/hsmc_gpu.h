@@ -76,6 +76,11 @@ int hsmc_gpu_destroy(hsmc_gpu *h);
 
 int hsmc_gpu_get_info(hsmc_gpu *h, hsmc_gpu_info *out);
 
+/* Host-only planning (no CUDA call): the cell grid and the x-slab this rank would own for
+   a box, minimum cell edge and world size; fills cells, cell_size, box, own_x0/own_x1,
+   rank, world.  Lets launchers and CPU tests reason about the decomposition. */
+int hsmc_gpu_plan(const double box[3], double cell_min, int world, int rank, hsmc_gpu_info *out);
+
 /* CUDA stream (cudaStream_t) all work of this handle is enqueued on. */
 void *hsmc_gpu_stream(hsmc_gpu *h);
 

@@ -1,5 +1,5 @@
 """Error analysis used by the 3-sigma statistical tests: Flyvbjerg-Petersen blocking,
-restated from the reference's own python/hsmc_stat.py:6-50 (`blocking_std`) without its
+restated from the reference's own python/hsmcblocking.py:6-50 (`blocking_std`) without its
 matplotlib dependency.  test_stat_cpu.py checks it against the reference's function when
 /root/reference is present."""
 import numpy as np

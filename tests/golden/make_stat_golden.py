@@ -2,7 +2,7 @@
 inputs tests/golden/stat/*.in and store the per-sample observable series it writes
 (press_virial.dat, press_thermo.dat, chem_pot.dat, rdf, order_param.dat, density.dat) as
 compact .npz fixtures.  The GPU statistical tests run this repo's host driver on the same
-inputs and require agreement within 3 sigma (blocking analysis, tests/_stat.py)."""
+inputs and require agreement within 3 sigma (blocking analysis, tests/blocking.py)."""
 import os
 import subprocess
 import sys
@@ -13,7 +13,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from _outputs import collect  # noqa: E402
+from hsmc_outputs import collect  # noqa: E402
 
 EXE = os.path.join(ROOT, "oracle", "_ref", "hsmc_ref")
 

@@ -1,7 +1,7 @@
 """Statistical parity of equilibrium observables (the second correctness level of
 BASELINE.json's north_star): this repo's host driver (C, over the C ABI, on the GPU) against
 the reference executable's CPU run of the SAME input file, within 3 sigma of the combined
-blocking-analysis error (the reference's own hsmc_stat.blocking_std, restated in _stat.py).
+blocking-analysis error (the reference's own hsmc_stat.blocking_std, restated in blocking.py).
 
 Reference series: tests/golden/stat/*_ref.npz (tests/golden/make_stat_golden.py).  The two
 chains differ (checkerboard vs random sequential updates), the stationary distribution does
@@ -14,8 +14,8 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN, ROOT
-from _outputs import collect
-from _stat import agree, std_error
+from hsmc_outputs import collect
+from blocking import agree, std_error
 
 pytestmark = pytest.mark.gpu
 STAT = os.path.join(GOLDEN, "stat")

@@ -1,0 +1,120 @@
+"""CPU tests of the host-side logic: slab planning (single process and world_size 2 / 4 over
+gloo), the blocking error analysis against the reference's own python/hsmc_stat.py, the
+output-file parsers against the reference executable's files, and the benchmark's
+reference-arm rank gating."""
+import os
+import subprocess
+import sys
+import types
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+
+def test_plan_single(lib_built):
+    from hsmc_b200 import gpu as G
+    p = G.plan([32.8829, 32.8829, 32.8829], 1.0)
+    assert p["cells"] == (32, 32, 32) and p["own_x"] == (0, 32)
+    assert all(c % 2 == 0 for c in p["cells"]) and min(p["cell_size"]) >= 1.0
+    p = G.plan([12.5992, 12.5992, 12.5992], 1.05)            # config-1 shape: 11.99 -> 10 even cells
+    assert p["cells"] == (10, 10, 10) and min(p["cell_size"]) >= 1.05
+    with pytest.raises(G.HsmcError, match="too small"):
+        G.plan([3.5, 20, 20], 1.0)
+    with pytest.raises(G.HsmcError, match="too few cell layers"):
+        G.plan([10.0, 10.0, 10.0], 1.0, world=4, rank=0)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_plan_slabs_tile_the_box(lib_built, world):
+    from hsmc_b200 import gpu as G
+    box = [420.9, 210.45, 210.45]
+    plans = [G.plan(box, 1.0, world, r) for r in range(world)]
+    nx = plans[0]["cells"][0]
+    edges = [p["own_x"] for p in plans]
+    assert edges[0][0] == 0 and edges[-1][1] == nx
+    for a, b in zip(edges[:-1], edges[1:]):
+        assert a[1] == b[0]
+    assert all((e[1] - e[0]) % 2 == 0 and e[0] % 2 == 0 and e[1] - e[0] >= 4 for e in edges)
+    assert max(e[1] - e[0] for e in edges) - min(e[1] - e[0] for e in edges) <= 2
+
+
+_WORKER = r'''
+import os, sys, json
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, os.environ["HSMC_ROOT"])
+from hsmc_b200 import gpu as G
+from bench import fcc_lattice
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+# the 128-byte communicator id travels rank 0 -> all exactly as in bench.py
+ids = [bytes(range(128)) if rank == 0 else None]
+dist.broadcast_object_list(ids, src=0)
+assert ids[0] == bytes(range(128))
+box, conf = fcc_lattice(12, 4, 4, 0.9)
+p = G.plan(box, 1.0, world, rank)
+nx = p["cells"][0]
+w = p["cell_size"][0]
+ix = np.floor(conf[:, 1] / w).astype(int) % nx            # unshifted grid: what upload() keeps
+mine = conf[(ix >= p["own_x"][0]) & (ix < p["own_x"][1])]
+got = [None] * world
+dist.all_gather_object(got, (p["own_x"], mine[:, 0].astype(int).tolist()))
+if rank == 0:
+    ids_all = sorted(i for _, l in got for i in l)
+    ok = ids_all == list(range(conf.shape[0])) and [g[0] for g in got] == sorted(g[0] for g in got)
+    print("HOST_LOGIC", "PASS" if ok else "FAIL", [g[0] for g in got], [len(g[1]) for g in got])
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_slab_ownership_over_gloo(lib_built, tmp_path, world):
+    """world_size-2/4 processes on CPU (gloo): every particle of a full table is claimed by
+    exactly one rank's slab, slabs are ordered, the communicator id broadcast works."""
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, HSMC_ROOT=ROOT)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                          "--master-addr", "127.0.0.1", "--master-port", str(29600 + world), str(script)],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert "HOST_LOGIC PASS" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_reference_arm_runs_on_rank0_only():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                         capture_output=True, text=True, env=env, timeout=120)
+    assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_blocking_matches_reference_hsmc_stat():
+    ref_py = "/root/reference/python"
+    if not os.path.isdir(ref_py):
+        pytest.skip("reference python/ not present on this machine")
+    sys.modules.setdefault("matplotlib", types.ModuleType("matplotlib"))
+    sys.modules.setdefault("matplotlib.pyplot", types.ModuleType("matplotlib.pyplot"))
+    sys.path.insert(0, ref_py)
+    try:
+        import hsmc_stat
+    finally:
+        sys.path.remove(ref_py)
+    from blocking import blocking_std
+    rng = np.random.default_rng(0)
+    x = np.cumsum(rng.normal(size=5000)) * 0.01 + rng.normal(size=5000)     # correlated series
+    mine = blocking_std(x)
+    ref = hsmc_stat.blocking_std(x.copy(), plt_flag=False, print_flag=False)
+    assert np.allclose(mine, ref, rtol=0, atol=0)
+
+
+def test_output_parsers_on_reference_fixtures():
+    from blocking import std_error
+    s1 = dict(np.load(os.path.join(GOLDEN, "stat", "S1_nvt_rho08_ref.npz")))
+    assert s1["g_contact"].shape == (2048,) and s1["pressv_rr"].shape == (25,)
+    eta = np.pi * 0.8 / 6
+    assert abs(s1["g_contact"].mean() - (1 - eta / 2) / (1 - eta) ** 3) < 0.1       # Carnahan-Starling
+    assert 0 < std_error(s1["g_contact"]) < 0.05
+    s3 = dict(np.load(os.path.join(GOLDEN, "stat", "S3_npt_p3471_ref.npz")))
+    assert abs(np.pi * s3["density"].mean() / 6 - 0.349) < 0.01                     # README.md:151-158
