@@ -21,6 +21,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-fmad=false",            # bit-exact with the reference's unfused gcc -O2 arithmetic
+    "-DHSMC_FAST_U01",        # division-free u = raw/0xffffffff, proven equal by hsmc_gpu_selftest_u01
     "--extended-lambda",
     "-Xcompiler", "-fPIC", "-shared",
 ]

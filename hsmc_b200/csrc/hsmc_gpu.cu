@@ -916,11 +916,14 @@ static void setup_tiles(hsmc_gpu* h) {
   t.ax = fit(TILE_MAX_A, g.wrap_x ? g.nx : g.nlx, hx);
   t.ay = fit(TILE_MAX_A, g.ny, hy);
   t.az = fit(TILE_MAX_AZ, g.nz, hz);
+  double capf = 1.05;   // head-room over the mean region population; a denser tile takes the global-memory path
+  if (const char* e = getenv("HSMC_TILE_AZ")) t.az = std::max(1, std::min(t.az, atoi(e)));      // tuning knobs (bench/ablation)
+  if (const char* e = getenv("HSMC_TILE_CAPF")) capf = atof(e);
   double nbar = (double)h->N / ((double)g.nx * g.ny * g.nz);
   const int cap_max = 2240;   // ~35 KB of staged shadow entries: four CTAs per SM
   for (;;) {
     double region = (2.0 * t.ax + 1) * (2.0 * t.ay + 1) * (2.0 * t.az + 1);
-    int want = (int)(region * nbar * 1.15) + 96;
+    int want = (int)(region * nbar * capf) + 64;
     if (want <= cap_max || t.az == 1) { t.cap = std::min(std::max(want, 256), cap_max); break; }
     t.az = std::max(1, t.az / 2);
   }
@@ -1300,25 +1303,21 @@ static int sweep_once(hsmc_gpu* h, double dr_max, bool logged) {
     if (h->tile_ok) {
       int nb = h->tile.ntx * h->tile.nty * h->tile.ntz;
       int gb = 148 * 4;
-      // cells with >= 3 particles (same colour, hence independent) on the second stream
-      CU(cudaEventRecord(h->ev_fork, h->st));
-      CU(cudaStreamWaitEvent(h->st2, h->ev_fork, 0));
-      if (logged)
-        k_sweep_deep<true><<<gb, 256, 0, h->st2>>>(a, h->deep_list, h->deep_count, ph, (int)h->deep_stride, h->pos[h->cur],
-                                                   h->rel, h->cell_start, h->d_cnt, h->d_log, h->d_scratch,
-                                                   (long long)h->cap_log);
-      else
-        k_sweep_deep<false><<<gb, 256, 0, h->st2>>>(a, h->deep_list, h->deep_count, ph, (int)h->deep_stride, h->pos[h->cur],
-                                                    h->rel, h->cell_start, h->d_cnt, nullptr, nullptr, 0);
-      CU(cudaEventRecord(h->ev_join, h->st2));
       if (logged)
         k_sweep_tile<true><<<nb, TILE_THREADS, h->tile_smem, h->st>>>(a, h->tile, h->pos[h->cur], h->rel, h->cell_start, h->d_cnt,
                                                                       h->d_log, h->d_scratch, (long long)h->cap_log);
       else
         k_sweep_tile<false><<<nb, TILE_THREADS, h->tile_smem, h->st>>>(a, h->tile, h->pos[h->cur], h->rel, h->cell_start, h->d_cnt,
                                                                        nullptr, nullptr, 0);
-      CU(cudaStreamWaitEvent(h->st, h->ev_join, 0));
       h->launches++;
+      // third and later trials of the (2-3 %) cells holding >= 3 particles
+      if (logged)
+        k_sweep_deep<true><<<gb, 256, 0, h->st>>>(a, h->deep_list, h->deep_count, ph, (int)h->deep_stride, h->pos[h->cur],
+                                                  h->rel, h->cell_start, h->d_cnt, h->d_log, h->d_scratch,
+                                                  (long long)h->cap_log);
+      else
+        k_sweep_deep<false><<<gb, 256, 0, h->st>>>(a, h->deep_list, h->deep_count, ph, (int)h->deep_stride, h->pos[h->cur],
+                                                   h->rel, h->cell_start, h->d_cnt, nullptr, nullptr, 0);
     } else if (logged)
       k_sweep_phase<true><<<nblk(total, T), T, 0, h->st>>>(a, h->pos[h->cur], h->rel, h->cell_start, h->d_cnt, h->d_log,
                                                             h->d_scratch, (long long)h->cap_log);
@@ -1643,6 +1642,34 @@ extern "C" int hsmc_gpu_profile_read(hsmc_gpu* h, double ms[HSMC_GPU_PROFILE_BUC
 extern "C" int hsmc_gpu_set_sweep_counter(hsmc_gpu* h, uint64_t sweeps_done) {
   if (!h) return fail("null handle");
   h->sweeps_done = sweeps_done;
+  return 0;
+}
+
+__global__ void k_selftest_u01(unsigned long long* __restrict__ out) {
+  unsigned long long bad = 0;
+  unsigned int first = 0xffffffffu;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; r < (1ull << 32); r += stride) {
+    uint32_t raw = (uint32_t)r;
+    if (hsmc_u01_fast(raw) != hsmc_u01_div(raw)) { bad++; first = min(first, raw); }
+  }
+  if (bad) { atomicAdd(&out[0], bad); atomicMin(&out[1], (unsigned long long)first); }
+}
+
+extern "C" int hsmc_gpu_selftest_u01(hsmc_gpu* h, uint64_t* n_mismatch, uint32_t* first_bad) {
+  if (!h || !n_mismatch || !first_bad) return fail("null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  unsigned long long* hs = (unsigned long long*)h->h_stage;
+  hs[0] = 0; hs[1] = 0xffffffffull;
+  CU(cudaMemcpyAsync(h->d_scratch, hs, 16, cudaMemcpyHostToDevice, h->st));
+  k_selftest_u01<<<148 * 8, 256, 0, h->st>>>(h->d_scratch);
+  h->launches++;
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(h->st));
+  CU(cudaMemcpyAsync(hs, h->d_scratch, 16, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  *n_mismatch = hs[0];
+  *first_bad = (uint32_t)hs[1];
   return 0;
 }
 

@@ -45,4 +45,22 @@ HSMC_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3
 #define HSMC_STREAM_SHIFT 2u
 
 // u in [0,1] with the reference's resolution: rng.c:29-31, u = raw / 0xffffffff
-HSMC_HD double hsmc_u01(uint32_t raw) { return (double)raw / 4294967295.0; }
+HSMC_HD double hsmc_u01_div(uint32_t raw) { return (double)raw / 4294967295.0; }
+
+// The same value without a division: raw/(2^32-1) = raw*2^-32 * (1 + 2^-32 + 2^-64 + ...).
+// q = raw*2^-32 is exact; the tail t = q*2^-32 + q*2^-64 carries everything that can
+// influence the 53-bit rounding (the binary expansion of raw/(2^32-1) is the 32-bit
+// pattern of raw repeated, so it never comes closer than 2^-33 ulp to a rounding
+// boundary, while t is accurate to 2^-33 ulp of q... hence the EXHAUSTIVE device test
+// hsmc_gpu_selftest_u01, which must report zero mismatches over all 2^32 inputs).
+HSMC_HD double hsmc_u01_fast(uint32_t raw) {
+  const double q = (double)raw * 2.3283064365386963e-10;                 // 2^-32, exact
+  const double t = q * 2.3283064365386963e-10 + q * 5.421010862427522e-20;   // q*2^-32 + q*2^-64
+  return q + t;
+}
+
+#ifdef HSMC_FAST_U01
+HSMC_HD double hsmc_u01(uint32_t raw) { return hsmc_u01_fast(raw); }
+#else
+HSMC_HD double hsmc_u01(uint32_t raw) { return hsmc_u01_div(raw); }
+#endif

@@ -238,7 +238,7 @@ k_sweep_tile(SweepArgs a, TileCfg tc, double4* __restrict__ pos, float4* __restr
         int row = rxc * nry + ryc;
         const int* cp = s_cs + row * cs_stride + s_row[row].shift + rz;
         int n = cp[1] - cp[0];
-        if (n > 0 && n < 3) {    // cells with >= 3 particles belong to k_sweep_deep
+        if (n > 0) {
           int cls = n >= 2 ? 0 : 1;
           my_rank[m] = atomicAdd(&s_n[cls], 1);
           my_code[m] = (cls << 15) | (rxc << 10) | (ryc << 6) | rz;      // rxc,ryc <= 9, rz <= 33
@@ -253,7 +253,7 @@ k_sweep_tile(SweepArgs a, TileCfg tc, double4* __restrict__ pos, float4* __restr
         s_items[((my_code[m] >> 15) ? nA : 0) + my_rank[m]] = (unsigned short)(my_code[m] & 0x7fff);
     __syncthreads();
 
-    // ---- trials: cells with one or two particles (deeper cells run in k_sweep_deep) ------
+    // ---- trials: at most two per cell here (deeper cells finish in k_sweep_deep) ---------
     // lane t runs item t; lanes whose first item was a single take further singles, so
     // every lane does about two trials
     const float wxf = (float)g.wx, wyf = (float)g.wy, wzf = (float)g.wz;
@@ -390,7 +390,7 @@ k_sweep_tile(SweepArgs a, TileCfg tc, double4* __restrict__ pos, float4* __restr
     for (int q = tid; q < ncell_t; q += TILE_THREADS) {
       int qz = q % naz, qy = (q / naz) % nay, qx = q / (naz * nay);
       int l = x0 + 2 * qx + 1, iy = y0 + 2 * qy + 1, iz = z0 + 2 * qz + 1;
-      cell_update_global_noinline<LOG>(a, pos, rel, cs, l, iy, iz, -2, 2, n_acc, n_ov, n_cell, log, nlog, logcap);
+      cell_update_global_noinline<LOG>(a, pos, rel, cs, l, iy, iz, 0, 2, n_acc, n_ov, n_cell, log, nlog, logcap);
     }
   }
 
@@ -415,13 +415,11 @@ k_sweep_tile(SweepArgs a, TileCfg tc, double4* __restrict__ pos, float4* __restr
   }
 }
 
-// ---- all trials of cells holding three or more particles -------------------------------
-// (2-3 % of the cells at rho 0.9; the tile kernel skips them).  Same colour => independent
-// of every cell the tile kernel touches, so the two kernels run concurrently on two streams.
-// The per-colour lists are built with the cell list.
+// ---- trials beyond the second in cells holding three or more particles ----------------
+// (2-3 % of the cells at rho 0.9).  The per-colour lists are built with the cell list.
 // One WARP per listed cell: the trial is generated redundantly by all lanes (uniform),
 // lanes 0..26 each test one stencil cell against the master table with the reference's
-// double arithmetic, the verdict is a ballot.
+// double arithmetic, the verdict is a ballot.  Trial index continues at j = 2.
 template <bool LOG>
 __global__ void __launch_bounds__(256)
 k_sweep_deep(SweepArgs a, const int* __restrict__ deep_list, const int* __restrict__ deep_count, int colour,
@@ -461,6 +459,7 @@ k_sweep_deep(SweepArgs a, const int* __restrict__ deep_list, const int* __restri
         if (id > last_id && id < best) { best = id; sel = k; }
       }
       last_id = best;
+      if (j < 2) continue;     // trials 0 and 1 were done by the tile kernel
       const double4 p = pos[sel];
       Philox4 rn = philox4x32_10((uint32_t)gcell, (HSMC_STREAM_MOVE << 24) | (uint32_t)j, a.sweep_lo, a.sweep_hi,
                                  a.key0, a.key1);

@@ -23,7 +23,7 @@ ABI_SYMBOLS = [
     "hsmc_gpu_rescale", "hsmc_gpu_widom", "hsmc_gpu_rdf_counts", "hsmc_gpu_contact_counts",
     "hsmc_gpu_presst_flags", "hsmc_gpu_counters", "hsmc_gpu_reset_counters", "hsmc_gpu_add_vol_move",
     "hsmc_gpu_cell_rejects", "hsmc_gpu_profile", "hsmc_gpu_profile_read", "hsmc_gpu_set_sweep_counter", "hsmc_gpu_trial_verdicts",
-    "hsmc_gpu_widom_verdicts", "hsmc_gpu_sweep_nvt_logged", "hsmc_gpu_min_dist2",
+    "hsmc_gpu_widom_verdicts", "hsmc_gpu_sweep_nvt_logged", "hsmc_gpu_selftest_u01", "hsmc_gpu_min_dist2",
 ]
 
 
@@ -96,6 +96,7 @@ def load_library():
     L.hsmc_gpu_widom_verdicts.argtypes = [vp, C.c_int, vp, vp]
     L.hsmc_gpu_sweep_nvt_logged.argtypes = [vp, C.c_double, vp, C.c_int64, C.POINTER(C.c_int64)]
     L.hsmc_gpu_min_dist2.argtypes = [vp, dp]
+    L.hsmc_gpu_selftest_u01.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
     _lib = L
     return L
 
@@ -291,6 +292,11 @@ class HsmcGpu:
         self._ck(self.L.hsmc_gpu_sweep_nvt_logged(self.h, float(dr_max), _ptr(log), cap, C.byref(n)))
         log = log[: n.value]
         return log[np.argsort(log["seq"], kind="stable")]
+
+    def selftest_u01(self):
+        n, first = C.c_uint64(0), C.c_uint32(0)
+        self._ck(self.L.hsmc_gpu_selftest_u01(self.h, C.byref(n), C.byref(first)))
+        return n.value, first.value
 
     def min_dist2(self):
         o = C.c_double(0)

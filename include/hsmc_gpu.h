@@ -183,6 +183,11 @@ typedef struct hsmc_gpu_trial {
 int hsmc_gpu_sweep_nvt_logged(hsmc_gpu *h, double dr_max, hsmc_gpu_trial *log, int64_t capacity,
                               int64_t *n_logged);
 
+/* Exhaustive self-test of the division-free evaluation of u = raw/0xffffffff used for the
+   trial displacements: counts, over all 2^32 raw values, those for which it differs from the
+   IEEE double division the reference performs (rng.c:29-31).  Must report 0. */
+int hsmc_gpu_selftest_u01(hsmc_gpu *h, uint64_t *n_mismatch, uint32_t *first_bad);
+
 /* min over all stencil pairs of the pair distance squared (invariant checks). */
 int hsmc_gpu_min_dist2(hsmc_gpu *h, double *out);
 

@@ -171,3 +171,11 @@ def test_errors_follow_reference_convention(hs):
             h.sweep_nvt(1, 0.1)
         with pytest.raises(hs.HsmcError, match="n_rows"):
             h.upload(np.zeros((10, 4)))
+
+
+def test_division_free_u01_is_exact_for_all_raw_values(hs):
+    """u = raw/0xffffffff (rng.c:29-31) evaluated without a division must equal the IEEE
+    division for every one of the 2^32 possible draws."""
+    with hs.HsmcGpu(500, [8.5, 8.5, 8.5]) as h:
+        n_bad, first = h.selftest_u01()
+        assert n_bad == 0, f"{n_bad} mismatches, first at raw={first}"
