@@ -653,24 +653,26 @@ k_contact_hist(Grid g, Box box, const double4* __restrict__ pos, const int* __re
 // min pair r2 over the stencil (invariant check: never below 1.0 in a valid run)
 __global__ void k_min_r2(Grid g, Box box, const double4* __restrict__ pos, const int* __restrict__ cs,
                          unsigned long long* __restrict__ out) {
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)(g.own_hi - g.own_lo) * g.ny * g.nz;
-  if (t >= total) return;
-  int iz = (int)(t % g.nz);
-  long long r = t / g.nz;
-  int iy = (int)(r % g.ny), l = g.own_lo + (int)(r / g.ny);
-  long long c = ((long long)l * g.ny + iy) * g.nz + iz;
-  int beg = cs[c], end = cs[c + 1];
   double best = 1e300;
-  for (int s = beg; s < end; s++) {
-    double4 p = pos[s];
-    stencil_any(g, cs, l, iy, iz, [&](int k) {
-      double4 q = pos[k];
-      if (q.w > p.w) best = fmin(best, pair_r2(p.x, p.y, p.z, q.x, q.y, q.z, box));
-      return false;
-    });
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    int iz = (int)(t % g.nz);
+    long long r = t / g.nz;
+    int iy = (int)(r % g.ny), l = g.own_lo + (int)(r / g.ny);
+    long long c = ((long long)l * g.ny + iy) * g.nz + iz;
+    int beg = cs[c], end = cs[c + 1];
+    for (int s = beg; s < end; s++) {
+      double4 p = pos[s];
+      stencil_any(g, cs, l, iy, iz, [&](int k) {
+        double4 q = pos[k];
+        if (q.w > p.w) best = fmin(best, pair_r2(p.x, p.y, p.z, q.x, q.y, q.z, box));
+        return false;
+      });
+    }
   }
-  if (best < 1e299) atomicMin(out, (unsigned long long)__double_as_longlong(best));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) best = fmin(best, __shfl_xor_sync(0xffffffffu, best, o));
+  if ((threadIdx.x & 31) == 0 && best < 1e299) atomicMin(out, (unsigned long long)__double_as_longlong(best));
 }
 
 // ----------------------------------------------------------------------------------
@@ -803,6 +805,20 @@ __global__ void k_rel_layer(Grid g, const double4* __restrict__ pos, float4* __r
   if (t >= per) return;
   long long c = (long long)layer * per + t;
   for (int i = cs[c]; i < cs[c + 1]; i++) rel[i] = make_rel_cell(g, c, pos[i]);
+}
+
+// slab mode: the six layer offsets and the error flags in one staging vector (one D2H copy)
+__global__ void k_gather_layout(Grid g, const int* __restrict__ cs, const int* __restrict__ halo_cnt,
+                                int* __restrict__ out) {
+  long long per = (long long)g.ny * g.nz;
+  int k = threadIdx.x;
+  if (k < 6) {
+    long long offs = (k == 0) ? 0 : (k == 1) ? per : (k == 2) ? 2 * per : (k == 3) ? (long long)(g.nlx - 2) * per
+                   : (k == 4) ? (long long)(g.nlx - 1) * per : (long long)g.nlx * per;
+    out[k] = cs[offs];
+  } else if (k < 9) {
+    out[k] = halo_cnt[k - 6];
+  }
 }
 
 // ----------------------------------------------------------------------------------
@@ -1022,11 +1038,10 @@ static int rebuild(hsmc_gpu* h, const double4* src, int64_t n_in, int rows_layou
   TRY(build_deep_lists(h));
   // layer offsets + error flags back to the host (one small sync per rebuild)
   int* hs = (int*)h->h_stage;
-  long long offs[6] = {0, per, 2 * per, (long long)(g.nlx - 2) * per, (long long)(g.nlx - 1) * per,
-                       (long long)g.nlx * per};
-  for (int k = 0; k < 6; k++)
-    CU(cudaMemcpyAsync(&hs[k], h->cell_start + offs[k], sizeof(int), cudaMemcpyDeviceToHost, h->st));
-  CU(cudaMemcpyAsync(&hs[6], h->d_halo_cnt, sizeof(int) * 3, cudaMemcpyDeviceToHost, h->st));
+  int* d_lay = (int*)(h->d_scratch + 64);
+  k_gather_layout<<<1, 32, 0, h->st>>>(g, h->cell_start, h->d_halo_cnt, d_lay);
+  h->launches++;
+  CU(cudaMemcpyAsync(hs, d_lay, sizeof(int) * 9, cudaMemcpyDeviceToHost, h->st));
   CU(cudaStreamSynchronize(h->st));
   for (int k = 0; k < 6; k++) h->lay[k] = hs[k];
   if (hs[8] & 1) return fail("slab decomposition: a particle moved more than one cell layer between regrids");
@@ -1545,8 +1560,8 @@ extern "C" int hsmc_gpu_min_dist2(hsmc_gpu* h, double* out) {
   memcpy(&hs[0], &big, 8);
   CU(cudaMemcpyAsync(h->d_scratch, hs, 8, cudaMemcpyHostToDevice, h->st));
   long long total = (long long)(g.own_hi - g.own_lo) * g.ny * g.nz;
-  k_min_r2<<<nblk(total, 128), 128, 0, h->st>>>(g, make_box(g.Lx, g.Ly, g.Lz, 1.0), h->pos[h->cur], h->cell_start,
-                                                 h->d_scratch);
+  k_min_r2<<<(int)std::min<long long>(nblk(total, 128), 148 * 16), 128, 0, h->st>>>(g, make_box(g.Lx, g.Ly, g.Lz, 1.0), h->pos[h->cur],
+                                                                                     h->cell_start, h->d_scratch);
   h->launches++;
   CU(cudaGetLastError());
   if (h->cfg.world > 1) {

@@ -103,7 +103,6 @@ k_sweep_tile(SweepArgs a, TileCfg tc, double4* __restrict__ pos, float4* __restr
   __shared__ int s_cnt[TILE_MAX_ROWS + 1];
   __shared__ unsigned short s_items[TILE_MAX_CELLS];
   __shared__ int s_n[4];                                   // [0] cells with >= 2, [1] cells with 1
-  __shared__ int s_acc[3];
   __shared__ __align__(8) uint64_t s_bar;
   const int tid = threadIdx.x;
   const int cs_stride = tc.cs_stride;
@@ -127,16 +126,19 @@ k_sweep_tile(SweepArgs a, TileCfg tc, double4* __restrict__ pos, float4* __restr
 
   if (tid == 0) {
     mbar_init(&s_bar, TILE_THREADS);
-    s_acc[0] = s_acc[1] = s_acc[2] = 0;
     s_n[0] = s_n[1] = 0;
   }
 
   // ---- row pieces: each (x,y) row of the region is one contiguous slot range, or two
   //      when it wraps in z
+  // row `myrow` belongs to thread (warp, lane) with myrow = lane * W + warp: every warp
+  // issues the same number of (serialised) TMA copies
   long long my_rbase = 0;
   int my_cntB = 0;
-  if (tid < nrows) {
-    int rx = tid / nry, ry = tid - rx * nry;
+  const int myrow = ((tid & 31) < (TILE_MAX_ROWS + TILE_THREADS / 32 - 1) / (TILE_THREADS / 32))
+                        ? (tid & 31) * (TILE_THREADS / 32) + (tid >> 5) : TILE_MAX_ROWS;
+  if (myrow < nrows) {
+    int rx = myrow / nry, ry = myrow - rx * nry;
     int lx = x0 + rx;
     if (g.wrap_x) { if (lx < 0) lx += g.nlx; else if (lx >= g.nlx) lx -= g.nlx; }
     int y = y0 + ry;
@@ -146,8 +148,8 @@ k_sweep_tile(SweepArgs a, TileCfg tc, double4* __restrict__ pos, float4* __restr
     int gbB = 0, geB = 0;
     if (zwrap) { gbB = cs[my_rbase]; geB = cs[my_rbase + (zs + lenz - g.nz)]; }
     my_cntB = geB - gbB;
-    s_row[tid].gbA = gbA; s_row[tid].gbB = gbB; s_row[tid].cntA = geA - gbA;
-    s_cnt[tid] = (geA - gbA) + my_cntB;
+    s_row[myrow].gbA = gbA; s_row[myrow].gbB = gbB; s_row[myrow].cntA = geA - gbA;
+    s_cnt[myrow] = (geA - gbA) + my_cntB;
   }
   __syncthreads();
   // ---- exclusive scan of the row counts (<= 81 rows) by warp 0 ----------------------
@@ -176,9 +178,9 @@ k_sweep_tile(SweepArgs a, TileCfg tc, double4* __restrict__ pos, float4* __restr
   if (staged) {
     // ---- stage shadow rows and CSR rows: TMA bulk copies, completion on s_bar ----------
     const bool tma_cs = tc.use_tma && !zwrap;
-    if (tid < nrows) {
-      TileRow& rw = s_row[tid];
-      const int off = s_cnt[tid], cA = rw.cntA;
+    if (myrow < nrows) {
+      TileRow& rw = s_row[myrow];
+      const int off = s_cnt[myrow], cA = rw.cntA;
       const long long i0 = my_rbase + zs;
       const int shift = tma_cs ? (int)(i0 & 3) : 0;
       rw.off = off; rw.shift = shift; rw.delta = rw.gbA - off;
@@ -188,7 +190,7 @@ k_sweep_tile(SweepArgs a, TileCfg tc, double4* __restrict__ pos, float4* __restr
         if (bytes + cs_bytes) mbar_arrive_tx(&s_bar, bytes + cs_bytes); else mbar_arrive(&s_bar);
         if (cA) tma_bulk_g2s(&s_rel[off], &rel[rw.gbA], (uint32_t)cA * 16u, &s_bar);
         if (my_cntB) tma_bulk_g2s(&s_rel[off + cA], &rel[rw.gbB], (uint32_t)my_cntB * 16u, &s_bar);
-        if (cs_bytes) tma_bulk_g2s(&s_cs[tid * cs_stride], &cs[i0 - shift], cs_bytes, &s_bar);
+        if (cs_bytes) tma_bulk_g2s(&s_cs[myrow * cs_stride], &cs[i0 - shift], cs_bytes, &s_bar);
       }
     } else if (tc.use_tma) {
       mbar_arrive(&s_bar);
@@ -394,24 +396,15 @@ k_sweep_tile(SweepArgs a, TileCfg tc, double4* __restrict__ pos, float4* __restr
     }
   }
 
-  // ---- counters: one shared-memory atomic per warp, one global atomic set per CTA -------
+  // ---- counters: warp reduce, then straight to the global counters (no CTA barrier) -----
   n_acc = __reduce_add_sync(0xffffffffu, n_acc);
   n_ov = __reduce_add_sync(0xffffffffu, n_ov);
   n_cell = __reduce_add_sync(0xffffffffu, n_cell);
-  if ((tid & 31) == 0) {
-    if (n_acc) atomicAdd(&s_acc[0], n_acc);
-    if (n_ov) atomicAdd(&s_acc[1], n_ov);
-    if (n_cell) atomicAdd(&s_acc[2], n_cell);
-  }
-  __syncthreads();
-  if (tid == 0) {
-    int tot = s_acc[0] + s_acc[1] + s_acc[2];
-    if (tot) {
-      atomicAdd(&cnt[CNT_TRIALS], (unsigned long long)tot);
-      if (s_acc[0]) atomicAdd(&cnt[CNT_ACC], (unsigned long long)s_acc[0]);
-      if (s_acc[1]) atomicAdd(&cnt[CNT_REJ_OVERLAP], (unsigned long long)s_acc[1]);
-      if (s_acc[2]) atomicAdd(&cnt[CNT_REJ_CELL], (unsigned long long)s_acc[2]);
-    }
+  if ((tid & 31) == 0 && (n_acc | n_ov | n_cell)) {
+    atomicAdd(&cnt[CNT_TRIALS], (unsigned long long)(n_acc + n_ov + n_cell));
+    if (n_acc) atomicAdd(&cnt[CNT_ACC], (unsigned long long)n_acc);
+    if (n_ov) atomicAdd(&cnt[CNT_REJ_OVERLAP], (unsigned long long)n_ov);
+    if (n_cell) atomicAdd(&cnt[CNT_REJ_CELL], (unsigned long long)n_cell);
   }
 }
 
