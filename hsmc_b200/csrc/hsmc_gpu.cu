@@ -32,8 +32,10 @@
 // ----------------------------------------------------------------------------------
 static thread_local std::string g_err;
 
+static thread_local std::string g_dbg;
+
 static int fail(const std::string& m) {
-  g_err = m;
+  g_err = m + g_dbg;
   return 1;
 }
 
@@ -115,7 +117,9 @@ struct hsmc_gpu {
   double4 *send_l = nullptr, *send_r = nullptr, *recv_l = nullptr, *recv_r = nullptr;
   int64_t cap_halo = 0;                  // slots per halo buffer, slot 0 = header
   int* d_halo_cnt = nullptr;             // [0]=send_l count [1]=send_r count [2]=error flags
-  int lay[6] = {0, 0, 0, 0, 0, 0};       // slot offsets of layers 0,1,2,nlx-2,nlx-1,nlx
+  int lay[6] = {0, 0, 0, 0, 0, 0};       // slot offsets of layers 0,1,2,nlx-2,nlx-1,nlx (host mirror)
+  int* d_lay = nullptr;                  // the same + error flags on the device (slab rebuilds never sync)
+  bool lay_valid = true;                 // host mirror current?
   void* d_sfargs = nullptr;
   TileCfg tile;
   int* deep_list = nullptr;              // [8][deep_stride] cells with >= 3 particles, per colour
@@ -230,8 +234,11 @@ __global__ void k_scan_top(int* bsum, int nb) {
   }
 }
 
+// last pass of the scan; cells found to hold >= 3 particles are appended to the per-colour
+// deep lists on the way (owned layers only)
 __global__ void k_scan_final(const int* __restrict__ in, long long n, const int* __restrict__ bsum,
-                             int* __restrict__ out) {
+                             int* __restrict__ out, Grid g, int* __restrict__ deep_list,
+                             int* __restrict__ deep_count, int list_stride) {
   long long base = (long long)blockIdx.x * SCAN_CHUNK + (long long)threadIdx.x * SCAN_V;
   int v[SCAN_V];
   int s = 0;
@@ -249,6 +256,16 @@ __global__ void k_scan_final(const int* __restrict__ in, long long n, const int*
     if (i < n) out[i] = ex;
     ex += v[j];
     if (i == n - 1) out[n] = ex;
+    if (v[j] >= 3 && deep_list) {
+      int iz = (int)(i % g.nz);
+      long long r = i / g.nz;
+      int iy = (int)(r % g.ny), l = (int)(r / g.ny);
+      if (l >= g.own_lo && l < g.own_hi) {
+        int colour = (((g.gx0 + l) & 1) << 2) | ((iy & 1) << 1) | (iz & 1);
+        int slot = atomicAdd(&deep_count[colour], 1);
+        if (slot < list_stride) deep_list[(long long)colour * list_stride + slot] = (int)i;
+      }
+    }
   }
 }
 
@@ -700,8 +717,13 @@ __global__ void k_rescale(double4* __restrict__ pos, int n, double sf, double lx
 __global__ void k_slab_classify(Grid g, const double4* __restrict__ in, int n, int rows_layout,
                                 int upload_mode, int* __restrict__ key, int* __restrict__ rnk,
                                 int* __restrict__ count, double4* __restrict__ send_l,
-                                double4* __restrict__ send_r, int* __restrict__ halo_cnt, int cap_halo) {
+                                double4* __restrict__ send_r, int* __restrict__ halo_cnt, int cap_halo,
+                                const int* __restrict__ d_lay) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d_lay) {                       // source = the previously owned slot range, known on the device only
+    n = d_lay[4] - d_lay[1];
+    in += d_lay[1];
+  }
   if (i >= n) return;
   double4 p = in[i];
   if (rows_layout) p = make_double4(p.y, p.z, p.w, p.x);
@@ -736,8 +758,12 @@ __global__ void k_halo_headers(double4* send_l, double4* send_r, const int* halo
 }
 
 // key the received particles (count in the header slot)
-__global__ void k_recv_count(Grid g, const double4* __restrict__ buf, int cap_halo, int* __restrict__ key,
-                             int* __restrict__ rnk, int* __restrict__ count, int* __restrict__ halo_cnt) {
+__global__ void k_recv_count(Grid g, const double4* __restrict__ buf0, const double4* __restrict__ buf1,
+                             int cap_halo, int* __restrict__ key, int* __restrict__ rnk, int* __restrict__ count,
+                             int* __restrict__ halo_cnt) {
+  const double4* buf = blockIdx.y ? buf1 : buf0;
+  key += (size_t)blockIdx.y * cap_halo;
+  rnk += (size_t)blockIdx.y * cap_halo;
   int n = (int)buf[0].x;
   if (n > cap_halo - 1) n = cap_halo - 1;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -749,9 +775,13 @@ __global__ void k_recv_count(Grid g, const double4* __restrict__ buf, int cap_ha
   }
 }
 
-__global__ void k_recv_scatter(Grid g, const double4* __restrict__ buf, int cap_halo, const int* __restrict__ key,
-                               const int* __restrict__ rnk, const int* __restrict__ cs,
-                               double4* __restrict__ out, float4* __restrict__ rel) {
+__global__ void k_recv_scatter(Grid g, const double4* __restrict__ buf0, const double4* __restrict__ buf1,
+                               int cap_halo, const int* __restrict__ key, const int* __restrict__ rnk,
+                               const int* __restrict__ cs, double4* __restrict__ out, float4* __restrict__ rel,
+                               int cap, int* __restrict__ flags) {
+  const double4* buf = blockIdx.y ? buf1 : buf0;
+  key += (size_t)blockIdx.y * cap_halo;
+  rnk += (size_t)blockIdx.y * cap_halo;
   int n = (int)buf[0].x;
   if (n > cap_halo - 1) n = cap_halo - 1;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -759,22 +789,58 @@ __global__ void k_recv_scatter(Grid g, const double4* __restrict__ buf, int cap_
     if (c >= 0) {
       double4 p = buf[i + 1];
       int d = cs[c] + rnk[i];
+      if (d >= cap) { atomicOr(flags, 32); continue; }
       out[d] = p;
       rel[d] = make_rel_cell(g, c, p);
     }
   }
 }
 
+// boundary layer -> message buffer (count in the header slot); the slot range of the layer
+// is only known on the device
+__global__ void k_halo_pack(Grid g, const double4* __restrict__ pos, const int* __restrict__ cs, int layer,
+                            double4* __restrict__ buf, int cap_msg, int* __restrict__ flags) {
+  long long per = (long long)g.ny * g.nz;
+  int b = cs[(long long)layer * per], e = cs[(long long)(layer + 1) * per];
+  int n = e - b;
+  if (n > cap_msg - 1) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(flags, 2); n = cap_msg - 1; }
+  if (blockIdx.x == 0 && threadIdx.x == 0) buf[0] = make_double4((double)n, 0, 0, 0);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) buf[1 + i] = pos[b + i];
+}
+
+// message buffer -> ghost layer, slot for slot (both sides keep these layers id-sorted),
+// plus the fp32 shadow of the refreshed slots
+__global__ void k_halo_unpack(Grid g, double4* __restrict__ pos, float4* __restrict__ rel, const int* __restrict__ cs,
+                              int layer, const double4* __restrict__ buf, int* __restrict__ flags) {
+  long long per = (long long)g.ny * g.nz;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int b0 = cs[(long long)layer * per];
+  if (t == 0 && (int)buf[0].x != cs[(long long)(layer + 1) * per] - b0) atomicOr(flags, 16);
+  if (t >= per) return;
+  long long c = (long long)layer * per + t;
+  for (int i = cs[c]; i < cs[c + 1]; i++) {
+    double4 p = buf[1 + (i - b0)];
+    pos[i] = p;
+    rel[i] = make_rel_cell(g, c, p);
+  }
+}
+
 __global__ void k_scatter_layout(Grid g, const double4* __restrict__ in, int n, int rows_layout,
                                  const int* __restrict__ key, const int* __restrict__ rnk,
-                                 const int* __restrict__ cs, double4* __restrict__ out, float4* __restrict__ rel) {
+                                 const int* __restrict__ cs, double4* __restrict__ out, float4* __restrict__ rel,
+                                 const int* __restrict__ d_lay, int cap, int* __restrict__ flags) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d_lay) {
+    n = d_lay[4] - d_lay[1];
+    in += d_lay[1];
+  }
   if (i >= n) return;
   int c = key[i];
   if (c < 0) return;
   double4 p = in[i];
   if (rows_layout) p = make_double4(p.y, p.z, p.w, p.x);
   int d = cs[c] + rnk[i];
+  if (d >= cap) { atomicOr(flags, 32); return; }
   out[d] = p;
   rel[d] = make_rel_cell(g, c, p);
 }
@@ -786,6 +852,7 @@ __global__ void k_sort_cells_by_id(Grid g, double4* __restrict__ pos, float4* __
   long long per = (long long)g.ny * g.nz;
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= 2 * per) return;
+  if (blockIdx.y) { layer_a = g.nlx - 2; layer_b = g.nlx - 1; }     // second pair of layers
   long long c = (t < per) ? (long long)layer_a * per + t : (long long)layer_b * per + (t - per);
   int beg = cs[c], end = cs[c + 1];
   for (int i = beg + 1; i < end; i++) {
@@ -816,8 +883,10 @@ __global__ void k_gather_layout(Grid g, const int* __restrict__ cs, const int* _
     long long offs = (k == 0) ? 0 : (k == 1) ? per : (k == 2) ? 2 * per : (k == 3) ? (long long)(g.nlx - 2) * per
                    : (k == 4) ? (long long)(g.nlx - 1) * per : (long long)g.nlx * per;
     out[k] = cs[offs];
-  } else if (k < 9) {
+  } else if (k < 8) {
     out[k] = halo_cnt[k - 6];
+  } else if (k == 8) {
+    out[8] |= halo_cnt[2];           // error bits are sticky until the host reads them
   }
 }
 
@@ -833,6 +902,7 @@ static int even_cells(double L, double cell_min) {
 }
 
 static void setup_tiles(hsmc_gpu* h);
+static int sync_layout(hsmc_gpu* h);
 
 static int setup_grid(hsmc_gpu* h) {
   double cm = h->cfg.cell_min;
@@ -912,9 +982,10 @@ static void draw_shift(hsmc_gpu* h) {
 
 static int exclusive_scan(hsmc_gpu* h, const int* in, int64_t n, int* out) {
   int nb = (int)((n + SCAN_CHUNK - 1) / SCAN_CHUNK);
+  CU(cudaMemsetAsync(h->deep_count, 0, sizeof(int) * 8, h->st));
   k_scan_blocksum<<<nb, SCAN_T, 0, h->st>>>(in, n, h->bsum);
   k_scan_top<<<1, SCAN_T, 0, h->st>>>(h->bsum, nb);
-  k_scan_final<<<nb, SCAN_T, 0, h->st>>>(in, n, h->bsum, out);
+  k_scan_final<<<nb, SCAN_T, 0, h->st>>>(in, n, h->bsum, out, h->g, h->deep_list, h->deep_count, (int)h->deep_stride);
   h->launches += 3;
   CU(cudaGetLastError());
   return 0;
@@ -951,26 +1022,16 @@ static void setup_tiles(hsmc_gpu* h) {
   h->tile_ok = h->cfg.sweep_impl != 1 && t.cap * 1 <= 65535;
 }
 
-static int build_deep_lists(hsmc_gpu* h) {
-  Grid& g = h->g;
-  CU(cudaMemsetAsync(h->deep_count, 0, sizeof(int) * 8, h->st));
-  long long total = (long long)(g.own_hi - g.own_lo) * g.ny * g.nz;
-  k_deep_lists<<<nblk(total, 256), 256, 0, h->st>>>(g, h->cell_start, h->deep_list, h->deep_count,
-                                                     (int)h->deep_stride, h->d_halo_cnt + 2);
-  h->launches++;
-  CU(cudaGetLastError());
-  return 0;
-}
-
 static inline int left_of(const hsmc_gpu* h) { return (h->cfg.rank + h->cfg.world - 1) % h->cfg.world; }
 static inline int right_of(const hsmc_gpu* h) { return (h->cfg.rank + 1) % h->cfg.world; }
 
 // Rebuild the cell-ordered table from `src` (n_in particles; rows_layout: {id,x,y,z}
 // instead of {x,y,z,id}) under the current grid.  Output goes to pos[cur^1]; cur flips.
-static int rebuild(hsmc_gpu* h, const double4* src, int64_t n_in, int rows_layout, int upload_mode) {
+static int rebuild(hsmc_gpu* h, const double4* src, int64_t n_in, int rows_layout, int upload_mode, bool dev_range = false) {
   ProfSpan span(h, 1);
   TRY(ensure_cell_arrays(h));
   TRY(ensure_keys(h, std::max<int64_t>(n_in, h->cap)));
+  if (dev_range) n_in = 0;   // source range read from d_lay on the device
   Grid& g = h->g;
   const int T = 256;
   double4* dst = h->pos[h->cur ^ 1];
@@ -989,18 +1050,20 @@ static int rebuild(hsmc_gpu* h, const double4* src, int64_t n_in, int rows_layou
     k_cell_scatter<<<nblk(n_in, T), T, 0, h->st>>>(g, src, (int)n_in, h->key, h->rnk, h->cell_start, dst, h->rel);
     h->launches++;
     CU(cudaGetLastError());
-    TRY(build_deep_lists(h));
     h->cur ^= 1;
     h->n_local = h->n_owned = h->N;
     h->own_first = 0;
     return 0;
   }
-  // ---- slab mode ----
+  // ---- slab mode: fully asynchronous (no host round trip); sync_layout() fetches the layer
+  //      offsets and the error flags when the host needs them ----
+  const int* d_range = dev_range ? h->d_lay : nullptr;
+  const int64_t n_src = dev_range ? h->cap : n_in;
   CU(cudaMemsetAsync(h->d_halo_cnt, 0, sizeof(int) * 4, h->st));
-  if (n_in > 0) {
-    k_slab_classify<<<nblk(n_in, T), T, 0, h->st>>>(g, src, (int)n_in, rows_layout, upload_mode, h->key,
+  if (n_src > 0) {
+    k_slab_classify<<<nblk(n_src, T), T, 0, h->st>>>(g, src, (int)n_in, rows_layout, upload_mode, h->key,
                                                      h->rnk, h->cell_count, h->send_l, h->send_r,
-                                                     h->d_halo_cnt, (int)h->cap_halo);
+                                                     h->d_halo_cnt, (int)h->cap_halo, d_range);
     h->launches++;
   }
   k_halo_headers<<<1, 1, 0, h->st>>>(h->send_l, h->send_r, h->d_halo_cnt);
@@ -1013,45 +1076,54 @@ static int rebuild(hsmc_gpu* h, const double4* src, int64_t n_in, int rows_layou
   NC(ncclRecv(h->recv_l, cnt, ncclDouble, left_of(h), h->comm, h->st));
   NC(ncclGroupEnd());
   h->nccl_calls += 4;
-  int* key_l = h->key_halo;
-  int* rnk_l = h->rnk_halo;
-  int* key_r = key_l + h->cap_halo;
-  int* rnk_r = rnk_l + h->cap_halo;
-  int gb = 148 * 4;
-  k_recv_count<<<gb, T, 0, h->st>>>(g, h->recv_l, (int)h->cap_halo, key_l, rnk_l, h->cell_count, h->d_halo_cnt);
-  k_recv_count<<<gb, T, 0, h->st>>>(g, h->recv_r, (int)h->cap_halo, key_r, rnk_r, h->cell_count, h->d_halo_cnt);
-  h->launches += 2;
+  dim3 gb2(148 * 2, 2);
+  k_recv_count<<<gb2, T, 0, h->st>>>(g, h->recv_l, h->recv_r, (int)h->cap_halo, h->key_halo, h->rnk_halo,
+                                     h->cell_count, h->d_halo_cnt);
+  h->launches++;
   TRY(exclusive_scan(h, h->cell_count, h->ncell, h->cell_start));
-  if (n_in > 0) {
-    k_scatter_layout<<<nblk(n_in, T), T, 0, h->st>>>(g, src, (int)n_in, rows_layout, h->key, h->rnk,
-                                                      h->cell_start, dst, h->rel);
+  if (n_src > 0) {
+    k_scatter_layout<<<nblk(n_src, T), T, 0, h->st>>>(g, src, (int)n_in, rows_layout, h->key, h->rnk,
+                                                      h->cell_start, dst, h->rel, d_range, (int)h->cap,
+                                                      h->d_halo_cnt + 2);
     h->launches++;
   }
-  k_recv_scatter<<<gb, T, 0, h->st>>>(g, h->recv_l, (int)h->cap_halo, key_l, rnk_l, h->cell_start, dst, h->rel);
-  k_recv_scatter<<<gb, T, 0, h->st>>>(g, h->recv_r, (int)h->cap_halo, key_r, rnk_r, h->cell_start, dst, h->rel);
-  h->launches += 2;
-  long long per = (long long)g.ny * g.nz;
-  k_sort_cells_by_id<<<nblk(2 * per, 128), 128, 0, h->st>>>(g, dst, h->rel, h->cell_start, 0, 1);
-  k_sort_cells_by_id<<<nblk(2 * per, 128), 128, 0, h->st>>>(g, dst, h->rel, h->cell_start, g.nlx - 2, g.nlx - 1);
-  h->launches += 2;
-  CU(cudaGetLastError());
-  TRY(build_deep_lists(h));
-  // layer offsets + error flags back to the host (one small sync per rebuild)
-  int* hs = (int*)h->h_stage;
-  int* d_lay = (int*)(h->d_scratch + 64);
-  k_gather_layout<<<1, 32, 0, h->st>>>(g, h->cell_start, h->d_halo_cnt, d_lay);
+  k_recv_scatter<<<gb2, T, 0, h->st>>>(g, h->recv_l, h->recv_r, (int)h->cap_halo, h->key_halo, h->rnk_halo,
+                                       h->cell_start, dst, h->rel, (int)h->cap, h->d_halo_cnt + 2);
   h->launches++;
-  CU(cudaMemcpyAsync(hs, d_lay, sizeof(int) * 9, cudaMemcpyDeviceToHost, h->st));
+  long long per = (long long)g.ny * g.nz;
+  k_sort_cells_by_id<<<dim3(nblk(2 * per, 128), 2), 128, 0, h->st>>>(g, dst, h->rel, h->cell_start, 0, 1);
+  h->launches++;
+  k_gather_layout<<<1, 32, 0, h->st>>>(g, h->cell_start, h->d_halo_cnt, h->d_lay);
+  h->launches++;
+  CU(cudaGetLastError());
+  h->cur ^= 1;
+  h->lay_valid = false;
+  if (getenv("HSMC_DEBUG_SYNC") && sync_layout(h)) return fail(std::string(g_err) + " (after rebuild)");
+  return 0;
+}
+
+// slab mode: bring the layer offsets and the accumulated error flags to the host
+static int sync_layout(hsmc_gpu* h) {
+  if (h->cfg.world == 1 || h->lay_valid) return 0;
+  int* hs = (int*)h->h_stage;
+  CU(cudaMemcpyAsync(hs, h->d_lay, sizeof(int) * 9, cudaMemcpyDeviceToHost, h->st));
   CU(cudaStreamSynchronize(h->st));
   for (int k = 0; k < 6; k++) h->lay[k] = hs[k];
-  if (hs[8] & 1) return fail("slab decomposition: a particle moved more than one cell layer between regrids");
-  if (hs[8] & 2) return fail("slab decomposition: halo buffer overflow");
-  if (hs[8] & 4) return fail("slab decomposition: received a particle outside the local layers");
-  if (hs[5] > h->cap) return fail("slab decomposition: local particle capacity exceeded");
-  h->cur ^= 1;
   h->n_local = h->lay[5];
   h->own_first = h->lay[1];
   h->n_owned = h->lay[4] - h->lay[1];
+  h->lay_valid = true;
+  if (hs[8]) {
+    char dbg[256];
+    snprintf(dbg, sizeof(dbg), " [layers %d %d %d %d %d %d, sent %d %d, flags %d, cap %lld, halo cap %lld]", hs[0], hs[1],
+             hs[2], hs[3], hs[4], hs[5], hs[6], hs[7], hs[8], (long long)h->cap, (long long)h->cap_halo);
+    g_dbg = dbg;
+  } else g_dbg.clear();
+  if (hs[8] & 1) return fail("slab decomposition: a particle moved more than one cell layer between regrids");
+  if (hs[8] & 2) return fail("slab decomposition: halo buffer overflow");
+  if (hs[8] & 4) return fail("slab decomposition: received a particle outside the local layers");
+  if (hs[8] & 16) return fail("slab decomposition: boundary-layer message does not match the ghost layer");
+  if ((hs[8] & 32) || hs[5] > h->cap) return fail("slab decomposition: local particle capacity exceeded");
   return 0;
 }
 
@@ -1076,7 +1148,7 @@ extern "C" int hsmc_gpu_destroy(hsmc_gpu* h) {
   if (h->comm) ncclCommDestroy(h->comm);
   void* ptrs[] = {h->pos[0], h->pos[1], h->rel, h->key, h->rnk, h->cell_count, h->cell_start, h->bsum, h->d_cnt,
                   h->d_scratch, h->d_slot_of_id, h->d_io, h->send_l, h->send_r, h->recv_l, h->recv_r,
-                  h->d_halo_cnt, h->d_sfargs, h->d_log, h->key_halo, h->rnk_halo, h->deep_list, h->deep_count};
+                  h->d_halo_cnt, h->d_sfargs, h->d_log, h->key_halo, h->rnk_halo, h->deep_list, h->deep_count, h->d_lay};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -1131,8 +1203,9 @@ extern "C" int hsmc_gpu_create(hsmc_gpu** out, const hsmc_gpu_config* cfg, int64
     // owned share + two ghost layers, with head-room for density fluctuations
     double own_frac = (double)(h->g.own_hi - h->g.own_lo) / h->g.nx;
     double lay_frac = 1.0 / h->g.nx;
-    h->cap = (int64_t)((own_frac + 2 * lay_frac) * h->N * 1.25) + 4096;
-    h->cap_halo = (int64_t)(2 * lay_frac * h->N * 1.5) + 4096;
+    h->cap = (int64_t)((own_frac + 2 * 2.5 * lay_frac) * h->N * 1.25) + 4096;
+    // a cell layer of a crystal can hold 1.6x the mean (lattice planes beat against the cell grid)
+    h->cap_halo = (int64_t)(2 * lay_frac * h->N * 2.5) + 4096;
   }
   CUD(cudaMalloc(&h->pos[0], sizeof(double4) * (size_t)h->cap));
   CUD(cudaMalloc(&h->pos[1], sizeof(double4) * (size_t)h->cap));
@@ -1147,6 +1220,8 @@ extern "C" int hsmc_gpu_create(hsmc_gpu** out, const hsmc_gpu_config* cfg, int64
   CUD(cudaMalloc(&h->d_halo_cnt, sizeof(int) * 4));
   CUD(cudaMemset(h->d_halo_cnt, 0, sizeof(int) * 4));
   CUD(cudaMalloc(&h->d_sfargs, sizeof(SfArgs)));
+  CUD(cudaMalloc(&h->d_lay, sizeof(int) * 16));
+  CUD(cudaMemset(h->d_lay, 0, sizeof(int) * 16));
   CUD(cudaMallocHost(&h->h_stage, sizeof(unsigned long long) * SCRATCH_N));
   if (ensure_cell_arrays(h)) { hsmc_gpu_destroy(h); return 1; }
   CUD(cudaFuncSetAttribute(k_sweep_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
@@ -1173,6 +1248,8 @@ extern "C" int hsmc_gpu_create(hsmc_gpu** out, const hsmc_gpu_config* cfg, int64
 
 extern "C" int hsmc_gpu_get_info(hsmc_gpu* h, hsmc_gpu_info* o) {
   if (!h || !o) return fail("null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  TRY(sync_layout(h));
   memset(o, 0, sizeof(*o));
   o->abi_version = HSMC_GPU_ABI_VERSION;
   o->rank = h->cfg.rank; o->world = h->cfg.world;
@@ -1215,6 +1292,7 @@ extern "C" int hsmc_gpu_sync(hsmc_gpu* h) {
   if (!h) return fail("null handle");
   CU(cudaSetDevice(h->cfg.device));
   CU(cudaStreamSynchronize(h->st));
+  TRY(sync_layout(h));
   return 0;
 }
 
@@ -1226,6 +1304,7 @@ extern "C" int hsmc_gpu_upload(hsmc_gpu* h, const double* rows, int64_t n_rows) 
   TRY(ensure_io(h, std::max<int64_t>(n_rows, 1)));
   CU(cudaMemcpyAsync(h->d_io, rows, sizeof(double) * 4 * (size_t)n_rows, cudaMemcpyHostToDevice, h->st));
   TRY(rebuild(h, reinterpret_cast<const double4*>(h->d_io), n_rows, 1, 1));
+  TRY(sync_layout(h));
   h->have_conf = true;
   h->since_regrid = 0;
   return 0;
@@ -1249,6 +1328,7 @@ extern "C" int hsmc_gpu_download_owned(hsmc_gpu* h, double* rows, int64_t capaci
   if (!h || !rows || !n_rows) return fail("null argument");
   if (!h->have_conf) return fail("download: no configuration uploaded");
   CU(cudaSetDevice(h->cfg.device));
+  TRY(sync_layout(h));
   if (capacity_rows < h->n_owned) return fail("download_owned: buffer too small");
   TRY(ensure_io(h, std::max<int64_t>(h->n_owned, 1)));
   if (h->n_owned > 0) {
@@ -1267,35 +1347,37 @@ extern "C" int hsmc_gpu_download_owned(hsmc_gpu* h, double* rows, int64_t capaci
 // neighbour, slot-for-slot in the same order.
 static int halo_refresh(hsmc_gpu* h, int cx) {
   ProfSpan span(h, 2);
+  Grid& g = h->g;
   double4* p = h->pos[h->cur];
+  const int cap_msg = (int)(h->cap_halo / 2);          // one layer with head-room
+  const long long per = (long long)g.ny * g.nz;
+  // x-parity 0: first owned layer -> left neighbour's right ghost; parity 1: last owned layer ->
+  // right neighbour's left ghost
+  const int src_layer = (cx == 0) ? g.own_lo : g.own_hi - 1;
+  const int dst_layer = (cx == 0) ? g.nlx - 1 : 0;
+  double4* sbuf = (cx == 0) ? h->send_l : h->send_r;
+  double4* rbuf = (cx == 0) ? h->recv_r : h->recv_l;
+  const int to = (cx == 0) ? left_of(h) : right_of(h), from = (cx == 0) ? right_of(h) : left_of(h);
+  k_halo_pack<<<148, 256, 0, h->st>>>(g, p, h->cell_start, src_layer, sbuf, cap_msg, h->d_lay + 8);
   NC(ncclGroupStart());
-  if (cx == 0) {
-    // first owned layer (even global index) -> left neighbour's right ghost
-    size_t ns = (size_t)(h->lay[2] - h->lay[1]) * 4, nr = (size_t)(h->lay[5] - h->lay[4]) * 4;
-    NC(ncclSend(p + h->lay[1], ns, ncclDouble, left_of(h), h->comm, h->st));
-    NC(ncclRecv(p + h->lay[4], nr, ncclDouble, right_of(h), h->comm, h->st));
-  } else {
-    // last owned layer (odd) -> right neighbour's left ghost
-    size_t ns = (size_t)(h->lay[4] - h->lay[3]) * 4, nr = (size_t)(h->lay[1] - h->lay[0]) * 4;
-    NC(ncclSend(p + h->lay[3], ns, ncclDouble, right_of(h), h->comm, h->st));
-    NC(ncclRecv(p + h->lay[0], nr, ncclDouble, left_of(h), h->comm, h->st));
-  }
+  NC(ncclSend(sbuf, (size_t)cap_msg * 4, ncclDouble, to, h->comm, h->st));
+  NC(ncclRecv(rbuf, (size_t)cap_msg * 4, ncclDouble, from, h->comm, h->st));
   NC(ncclGroupEnd());
   h->nccl_calls += 2;
-  {
-    long long per = (long long)h->g.ny * h->g.nz;
-    int layer = (cx == 0) ? h->g.nlx - 1 : 0;
-    k_rel_layer<<<nblk(per, 128), 128, 0, h->st>>>(h->g, p, h->rel, h->cell_start, layer);
-    h->launches++;
-    CU(cudaGetLastError());
+  k_halo_unpack<<<nblk(per, 128), 128, 0, h->st>>>(g, p, h->rel, h->cell_start, dst_layer, rbuf, h->d_lay + 8);
+  h->launches += 2;
+  CU(cudaGetLastError());
+  if (getenv("HSMC_DEBUG_SYNC")) {
+    h->lay_valid = false;
+    if (sync_layout(h)) return fail(std::string(g_err) + (cx ? " (after halo refresh 1)" : " (after halo refresh 0)"));
   }
   return 0;
 }
 
 static int do_regrid(hsmc_gpu* h) {
   draw_shift(h);
-  const double4* src = h->pos[h->cur] + h->own_first;
-  return rebuild(h, src, h->n_owned, 0, 0);
+  if (h->cfg.world > 1) return rebuild(h, h->pos[h->cur], 0, 0, 0, true);
+  return rebuild(h, h->pos[h->cur], h->N, 0, 0);
 }
 
 static int sweep_once(hsmc_gpu* h, double dr_max, bool logged) {
@@ -1360,7 +1442,7 @@ extern "C" int hsmc_gpu_sweep_nvt(hsmc_gpu* h, int n_sweeps, double dr_max) {
     return fail("sweep: dr_max out of range");
   CU(cudaSetDevice(h->cfg.device));
   for (int s = 0; s < n_sweeps; s++) TRY(sweep_once(h, dr_max, false));
-  return 0;
+  return sync_layout(h);
 }
 
 extern "C" int hsmc_gpu_sweep_nvt_logged(hsmc_gpu* h, double dr_max, hsmc_gpu_trial* log, int64_t capacity,

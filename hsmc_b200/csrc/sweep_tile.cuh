@@ -410,22 +410,26 @@ k_sweep_tile(SweepArgs a, TileCfg tc, double4* __restrict__ pos, float4* __restr
 
 // ---- trials beyond the second in cells holding three or more particles ----------------
 // (2-3 % of the cells at rho 0.9).  The per-colour lists are built with the cell list.
-// One WARP per listed cell: the trial is generated redundantly by all lanes (uniform),
-// lanes 0..26 each test one stencil cell against the master table with the reference's
-// double arithmetic, the verdict is a ballot.  Trial index continues at j = 2.
+// One WARP per listed cell, two memory round trips per cell: (1) the CSR entries of the
+// 27 stencil cells, lane c < 27 its own cell; (2) the cell's own particles (lane i the
+// i-th) and up to three particles of each neighbour cell, cached in registers -- they do
+// not change while this cell is updated.  Trials (index continues at j = 2) are generated
+// redundantly by all lanes (uniform), each lane tests its cached particles with the
+// reference's double arithmetic, the verdict is a ballot.
+#define DEEP_CACHE 3
 template <bool LOG>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 k_sweep_deep(SweepArgs a, const int* __restrict__ deep_list, const int* __restrict__ deep_count, int colour,
              int list_stride, double4* __restrict__ pos, float4* __restrict__ rel, const int* __restrict__ cs,
              unsigned long long* __restrict__ cnt, hsmc_gpu_trial* __restrict__ log,
              unsigned long long* __restrict__ nlog, long long logcap) {
   const Grid& g = a.g;
+  const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   int n_acc = 0, n_ov = 0, n_cell = 0;
   const int nlist = min(deep_count[colour], list_stride);
-  // this lane's stencil cell
-  const int ddx = lane / 9 - 1, ddy = (lane / 3) % 3 - 1, ddz = lane % 3 - 1;
+  const int ddx = lane / 9 - 1, ddy = (lane / 3) % 3 - 1, ddz = lane % 3 - 1;   // this lane's stencil cell
   for (int i = warp; i < nlist; i += nwarps) {
     const int c = deep_list[(long long)colour * list_stride + i];
     const int iz = c % g.nz;
@@ -433,7 +437,7 @@ k_sweep_deep(SweepArgs a, const int* __restrict__ deep_list, const int* __restri
     const int iy = r % g.ny, l = r / g.ny;
     const int gx = (g.gx0 + l >= g.nx) ? g.gx0 + l - g.nx : g.gx0 + l;
     const long long gcell = ((long long)gx * g.ny + iy) * g.nz + iz;
-    const int beg = cs[c], end = cs[c + 1];
+    // round trip 1: CSR of the stencil
     int nb = 0, ne = 0;
     if (lane < 27) {
       int ll = l + ddx, yy = iy + ddy, zz = iz + ddz;
@@ -443,22 +447,35 @@ k_sweep_deep(SweepArgs a, const int* __restrict__ deep_list, const int* __restri
       long long cc = ((long long)ll * g.ny + yy) * g.nz + zz;
       nb = cs[cc]; ne = cs[cc + 1];
     }
-    double last_id = -1.0;
-    for (int j = 0; j < end - beg; j++) {
-      int sel = beg;
-      double best = 1e300;
-      for (int k = beg; k < end; k++) {
-        double id = pos[k].w;
-        if (id > last_id && id < best) { best = id; sel = k; }
-      }
-      last_id = best;
-      if (j < 2) continue;     // trials 0 and 1 were done by the tile kernel
-      const double4 p = pos[sel];
+    const int beg = __shfl_sync(FULL, nb, 13), end = __shfl_sync(FULL, ne, 13);
+    if (end - beg > 32) {      // more particles than lanes (only with very wide cells): generic path
+      if (lane == 0) cell_update_global<LOG>(a, pos, rel, cs, l, iy, iz, 2, 1 << 30, n_acc, n_ov, n_cell, log, nlog, logcap);
+      __syncwarp();
+      continue;
+    }
+    const int n = end - beg;
+    if (lane == 13) ne = nb;                         // the own cell is handled through `own`
+    // round trip 2: own particles + cached neighbours
+    double4 own = make_double4(0, 0, 0, 1e300);
+    if (lane < n) own = pos[beg + lane];
+    double4 q[DEEP_CACHE];
+#pragma unroll
+    for (int s = 0; s < DEEP_CACHE; s++) q[s] = (nb + s < ne) ? pos[nb + s] : make_double4(1e30, 1e30, 1e30, 0);
+    // rank of this lane's own particle in ascending-id order
+    int rank = 0;
+    for (int k = 0; k < n; k++) {
+      double idk = __shfl_sync(FULL, own.w, k);
+      rank += (idk < own.w) ? 1 : 0;
+    }
+    for (int j = 2; j < n; j++) {
+      const int src = __ffs(__ballot_sync(FULL, lane < n && rank == j)) - 1;   // lane holding trial j's particle
+      const double px = __shfl_sync(FULL, own.x, src), py = __shfl_sync(FULL, own.y, src);
+      const double pz = __shfl_sync(FULL, own.z, src), pw = __shfl_sync(FULL, own.w, src);
       Philox4 rn = philox4x32_10((uint32_t)gcell, (HSMC_STREAM_MOVE << 24) | (uint32_t)j, a.sweep_lo, a.sweep_hi,
                                  a.key0, a.key1);
-      double xn = p.x + (hsmc_u01(rn.v[0]) - 0.5) * a.dr_max;
-      double yn = p.y + (hsmc_u01(rn.v[1]) - 0.5) * a.dr_max;
-      double zn = p.z + (hsmc_u01(rn.v[2]) - 0.5) * a.dr_max;
+      double xn = px + (hsmc_u01(rn.v[0]) - 0.5) * a.dr_max;
+      double yn = py + (hsmc_u01(rn.v[1]) - 0.5) * a.dr_max;
+      double zn = pz + (hsmc_u01(rn.v[2]) - 0.5) * a.dr_max;
       if (xn > g.Lx) xn -= g.Lx; else if (xn < 0.0) xn += g.Lx;
       if (yn > g.Ly) yn -= g.Ly; else if (yn < 0.0) yn += g.Ly;
       if (zn > g.Lz) zn -= g.Lz; else if (zn < 0.0) zn += g.Lz;
@@ -469,30 +486,33 @@ k_sweep_deep(SweepArgs a, const int* __restrict__ deep_list, const int* __restri
         if (lane == 0) n_cell++;
       } else {
         bool ov = false;
-        for (int k = nb; k < ne; k++) {
-          if (k == sel) continue;
-          double4 q = pos[k];
-          ov |= pair_r2(xn, yn, zn, q.x, q.y, q.z, a.box) < 1.0;
+        if (lane < n && lane != src) ov = pair_r2(xn, yn, zn, own.x, own.y, own.z, a.box) < 1.0;
+#pragma unroll
+        for (int s = 0; s < DEEP_CACHE; s++)
+          ov |= (nb + s < ne) && pair_r2(xn, yn, zn, q[s].x, q[s].y, q[s].z, a.box) < 1.0;
+        for (int k = nb + DEEP_CACHE; k < ne; k++) {                 // rare: a neighbour cell with > 4 particles
+          double4 qq = pos[k];
+          ov |= pair_r2(xn, yn, zn, qq.x, qq.y, qq.z, a.box) < 1.0;
         }
-        if (__any_sync(0xffffffffu, ov)) {
+        if (__any_sync(FULL, ov)) {
           verdict = 1;
           if (lane == 0) n_ov++;
         } else {
           verdict = 0;
-          if (lane == 0) {
-            n_acc++;
-            pos[sel] = make_double4(xn, yn, zn, p.w);
-            rel[sel] = make_rel(g, gx, iy, iz, xn, yn, zn, p.w);
+          if (lane == 0) n_acc++;
+          if (lane == src) {
+            own.x = xn; own.y = yn; own.z = zn;
+            pos[beg + src] = own;
+            rel[beg + src] = make_rel(g, gx, iy, iz, xn, yn, zn, pw);
           }
         }
-        __syncwarp();
       }
       if (LOG && lane == 0) {
         unsigned long long s = atomicAdd(nlog, 1ull);
         if ((long long)s < logcap) {
           hsmc_gpu_trial tr;
           tr.seq = ((unsigned long long)a.phase << 56) | ((unsigned long long)gcell << 8) | (unsigned)j;
-          tr.id = (int)p.w; tr.verdict = verdict;
+          tr.id = (int)pw; tr.verdict = verdict;
           tr.raw[0] = rn.v[0]; tr.raw[1] = rn.v[1]; tr.raw[2] = rn.v[2]; tr.pad = 0;
           log[s] = tr;
         }
@@ -505,23 +525,4 @@ k_sweep_deep(SweepArgs a, const int* __restrict__ deep_list, const int* __restri
     if (n_ov) atomicAdd(&cnt[CNT_REJ_OVERLAP], (unsigned long long)n_ov);
     if (n_cell) atomicAdd(&cnt[CNT_REJ_CELL], (unsigned long long)n_cell);
   }
-}
-
-// cells with >= 3 particles, listed per colour (built right after the counting sort)
-__global__ void k_deep_lists(Grid g, const int* __restrict__ cs, int* __restrict__ deep_list,
-                             int* __restrict__ deep_count, int list_stride, int* __restrict__ flags) {
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long per = (long long)g.ny * g.nz;
-  long long total = (long long)(g.own_hi - g.own_lo) * per;
-  if (t >= total) return;
-  long long c = (long long)g.own_lo * per + t;
-  if (cs[c + 1] - cs[c] < 3) return;
-  int iz = (int)(c % g.nz);
-  long long r = c / g.nz;
-  int iy = (int)(r % g.ny), l = (int)(r / g.ny);
-  int gx = g.gx0 + l;
-  int colour = ((gx & 1) << 2) | ((iy & 1) << 1) | (iz & 1);
-  int s = atomicAdd(&deep_count[colour], 1);
-  if (s < list_stride) deep_list[(long long)colour * list_stride + s] = (int)c;
-  else atomicOr(flags, 8);
 }
