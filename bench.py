@@ -228,6 +228,7 @@ def main():
         "N": N, "rho": RHO, "dr_max": DR_MAX, "sweeps_per_step": args.sweeps_per_step,
         "regrid_interval": args.regrid, "positions": "double4 {x,y,z,id}, cell-ordered",
     }
+    workload_extra = {}
 
     if args.impl == "reference":
         if rank != 0:
@@ -284,6 +285,16 @@ def main():
     box, conf = fcc_lattice(nx, ny, nz, RHO)
     h = hsmc_b200.HsmcGpu(N, box, seed=20261017, device=local_rank, rank=rank, world=world, nccl_id=nccl_id,
                           cell_min=1.0, regrid_interval=args.regrid, sweep_impl=args.sweep_impl)
+    halo = "single GPU"
+    if world > 1:
+        halo = "nccl send/recv"
+        if os.environ.get("HSMC_P2P", "1") == "1":
+            # NVLink peer-to-peer halo path: every rank attaches its neighbours' receive windows
+            blobs = [None] * world
+            dist.all_gather_object(blobs, h.ipc_export())
+            h.ipc_attach(blobs[(rank - 1) % world], blobs[(rank + 1) % world])
+            dist.barrier()
+            halo = "NVLink peer-to-peer windows (kernels store into the neighbour's HBM, sequence flags)"
     h.upload(conf)
     info = h.info()
     del conf
@@ -410,7 +421,7 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(workload, cells=list(info["cells"]), cell_size=list(info["cell_size"]),
                            acceptance=acc, l2="inputs larger than L2" if flush is None else "L2 flushed between steps",
-                           resident_bytes_per_rank=resident, wall_s_timed_region=t_wall, min_r2_after=min_r2),
+                           resident_bytes_per_rank=resident, wall_s_timed_region=t_wall, min_r2_after=min_r2, halo=halo),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(line))

@@ -120,6 +120,12 @@ struct hsmc_gpu {
   int lay[6] = {0, 0, 0, 0, 0, 0};       // slot offsets of layers 0,1,2,nlx-2,nlx-1,nlx (host mirror)
   int* d_lay = nullptr;                  // the same + error flags on the device (slab rebuilds never sync)
   bool lay_valid = true;                 // host mirror current?
+  bool ghost1_stale = false;
+  // NVLink peer-to-peer windows (optional, see hsmc_gpu_ipc_attach)
+  unsigned char* win = nullptr;          // my receive window: [flags | A_l x2 | A_r x2 | B | C]
+  unsigned char *win_left = nullptr, *win_right = nullptr;   // neighbours' windows, mapped
+  bool p2p = false;
+  uint32_t seqA = 0, seqB = 0, seqC = 0; // exchanges issued so far (same on every rank)             // left ghost layer not refreshed since the last odd-x phases
   void* d_sfargs = nullptr;
   TileCfg tile;
   int* deep_list = nullptr;              // [8][deep_stride] cells with >= 3 particles, per colour
@@ -752,6 +758,19 @@ __global__ void k_slab_classify(Grid g, const double4* __restrict__ in, int n, i
   }
 }
 
+// p2p: publish "message seq is complete" to a neighbour's window / wait for a neighbour's
+__global__ void k_flag_post(volatile uint32_t* flag_a, volatile uint32_t* flag_b, uint32_t seq) {
+  __threadfence_system();
+  if (flag_a) *flag_a = seq;
+  if (flag_b) *flag_b = seq;
+  __threadfence_system();
+}
+__global__ void k_flag_wait(volatile uint32_t* flag_a, volatile uint32_t* flag_b, uint32_t seq) {
+  if (flag_a) while ((int32_t)(*flag_a - seq) < 0) __nanosleep(200);
+  if (flag_b) while ((int32_t)(*flag_b - seq) < 0) __nanosleep(200);
+  __threadfence_system();
+}
+
 __global__ void k_halo_headers(double4* send_l, double4* send_r, const int* halo_cnt) {
   send_l[0] = make_double4((double)halo_cnt[0], 0, 0, 0);
   send_r[0] = make_double4((double)halo_cnt[1], 0, 0, 0);
@@ -1022,6 +1041,16 @@ static void setup_tiles(hsmc_gpu* h) {
   h->tile_ok = h->cfg.sweep_impl != 1 && t.cap * 1 <= 65535;
 }
 
+// ---- NVLink peer-to-peer receive window layout (identical on every rank) ----
+static inline size_t win_off_A(const hsmc_gpu* h, int from_right, int parity) {
+  return 256 + ((size_t)(from_right * 2 + parity) * (size_t)h->cap_halo) * sizeof(double4);
+}
+static inline size_t win_off_B(const hsmc_gpu* h) { return 256 + (size_t)4 * h->cap_halo * sizeof(double4); }
+static inline size_t win_off_C(const hsmc_gpu* h) { return win_off_B(h) + (size_t)(h->cap_halo / 2) * sizeof(double4); }
+static inline size_t win_bytes(const hsmc_gpu* h) { return win_off_C(h) + (size_t)(h->cap_halo / 2) * sizeof(double4); }
+static inline volatile uint32_t* win_flag(unsigned char* w, int k) { return reinterpret_cast<volatile uint32_t*>(w) + k; }
+enum { FLAG_A_FROM_LEFT = 0, FLAG_A_FROM_RIGHT = 1, FLAG_B = 2, FLAG_C = 3 };
+
 static inline int left_of(const hsmc_gpu* h) { return (h->cfg.rank + h->cfg.world - 1) % h->cfg.world; }
 static inline int right_of(const hsmc_gpu* h) { return (h->cfg.rank + 1) % h->cfg.world; }
 
@@ -1060,24 +1089,40 @@ static int rebuild(hsmc_gpu* h, const double4* src, int64_t n_in, int rows_layou
   const int* d_range = dev_range ? h->d_lay : nullptr;
   const int64_t n_src = dev_range ? h->cap : n_in;
   CU(cudaMemsetAsync(h->d_halo_cnt, 0, sizeof(int) * 4, h->st));
+  double4 *out_l = h->send_l, *out_r = h->send_r, *in_l = h->recv_l, *in_r = h->recv_r;
+  if (h->p2p) {
+    // messages are written straight into the neighbours' windows (double-buffered by parity)
+    h->seqA++;
+    const int par = h->seqA & 1;
+    out_l = reinterpret_cast<double4*>(h->win_left + win_off_A(h, 1, par));    // I am my left neighbour's right
+    out_r = reinterpret_cast<double4*>(h->win_right + win_off_A(h, 0, par));
+    in_l = reinterpret_cast<double4*>(h->win + win_off_A(h, 0, par));
+    in_r = reinterpret_cast<double4*>(h->win + win_off_A(h, 1, par));
+  }
   if (n_src > 0) {
     k_slab_classify<<<nblk(n_src, T), T, 0, h->st>>>(g, src, (int)n_in, rows_layout, upload_mode, h->key,
-                                                     h->rnk, h->cell_count, h->send_l, h->send_r,
+                                                     h->rnk, h->cell_count, out_l, out_r,
                                                      h->d_halo_cnt, (int)h->cap_halo, d_range);
     h->launches++;
   }
-  k_halo_headers<<<1, 1, 0, h->st>>>(h->send_l, h->send_r, h->d_halo_cnt);
+  k_halo_headers<<<1, 1, 0, h->st>>>(out_l, out_r, h->d_halo_cnt);
   h->launches++;
-  size_t cnt = (size_t)h->cap_halo * 4;
-  NC(ncclGroupStart());
-  NC(ncclSend(h->send_l, cnt, ncclDouble, left_of(h), h->comm, h->st));
-  NC(ncclRecv(h->recv_r, cnt, ncclDouble, right_of(h), h->comm, h->st));
-  NC(ncclSend(h->send_r, cnt, ncclDouble, right_of(h), h->comm, h->st));
-  NC(ncclRecv(h->recv_l, cnt, ncclDouble, left_of(h), h->comm, h->st));
-  NC(ncclGroupEnd());
-  h->nccl_calls += 4;
+  if (h->p2p) {
+    k_flag_post<<<1, 1, 0, h->st>>>(win_flag(h->win_left, FLAG_A_FROM_RIGHT), win_flag(h->win_right, FLAG_A_FROM_LEFT), h->seqA);
+    k_flag_wait<<<1, 1, 0, h->st>>>(win_flag(h->win, FLAG_A_FROM_LEFT), win_flag(h->win, FLAG_A_FROM_RIGHT), h->seqA);
+    h->launches += 2;
+  } else {
+    size_t cnt = (size_t)h->cap_halo * 4;
+    NC(ncclGroupStart());
+    NC(ncclSend(h->send_l, cnt, ncclDouble, left_of(h), h->comm, h->st));
+    NC(ncclRecv(h->recv_r, cnt, ncclDouble, right_of(h), h->comm, h->st));
+    NC(ncclSend(h->send_r, cnt, ncclDouble, right_of(h), h->comm, h->st));
+    NC(ncclRecv(h->recv_l, cnt, ncclDouble, left_of(h), h->comm, h->st));
+    NC(ncclGroupEnd());
+    h->nccl_calls += 4;
+  }
   dim3 gb2(148 * 2, 2);
-  k_recv_count<<<gb2, T, 0, h->st>>>(g, h->recv_l, h->recv_r, (int)h->cap_halo, h->key_halo, h->rnk_halo,
+  k_recv_count<<<gb2, T, 0, h->st>>>(g, in_l, in_r, (int)h->cap_halo, h->key_halo, h->rnk_halo,
                                      h->cell_count, h->d_halo_cnt);
   h->launches++;
   TRY(exclusive_scan(h, h->cell_count, h->ncell, h->cell_start));
@@ -1087,7 +1132,7 @@ static int rebuild(hsmc_gpu* h, const double4* src, int64_t n_in, int rows_layou
                                                       h->d_halo_cnt + 2);
     h->launches++;
   }
-  k_recv_scatter<<<gb2, T, 0, h->st>>>(g, h->recv_l, h->recv_r, (int)h->cap_halo, h->key_halo, h->rnk_halo,
+  k_recv_scatter<<<gb2, T, 0, h->st>>>(g, in_l, in_r, (int)h->cap_halo, h->key_halo, h->rnk_halo,
                                        h->cell_start, dst, h->rel, (int)h->cap, h->d_halo_cnt + 2);
   h->launches++;
   long long per = (long long)g.ny * g.nz;
@@ -1141,10 +1186,46 @@ extern "C" int hsmc_gpu_nccl_id(void* out_id) {
   return 0;
 }
 
+extern "C" int hsmc_gpu_ipc_export(hsmc_gpu* h, void* out_blob) {
+  if (!h || !out_blob) return fail("null argument");
+  if (h->cfg.world < 2) return fail("ipc_export: only meaningful with world > 1");
+  CU(cudaSetDevice(h->cfg.device));
+  if (!h->win) {
+    CU(cudaMalloc(&h->win, win_bytes(h)));
+    CU(cudaMemset(h->win, 0, win_bytes(h)));
+  }
+  cudaIpcMemHandle_t mh;
+  CU(cudaIpcGetMemHandle(&mh, h->win));
+  static_assert(sizeof(cudaIpcMemHandle_t) == HSMC_GPU_IPC_BYTES, "ipc handle size");
+  memcpy(out_blob, &mh, sizeof(mh));
+  return 0;
+}
+
+extern "C" int hsmc_gpu_ipc_attach(hsmc_gpu* h, const void* left_blob, const void* right_blob) {
+  if (!h || !left_blob || !right_blob) return fail("null argument");
+  if (!h->win) return fail("ipc_attach: call ipc_export first");
+  if (h->p2p) return fail("ipc_attach: already attached");
+  CU(cudaSetDevice(h->cfg.device));
+  cudaIpcMemHandle_t ml, mr;
+  memcpy(&ml, left_blob, sizeof(ml));
+  memcpy(&mr, right_blob, sizeof(mr));
+  void* pl = nullptr; void* pr = nullptr;
+  CU(cudaIpcOpenMemHandle(&pl, ml, cudaIpcMemLazyEnablePeerAccess));
+  if (memcmp(&ml, &mr, sizeof(ml)) == 0) pr = pl;        // two ranks: both neighbours are the same process
+  else CU(cudaIpcOpenMemHandle(&pr, mr, cudaIpcMemLazyEnablePeerAccess));
+  h->win_left = (unsigned char*)pl;
+  h->win_right = (unsigned char*)pr;
+  h->p2p = true;
+  return 0;
+}
+
 extern "C" int hsmc_gpu_destroy(hsmc_gpu* h) {
   if (!h) return 0;
   cudaSetDevice(h->cfg.device);
   if (h->st) cudaStreamSynchronize(h->st);
+  if (h->win_left) cudaIpcCloseMemHandle(h->win_left);
+  if (h->win_right && h->win_right != h->win_left) cudaIpcCloseMemHandle(h->win_right);
+  if (h->win) cudaFree(h->win);
   if (h->comm) ncclCommDestroy(h->comm);
   void* ptrs[] = {h->pos[0], h->pos[1], h->rel, h->key, h->rnk, h->cell_count, h->cell_start, h->bsum, h->d_cnt,
                   h->d_scratch, h->d_slot_of_id, h->d_io, h->send_l, h->send_r, h->recv_l, h->recv_r,
@@ -1303,6 +1384,7 @@ extern "C" int hsmc_gpu_upload(hsmc_gpu* h, const double* rows, int64_t n_rows) 
   if (n_rows < 0 || n_rows > h->N) return fail("upload: bad row count");
   TRY(ensure_io(h, std::max<int64_t>(n_rows, 1)));
   CU(cudaMemcpyAsync(h->d_io, rows, sizeof(double) * 4 * (size_t)n_rows, cudaMemcpyHostToDevice, h->st));
+  h->ghost1_stale = false;
   TRY(rebuild(h, reinterpret_cast<const double4*>(h->d_io), n_rows, 1, 1));
   TRY(sync_layout(h));
   h->have_conf = true;
@@ -1358,12 +1440,24 @@ static int halo_refresh(hsmc_gpu* h, int cx) {
   double4* sbuf = (cx == 0) ? h->send_l : h->send_r;
   double4* rbuf = (cx == 0) ? h->recv_r : h->recv_l;
   const int to = (cx == 0) ? left_of(h) : right_of(h), from = (cx == 0) ? right_of(h) : left_of(h);
-  k_halo_pack<<<148, 256, 0, h->st>>>(g, p, h->cell_start, src_layer, sbuf, cap_msg, h->d_lay + 8);
-  NC(ncclGroupStart());
-  NC(ncclSend(sbuf, (size_t)cap_msg * 4, ncclDouble, to, h->comm, h->st));
-  NC(ncclRecv(rbuf, (size_t)cap_msg * 4, ncclDouble, from, h->comm, h->st));
-  NC(ncclGroupEnd());
-  h->nccl_calls += 2;
+  if (h->p2p) {
+    // pack straight into the neighbour's window over NVLink, then flag; consume from my own window
+    uint32_t seq = (cx == 0) ? ++h->seqB : ++h->seqC;
+    unsigned char* peer = (cx == 0) ? h->win_left : h->win_right;
+    sbuf = reinterpret_cast<double4*>(peer + (cx == 0 ? win_off_B(h) : win_off_C(h)));
+    rbuf = reinterpret_cast<double4*>(h->win + (cx == 0 ? win_off_B(h) : win_off_C(h)));
+    k_halo_pack<<<148, 256, 0, h->st>>>(g, p, h->cell_start, src_layer, sbuf, cap_msg, h->d_lay + 8);
+    k_flag_post<<<1, 1, 0, h->st>>>(win_flag(peer, cx == 0 ? FLAG_B : FLAG_C), nullptr, seq);
+    k_flag_wait<<<1, 1, 0, h->st>>>(win_flag(h->win, cx == 0 ? FLAG_B : FLAG_C), nullptr, seq);
+    h->launches += 2;
+  } else {
+    k_halo_pack<<<148, 256, 0, h->st>>>(g, p, h->cell_start, src_layer, sbuf, cap_msg, h->d_lay + 8);
+    NC(ncclGroupStart());
+    NC(ncclSend(sbuf, (size_t)cap_msg * 4, ncclDouble, to, h->comm, h->st));
+    NC(ncclRecv(rbuf, (size_t)cap_msg * 4, ncclDouble, from, h->comm, h->st));
+    NC(ncclGroupEnd());
+    h->nccl_calls += 2;
+  }
   k_halo_unpack<<<nblk(per, 128), 128, 0, h->st>>>(g, p, h->rel, h->cell_start, dst_layer, rbuf, h->d_lay + 8);
   h->launches += 2;
   CU(cudaGetLastError());
@@ -1374,7 +1468,17 @@ static int halo_refresh(hsmc_gpu* h, int cx) {
   return 0;
 }
 
+// make the ghost layers current (no-op unless a refresh was deferred)
+static int fresh_ghosts(hsmc_gpu* h) {
+  if (h->cfg.world > 1 && h->ghost1_stale) {
+    h->ghost1_stale = false;
+    TRY(halo_refresh(h, 1));
+  }
+  return 0;
+}
+
 static int do_regrid(hsmc_gpu* h) {
+  h->ghost1_stale = false;   // the rebuild's exchange refreshes both ghost layers
   draw_shift(h);
   if (h->cfg.world > 1) return rebuild(h, h->pos[h->cur], 0, 0, 0, true);
   return rebuild(h, h->pos[h->cur], h->N, 0, 0);
@@ -1427,7 +1531,13 @@ static int sweep_once(hsmc_gpu* h, double dr_max, bool logged) {
       // ghosts of parity cx are read only by phases of the other parity: one refresh
       // after the last phase of each parity is enough
       if (ph == 3) TRY(halo_refresh(h, 0));
-      if (ph == 7) TRY(halo_refresh(h, 1));
+      // the odd-parity boundary layer is read next by phases 0-3 of the FOLLOWING sweep; when
+      // that sweep regrids first, its exchange rebuilds the ghost layers anyway, so the refresh
+      // is deferred until somebody needs current ghosts (observables, end of the call)
+      if (ph == 7) {
+        if (h->since_regrid % h->cfg.regrid_interval == 0) h->ghost1_stale = true;
+        else TRY(halo_refresh(h, 1));
+      }
     }
   }
   CU(cudaGetLastError());
@@ -1442,6 +1552,7 @@ extern "C" int hsmc_gpu_sweep_nvt(hsmc_gpu* h, int n_sweeps, double dr_max) {
     return fail("sweep: dr_max out of range");
   CU(cudaSetDevice(h->cfg.device));
   for (int s = 0; s < n_sweeps; s++) TRY(sweep_once(h, dr_max, false));
+  TRY(fresh_ghosts(h));
   return sync_layout(h);
 }
 
@@ -1457,6 +1568,7 @@ extern "C" int hsmc_gpu_sweep_nvt_logged(hsmc_gpu* h, double dr_max, hsmc_gpu_tr
   }
   CU(cudaMemsetAsync(h->d_scratch, 0, sizeof(unsigned long long), h->st));
   TRY(sweep_once(h, dr_max, true));
+  TRY(fresh_ghosts(h));
   unsigned long long* hs = (unsigned long long*)h->h_stage;
   CU(cudaMemcpyAsync(hs, h->d_scratch, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->st));
   CU(cudaStreamSynchronize(h->st));

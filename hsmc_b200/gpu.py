@@ -18,7 +18,7 @@ NCCL_ID_BYTES = 128
 # every symbol include/hsmc_gpu.h declares
 ABI_SYMBOLS = [
     "hsmc_gpu_last_error", "hsmc_gpu_device_count", "hsmc_gpu_nccl_id", "hsmc_gpu_create",
-    "hsmc_gpu_destroy", "hsmc_gpu_get_info", "hsmc_gpu_plan", "hsmc_gpu_stream", "hsmc_gpu_sync", "hsmc_gpu_upload",
+    "hsmc_gpu_destroy", "hsmc_gpu_ipc_export", "hsmc_gpu_ipc_attach", "hsmc_gpu_get_info", "hsmc_gpu_plan", "hsmc_gpu_stream", "hsmc_gpu_sync", "hsmc_gpu_upload",
     "hsmc_gpu_download", "hsmc_gpu_download_owned", "hsmc_gpu_sweep_nvt", "hsmc_gpu_overlap_scaled",
     "hsmc_gpu_rescale", "hsmc_gpu_widom", "hsmc_gpu_rdf_counts", "hsmc_gpu_contact_counts",
     "hsmc_gpu_presst_flags", "hsmc_gpu_counters", "hsmc_gpu_reset_counters", "hsmc_gpu_add_vol_move",
@@ -70,6 +70,8 @@ def load_library():
     L.hsmc_gpu_nccl_id.argtypes = [vp]
     L.hsmc_gpu_create.argtypes = [C.POINTER(vp), C.POINTER(_Config), C.c_int64, dp]
     L.hsmc_gpu_destroy.argtypes = [vp]
+    L.hsmc_gpu_ipc_export.argtypes = [vp, vp]
+    L.hsmc_gpu_ipc_attach.argtypes = [vp, vp, vp]
     L.hsmc_gpu_get_info.argtypes = [vp, C.POINTER(_Info)]
     L.hsmc_gpu_plan.argtypes = [dp, C.c_double, C.c_int, C.c_int, C.POINTER(_Info)]
     L.hsmc_gpu_stream.restype = vp
@@ -161,6 +163,17 @@ class HsmcGpu:
         self.close()
 
     # ---- plumbing ----
+    def ipc_export(self):
+        """Opaque 64-byte description of this rank's NVLink receive window."""
+        buf = C.create_string_buffer(64)
+        self._ck(self.L.hsmc_gpu_ipc_export(self.h, buf))
+        return buf.raw
+
+    def ipc_attach(self, left_blob, right_blob):
+        """Map the neighbours' windows: halo traffic then goes peer-to-peer over NVLink."""
+        lb, rb = C.create_string_buffer(left_blob, 64), C.create_string_buffer(right_blob, 64)
+        self._ck(self.L.hsmc_gpu_ipc_attach(self.h, lb, rb))
+
     def info(self):
         i = _Info()
         self._ck(self.L.hsmc_gpu_get_info(self.h, C.byref(i)))

@@ -71,6 +71,17 @@ int hsmc_gpu_nccl_id(void *out_id /* HSMC_GPU_NCCL_ID_BYTES */);
 int hsmc_gpu_create(hsmc_gpu **out, const hsmc_gpu_config *cfg, int64_t n_particles,
                     const double box[3]);
 
+/* Optional NVLink peer-to-peer halo path (world > 1, one process per GPU on one node).
+   Every rank exports an opaque blob (HSMC_GPU_IPC_BYTES) describing its receive window, the
+   launcher gathers the blobs, and each rank attaches its left and right neighbours' blobs.
+   After that the migration/ghost messages of the cell-list rebuild and the boundary-layer
+   refreshes are written by the producing kernels straight into the neighbour's HBM over
+   NVLink (exact sizes, no NCCL launch), ordered by sequence flags; NCCL is only used for
+   the all-reduces.  Without attach the same exchanges go through ncclSend/ncclRecv. */
+#define HSMC_GPU_IPC_BYTES 64
+int hsmc_gpu_ipc_export(hsmc_gpu *h, void *out_blob);
+int hsmc_gpu_ipc_attach(hsmc_gpu *h, const void *left_blob, const void *right_blob);
+
 /* Replaces cell_list_free (cell_list.c:83-90; nvt.c:99, npt.c:101). */
 int hsmc_gpu_destroy(hsmc_gpu *h);
 

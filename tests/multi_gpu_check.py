@@ -36,6 +36,12 @@ def main():
     N = conf.shape[0]
     ok = True
     with hsmc_b200.HsmcGpu(N, box, seed=seed, device=lr, rank=rank, world=world, nccl_id=ids[0]) as h:
+        if os.environ.get("HSMC_CHECK_P2P", "1") == "1":
+            # NVLink peer-to-peer halo path: gather every rank's window blob, attach the neighbours'
+            blobs = [None] * world
+            dist.all_gather_object(blobs, h.ipc_export())
+            h.ipc_attach(blobs[(rank - 1) % world], blobs[(rank + 1) % world])
+            dist.barrier()
         h.upload(conf)
         info0 = h.info()
         h.sweep_nvt(sweeps, dr_max)
@@ -81,7 +87,8 @@ def main():
         for k, v in checks.items():
             print(f"{k}: {'ok' if v else 'MISMATCH'}", flush=True)
             ok &= bool(v)
-        print("MULTI_GPU_CHECK", "PASS" if ok else "FAIL", f"world={world} N={N}", flush=True)
+        print("MULTI_GPU_CHECK", "PASS" if ok else "FAIL", f"world={world} N={N}",
+              "halo=" + ("p2p" if os.environ.get("HSMC_CHECK_P2P", "1") == "1" else "nccl"), flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
