@@ -1011,34 +1011,55 @@ static int exclusive_scan(hsmc_gpu* h, const int* in, int64_t n, int* out) {
 }
 
 // tile shape of the staged sweep kernel for the current grid / density
+// Tile shape of the staged sweep kernel for the current grid / density: among the shapes
+// that fit shared memory, the one with the fewest "CTA waves x (fixed prologue + cells)"
+// over the 148 SMs -- keeps partial tiles and a ragged last wave from wasting the machine
+// when a rank's slab is small.
 static void setup_tiles(hsmc_gpu* h) {
   Grid& g = h->g;
   TileCfg& t = h->tile;
-  int hx = (g.own_hi - g.own_lo) / 2, hy = g.ny / 2, hz = g.nz / 2;
-  auto fit = [](int amax, int n_cells, int half) {
+  const int hx = (g.own_hi - g.own_lo) / 2, hy = g.ny / 2, hz = g.nz / 2;
+  const double nbar = (double)h->N / ((double)g.nx * g.ny * g.nz);
+  double capf = 1.05;   // head-room over the mean region population; a denser tile takes the global-memory path
+  int az_max = TILE_MAX_AZ, force_az = 0;
+  if (const char* e = getenv("HSMC_TILE_AZ")) { force_az = std::max(1, std::min(TILE_MAX_AZ, atoi(e))); }   // tuning knobs
+  if (const char* e = getenv("HSMC_TILE_CAPF")) capf = atof(e);
+  auto lim = [](int amax, int n_cells, int half) {       // region (2a+1 cells) must not wrap onto itself
     int a = std::min(amax, std::max(1, (n_cells - 1) / 2));
     return std::min(a, std::max(1, half));
   };
-  t.ax = fit(TILE_MAX_A, g.wrap_x ? g.nx : g.nlx, hx);
-  t.ay = fit(TILE_MAX_A, g.ny, hy);
-  t.az = fit(TILE_MAX_AZ, g.nz, hz);
-  double capf = 1.05;   // head-room over the mean region population; a denser tile takes the global-memory path
-  if (const char* e = getenv("HSMC_TILE_AZ")) t.az = std::max(1, std::min(t.az, atoi(e)));      // tuning knobs (bench/ablation)
-  if (const char* e = getenv("HSMC_TILE_CAPF")) capf = atof(e);
-  double nbar = (double)h->N / ((double)g.nx * g.ny * g.nz);
-  const int cap_max = 2240;   // ~35 KB of staged shadow entries: four CTAs per SM
-  for (;;) {
-    double region = (2.0 * t.ax + 1) * (2.0 * t.ay + 1) * (2.0 * t.az + 1);
-    int want = (int)(region * nbar * capf) + 64;
-    if (want <= cap_max || t.az == 1) { t.cap = std::min(std::max(want, 256), cap_max); break; }
-    t.az = std::max(1, t.az / 2);
-  }
-  t.cap = (t.cap + 31) & ~31;
+  const int ax_max = lim(TILE_MAX_A, g.wrap_x ? g.nx : g.nlx, hx), ay_max = lim(TILE_MAX_A, g.ny, hy);
+  az_max = lim(az_max, g.nz, hz);
+  const int cap_max = 2240;
+  double best_cost = 1e300;
+  int bx = 1, by = 1, bz = 1, bcap = 256;
+  for (int ax = 1; ax <= ax_max; ax++)
+    for (int ay = 1; ay <= ay_max; ay++)
+      for (int az = (force_az ? std::min(force_az, az_max) : 1); az <= (force_az ? std::min(force_az, az_max) : az_max); az++) {
+        double region = (2.0 * ax + 1) * (2.0 * ay + 1) * (2.0 * az + 1);
+        int cap = ((int)(region * nbar * capf) + 64 + 31) & ~31;
+        if (cap > cap_max) continue;
+        cap = std::max(cap, 256);
+        size_t smem = (size_t)cap * 16 + (size_t)(2 * ax + 1) * (2 * ay + 1) * (((2 * az + 2 + 3 + 3) & ~3)) * 4 + 3072 + 1024;
+        int per_sm = std::max(1, std::min(5, (int)((size_t)227 * 1024 / smem)));
+        long long tiles = (long long)((hx + ax - 1) / ax) * ((hy + ay - 1) / ay) * ((hz + az - 1) / az);
+        long long waves = (tiles + 148LL * per_sm - 1) / (148LL * per_sm);
+        // time of one CTA ~ fixed prologue (about 100 cell-equivalents) + its cells, shared by the
+        // per_sm CTAs of an SM
+        double cost = (double)waves * (100.0 + (double)ax * ay * az) * per_sm / 5.0;
+        // the largest shape is the measured optimum on big grids: smaller ones must beat it by 10 %
+        if (!(ax == ax_max && ay == ay_max && az == az_max)) cost *= 1.1;
+        if (cost < best_cost) { best_cost = cost; bx = ax; by = ay; bz = az; bcap = cap; }
+      }
+  t.ax = bx; t.ay = by; t.az = bz; t.cap = bcap;
   t.ntx = (hx + t.ax - 1) / t.ax; t.nty = (hy + t.ay - 1) / t.ay; t.ntz = (hz + t.az - 1) / t.az;
   t.use_tma = (h->cfg.sweep_impl == 2) ? 0 : 1;
   t.cs_stride = (2 * t.az + 2 + 3 + 3) & ~3;
-  h->tile_smem = (size_t)t.cap * 16 + (size_t)TILE_MAX_ROWS * t.cs_stride * sizeof(int);
+  h->tile_smem = (size_t)t.cap * 16 + (size_t)(2 * t.ax + 1) * (2 * t.ay + 1) * t.cs_stride * sizeof(int);
   h->tile_ok = h->cfg.sweep_impl != 1 && t.cap * 1 <= 65535;
+  if (getenv("HSMC_DEBUG_TILES"))
+    fprintf(stderr, "[hsmc_gpu] rank %d: active lattice %dx%dx%d, tile %dx%dx%d, %d tiles/phase, cap %d, smem %zu B\n", h->cfg.rank,
+            hx, hy, hz, t.ax, t.ay, t.az, t.ntx * t.nty * t.ntz, t.cap, h->tile_smem);
 }
 
 // ---- NVLink peer-to-peer receive window layout (identical on every rank) ----
