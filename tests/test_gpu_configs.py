@@ -1,0 +1,128 @@
+"""BASELINE.json configurations 1-3 run end to end through the C host driver on the GPU
+(short versions: the point is that every shape, keyword and code path works and keeps the
+hard-sphere invariants; speed is bench.py's business, statistics test_gpu_stat.py's)."""
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from hsmc_outputs import collect
+
+pytestmark = pytest.mark.gpu
+EXE = os.path.join(ROOT, "hsmc_b200", "host", "hsmc_b200")
+
+CONFIG1 = """# config 1: the `hsmc -e` example shape (SC, N=1000, rho 0.5), neigh_list 1.05 (SURVEY 0.10)
+rho 0.5
+cells_x 10
+cells_y 10
+cells_z 10
+type 1
+neigh_list 1.05 10
+dr_max 0.05
+opt 1 200 10 0.5 0.5
+press_virial 0.002 10
+seed 124787
+restart_write 200
+config_write 200 100
+sweep_eq 300
+sweep_stat 400
+out 100
+"""
+
+CONFIG2 = """# config 2: NVT rho 0.9, N = 32000, pressure + rdf + widom
+rho 0.9
+cells_x 20
+cells_y 20
+cells_z 20
+type 2
+neigh_list 1.05 10
+dr_max 0.1
+opt 1 100 10 0.5 0.5
+press_virial 0.002 20
+press_thermo 0.0001 0.002 20
+rdf 0.01 5.0 50 100
+widom 1000 20
+seed 7
+sweep_eq 100
+sweep_stat 200
+out 50
+"""
+
+CONFIG3 = """# config 3: NpT P = 10 from rho 0.94, N = 108000
+npt 10 0.001
+rho 0.94
+cells_x 30
+cells_y 30
+cells_z 30
+type 2
+neigh_list 1.1 12
+dr_max 0.05
+opt 0 100 10 0.5 0.5
+press_thermo 0.0001 0.002 20
+seed 99
+sweep_eq 60
+sweep_stat 100
+out 20
+"""
+
+
+def _run(text):
+    d = tempfile.mkdtemp(prefix="hsmc_b200_cfg_")
+    with open(os.path.join(d, "in.dat"), "w") as f:
+        f.write(text)
+    r = subprocess.run([EXE, "-o", "out.txt"], cwd=d, capture_output=True, text=True, timeout=900)
+    log = open(os.path.join(d, "out.txt")).read() if os.path.exists(os.path.join(d, "out.txt")) else ""
+    assert r.returncode == 0 and "Simulation complete!" in log, (r.stdout + r.stderr + log)[-3000:]
+    return d, log
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built(lib_built):
+    if lib_built.load_library().hsmc_gpu_device_count() < 1:
+        pytest.fail("no CUDA device visible")
+    from hsmc_b200 import build
+    build.build_host()
+
+
+def test_config1_example_shape():
+    d, log = _run(CONFIG1)
+    assert "Number of particles: 1000" in log and "Optimal maximum displacement:" in log
+    obs = collect(d)
+    assert obs["g_contact"].shape[0] == 40                       # sweeps 300..699 sampled every 10
+    assert abs(obs["g_contact"].mean() - 2.16) < 0.25            # Carnahan-Starling at rho 0.5
+    # restart file: the reference's byte layout (16 + 64 + 8 + N*32 + 5000) + 16 bytes of Philox state
+    rs = [f for f in os.listdir(d) if f.startswith("restart_")]
+    assert rs and os.path.getsize(os.path.join(d, sorted(rs)[-1])) == 16 + 64 + 8 + 1000 * 32 + 5000 + 16
+    assert os.path.exists(os.path.join(d, "config_000000.dat.gz"))
+
+
+def test_config2_nvt_32000():
+    d, log = _run(CONFIG2)
+    assert "Number of particles: 32000" in log
+    obs = collect(d)
+    assert obs["g_contact"].shape[0] == 10 and obs["presst_h"].shape == (10, 20)
+    assert obs["rdf_g"].shape[0] == 4 and obs["widom_frac"].shape[0] == 10
+    assert np.all(obs["rdf_g"] >= 0) and obs["rdf_g"][:, 0].mean() > 3.0      # g(1+) of a dense fluid/solid
+    moves = float(log.split("-- Particle moves:")[1].split()[0])
+    assert moves == 300 * 32000
+
+
+def test_config3_npt_108000():
+    d, log = _run(CONFIG3)
+    assert "Number of particles: 108000" in log and "Pressure: 10.00000000" in log
+    obs = collect(d)
+    assert obs["density"].shape[0] == 5
+    assert np.all((obs["density"] > 0.85) & (obs["density"] < 1.0))
+    vol_moves = float(log.split("-- Volume moves:")[1].split()[0])
+    assert 100 < vol_moves < 250                                  # about one per sweep
+
+
+def test_restart_round_trip():
+    d, log = _run(CONFIG1)
+    rs = sorted(f for f in os.listdir(d) if f.startswith("restart_"))
+    text = CONFIG1.replace("opt 1 200 10 0.5 0.5", "opt 0 200 10 0.5 0.5") + f"restart_read 1 {os.path.join(d, rs[-1])}\n"
+    d2, log2 = _run(text)
+    assert "Reading data from restart file" in log2 and "Number of particles: 1000" in log2
