@@ -42,7 +42,7 @@ def nvcc_path():
 
 
 def build_lib(force=False, verbose=False):
-    srcs = [os.path.join(CSRC, f) for f in ("hsmc_gpu.cu", "geom.cuh", "philox.cuh")]
+    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))]
     srcs.append(os.path.join(ROOT, "include", "hsmc_gpu.h"))
     if not force and _newer(LIB, srcs):
         return LIB

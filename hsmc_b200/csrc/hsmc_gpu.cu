@@ -80,8 +80,26 @@ struct TileCfg {
   int cs_stride;           // ints per staged CSR row
 };
 
+// block-resident sweep (sweep_block.cuh)
+struct BlockCfg {
+  int nbx, nby, nbz;      // blocks per axis (even); x: over the layers this rank owns
+  int mbx, mby, mbz;      // largest block extent per axis (cells)
+  int cap;                // staged shadow capacity (float4 entries, pad included)
+  int cs_stride;          // ints per raw (TMA'd) CSR row
+  int cz_stride;          // ushorts per compact CSR row
+  int max_rows;           // (mbx+2)*(mby+2)
+  int use_tma;
+  int force_global;       // ablation: every block takes the global-memory path (same chain)
+};
+
+// cfg.sweep_impl: low byte = kernel variant, next byte = virtual world of the x block partition
+enum { IMPL_BLOCK = 0, IMPL_CELL_GLOBAL = 1, IMPL_TILE_LDG = 2, IMPL_EPS0 = 3, IMPL_TILE_TMA = 4,
+       IMPL_BLOCK_GLOBAL = 5, IMPL_BLOCK_LDG = 6 };
+
 struct hsmc_gpu {
   hsmc_gpu_config cfg;
+  int impl = 0;            // cfg.sweep_impl & 0xff
+  int xpart_world = 0;     // (cfg.sweep_impl >> 8) & 0xff; 0 = cfg.world
   int64_t N = 0;           // global particle count
   int64_t n_local = 0;     // resident particles (owned + ghosts)
   int64_t n_owned = 0;
@@ -133,6 +151,14 @@ struct hsmc_gpu {
   int64_t deep_stride = 0;
   size_t tile_smem = 0;
   bool tile_ok = false;
+  BlockCfg blk;
+  size_t blk_smem = 0;
+  bool blk_ok = false;
+  float blk_eps = 0.f;
+  std::vector<int> xoff;                 // x block boundaries (local layers), blk.nbx + 1 entries
+  int* d_xoff = nullptr;
+  int64_t cap_xoff = 0;
+  bool xoff_dirty = true;
   hsmc_gpu_trial* d_log = nullptr;
   int64_t cap_log = 0;
   // optional event timing
@@ -346,7 +372,7 @@ struct SweepArgs {
 // all trials of one active cell straight from global memory (generic path: any grid,
 // minimum image always evaluated)
 template <bool LOG>
-__device__ __forceinline__ void cell_update_global(const SweepArgs& a, double4* __restrict__ pos,
+__device__ __forceinline__ void cell_update_global(const SweepArgs& a, int phase, double4* __restrict__ pos,
                                                    float4* __restrict__ rel, const int* __restrict__ cs, int l,
                                                    int iy, int iz, int j0, int j1, int& n_acc,
                                                    int& n_ov, int& n_cell, hsmc_gpu_trial* __restrict__ log,
@@ -408,7 +434,7 @@ __device__ __forceinline__ void cell_update_global(const SweepArgs& a, double4* 
       unsigned long long s = atomicAdd(nlog, 1ull);
       if ((long long)s < logcap) {
         hsmc_gpu_trial tr;
-        tr.seq = ((unsigned long long)a.phase << 56) | ((unsigned long long)gcell << 8) | (unsigned)j;
+        tr.seq = ((unsigned long long)phase << 56) | ((unsigned long long)gcell << 8) | (unsigned)j;
         tr.id = (int)p.w; tr.verdict = verdict;
         tr.raw[0] = rn.v[0]; tr.raw[1] = rn.v[1]; tr.raw[2] = rn.v[2]; tr.pad = 0;
         log[s] = tr;
@@ -435,7 +461,7 @@ k_sweep_phase(SweepArgs a, double4* __restrict__ pos, float4* __restrict__ rel, 
     int par0 = (g.gx0 + g.own_lo) & 1;
     int l = g.own_lo + 2 * ax + ((a.cx - par0) & 1);
     int iy = 2 * ay + a.cy, iz = 2 * az + a.cz;
-    cell_update_global<LOG>(a, pos, rel, cs, l, iy, iz, 0, 1 << 30, n_acc, n_ov, n_cell, log, nlog, logcap);
+    cell_update_global<LOG>(a, a.phase, pos, rel, cs, l, iy, iz, 0, 1 << 30, n_acc, n_ov, n_cell, log, nlog, logcap);
   }
   // block-aggregated counters
   __shared__ int s_cnt[3];
@@ -457,6 +483,7 @@ k_sweep_phase(SweepArgs a, double4* __restrict__ pos, float4* __restrict__ rel, 
 }
 
 #include "sweep_tile.cuh"
+#include "sweep_block.cuh"
 
 // ----------------------------------------------------------------------------------
 // K3: global scaled-overlap verdict for nsf scale factors in one pass over the pairs.
@@ -921,6 +948,7 @@ static int even_cells(double L, double cell_min) {
 }
 
 static void setup_tiles(hsmc_gpu* h);
+static void setup_blocks(hsmc_gpu* h);
 static int sync_layout(hsmc_gpu* h);
 
 static int setup_grid(hsmc_gpu* h) {
@@ -951,6 +979,7 @@ static int setup_grid(hsmc_gpu* h) {
   h->ncell = (int64_t)g.nlx * g.ny * g.nz;
   if (h->ncell + 1 > (int64_t)INT32_MAX) return fail("too many cells for 32-bit cell indices");
   setup_tiles(h);
+  setup_blocks(h);
   return 0;
 }
 
@@ -1004,7 +1033,8 @@ static int exclusive_scan(hsmc_gpu* h, const int* in, int64_t n, int* out) {
   CU(cudaMemsetAsync(h->deep_count, 0, sizeof(int) * 8, h->st));
   k_scan_blocksum<<<nb, SCAN_T, 0, h->st>>>(in, n, h->bsum);
   k_scan_top<<<1, SCAN_T, 0, h->st>>>(h->bsum, nb);
-  k_scan_final<<<nb, SCAN_T, 0, h->st>>>(in, n, h->bsum, out, h->g, h->deep_list, h->deep_count, (int)h->deep_stride);
+  k_scan_final<<<nb, SCAN_T, 0, h->st>>>(in, n, h->bsum, out, h->g, h->tile_ok ? h->deep_list : nullptr, h->deep_count,
+                                         (int)h->deep_stride);
   h->launches += 3;
   CU(cudaGetLastError());
   return 0;
@@ -1053,13 +1083,131 @@ static void setup_tiles(hsmc_gpu* h) {
       }
   t.ax = bx; t.ay = by; t.az = bz; t.cap = bcap;
   t.ntx = (hx + t.ax - 1) / t.ax; t.nty = (hy + t.ay - 1) / t.ay; t.ntz = (hz + t.az - 1) / t.az;
-  t.use_tma = (h->cfg.sweep_impl == 2) ? 0 : 1;
+  t.use_tma = (h->impl == IMPL_TILE_LDG) ? 0 : 1;
   t.cs_stride = (2 * t.az + 2 + 3 + 3) & ~3;
   h->tile_smem = (size_t)t.cap * 16 + (size_t)(2 * t.ax + 1) * (2 * t.ay + 1) * t.cs_stride * sizeof(int);
-  h->tile_ok = h->cfg.sweep_impl != 1 && t.cap * 1 <= 65535;
+  h->tile_ok = (h->impl == IMPL_TILE_LDG || h->impl == IMPL_TILE_TMA) && t.cap * 1 <= 65535;
   if (getenv("HSMC_DEBUG_TILES"))
     fprintf(stderr, "[hsmc_gpu] rank %d: active lattice %dx%dx%d, tile %dx%dx%d, %d tiles/phase, cap %d, smem %zu B\n", h->cfg.rank,
             hx, hy, hz, t.ax, t.ay, t.az, t.ntx * t.nty * t.ntz, t.cap, h->tile_smem);
+}
+
+
+// ---- block-resident sweep: block shape, x partition, error band ------------------------
+// Even number of blocks per axis, extents differing by at most one cell.  Along x the
+// partition is made slab by slab (every slab gets an even number of blocks) so that a
+// single-GPU run told to use the partition of a W-slab run (sweep_impl bits 8..15) is the
+// same Markov chain as the W-GPU run.
+static int even_blocks(int n_cells, int b) { return 2 * std::max(1, (n_cells + 2 * b - 1) / (2 * b)); }
+
+static void setup_blocks(hsmc_gpu* h) {
+  Grid& g = h->g;
+  BlockCfg& b = h->blk;
+  h->blk_ok = false;
+  h->xoff_dirty = true;
+  const int W = h->cfg.world;
+  const int Wv = (W > 1) ? W : std::max(1, h->xpart_world);
+  const double nbar = (double)h->N / ((double)g.nx * g.ny * g.nz);
+  // x slabs of the (virtual) world: [lo, hi) in global layers
+  std::vector<std::pair<int, int>> slabs;
+  {
+    const int pairs = g.nx / 2;
+    if (Wv > 1 && pairs < 2 * Wv) return;            // cannot honour the requested partition
+    for (int r = 0; r < Wv; r++) {
+      int x0 = 2 * (int)(((long long)pairs * r) / Wv), x1 = 2 * (int)(((long long)pairs * (r + 1)) / Wv);
+      if (W > 1 && r != h->cfg.rank) continue;
+      slabs.push_back({x0, x1});
+    }
+  }
+  int max_slab = 0;
+  for (auto& sl : slabs) max_slab = std::max(max_slab, sl.second - sl.first);
+  double capf = 1.08;
+  if (const char* e = getenv("HSMC_BLOCK_CAPF")) capf = atof(e);
+  int want[3] = {0, 0, 0};
+  if (const char* e = getenv("HSMC_BLOCK")) sscanf(e, "%d,%d,%d", &want[0], &want[1], &want[2]);
+  struct Shape { int bx, by, bz, mx, my, mz, cap; size_t smem; };
+  auto eval = [&](int bx, int by, int bz, Shape& s) -> bool {
+    // a block and its halo must not cover a cell twice: extent + 2 <= cells of the axis
+    int mx = 0;
+    for (auto& sl : slabs) {
+      int n = sl.second - sl.first, nb = even_blocks(n, bx);
+      if (nb > n) return false;
+      mx = std::max(mx, (n + nb - 1) / nb);
+    }
+    int nby = even_blocks(g.ny, by), nbz = even_blocks(g.nz, bz);
+    if (nby > g.ny || nbz > g.nz) return false;
+    int my = (g.ny + nby - 1) / nby, mz = (g.nz + nbz - 1) / nbz;
+    if (mx + 2 > (g.wrap_x ? g.nx : g.nlx) || my + 2 > g.ny || mz + 2 > g.nz) return false;
+    if ((mx + 2) * (my + 2) > std::min(BLK_MAX_ROWS, BLK_THREADS) || mz + 3 > 32 || mx + 2 > 31 || my + 2 > 31) return false;
+    double region = (double)(mx + 2) * (my + 2) * (mz + 2);
+    int cap = ((int)(region * nbar * capf) + 48 + BLK_PAD + 31) & ~31;
+    if (cap > 8192) return false;
+    int cs_stride = (mz + 3 + 3 + 3) & ~3, cz_stride = (mz + 3 + 1) & ~1;
+    size_t smem = (size_t)cap * 16 + (size_t)(mx + 2) * (my + 2) * (cs_stride * 4 + cz_stride * 2);
+    if (smem > 100 * 1024) return false;
+    s = {bx, by, bz, mx, my, mz, cap, smem};
+    return true;
+  };
+  Shape best{};
+  bool have = false;
+  if (want[0] > 0 && want[1] > 0 && want[2] > 0) have = eval(want[0], want[1], want[2], best);
+  if (!have) {
+    // the largest shape whose CTAs still fit four to an SM wins on big grids; on small grids
+    // prefer shapes that give every SM at least two CTAs per phase
+    double best_score = -1.0;
+    const int cand_xy[] = {2, 3, 4, 5, 6, 8}, cand_z[] = {2, 4, 6, 8, 12, 16, 20, 24};
+    for (int bx : cand_xy) for (int by : cand_xy) for (int bz : cand_z) {
+      Shape s;
+      if (!eval(bx, by, bz, s)) continue;
+      long long ctas = 0;
+      for (auto& sl : slabs) ctas += even_blocks(sl.second - sl.first, bx) / 2;
+      ctas *= (long long)(even_blocks(g.ny, by) / 2) * (even_blocks(g.nz, bz) / 2);
+      int per_sm = (int)std::min<size_t>(4, (size_t)(227 * 1024) / (s.smem + 8 * 1024));
+      if (per_sm < 1) continue;
+      double interior = (double)s.mx * s.my * s.mz, region = (double)(s.mx + 2) * (s.my + 2) * (s.mz + 2);
+      // work per CTA in cell-equivalents: prologue + staging + trials; lanes idle when a colour has
+      // fewer non-empty cells than threads
+      double items = interior / 8.0 * std::min(1.0, nbar);
+      double lane_eff = std::min(1.0, items / BLK_THREADS) * 0.8 + 0.2;
+      double work = 60.0 + 0.12 * region + interior / lane_eff;
+      double waves = std::ceil((double)ctas / (148.0 * per_sm));
+      double t = waves * work * per_sm / 4.0 + 0.0;
+      double score = ((double)ctas * interior) / t;
+      if (score > best_score) { best_score = score; best = s; have = true; }
+    }
+  }
+  if (!have) return;
+  b.mbx = best.mx; b.mby = best.my; b.mbz = best.mz; b.cap = best.cap;
+  b.nby = even_blocks(g.ny, best.by); b.nbz = even_blocks(g.nz, best.bz);
+  b.cs_stride = (best.mz + 3 + 3 + 3) & ~3; b.cz_stride = (best.mz + 3 + 1) & ~1;
+  b.max_rows = (best.mx + 2) * (best.my + 2);
+  b.use_tma = (h->impl == IMPL_BLOCK_LDG) ? 0 : 1;
+  b.force_global = (h->impl == IMPL_BLOCK_GLOBAL) ? 1 : 0;
+  h->xoff.clear();
+  for (auto& sl : slabs) {
+    int n = sl.second - sl.first, nb = even_blocks(n, best.bx);
+    int base = (W > 1) ? g.own_lo : sl.first;      // local layer of the slab's first owned layer
+    for (int j = 0; j < nb; j++) h->xoff.push_back(base + (int)(((long long)j * n) / nb));
+  }
+  h->xoff.push_back((W > 1) ? g.own_hi : g.nx);
+  b.nbx = (int)h->xoff.size() - 1;
+  h->blk_smem = best.smem;
+  // fp32 filter error bound: staged coordinates are block-relative,
+  // |X| <= (m/2 + 2) cells; per pair and axis: two final roundings at that magnitude, the
+  // rounding of the cell edge times the <= 2 cells between a stencil pair, two offset
+  // roundings; r2 error <= 2 |d| sum(delta) with |d| <= ~1, plus the fp32 sum itself
+  auto half_ulp = [](double m) { int e; frexp(m, &e); return ldexp(1.0, e - 25); };
+  double mag[3] = {(0.5 * (best.mx + 2) + 1.0) * g.wx, (0.5 * (best.my + 2) + 1.0) * g.wy, (0.5 * (best.mz + 2) + 1.0) * g.wz};
+  double wv[3] = {g.wx, g.wy, g.wz};
+  double sum = 0.0;
+  for (int k = 0; k < 3; k++) sum += 2.0 * half_ulp(mag[k]) + 2.0 * wv[k] * ldexp(1.0, -24) + 2.0 * wv[k] * ldexp(1.0, -25);
+  double r2err = 2.0 * 1.01 * sum + 8.0 * ldexp(1.0, -24);
+  h->blk_eps = (float)(2.0 * r2err);
+  h->blk_ok = (h->impl == IMPL_BLOCK || h->impl == IMPL_EPS0 || h->impl == IMPL_BLOCK_GLOBAL || h->impl == IMPL_BLOCK_LDG);
+  if (getenv("HSMC_DEBUG_TILES"))
+    fprintf(stderr, "[hsmc_gpu] rank %d: blocks %dx%dx%d of up to %dx%dx%d cells, %d CTAs/phase, cap %d, smem %zu B, eps %.3g\n",
+            h->cfg.rank, b.nbx, b.nby, b.nbz, b.mbx, b.mby, b.mbz, (b.nbx / 2) * (b.nby / 2) * (b.nbz / 2), b.cap,
+            h->blk_smem, (double)h->blk_eps);
 }
 
 // ---- NVLink peer-to-peer receive window layout (identical on every rank) ----
@@ -1250,7 +1398,8 @@ extern "C" int hsmc_gpu_destroy(hsmc_gpu* h) {
   if (h->comm) ncclCommDestroy(h->comm);
   void* ptrs[] = {h->pos[0], h->pos[1], h->rel, h->key, h->rnk, h->cell_count, h->cell_start, h->bsum, h->d_cnt,
                   h->d_scratch, h->d_slot_of_id, h->d_io, h->send_l, h->send_r, h->recv_l, h->recv_r,
-                  h->d_halo_cnt, h->d_sfargs, h->d_log, h->key_halo, h->rnk_halo, h->deep_list, h->deep_count, h->d_lay};
+                  h->d_halo_cnt, h->d_sfargs, h->d_log, h->key_halo, h->rnk_halo, h->deep_list, h->deep_count, h->d_lay,
+                  h->d_xoff};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -1277,6 +1426,9 @@ extern "C" int hsmc_gpu_create(hsmc_gpu** out, const hsmc_gpu_config* cfg, int64
   if (n_particles <= 0 || n_particles >= (int64_t)INT32_MAX) return fail("invalid particle count");
   hsmc_gpu* h = new hsmc_gpu();
   h->cfg = *cfg;
+  h->impl = cfg->sweep_impl & 0xff;
+  h->xpart_world = (cfg->sweep_impl >> 8) & 0xff;
+  if (h->impl > IMPL_BLOCK_LDG) { delete h; return fail("unknown sweep_impl variant"); }
   if (h->cfg.cell_min == 0.0) h->cfg.cell_min = 1.0;
   if (h->cfg.cell_min < 1.0) { delete h; return fail("cell_min must be >= 1.0 (the particle diameter)"); }
   if (h->cfg.regrid_interval <= 0) h->cfg.regrid_interval = 1;
@@ -1328,6 +1480,8 @@ extern "C" int hsmc_gpu_create(hsmc_gpu** out, const hsmc_gpu_config* cfg, int64
   if (ensure_cell_arrays(h)) { hsmc_gpu_destroy(h); return 1; }
   CUD(cudaFuncSetAttribute(k_sweep_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
   CUD(cudaFuncSetAttribute(k_sweep_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+  CUD(cudaFuncSetAttribute(k_sweep_block<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+  CUD(cudaFuncSetAttribute(k_sweep_block<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
   if (W > 1) {
     CUD(cudaMalloc(&h->send_l, sizeof(double4) * (size_t)h->cap_halo));
     CUD(cudaMalloc(&h->send_r, sizeof(double4) * (size_t)h->cap_halo));
@@ -1373,6 +1527,7 @@ extern "C" int hsmc_gpu_plan(const double box[3], double cell_min, int world, in
   hsmc_gpu tmp;
   tmp.cfg.device = 0; tmp.cfg.rank = rank; tmp.cfg.world = world; tmp.cfg.nccl_id = nullptr; tmp.cfg.seed = 0;
   tmp.cfg.cell_min = cell_min == 0.0 ? 1.0 : cell_min; tmp.cfg.regrid_interval = 1; tmp.cfg.sweep_impl = 0;
+  tmp.impl = 0; tmp.xpart_world = 0;
   if (tmp.cfg.cell_min < 1.0) return fail("cell_min must be >= 1.0 (the particle diameter)");
   tmp.N = 1;
   tmp.box[0] = box[0]; tmp.box[1] = box[1]; tmp.box[2] = box[2];
@@ -1515,14 +1670,37 @@ static int sweep_once(hsmc_gpu* h, double dr_max, bool logged) {
   a.dr_max = dr_max;
   a.key0 = (uint32_t)h->cfg.seed; a.key1 = (uint32_t)(h->cfg.seed >> 32);
   a.sweep_lo = (uint32_t)h->sweeps_done; a.sweep_hi = (uint32_t)(h->sweeps_done >> 32);
-  a.eps = (h->cfg.sweep_impl == 3) ? 0.0f : 1.0e-5f * (float)std::max(1.0, std::max(g.wx, std::max(g.wy, g.wz)));
+  a.eps = 1.0e-5f * (float)std::max(1.0, std::max(g.wx, std::max(g.wy, g.wz)));
+  if (h->blk_ok) {
+    a.eps = (h->impl == IMPL_EPS0) ? 0.0f : h->blk_eps;
+    if (h->xoff_dirty) {
+      if ((int64_t)h->xoff.size() > h->cap_xoff) {
+        if (h->d_xoff) cudaFree(h->d_xoff);
+        h->cap_xoff = (int64_t)h->xoff.size() + 64;
+        CU(cudaMalloc(&h->d_xoff, sizeof(int) * (size_t)h->cap_xoff));
+      }
+      CU(cudaMemcpyAsync(h->d_xoff, h->xoff.data(), sizeof(int) * h->xoff.size(), cudaMemcpyHostToDevice, h->st));
+      CU(cudaStreamSynchronize(h->st));        // the source is pageable host memory
+      h->xoff_dirty = false;
+    }
+  }
   long long total = (long long)((g.own_hi - g.own_lo) / 2) * (g.ny / 2) * (g.nz / 2);
   const int T = 128;
   for (int ph = 0; ph < 8; ph++) {
     a.cx = (ph >> 2) & 1; a.cy = (ph >> 1) & 1; a.cz = ph & 1; a.phase = ph;
     {
     ProfSpan span(h, 0);
-    if (h->tile_ok) {
+    if (h->blk_ok) {
+      // block phase ph: all blocks of block-index parity (cx,cy,cz); each CTA runs the eight
+      // cell colours of its block
+      const int nb = (h->blk.nbx / 2) * (h->blk.nby / 2) * (h->blk.nbz / 2);
+      if (logged)
+        k_sweep_block<true><<<nb, BLK_THREADS, h->blk_smem, h->st>>>(a, h->blk, h->d_xoff, h->pos[h->cur], h->rel, h->cell_start,
+                                                                      h->d_cnt, h->d_log, h->d_scratch, (long long)h->cap_log);
+      else
+        k_sweep_block<false><<<nb, BLK_THREADS, h->blk_smem, h->st>>>(a, h->blk, h->d_xoff, h->pos[h->cur], h->rel, h->cell_start,
+                                                                       h->d_cnt, nullptr, nullptr, 0);
+    } else if (h->tile_ok) {
       int nb = h->tile.ntx * h->tile.nty * h->tile.ntz;
       int gb = 148 * 4;
       if (logged)

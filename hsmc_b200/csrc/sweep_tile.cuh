@@ -48,12 +48,12 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
 }
 
 template <bool LOG>
-__device__ __noinline__ void cell_update_global_noinline(const SweepArgs& a, double4* __restrict__ pos,
+__device__ __noinline__ void cell_update_global_noinline(const SweepArgs& a, int phase, double4* __restrict__ pos,
                                                          float4* __restrict__ rel, const int* __restrict__ cs, int l,
                                                          int iy, int iz, int j0, int j1, int& n_acc, int& n_ov,
                                                          int& n_cell, hsmc_gpu_trial* __restrict__ log,
                                                          unsigned long long* __restrict__ nlog, long long logcap) {
-  cell_update_global<LOG>(a, pos, rel, cs, l, iy, iz, j0, j1, n_acc, n_ov, n_cell, log, nlog, logcap);
+  cell_update_global<LOG>(a, phase, pos, rel, cs, l, iy, iz, j0, j1, n_acc, n_ov, n_cell, log, nlog, logcap);
 }
 
 #define TILE_SLOTS 7     // padded stencil slots evaluated per row and pass (a z-column of 3 cells holds <= 6 in 99.7 %)
@@ -392,7 +392,7 @@ k_sweep_tile(SweepArgs a, TileCfg tc, double4* __restrict__ pos, float4* __restr
     for (int q = tid; q < ncell_t; q += TILE_THREADS) {
       int qz = q % naz, qy = (q / naz) % nay, qx = q / (naz * nay);
       int l = x0 + 2 * qx + 1, iy = y0 + 2 * qy + 1, iz = z0 + 2 * qz + 1;
-      cell_update_global_noinline<LOG>(a, pos, rel, cs, l, iy, iz, 0, 2, n_acc, n_ov, n_cell, log, nlog, logcap);
+      cell_update_global_noinline<LOG>(a, a.phase, pos, rel, cs, l, iy, iz, 0, 2, n_acc, n_ov, n_cell, log, nlog, logcap);
     }
   }
 
@@ -449,7 +449,7 @@ k_sweep_deep(SweepArgs a, const int* __restrict__ deep_list, const int* __restri
     }
     const int beg = __shfl_sync(FULL, nb, 13), end = __shfl_sync(FULL, ne, 13);
     if (end - beg > 32) {      // more particles than lanes (only with very wide cells): generic path
-      if (lane == 0) cell_update_global<LOG>(a, pos, rel, cs, l, iy, iz, 2, 1 << 30, n_acc, n_ov, n_cell, log, nlog, logcap);
+      if (lane == 0) cell_update_global<LOG>(a, a.phase, pos, rel, cs, l, iy, iz, 2, 1 << 30, n_acc, n_ov, n_cell, log, nlog, logcap);
       __syncwarp();
       continue;
     }

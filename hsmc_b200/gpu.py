@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "csrc", "libhsmc_gpu.so")
+_LIB_PATH = os.environ.get("HSMC_GPU_LIB") or os.path.join(_HERE, "csrc", "libhsmc_gpu.so")   # env: kernel-variant experiments
 _lib = None
 
 NCCL_ID_BYTES = 128
@@ -130,7 +130,13 @@ class HsmcGpu:
     """One GPU's (slab of the) hard-sphere system.  Thin, stateful, not thread-safe."""
 
     def __init__(self, n_particles, box, seed=0, device=0, rank=0, world=1, nccl_id=None, cell_min=1.0,
-                 regrid_interval=1, sweep_impl=0):
+                 regrid_interval=1, sweep_impl=0, xpart_world=0):
+        # sweep_impl: 0 block-resident kernel (default), 5 same chain from global memory, 6 same chain
+        # with plain-load staging, 3 block kernel with the fp32 error band forced to zero (negative
+        # control); 4 / 2 / 1: the single-level (one launch per cell colour) chain, TMA-staged tiles /
+        # plain-load tiles / global memory.  xpart_world: a single-GPU run uses the x block
+        # partition of a run on that many slabs (bitwise identity checks).
+        sweep_impl = int(sweep_impl) | (int(xpart_world) << 8)
         self.L = load_library()
         self.h = C.c_void_p()
         self._idbuf = C.create_string_buffer(nccl_id, NCCL_ID_BYTES) if nccl_id is not None else None

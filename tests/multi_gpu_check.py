@@ -7,7 +7,8 @@ Every rank builds the same fcc start, keeps its x-slab (+ ghost layers), runs th
 number of sweeps with NCCL halo exchange, and returns its owned rows; rank 0 repeats the
 run on one GPU with the same seed and compares coordinates, counters and observables bit
 for bit (the Philox stream is keyed by global cell, so the chain cannot depend on the
-decomposition -- SURVEY.md section 4, item 4)."""
+decomposition -- SURVEY.md section 4, item 4; the single-GPU run is told to use the
+x block partition of the slab run, which is part of the chain's definition)."""
 import os
 import sys
 
@@ -66,7 +67,7 @@ def main():
         ok &= allrows.shape[0] == N and np.array_equal(np.sort(allrows[:, 0]), np.arange(N))
         multi = allrows[np.argsort(allrows[:, 0])]
         multi2 = allrows2[np.argsort(allrows2[:, 0])]
-        with hsmc_b200.HsmcGpu(N, box, seed=seed, device=lr) as s:
+        with hsmc_b200.HsmcGpu(N, box, seed=seed, device=lr, xpart_world=world) as s:
             s.upload(conf)
             s.sweep_nvt(sweeps, dr_max)
             single = s.download()

@@ -33,7 +33,8 @@ def _replay(checker, log, dr_max):
     return keep, acc
 
 
-@pytest.mark.parametrize("impl", [0, 1, 2], ids=["tile_tma", "global", "tile_ldg"])
+@pytest.mark.parametrize("impl", [0, 5, 6, 4, 1, 2],
+                         ids=["block_tma", "block_global", "block_ldg", "tile_tma", "cell_global", "tile_ldg"])
 @pytest.mark.parametrize("path", GOLDEN_FILES, ids=IDS)
 def test_every_trial_verdict_replays_through_oracle(hs, path, impl, oracle_built):
     g = dict(np.load(path))
@@ -138,14 +139,22 @@ def test_counters_reset_and_64bit(hs, oracle_built):
         assert h.counters().dtype == np.int64
 
 
-def test_kernel_variants_produce_the_same_chain(hs, oracle_built):
-    """The tile-staged kernel (TMA or plain-load staging) and the generic global-memory
-    kernel are the same Markov chain, bit for bit, on a box large enough to have interior
-    (no minimum image) cells, boundary cells and partial tiles."""
+@pytest.mark.parametrize("impls", [(0, 5, 6), (4, 1, 2)], ids=["block_chain", "cell_colour_chain"])
+@pytest.mark.parametrize("block", [None, "2,3,4", "4,4,8", "8,8,24"])
+def test_kernel_variants_produce_the_same_chain(hs, oracle_built, impls, block, monkeypatch):
+    """The staged kernels (TMA or plain-load staging, fp32 filter + exact re-check) and the
+    all-double global-memory evaluation of the same update order are the same Markov chain,
+    bit for bit, on a box large enough to have interior cells, boundary cells, wrapped
+    regions and ragged blocks / partial tiles.  (The block-resident chain and the
+    one-launch-per-cell-colour chain order the updates differently and are different chains.)"""
+    if block is not None:
+        if impls[0] != 0:
+            pytest.skip("block shape only matters for the block-resident kernels")
+        monkeypatch.setenv("HSMC_BLOCK", block)
     box, conf = oracle_built.Port.lattice(2, 14, 9, 11, 0.85)
     N = conf.shape[0]
     outs, cnts = [], []
-    for impl in (0, 1, 2):
+    for impl in impls:
         with hs.HsmcGpu(N, box[:3], seed=77, sweep_impl=impl) as h:
             h.upload(conf)
             h.sweep_nvt(12, 0.15)
@@ -154,6 +163,7 @@ def test_kernel_variants_produce_the_same_chain(hs, oracle_built):
             assert h.min_dist2() >= 1.0
     assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
     assert np.array_equal(cnts[0], cnts[1]) and np.array_equal(cnts[0], cnts[2])
+    assert cnts[0][0] == 12 * N
 
 
 def test_interior_fast_path_replays_through_oracle(hs, oracle_built):
