@@ -85,16 +85,19 @@ struct BlockCfg {
   int nbx, nby, nbz;      // blocks per axis (even); x: over the layers this rank owns
   int mbx, mby, mbz;      // largest block extent per axis (cells)
   int cap;                // staged shadow capacity (float4 entries, pad included)
-  int cs_stride;          // ints per raw (TMA'd) CSR row
-  int cz_stride;          // ushorts per compact CSR row
+  int cs_stride;          // (unused)
+  int cz_stride;          // ushorts per staged CSR row (multiple of 8: rows are TMA destinations)
   int max_rows;           // (mbx+2)*(mby+2)
+  int max_cells;          // mbx*mby*mbz
+  int tr_cap;             // trial slots per colour (multiple of 32)
   int use_tma;
   int force_global;       // ablation: every block takes the global-memory path (same chain)
+  int dbg;                // timing ablations (env HSMC_BLOCK_DBG), 0 in production
 };
 
 // cfg.sweep_impl: low byte = kernel variant, next byte = virtual world of the x block partition
 enum { IMPL_BLOCK = 0, IMPL_CELL_GLOBAL = 1, IMPL_TILE_LDG = 2, IMPL_EPS0 = 3, IMPL_TILE_TMA = 4,
-       IMPL_BLOCK_GLOBAL = 5, IMPL_BLOCK_LDG = 6 };
+       IMPL_BLOCK_GLOBAL = 5, IMPL_BLOCK_TMA = 6 };
 
 struct hsmc_gpu {
   hsmc_gpu_config cfg;
@@ -119,6 +122,7 @@ struct hsmc_gpu {
   int64_t cap_keys = 0;
   int *key_halo = nullptr, *rnk_halo = nullptr;   // [2*cap_halo]
   int *cell_count = nullptr, *cell_start = nullptr, *bsum = nullptr;
+  unsigned short* cs16 = nullptr;        // 16-bit row-relative CSR: [(x,y) row][nz + 1], what the block kernel stages
   unsigned long long* d_cnt = nullptr;       // CNT_N counters
   unsigned long long* d_scratch = nullptr;   // SCRATCH_N x u64 general scratch (flags, hist, min)
   int* d_slot_of_id = nullptr;           // parity entry points only
@@ -313,6 +317,20 @@ __global__ void k_cell_scatter(Grid g, const double4* __restrict__ in, int n, co
   int d = cs[c] + rnk[i];
   out[d] = p;
   rel[d] = make_rel_cell(g, c, p);
+}
+
+// 16-bit row-relative copy of the CSR offsets: cs16[row][z] = cs[row*nz + z] - cs[row*nz], z = 0..nz
+// (entry nz = population of the row).  Half the bytes to stage, and directly usable as
+// shared-memory indices after adding the row's staging offset.
+__global__ void k_cs16(const int* __restrict__ cs, long long nrow, int nz, unsigned short* __restrict__ out,
+                       int* __restrict__ flags) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nrow * (nz + 1)) return;
+  const long long row = t / (nz + 1);
+  const int z = (int)(t - row * (nz + 1));
+  const int v = cs[row * nz + z] - cs[row * nz];
+  if (v > 65535) atomicOr(flags, 64);
+  out[t] = (unsigned short)v;
 }
 
 // ----------------------------------------------------------------------------------
@@ -992,6 +1010,9 @@ static int ensure_cell_arrays(hsmc_gpu* h) {
   CU(cudaMalloc(&h->cell_start, sizeof(int) * (size_t)h->cap_cells));
   CU(cudaMalloc(&h->cell_count, sizeof(int) * (size_t)h->cap_cells));
   CU(cudaMalloc(&h->bsum, sizeof(int) * (size_t)((h->cap_cells + SCAN_CHUNK - 1) / SCAN_CHUNK + 1)));
+  if (h->cs16) cudaFree(h->cs16);
+  // rows x (nz + 1) <= cells + rows <= 2 x cells; tail padding for the 16-byte TMA granules
+  CU(cudaMalloc(&h->cs16, sizeof(unsigned short) * (size_t)(2 * h->cap_cells + 64)));
   if (h->deep_list) cudaFree(h->deep_list);
   h->deep_stride = h->cap_cells / 8 + 64;
   CU(cudaMalloc(&h->deep_list, sizeof(int) * (size_t)(8 * h->deep_stride)));
@@ -1036,6 +1057,11 @@ static int exclusive_scan(hsmc_gpu* h, const int* in, int64_t n, int* out) {
   k_scan_final<<<nb, SCAN_T, 0, h->st>>>(in, n, h->bsum, out, h->g, h->tile_ok ? h->deep_list : nullptr, h->deep_count,
                                          (int)h->deep_stride);
   h->launches += 3;
+  if (h->blk_ok && out == h->cell_start) {
+    const long long nrow = (long long)h->g.nlx * h->g.ny;
+    k_cs16<<<nblk(nrow * (h->g.nz + 1), 256), 256, 0, h->st>>>(out, nrow, h->g.nz, h->cs16, h->d_lay + 8);
+    h->launches++;
+  }
   CU(cudaGetLastError());
   return 0;
 }
@@ -1108,6 +1134,7 @@ static void setup_blocks(hsmc_gpu* h) {
   const int W = h->cfg.world;
   const int Wv = (W > 1) ? W : std::max(1, h->xpart_world);
   const double nbar = (double)h->N / ((double)g.nx * g.ny * g.nz);
+  if ((long long)g.nz * 16 > 65535) return;        // 16-bit row-relative CSR
   // x slabs of the (virtual) world: [lo, hi) in global layers
   std::vector<std::pair<int, int>> slabs;
   {
@@ -1125,7 +1152,7 @@ static void setup_blocks(hsmc_gpu* h) {
   if (const char* e = getenv("HSMC_BLOCK_CAPF")) capf = atof(e);
   int want[3] = {0, 0, 0};
   if (const char* e = getenv("HSMC_BLOCK")) sscanf(e, "%d,%d,%d", &want[0], &want[1], &want[2]);
-  struct Shape { int bx, by, bz, mx, my, mz, cap; size_t smem; };
+  struct Shape { int bx, by, bz, mx, my, mz, cap, tr_cap; size_t smem; };
   auto eval = [&](int bx, int by, int bz, Shape& s) -> bool {
     // a block and its halo must not cover a cell twice: extent + 2 <= cells of the axis
     int mx = 0;
@@ -1142,47 +1169,48 @@ static void setup_blocks(hsmc_gpu* h) {
     double region = (double)(mx + 2) * (my + 2) * (mz + 2);
     int cap = ((int)(region * nbar * capf) + 48 + BLK_PAD + 31) & ~31;
     if (cap > 8192) return false;
-    int cs_stride = (mz + 3 + 3 + 3) & ~3, cz_stride = (mz + 3 + 1) & ~1;
-    size_t smem = (size_t)cap * 16 + (size_t)(mx + 2) * (my + 2) * (cs_stride * 4 + cz_stride * 2);
+    int cz_stride = (mz + 3 + 7) & ~7;
+    double per_colour = (double)((mx + 1) / 2) * ((my + 1) / 2) * ((mz + 1) / 2);
+    int tr_cap = ((int)(per_colour * std::max(nbar, 0.2) * 1.4) + 48 + 31) & ~31;
+    size_t smem = (size_t)cap * 16 + (size_t)(mx + 2) * (my + 2) * cz_stride * 2 + (size_t)8 * tr_cap * 4;
+    smem = (smem + 15) & ~(size_t)15;
     if (smem > 100 * 1024) return false;
-    s = {bx, by, bz, mx, my, mz, cap, smem};
+    s = {bx, by, bz, mx, my, mz, cap, tr_cap, smem};
     return true;
   };
   Shape best{};
   bool have = false;
   if (want[0] > 0 && want[1] > 0 && want[2] > 0) have = eval(want[0], want[1], want[2], best);
   if (!have) {
-    // the largest shape whose CTAs still fit four to an SM wins on big grids; on small grids
-    // prefer shapes that give every SM at least two CTAs per phase
+    // Measured on B200 (profiles/): the cost per trial is flat once a CTA holds >= ~1000 trials and
+    // four CTAs fit an SM; smaller blocks pay the fixed prologue more often, larger ones lose
+    // residency.  Score = (fraction of the 4 x 148 CTA slots a phase can fill) x (prologue
+    // amortisation) x (residency), ties to the larger block.
     double best_score = -1.0;
-    const int cand_xy[] = {2, 3, 4, 5, 6, 8}, cand_z[] = {2, 4, 6, 8, 12, 16, 20, 24};
+    const int cand_xy[] = {2, 3, 4, 5, 6, 8}, cand_z[] = {2, 4, 6, 8, 10, 12, 16, 20, 24, 28};
     for (int bx : cand_xy) for (int by : cand_xy) for (int bz : cand_z) {
       Shape s;
       if (!eval(bx, by, bz, s)) continue;
       long long ctas = 0;
       for (auto& sl : slabs) ctas += even_blocks(sl.second - sl.first, bx) / 2;
       ctas *= (long long)(even_blocks(g.ny, by) / 2) * (even_blocks(g.nz, bz) / 2);
-      int per_sm = (int)std::min<size_t>(4, (size_t)(227 * 1024) / (s.smem + 8 * 1024));
+      const int per_sm = (int)std::min<size_t>(4, (size_t)(227 * 1024) / (s.smem + 5 * 1024));
       if (per_sm < 1) continue;
-      double interior = (double)s.mx * s.my * s.mz, region = (double)(s.mx + 2) * (s.my + 2) * (s.mz + 2);
-      // work per CTA in cell-equivalents: prologue + staging + trials; lanes idle when a colour has
-      // fewer non-empty cells than threads
-      double items = interior / 8.0 * std::min(1.0, nbar);
-      double lane_eff = std::min(1.0, items / BLK_THREADS) * 0.8 + 0.2;
-      double work = 60.0 + 0.12 * region + interior / lane_eff;
-      double waves = std::ceil((double)ctas / (148.0 * per_sm));
-      double t = waves * work * per_sm / 4.0 + 0.0;
-      double score = ((double)ctas * interior) / t;
+      const double interior = (double)s.mx * s.my * s.mz;
+      const double score = std::min(1.0, (double)ctas / (148.0 * 4)) * (interior / (interior + 400.0)) * (per_sm / 4.0) +
+                           1e-9 * interior;
       if (score > best_score) { best_score = score; best = s; have = true; }
     }
   }
   if (!have) return;
   b.mbx = best.mx; b.mby = best.my; b.mbz = best.mz; b.cap = best.cap;
   b.nby = even_blocks(g.ny, best.by); b.nbz = even_blocks(g.nz, best.bz);
-  b.cs_stride = (best.mz + 3 + 3 + 3) & ~3; b.cz_stride = (best.mz + 3 + 1) & ~1;
+  b.cs_stride = 0; b.cz_stride = (best.mz + 3 + 7) & ~7;
   b.max_rows = (best.mx + 2) * (best.my + 2);
-  b.use_tma = (h->impl == IMPL_BLOCK_LDG) ? 0 : 1;
+  b.max_cells = best.mx * best.my * best.mz; b.tr_cap = best.tr_cap;
+  b.use_tma = (h->impl == IMPL_BLOCK_TMA) ? 1 : 0;
   b.force_global = (h->impl == IMPL_BLOCK_GLOBAL) ? 1 : 0;
+  b.dbg = getenv("HSMC_BLOCK_DBG") ? atoi(getenv("HSMC_BLOCK_DBG")) : 0;
   h->xoff.clear();
   for (auto& sl : slabs) {
     int n = sl.second - sl.first, nb = even_blocks(n, best.bx);
@@ -1192,6 +1220,7 @@ static void setup_blocks(hsmc_gpu* h) {
   h->xoff.push_back((W > 1) ? g.own_hi : g.nx);
   b.nbx = (int)h->xoff.size() - 1;
   h->blk_smem = best.smem;
+  if (const char* e = getenv("HSMC_BLOCK_PADSMEM")) h->blk_smem += (size_t)atoi(e);    // occupancy experiments
   // fp32 filter error bound: staged coordinates are block-relative,
   // |X| <= (m/2 + 2) cells; per pair and axis: two final roundings at that magnitude, the
   // rounding of the cell edge times the <= 2 cells between a stencil pair, two offset
@@ -1203,7 +1232,7 @@ static void setup_blocks(hsmc_gpu* h) {
   for (int k = 0; k < 3; k++) sum += 2.0 * half_ulp(mag[k]) + 2.0 * wv[k] * ldexp(1.0, -24) + 2.0 * wv[k] * ldexp(1.0, -25);
   double r2err = 2.0 * 1.01 * sum + 8.0 * ldexp(1.0, -24);
   h->blk_eps = (float)(2.0 * r2err);
-  h->blk_ok = (h->impl == IMPL_BLOCK || h->impl == IMPL_EPS0 || h->impl == IMPL_BLOCK_GLOBAL || h->impl == IMPL_BLOCK_LDG);
+  h->blk_ok = (h->impl == IMPL_BLOCK || h->impl == IMPL_EPS0 || h->impl == IMPL_BLOCK_GLOBAL || h->impl == IMPL_BLOCK_TMA);
   if (getenv("HSMC_DEBUG_TILES"))
     fprintf(stderr, "[hsmc_gpu] rank %d: blocks %dx%dx%d of up to %dx%dx%d cells, %d CTAs/phase, cap %d, smem %zu B, eps %.3g\n",
             h->cfg.rank, b.nbx, b.nby, b.nbz, b.mbx, b.mby, b.mbz, (b.nbx / 2) * (b.nby / 2) * (b.nbz / 2), b.cap,
@@ -1337,6 +1366,7 @@ static int sync_layout(hsmc_gpu* h) {
   if (hs[8] & 2) return fail("slab decomposition: halo buffer overflow");
   if (hs[8] & 4) return fail("slab decomposition: received a particle outside the local layers");
   if (hs[8] & 16) return fail("slab decomposition: boundary-layer message does not match the ghost layer");
+  if (hs[8] & 64) return fail("cell list: more than 65535 particles in one row of cells");
   if ((hs[8] & 32) || hs[5] > h->cap) return fail("slab decomposition: local particle capacity exceeded");
   return 0;
 }
@@ -1399,7 +1429,7 @@ extern "C" int hsmc_gpu_destroy(hsmc_gpu* h) {
   void* ptrs[] = {h->pos[0], h->pos[1], h->rel, h->key, h->rnk, h->cell_count, h->cell_start, h->bsum, h->d_cnt,
                   h->d_scratch, h->d_slot_of_id, h->d_io, h->send_l, h->send_r, h->recv_l, h->recv_r,
                   h->d_halo_cnt, h->d_sfargs, h->d_log, h->key_halo, h->rnk_halo, h->deep_list, h->deep_count, h->d_lay,
-                  h->d_xoff};
+                  h->d_xoff, h->cs16};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -1428,7 +1458,7 @@ extern "C" int hsmc_gpu_create(hsmc_gpu** out, const hsmc_gpu_config* cfg, int64
   h->cfg = *cfg;
   h->impl = cfg->sweep_impl & 0xff;
   h->xpart_world = (cfg->sweep_impl >> 8) & 0xff;
-  if (h->impl > IMPL_BLOCK_LDG) { delete h; return fail("unknown sweep_impl variant"); }
+  if (h->impl > IMPL_BLOCK_TMA) { delete h; return fail("unknown sweep_impl variant"); }
   if (h->cfg.cell_min == 0.0) h->cfg.cell_min = 1.0;
   if (h->cfg.cell_min < 1.0) { delete h; return fail("cell_min must be >= 1.0 (the particle diameter)"); }
   if (h->cfg.regrid_interval <= 0) h->cfg.regrid_interval = 1;
@@ -1696,10 +1726,10 @@ static int sweep_once(hsmc_gpu* h, double dr_max, bool logged) {
       const int nb = (h->blk.nbx / 2) * (h->blk.nby / 2) * (h->blk.nbz / 2);
       if (logged)
         k_sweep_block<true><<<nb, BLK_THREADS, h->blk_smem, h->st>>>(a, h->blk, h->d_xoff, h->pos[h->cur], h->rel, h->cell_start,
-                                                                      h->d_cnt, h->d_log, h->d_scratch, (long long)h->cap_log);
+                                                                      h->cs16, h->d_cnt, h->d_log, h->d_scratch, (long long)h->cap_log);
       else
         k_sweep_block<false><<<nb, BLK_THREADS, h->blk_smem, h->st>>>(a, h->blk, h->d_xoff, h->pos[h->cur], h->rel, h->cell_start,
-                                                                       h->d_cnt, nullptr, nullptr, 0);
+                                                                       h->cs16, h->d_cnt, nullptr, nullptr, 0);
     } else if (h->tile_ok) {
       int nb = h->tile.ntx * h->tile.nty * h->tile.ntz;
       int gb = 148 * 4;
@@ -2044,6 +2074,18 @@ extern "C" int hsmc_gpu_profile_read(hsmc_gpu* h, double ms[HSMC_GPU_PROFILE_BUC
     ms[k] = h->prof_ms[k]; groups[k] = h->prof_n[k];
     h->prof_ms[k] = 0; h->prof_n[k] = 0;
   }
+  return 0;
+}
+
+// tuning aid (not part of the drop-in surface): per-stage cycle totals of the block kernel
+// collected when HSMC_BLOCK_DBG=10; reading resets them
+extern "C" int hsmc_gpu_debug_block_cycles(hsmc_gpu* h, uint64_t out[16]) {
+  if (!h || !out) return fail("null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaStreamSynchronize(h->st));
+  unsigned long long z[16] = {0};
+  CU(cudaMemcpyFromSymbol(out, g_blk_t, sizeof(z)));
+  CU(cudaMemcpyToSymbol(g_blk_t, z, sizeof(z)));
   return 0;
 }
 

@@ -36,23 +36,29 @@
 #define BLK_MIN_CTAS 4
 #endif
 #define BLK_MAX_ROWS 128        // (MBX+2)*(MBY+2) <= BLK_MAX_ROWS: one staging row per thread
+#ifndef BLK_SLOTS
 #define BLK_SLOTS 7
+#endif
 #define BLK_PAD 8               // far-away entries after the last staged particle
 #define BLK_FAR 1.0e15f
+#define BLK_MAX_OCC 15           // most particles per cell the trial-slot scheme handles (denser block: global path)
 
 // BlockCfg: see hsmc_gpu.cu (the handle keeps one)
+
+// per-row staging record: global slots of the row's one or two pieces, staged offset
+struct BlockRow { int gbA, gbB, cntA, off; };
 
 // exact re-evaluation of a whole stencil from the master table (moves.c:157-212, 400-431)
 // (`pos` deliberately not const __restrict__: entries of this block were written earlier in this
 // launch by other threads of the CTA, so the loads must not take the non-coherent path)
-__device__ __noinline__ bool block_exact_rescan(const double4* pos, const TileRow* s_row,
+__device__ __noinline__ bool block_exact_rescan(const double4* pos, const BlockRow* s_row,
                                                 const unsigned short* s_cz, int cz_stride, int nry, int rxc,
                                                 int ryc, int rz, int sel, double xn, double yn, double zn,
                                                 const Box& box) {
   for (int dx = -1; dx <= 1; dx++)
     for (int dy = -1; dy <= 1; dy++) {
       const int row = (rxc + dx) * nry + ryc + dy;
-      const TileRow rw = s_row[row];
+      const BlockRow rw = s_row[row];
       const unsigned short* cp = s_cz + row * cz_stride + rz;
       const int b = cp[-1], e = cp[2];
       for (int k = b; k < e; k++) {
@@ -66,24 +72,67 @@ __device__ __noinline__ bool block_exact_rescan(const double4* pos, const TileRo
   return false;
 }
 
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// prefetch a master-table entry (32 B) towards L1 for a later iteration of the same thread
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// One (x,y) row of a trial's stencil: the three z-cells are one contiguous staged range,
+// scanned in groups of BLK_SLOTS entries at fixed offsets, unmasked (see the file header).
+// NT = 2 keeps the running minimum for two trial points at once (the two trials of a unit).
+template <int NT>
+__device__ __forceinline__ void block_scan_row(const float4* __restrict__ s_rel, int b, int e, float x0, float y0,
+                                               float z0, float x1, float y1, float z1, float& r0, float& r1) {
+#pragma unroll 1
+  for (int k0 = b; k0 < e; k0 += BLK_SLOTS) {
+    const float4* q = s_rel + k0;
+#pragma unroll
+    for (int s = 0; s < BLK_SLOTS; s++) {
+      const float4 qv = q[s];
+      const float ax = x0 - qv.x, ay = y0 - qv.y, az = z0 - qv.z;
+      r0 = fminf(r0, __fmaf_rn(az, az, __fmaf_rn(ay, ay, ax * ax)));
+      if (NT == 2) {
+        const float bx = x1 - qv.x, by = y1 - qv.y, bz = z1 - qv.z;
+        r1 = fminf(r1, __fmaf_rn(bz, bz, __fmaf_rn(by, by, bx * bx)));
+      }
+    }
+  }
+}
+
+// slot-group class of a cell with n particles: groups of 16, 8, 4, 2, 1 slots
+__device__ __forceinline__ int occ_class(int n) { return n > 8 ? 0 : (n > 4 ? 1 : (n > 2 ? 2 : (n == 2 ? 3 : 4))); }
+
+// per-CTA cycle accounting for tuning (dbg == 10): accumulated clock64() deltas of thread 0
+__device__ unsigned long long g_blk_t[16];
+#define BLK_MARK(k)                                                         \
+  if (bc.dbg == 10 && threadIdx.x == 0) {                                   \
+    const long long t_now = clock64();                                      \
+    atomicAdd(&g_blk_t[k], (unsigned long long)(t_now - t_mark));           \
+    t_mark = t_now;                                                         \
+  }
+
 template <bool LOG>
 __global__ void __launch_bounds__(BLK_THREADS, BLK_MIN_CTAS)
 k_sweep_block(SweepArgs a, BlockCfg bc, const int* __restrict__ xoff, double4* __restrict__ pos,
-              float4* __restrict__ rel, const int* __restrict__ cs, unsigned long long* __restrict__ cnt,
-              hsmc_gpu_trial* __restrict__ log, unsigned long long* __restrict__ nlog, long long logcap) {
+              float4* __restrict__ rel, const int* __restrict__ cs, const unsigned short* __restrict__ cs16,
+              unsigned long long* __restrict__ cnt, hsmc_gpu_trial* __restrict__ log,
+              unsigned long long* __restrict__ nlog, long long logcap) {
   const Grid& g = a.g;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float4* s_rel = reinterpret_cast<float4*>(smem_raw);
-  int* s_raw = reinterpret_cast<int*>(s_rel + bc.cap);                         // [rows][cs_stride] raw CSR values
-  unsigned short* s_items = reinterpret_cast<unsigned short*>(s_raw);          // aliases s_raw once the CSR is compact
-  unsigned short* s_cz = reinterpret_cast<unsigned short*>(s_raw + bc.max_rows * bc.cs_stride);   // [rows][cz_stride]
-  __shared__ TileRow s_row[BLK_MAX_ROWS];
+  unsigned short* s_cz = reinterpret_cast<unsigned short*>(s_rel + bc.cap);    // [rows][cz_stride] staged index of each region cell
+  unsigned int* s_trials = reinterpret_cast<unsigned int*>(s_cz + bc.max_rows * bc.cz_stride);   // [8][tr_cap] trial slots per colour: cell code | j << 16 | n << 20
+  __shared__ BlockRow s_row[BLK_MAX_ROWS];
   __shared__ int s_cnt[BLK_MAX_ROWS + 1];
-  __shared__ int s_n[24], s_ibase[25], s_fill[24], s_next[8];
+  __shared__ int s_n[40], s_cbase[40], s_fill[40], s_next[8], s_ntr[8], s_flag;
   __shared__ __align__(8) uint64_t s_bar;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = BLK_THREADS / 32;
-  const int cs_stride = bc.cs_stride, czs = bc.cz_stride;
+  const int czs = bc.cz_stride;
+  long long t_mark = clock64();
 
   // ---- which block ------------------------------------------------------------------
   const int hbz = bc.nbz >> 1, hby = bc.nby >> 1;
@@ -101,12 +150,13 @@ k_sweep_block(SweepArgs a, BlockCfg bc, const int* __restrict__ xoff, double4* _
   const bool zwrap = zs + lenz > g.nz;      // block-uniform: the region crosses the periodic z edge
 
   if (tid == 0) mbar_init(&s_bar, BLK_THREADS);
-  if (tid < 24) { s_n[tid] = 0; }
-  if (tid < 8) s_next[tid] = BLK_THREADS;
+  if (tid < 40) s_n[tid] = 0;
+  if (tid < 8) s_next[tid] = BLK_THREADS / 32;
+  if (tid == 0) s_flag = 0;
 
   // ---- row pieces: row r belongs to thread (lane, warp) with r = lane*NW + warp, so every
   //      warp issues the same number of (serialised) TMA copies
-  long long my_rbase = 0;
+  long long my_row = 0;
   int my_cntB = 0;
   const int myrow = lane * NW + warp;
   if (myrow < nrows) {
@@ -115,15 +165,17 @@ k_sweep_block(SweepArgs a, BlockCfg bc, const int* __restrict__ xoff, double4* _
     if (g.wrap_x) { if (lx < 0) lx += g.nlx; else if (lx >= g.nlx) lx -= g.nlx; }
     int y = y0 + ry;
     if (y < 0) y += g.ny; else if (y >= g.ny) y -= g.ny;
-    my_rbase = ((long long)lx * g.ny + y) * g.nz;
-    int gbA = cs[my_rbase + zs], geA = cs[my_rbase + min(zs + lenz, g.nz)];
+    my_row = (long long)lx * g.ny + y;
+    const long long rbase = my_row * g.nz;
+    int gbA = cs[rbase + zs], geA = cs[rbase + min(zs + lenz, g.nz)];
     int gbB = 0, geB = 0;
-    if (zwrap) { gbB = cs[my_rbase]; geB = cs[my_rbase + (zs + lenz - g.nz)]; }
+    if (zwrap) { gbB = cs[rbase]; geB = cs[rbase + (zs + lenz - g.nz)]; }
     my_cntB = geB - gbB;
     s_row[myrow].gbA = gbA; s_row[myrow].gbB = gbB; s_row[myrow].cntA = geA - gbA;
     s_cnt[myrow] = (geA - gbA) + my_cntB;
   }
   __syncthreads();
+  BLK_MARK(0)     // row ends read
   // ---- exclusive scan of the row counts by warp 0 -----------------------------------
   if (tid < 32) {
     int carry = 0;
@@ -142,65 +194,60 @@ k_sweep_block(SweepArgs a, BlockCfg bc, const int* __restrict__ xoff, double4* _
     if (tid == 0) s_cnt[nrows] = carry;
   }
   __syncthreads();
+  BLK_MARK(1)     // row scan
+  if (bc.dbg == 1) return;
   const int total = s_cnt[nrows];
   const bool staged = !bc.force_global && total + BLK_PAD <= bc.cap;
 
   int n_acc = 0, n_ov = 0, n_cell = 0;
+  bool ok = false;     // staged, and every interior cell / colour fits the trial-slot scheme
 
   if (staged) {
-    // ---- stage shadow rows and CSR rows: TMA bulk copies, completion on s_bar ----------
-    const bool tma_cs = bc.use_tma && !zwrap;
+    // ---- stage the shadow rows --------------------------------------------------------------
+    // Default: per-thread 16-byte async copies (cp.async / LDGSTS), one per particle, all in
+    // flight at once -- the rows are short (~15 particles), and bulk-TMA copies that small are
+    // bound by the per-copy cost of the TMA engine (measured: ~50 cycles of engine time per
+    // copy, profiles/).  use_tma (ablation) issues one bulk copy per row piece instead.
     if (myrow < nrows) {
-      TileRow& rw = s_row[myrow];
+      BlockRow& rw = s_row[myrow];
       const int off = s_cnt[myrow], cA = rw.cntA;
-      const long long i0 = my_rbase + zs;
-      const int shift = tma_cs ? (int)(i0 & 3) : 0;
-      rw.off = off; rw.shift = shift; rw.delta = rw.gbA - off;
+      rw.off = off;
       if (bc.use_tma) {
         uint32_t bytes = (uint32_t)(cA + my_cntB) * 16u;
-        uint32_t cs_bytes = tma_cs ? (uint32_t)((shift + lenz + 1 + 3) & ~3) * 4u : 0u;
-        if (bytes + cs_bytes) mbar_arrive_tx(&s_bar, bytes + cs_bytes); else mbar_arrive(&s_bar);
+        if (bytes) mbar_arrive_tx(&s_bar, bytes); else mbar_arrive(&s_bar);
         if (cA) tma_bulk_g2s(&s_rel[off], &rel[rw.gbA], (uint32_t)cA * 16u, &s_bar);
         if (my_cntB) tma_bulk_g2s(&s_rel[off + cA], &rel[rw.gbB], (uint32_t)my_cntB * 16u, &s_bar);
-        if (cs_bytes) tma_bulk_g2s(&s_raw[myrow * cs_stride], &cs[i0 - shift], cs_bytes, &s_bar);
+      } else {
+        // the row's own thread streams it in: back-to-back independent 16-byte async copies
+        const float4* srcA = rel + rw.gbA;
+        float4* dst = s_rel + off;
+#pragma unroll 4
+        for (int k = 0; k < cA; k++) cp_async16(dst + k, srcA + k);
+        const float4* srcB = rel + rw.gbB;
+        for (int k = 0; k < my_cntB; k++) cp_async16(dst + cA + k, srcB + k);
+      }
+      // staged index of the first particle of every cell of the row, from the 16-bit
+      // row-relative CSR (a wrapped row continues at z = 0 of the same global row)
+      const unsigned short* crow = cs16 + my_row * (g.nz + 1);
+      unsigned short* out = s_cz + myrow * czs;
+      const int v0 = crow[zs];
+#pragma unroll 4
+      for (int zi = 0; zi <= lenz; zi++) {
+        const int z = zs + zi;
+        const int v = (z <= g.nz) ? off + (int)crow[z] - v0 : off + cA + (int)crow[z - g.nz];
+        out[zi] = (unsigned short)v;
       }
     } else if (bc.use_tma) {
       mbar_arrive(&s_bar);
     }
     if (tid < BLK_PAD) s_rel[total + tid] = make_float4(BLK_FAR, BLK_FAR, BLK_FAR, __int_as_float(-1));
+    BLK_MARK(2)     // copies issued, CSR rows done
+    if (bc.use_tma) mbar_wait(&s_bar, 0); else cp_async_wait_all();
+    if (bc.dbg == 2) return;
     __syncthreads();
-    if (!bc.use_tma) {
-      for (int r = warp; r < nrows; r += NW) {
-        TileRow rw = s_row[r];
-        int cT = s_cnt[r + 1] - s_cnt[r];
-        for (int k = lane; k < rw.cntA; k += 32) s_rel[rw.off + k] = rel[rw.gbA + k];
-        for (int k = lane + rw.cntA; k < cT; k += 32) s_rel[rw.off + k] = rel[rw.gbB + k - rw.cntA];
-      }
-    }
-    if (bc.use_tma) mbar_wait(&s_bar, 0);
-    // ---- compact CSR: staged index of the first particle of every region cell ----------
-#pragma unroll 1
-    for (int r = warp; r < nrows; r += NW) {
-      const TileRow rw = s_row[r];
-      if (lane <= lenz) {
-        int v;
-        if (tma_cs) v = s_raw[r * cs_stride + rw.shift + lane];
-        else {
-          int rx = r / nry, ry = r - rx * nry;
-          int lx = x0 + rx;
-          if (g.wrap_x) { if (lx < 0) lx += g.nlx; else if (lx >= g.nlx) lx -= g.nlx; }
-          int y = y0 + ry;
-          if (y < 0) y += g.ny; else if (y >= g.ny) y -= g.ny;
-          const long long rbase = ((long long)lx * g.ny + y) * g.nz;
-          const int z = zs + lane;
-          v = (z <= g.nz) ? cs[rbase + z] : cs[rbase + z - g.nz] - rw.gbB + rw.gbA + rw.cntA;
-        }
-        s_cz[r * czs + lane] = (unsigned short)(v - rw.delta);
-      }
-    }
-    __syncthreads();
+    BLK_MARK(3)     // staged data landed
 
-    // ---- block-relative coordinates; census of the interior cells by (colour, occupancy) ---
+    // ---- block-relative coordinates; census of the interior cells by colour ----------------
     const float wxf = (float)g.wx, wyf = (float)g.wy, wzf = (float)g.wz;
     const float hxr = 0.5f * (float)nrx, hyr = 0.5f * (float)nry, hzr = 0.5f * (float)lenz;
     const int parx = (g.gx0 + x0) & 1, pary = y0 & 1, parz = z0 & 1;    // parity of region cell (0,0,0); grids are even
@@ -224,162 +271,242 @@ k_sweep_block(SweepArgs a, BlockCfg bc, const int* __restrict__ xoff, double4* _
         }
         if (rowint && zi >= 1 && zi <= nbz && e > b) {
           const int n = e - b;
-          atomicAdd(&s_n[(colxy | ((parz + zi) & 1)) * 3 + (n >= 3 ? 0 : (n == 2 ? 1 : 2))], 1);
+          if (n > BLK_MAX_OCC) s_flag = 1;
+          else atomicAdd(&s_n[(colxy | ((parz + zi) & 1)) * 5 + occ_class(n)], 1);
         }
         b = e;
       }
     }
     __syncthreads();
-    if (tid == 0) {
-      int s = 0;
-      for (int k = 0; k < 24; k++) { s_ibase[k] = s; s_fill[k] = s; s += s_n[k]; }
-      s_ibase[24] = s;
+    BLK_MARK(4)     // block-relative conversion + census
+    // ---- trial slots: every particle of a colour gets one lane-slot.  The slots of a cell are a
+    //      group of 1, 2, 4, 8 or 16 consecutive slots (by occupancy), groups are laid out
+    //      largest first, so a group never straddles a warp-sized chunk: the trials of one cell
+    //      always sit in adjacent lanes of one warp.  Unused slots of a group hold 0xffffffff.
+    if (tid < 8) {
+      int base = 0;
+      for (int c = 0; c < 5; c++) {
+        s_cbase[tid * 5 + c] = base;
+        s_fill[tid * 5 + c] = 0;
+        base += s_n[tid * 5 + c] << (4 - c);
+      }
+      s_ntr[tid] = base;
+      if (base > bc.tr_cap) s_flag = 1;
     }
     __syncthreads();
-    // ---- item lists: per colour, cells with >= 3 particles first, then 2, then 1 --------
+    if (s_flag == 0) {
 #pragma unroll 1
-    for (int idx = tid; idx < 2 * nbx * nby; idx += BLK_THREADS) {
-      const int ri = idx >> 1, half = idx & 1;
-      const int rx = ri / nby + 1, ry = ri - (rx - 1) * nby + 1;
-      const int zlo = half ? (nbz >> 1) + 1 : 1, zhi = half ? nbz + 1 : (nbz >> 1) + 1;
-      const int colxy = (((parx + rx) & 1) << 2) | (((pary + ry) & 1) << 1);
-      const unsigned short* cz = s_cz + (rx * nry + ry) * czs;
-      int b = cz[zlo];
-      for (int zi = zlo; zi < zhi; zi++) {
-        const int e = cz[zi + 1];
-        const int n = e - b;
-        if (n > 0) {
-          const int p = atomicAdd(&s_fill[(colxy | ((parz + zi) & 1)) * 3 + (n >= 3 ? 0 : (n == 2 ? 1 : 2))], 1);
-          s_items[p] = (unsigned short)((rx << 11) | (ry << 6) | zi);
+      for (int idx = tid; idx < 2 * nbx * nby; idx += BLK_THREADS) {
+        const int ri = idx >> 1, half = idx & 1;
+        const int rx = ri / nby + 1, ry = ri - (rx - 1) * nby + 1;
+        const int zlo = half ? (nbz >> 1) + 1 : 1, zhi = half ? nbz + 1 : (nbz >> 1) + 1;
+        const int colxy = (((parx + rx) & 1) << 2) | (((pary + ry) & 1) << 1);
+        const unsigned short* cz = s_cz + (rx * nry + ry) * czs;
+        int b = cz[zlo];
+        for (int zi = zlo; zi < zhi; zi++) {
+          const int e = cz[zi + 1];
+          const int n = e - b;
+          if (n > 0) {
+            const int col = colxy | ((parz + zi) & 1), c = occ_class(n), G = 1 << (4 - c);
+            const int q = atomicAdd(&s_fill[col * 5 + c], 1);
+            unsigned int* tl = s_trials + col * bc.tr_cap + s_cbase[col * 5 + c] + q * G;
+            const unsigned int code = (unsigned)((rx << 11) | (ry << 6) | zi) | ((unsigned)n << 20);
+            for (int j = 0; j < G; j++) tl[j] = (j < n) ? (code | ((unsigned)j << 16)) : 0xffffffffu;
+          }
+          b = e;
         }
-        b = e;
       }
     }
     __syncthreads();
-
+    ok = s_flag == 0;
+    BLK_MARK(5)     // trial slots built
+    if (bc.dbg == 3) return;
+  }
+  if (ok) {
     // ---- trials -------------------------------------------------------------------------
+    // One lane per trial; a warp takes a chunk of 32 trial slots at a time.  Every particle of
+    // the cells in the chunk is hidden from the staged table while the chunk is scanned, so the
+    // fp32 scan only sees particles that do not move during the chunk; the pairs INSIDE a cell
+    // are then resolved exactly, in double, in ascending-id order with warp shuffles: trial j
+    // is tested against its mates i > j at their old positions and against its mates i < j at
+    // the positions their own trials left them in.
+    const unsigned FULL = 0xffffffffu;
+    const float wxf = (float)g.wx, wyf = (float)g.wy, wzf = (float)g.wz;
+    const float hxr = 0.5f * (float)nrx, hyr = 0.5f * (float)nry, hzr = 0.5f * (float)lenz;
     const float lo = 1.0f - a.eps, hi = 1.0f + a.eps;
-    struct Cur {
-      int rxc, ryc, rz, n, sel, gslot, gx, iy, iz, last_id;
-      long long gcell;
-    };
-    auto decode = [&](int item, int last_id) {
-      Cur c;
-      const int code = s_items[item];
-      c.rxc = code >> 11; c.ryc = (code >> 6) & 31; c.rz = code & 63;
-      const int rowc = c.rxc * nry + c.ryc;
-      const unsigned short* cpc = s_cz + rowc * czs + c.rz;
-      const int ob = cpc[0], oe = cpc[1];
-      c.n = oe - ob;
-      int l = x0 + c.rxc;
-      c.iy = y0 + c.ryc; c.iz = z0 + c.rz;
-      // interior cells never wrap: the block lies inside [0, n) on every axis
-      c.gx = (g.gx0 + l >= g.nx) ? g.gx0 + l - g.nx : g.gx0 + l;
-      c.gcell = ((long long)c.gx * g.ny + c.iy) * g.nz + c.iz;
-      // particle of this trial: ascending id inside the cell
-      c.sel = ob;
-      c.last_id = last_id;
-      if (c.n > 1) {
-        int best = 0x7fffffff;
-        for (int k = ob; k < oe; k++) {
-          int id = __float_as_int(s_rel[k].w);
-          if (id > last_id && id < best) { best = id; c.sel = k; }
+    struct Slot { int code, cell, sel, gs; };       // code < 0: padding / beyond the end
+    auto stage_a = [&](int col, int chunk) {
+      Slot u;
+      const int t = chunk * 32 + lane;
+      u.code = -1; u.cell = 0; u.sel = 0; u.gs = 0;
+      if (t < s_ntr[col]) {
+        const unsigned int c = s_trials[col * bc.tr_cap + t];
+        if (c != 0xffffffffu) {
+          u.code = (int)(c >> 16);                 // j | n << 4
+          u.cell = (int)(c & 0xffffu);
+          const int j = u.code & 15, n = u.code >> 4;
+          const int rowc = (u.cell >> 11) * nry + ((u.cell >> 6) & 31);
+          const int ob = s_cz[rowc * czs + (u.cell & 63)];
+          // the particle with exactly j smaller ids in its cell
+          u.sel = ob;
+          if (n > 1) {
+            for (int k = ob; k < ob + n; k++) {
+              const int idk = __float_as_int(s_rel[k].w);
+              int c2 = 0;
+              for (int m = ob; m < ob + n; m++) c2 += __float_as_int(s_rel[m].w) < idk;
+              if (c2 == j) u.sel = k;
+            }
+          }
+          const BlockRow rwc = s_row[rowc];
+          const int ro = u.sel - rwc.off;
+          u.gs = (ro < rwc.cntA) ? rwc.gbA + ro : rwc.gbB + ro - rwc.cntA;
+          prefetch_l1(&pos[u.gs]);
         }
-        c.last_id = best;
       }
-      const TileRow rwc = s_row[rowc];
-      const int ro = c.sel - rwc.off;
-      c.gslot = (ro < rwc.cntA) ? rwc.gbA + ro : rwc.gbB + ro - rwc.cntA;
-      return c;
+      return u;
     };
 #pragma unroll 1
     for (int col = 0; col < 8; col++) {
-      const int ib = s_ibase[3 * col], nit = s_ibase[3 * col + 3] - ib;
-      // One flat loop: every iteration is exactly one trial (item `it`, trial index `j`).
-      // Lanes start on item `tid` (deepest cells first) and fetch further items from a
-      // shared ticket; the master-table entry of the NEXT trial's particle is requested one
-      // iteration ahead (its latency is as long as a stencil scan).
-      int it = tid, j = 0;
-      Cur cur;
-      double4 p_next = make_double4(0, 0, 0, 0);
-      if (it < nit) { cur = decode(ib + it, -1); p_next = pos[cur.gslot]; }
+      const int ntr = s_ntr[col];
+      int chunk = warp;                            // warp-uniform
+      Slot nx;
+      if (chunk * 32 < ntr) nx = stage_a(col, chunk);
 #pragma unroll 1
-      while (it < nit) {
-        const double4 p = p_next;
-        const Cur c = cur;
-        int it2 = it, j2 = j + 1;
-        if (j2 >= c.n) { j2 = 0; it2 = atomicAdd(&s_next[col], 1); }
-        if (it2 < nit) { cur = decode(ib + it2, j2 ? c.last_id : -1); p_next = pos[cur.gslot]; }
-        {
-          const int rxc = c.rxc, ryc = c.ryc, rz = c.rz, sel = c.sel, gslot = c.gslot;
-          const int gx = c.gx, iy = c.iy, iz = c.iz;
-          const long long gcell = c.gcell;
-          Philox4 rn = philox4x32_10((uint32_t)gcell, (HSMC_STREAM_MOVE << 24) | (uint32_t)j, a.sweep_lo, a.sweep_hi,
-                                     a.key0, a.key1);
-          double xn = p.x + (hsmc_u01(rn.v[0]) - 0.5) * a.dr_max;
-          double yn = p.y + (hsmc_u01(rn.v[1]) - 0.5) * a.dr_max;
-          double zn = p.z + (hsmc_u01(rn.v[2]) - 0.5) * a.dr_max;
+      while (chunk * 32 < ntr) {
+        const Slot u = nx;
+        const bool valid = u.code >= 0;
+        const int j = u.code & 15, n = valid ? (u.code >> 4) : 0;
+        BLK_MARK(14)    // loop top (residual)
+        double4 p = make_double4(0, 0, 0, 0);
+        if (valid) p = pos[u.gs];
+        // next chunk of this warp: a ticket, and the early request for its master entries
+        int nxt = 0;
+        if (lane == 0) nxt = atomicAdd(&s_next[col], 1);
+        nxt = __shfl_sync(FULL, nxt, 0);
+        if (nxt * 32 < ntr) nx = stage_a(col, nxt);
+        BLK_MARK(8)     // ticket + stage_a of the next chunk
+        const int rxc = u.cell >> 11, ryc = (u.cell >> 6) & 31, rz = u.cell & 63;
+        const int iy = y0 + ryc, iz = z0 + rz;
+        const int gxl = g.gx0 + x0 + rxc;
+        const int gx = (gxl >= g.nx) ? gxl - g.nx : gxl;          // interior cells never wrap inside the block
+        const long long gcell = ((long long)gx * g.ny + iy) * g.nz + iz;
+        // ---- the trial point (moves.c:52-57, 215-226) ----
+        Philox4 rn;
+        double xn = 0, yn = 0, zn = 0;
+        bool act = false;
+        float4 nrel = make_float4(0.f, 0.f, 0.f, 0.f), keep = nrel;
+        float tx = 0.f, ty = 0.f, tz = 0.f;
+        if (valid) {
+          rn = philox4x32_10((uint32_t)gcell, (HSMC_STREAM_MOVE << 24) | (uint32_t)j, a.sweep_lo, a.sweep_hi, a.key0, a.key1);
+          xn = p.x + (hsmc_u01(rn.v[0]) - 0.5) * a.dr_max;
+          yn = p.y + (hsmc_u01(rn.v[1]) - 0.5) * a.dr_max;
+          zn = p.z + (hsmc_u01(rn.v[2]) - 0.5) * a.dr_max;
           if (xn > g.Lx) xn -= g.Lx; else if (xn < 0.0) xn += g.Lx;
           if (yn > g.Ly) yn -= g.Ly; else if (yn < 0.0) yn += g.Ly;
           if (zn > g.Lz) zn -= g.Lz; else if (zn < 0.0) zn += g.Lz;
-          int verdict;
-          if (axis_cell(xn, g.sx, g.iwx, g.nx) != gx || axis_cell(yn, g.sy, g.iwy, g.ny) != iy ||
-              axis_cell(zn, g.sz, g.iwz, g.nz) != iz) {
-            verdict = 2;
-            n_cell++;
-          } else {
-            const float4 nrel = make_rel(g, gx, iy, iz, xn, yn, zn, p.w);
-            const float tx = __fmaf_rn((float)rxc - hxr, wxf, nrel.x);
-            const float ty = __fmaf_rn((float)ryc - hyr, wyf, nrel.y);
-            const float tz = __fmaf_rn((float)rz - hzr, wzf, nrel.z);
-            const float4 keep = s_rel[sel];
-            s_rel[sel] = make_float4(BLK_FAR, BLK_FAR, BLK_FAR, keep.w);     // hide the trial particle from its own scan
-            float r2min = 3.0e38f;
-#pragma unroll 1
-            for (int dx = -1; dx <= 1; dx++) {
+          act = axis_cell(xn, g.sx, g.iwx, g.nx) == gx && axis_cell(yn, g.sy, g.iwy, g.ny) == iy &&
+                axis_cell(zn, g.sz, g.iwz, g.nz) == iz;
+          if (act) {
+            nrel = make_rel(g, gx, iy, iz, xn, yn, zn, p.w);
+            tx = __fmaf_rn((float)rxc - hxr, wxf, nrel.x);
+            ty = __fmaf_rn((float)ryc - hyr, wyf, nrel.y);
+            tz = __fmaf_rn((float)rz - hzr, wzf, nrel.z);
+          } else n_cell++;
+          keep = s_rel[u.sel];
+          s_rel[u.sel] = make_float4(BLK_FAR, BLK_FAR, BLK_FAR, keep.w);     // hidden while the chunk is scanned
+        }
+        __syncwarp();
+        BLK_MARK(9)     // master load + trial point + hide
+        float r2min = 3.0e38f;
+        if (act && bc.dbg != 4) {
+          // first BLK_SLOTS entries of all nine rows in straight-line code (independent loads the
+          // scheduler can overlap with the arithmetic of the previous row) ...
+          const unsigned short* cp0 = s_cz + ((rxc - 1) * nry + ryc - 1) * czs + rz;
+          bool more = false;
 #pragma unroll
-              for (int dy = -1; dy <= 1; dy++) {
-                const unsigned short* cp = s_cz + ((rxc + dx) * nry + ryc + dy) * czs + rz;
-                const int b = cp[-1], e = cp[2];
-#pragma unroll 1
-                for (int k0 = b; k0 < e; k0 += BLK_SLOTS) {
-                  const float4* q = s_rel + k0;
+          for (int r = 0; r < 9; r++) {
+            const unsigned short* cp = cp0 + ((r / 3) * nry + (r % 3)) * czs;
+            const int b = cp[-1];
+            more |= (int)cp[2] - b > BLK_SLOTS;
+            const float4* q = s_rel + b;
 #pragma unroll
-                  for (int s = 0; s < BLK_SLOTS; s++) {
-                    const float4 qv = q[s];
-                    const float ddx = tx - qv.x, ddy = ty - qv.y, ddz = tz - qv.z;
-                    r2min = fminf(r2min, __fmaf_rn(ddz, ddz, __fmaf_rn(ddy, ddy, ddx * ddx)));
-                  }
+            for (int s = 0; s < BLK_SLOTS; s++) {
+              const float4 qv = q[s];
+              const float ddx = tx - qv.x, ddy = ty - qv.y, ddz = tz - qv.z;
+              r2min = fminf(r2min, __fmaf_rn(ddz, ddz, __fmaf_rn(ddy, ddy, ddx * ddx)));
+            }
+          }
+          // ... and the rare rows holding more than BLK_SLOTS particles
+          if (more) {
+#pragma unroll 1
+            for (int r = 0; r < 9; r++) {
+              const unsigned short* cp = cp0 + ((r / 3) * nry + (r % 3)) * czs;
+              const int e = cp[2];
+#pragma unroll 1
+              for (int k0 = cp[-1] + BLK_SLOTS; k0 < e; k0 += BLK_SLOTS) {
+                const float4* q = s_rel + k0;
+#pragma unroll
+                for (int s = 0; s < BLK_SLOTS; s++) {
+                  const float4 qv = q[s];
+                  const float ddx = tx - qv.x, ddy = ty - qv.y, ddz = tz - qv.z;
+                  r2min = fminf(r2min, __fmaf_rn(ddz, ddz, __fmaf_rn(ddy, ddy, ddx * ddx)));
                 }
               }
             }
-            bool ov = r2min < lo;
-            if (!ov && r2min <= hi)
-              ov = block_exact_rescan(pos, s_row, s_cz, czs, nry, rxc, ryc, rz, sel, xn, yn, zn, a.box);
-            if (ov) {
-              verdict = 1; n_ov++;
-              s_rel[sel] = keep;
-            } else {
-              verdict = 0; n_acc++;
-              s_rel[sel] = make_float4(tx, ty, tz, keep.w);
-              rel[gslot] = nrel;
-              pos[gslot] = make_double4(xn, yn, zn, p.w);
-            }
-          }
-          if (LOG) {
-            unsigned long long s = atomicAdd(nlog, 1ull);
-            if ((long long)s < logcap) {
-              hsmc_gpu_trial tr;
-              tr.seq = ((unsigned long long)(a.phase * 8 + col) << 56) | ((unsigned long long)gcell << 8) | (unsigned)j;
-              tr.id = (int)p.w; tr.verdict = verdict;
-              tr.raw[0] = rn.v[0]; tr.raw[1] = rn.v[1]; tr.raw[2] = rn.v[2]; tr.pad = 0;
-              log[s] = tr;
-            }
           }
         }
-        it = it2; j = j2;
+        BLK_MARK(10)    // stencil scan
+        // ---- pairs inside a cell, exactly (moves.c:400-431), and the verdicts in trial order ----
+        const int maxn = __reduce_max_sync(FULL, n);
+        const int gb = lane - j;                       // lane of the cell's first trial
+        bool mate_ov = false;
+        for (int s = 1; s < maxn; s++) {               // mates with a LATER trial: still at their old positions
+          const int src = (gb + s) & 31;
+          const double qx = __shfl_sync(FULL, p.x, src), qy = __shfl_sync(FULL, p.y, src), qz = __shfl_sync(FULL, p.z, src);
+          if (act && j < s && s < n && !mate_ov) mate_ov = pair_r2(xn, yn, zn, qx, qy, qz, a.box) < 1.0;
+        }
+        double cx = p.x, cy = p.y, cz = p.z;           // where this lane's particle is after its own trial
+        int verdict = 2;
+        for (int s = 0; s < maxn; s++) {
+          if (valid && j == s) {
+            bool acc = false;
+            if (act) {
+              bool ov = mate_ov || r2min < lo;
+              if (!ov && r2min <= hi)
+                ov = block_exact_rescan(pos, s_row, s_cz, czs, nry, rxc, ryc, rz, u.sel, xn, yn, zn, a.box);
+              if (ov) { verdict = 1; n_ov++; }
+              else {
+                verdict = 0; n_acc++; acc = true;
+                cx = xn; cy = yn; cz = zn;
+                rel[u.gs] = nrel;
+                pos[u.gs] = make_double4(xn, yn, zn, p.w);
+              }
+            }
+            s_rel[u.sel] = acc ? make_float4(tx, ty, tz, keep.w) : keep;
+          }
+          if (s + 1 < maxn) {
+            __syncwarp();
+            const int src = (gb + s) & 31;
+            const double qx = __shfl_sync(FULL, cx, src), qy = __shfl_sync(FULL, cy, src), qz = __shfl_sync(FULL, cz, src);
+            if (act && j > s && !mate_ov) mate_ov = pair_r2(xn, yn, zn, qx, qy, qz, a.box) < 1.0;
+          }
+        }
+        BLK_MARK(11)    // mates + verdicts + commit
+        if (LOG && valid) {
+          unsigned long long s = atomicAdd(nlog, 1ull);
+          if ((long long)s < logcap) {
+            hsmc_gpu_trial tr;
+            tr.seq = ((unsigned long long)(a.phase * 8 + col) << 56) | ((unsigned long long)gcell << 8) | (unsigned)j;
+            tr.id = (int)p.w; tr.verdict = verdict;
+            tr.raw[0] = rn.v[0]; tr.raw[1] = rn.v[1]; tr.raw[2] = rn.v[2]; tr.pad = 0;
+            log[s] = tr;
+          }
+        }
+        chunk = nxt;
       }
+      BLK_MARK(6)     // own chunks of a colour done (warp 0)
       __syncthreads();
+      BLK_MARK(7)     // waiting for the other warps at the colour barrier
     }
   } else {
     // ---- staging capacity exceeded (unusually dense block) or ablation: global-memory path,
@@ -403,7 +530,7 @@ k_sweep_block(SweepArgs a, BlockCfg bc, const int* __restrict__ xoff, double4* _
   n_acc = __reduce_add_sync(0xffffffffu, n_acc);
   n_ov = __reduce_add_sync(0xffffffffu, n_ov);
   n_cell = __reduce_add_sync(0xffffffffu, n_cell);
-  if (lane == 0 && (n_acc | n_ov | n_cell)) {
+  if (lane == 0 && (n_acc | n_ov | n_cell) && bc.dbg != 5) {
     atomicAdd(&cnt[CNT_TRIALS], (unsigned long long)(n_acc + n_ov + n_cell));
     if (n_acc) atomicAdd(&cnt[CNT_ACC], (unsigned long long)n_acc);
     if (n_ov) atomicAdd(&cnt[CNT_REJ_OVERLAP], (unsigned long long)n_ov);

@@ -132,7 +132,7 @@ class HsmcGpu:
     def __init__(self, n_particles, box, seed=0, device=0, rank=0, world=1, nccl_id=None, cell_min=1.0,
                  regrid_interval=1, sweep_impl=0, xpart_world=0):
         # sweep_impl: 0 block-resident kernel (default), 5 same chain from global memory, 6 same chain
-        # with plain-load staging, 3 block kernel with the fp32 error band forced to zero (negative
+        # with bulk-TMA staging, 3 block kernel with the fp32 error band forced to zero (negative
         # control); 4 / 2 / 1: the single-level (one launch per cell colour) chain, TMA-staged tiles /
         # plain-load tiles / global memory.  xpart_world: a single-GPU run uses the x block
         # partition of a run on that many slabs (bitwise identity checks).

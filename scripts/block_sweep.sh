@@ -3,7 +3,7 @@ for cfg in "$@"; do
   set -- $cfg
   lib=$1; shape=$2
   if [ "$lib" != "default" ]; then export HSMC_GPU_LIB=$PWD/hsmc_b200/csrc/variants/$lib; else unset HSMC_GPU_LIB; fi
-  echo "$lib $shape: $(HSMC_DEBUG_TILES=1 HSMC_BLOCK=$shape python bench.py --steps 3 --warmup 3 --sweeps-per-step 5 --no-cpu-baseline --e2e-steps 1 2>&1 | python -c '
+  echo "$lib $shape: $(HSMC_DEBUG_TILES=1 HSMC_BLOCK=$shape python bench.py --steps 3 --warmup 3 --sweeps-per-step 5 --no-cpu-baseline --e2e-steps 1 $BENCH_EXTRA 2>&1 | python -c '
 import sys,json
 blk=""
 for ln in sys.stdin:

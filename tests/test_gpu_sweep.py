@@ -34,7 +34,7 @@ def _replay(checker, log, dr_max):
 
 
 @pytest.mark.parametrize("impl", [0, 5, 6, 4, 1, 2],
-                         ids=["block_tma", "block_global", "block_ldg", "tile_tma", "cell_global", "tile_ldg"])
+                         ids=["block", "block_global", "block_tma", "tile_tma", "cell_global", "tile_ldg"])
 @pytest.mark.parametrize("path", GOLDEN_FILES, ids=IDS)
 def test_every_trial_verdict_replays_through_oracle(hs, path, impl, oracle_built):
     g = dict(np.load(path))
