@@ -11,7 +11,8 @@ configs[3] -- the configuration the headline metric is quoted on; it fits one B2
 the same total system is slab-decomposed over N GPUs ("scaling": "strong").
 
 A step = one hsmc_gpu_sweep_nvt() call of --sweeps-per-step sweeps (each sweep = N trial
-moves = 8 checkerboard colour phases + one grid shift / cell-list rebuild).  `value` is
+moves = 8 checkerboard block phases, each running the 8 cell colours of its blocks inside
+the CTA, + one grid shift / cell-list rebuild).  `value` is
 timed on the device (CUDA events on the handle's stream) with the configuration resident
 in HBM; `e2e` is the same call driven from pinned HOST buffers: upload of the {id,x,y,z}
 table, the sweeps, download of the table and the move counters, wall-clock.
@@ -349,7 +350,7 @@ def main():
     assert moves == N * S * args.steps, (moves, N * S * args.steps)
     value = moves / (ms_total * 1e-3)
 
-    # ---- roofline of the dominant kernel (sweep colour phase) ----
+    # ---- roofline of the dominant kernel (one launch = one block phase = N/8 trial moves) ----
     ncell = info["cells"][0] * info["cells"][1] * info["cells"][2]
     nbar = N / ncell
     b_move = 32.0 * (27.0 * nbar + 2.0)               # double4 slots: 32 B, SURVEY 8(d) with 16 -> 32
@@ -360,7 +361,7 @@ def main():
     peak, peak_src = measured_peak()
     traffic = ncu_traffic()
     roofline = {
-        "bound": "hbm", "kernel": "k_sweep_phase", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "bound": "hbm", "kernel": "k_sweep_block" if (args.sweep_impl & 0xff) in (0, 3, 5, 6) else "k_sweep_tile+k_sweep_deep", "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "peak_source": peak_src,
         "algorithmic_bytes_per_move": b_move, "nbar": nbar, "moves_per_launch": moves_local / max(sweep_groups, 1),
         "avg_launch_ms": per_launch_s * 1e3, "launches_timed": sweep_groups,

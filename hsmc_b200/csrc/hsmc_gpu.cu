@@ -243,10 +243,19 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* total) {
 __global__ void k_scan_blocksum(const int* __restrict__ in, long long n, int* __restrict__ bsum) {
   long long base = (long long)blockIdx.x * SCAN_CHUNK;
   int s = 0;
+  if (base + SCAN_CHUNK <= n) {
+    const int4* p4 = reinterpret_cast<const int4*>(in + base);
 #pragma unroll
-  for (int j = 0; j < SCAN_V; j++) {
-    long long i = base + (long long)j * SCAN_T + threadIdx.x;
-    if (i < n) s += in[i];
+    for (int j = 0; j < SCAN_V / 4; j++) {
+      const int4 a = p4[j * SCAN_T + threadIdx.x];
+      s += a.x + a.y + a.z + a.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < SCAN_V; j++) {
+      long long i = base + (long long)j * SCAN_T + threadIdx.x;
+      if (i < n) s += in[i];
+    }
   }
   int tot;
   block_exclusive_scan(s, &tot);
@@ -278,28 +287,45 @@ __global__ void k_scan_final(const int* __restrict__ in, long long n, const int*
   long long base = (long long)blockIdx.x * SCAN_CHUNK + (long long)threadIdx.x * SCAN_V;
   int v[SCAN_V];
   int s = 0;
+  static_assert(SCAN_V == 8, "two int4 per thread");
+  if (base + SCAN_V <= n) {                       // 32-byte vector path (cudaMalloc'd arrays, base % 8 == 0)
+    const int4 a0 = reinterpret_cast<const int4*>(in + base)[0], a1 = reinterpret_cast<const int4*>(in + base)[1];
+    v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+  } else {
 #pragma unroll
-  for (int j = 0; j < SCAN_V; j++) {
-    long long i = base + j;
-    v[j] = (i < n) ? in[i] : 0;
-    s += v[j];
+    for (int j = 0; j < SCAN_V; j++) v[j] = (base + j < n) ? in[base + j] : 0;
   }
+#pragma unroll
+  for (int j = 0; j < SCAN_V; j++) s += v[j];
   int tot;
   int ex = block_exclusive_scan(s, &tot) + bsum[blockIdx.x];
+  int o[SCAN_V];
 #pragma unroll
-  for (int j = 0; j < SCAN_V; j++) {
-    long long i = base + j;
-    if (i < n) out[i] = ex;
-    ex += v[j];
-    if (i == n - 1) out[n] = ex;
-    if (v[j] >= 3 && deep_list) {
-      int iz = (int)(i % g.nz);
-      long long r = i / g.nz;
-      int iy = (int)(r % g.ny), l = (int)(r / g.ny);
-      if (l >= g.own_lo && l < g.own_hi) {
-        int colour = (((g.gx0 + l) & 1) << 2) | ((iy & 1) << 1) | (iz & 1);
-        int slot = atomicAdd(&deep_count[colour], 1);
-        if (slot < list_stride) deep_list[(long long)colour * list_stride + slot] = (int)i;
+  for (int j = 0; j < SCAN_V; j++) { o[j] = ex; ex += v[j]; }
+  if (base + SCAN_V <= n) {
+    reinterpret_cast<int4*>(out + base)[0] = make_int4(o[0], o[1], o[2], o[3]);
+    reinterpret_cast<int4*>(out + base)[1] = make_int4(o[4], o[5], o[6], o[7]);
+    if (base + SCAN_V == n) out[n] = ex;
+  } else {
+#pragma unroll
+    for (int j = 0; j < SCAN_V; j++) {
+      if (base + j < n) out[base + j] = o[j];
+      if (base + j == n - 1) out[n] = o[j] + v[j];
+    }
+  }
+  if (deep_list) {
+#pragma unroll
+    for (int j = 0; j < SCAN_V; j++) {
+      const long long i = base + j;
+      if (i < n && v[j] >= 3) {
+        int iz = (int)(i % g.nz);
+        long long r = i / g.nz;
+        int iy = (int)(r % g.ny), l = (int)(r / g.ny);
+        if (l >= g.own_lo && l < g.own_hi) {
+          int colour = (((g.gx0 + l) & 1) << 2) | ((iy & 1) << 1) | (iz & 1);
+          int slot = atomicAdd(&deep_count[colour], 1);
+          if (slot < list_stride) deep_list[(long long)colour * list_stride + slot] = (int)i;
+        }
       }
     }
   }
@@ -326,7 +352,7 @@ __global__ void k_cs16(const int* __restrict__ cs, long long nrow, int nz, unsig
                        int* __restrict__ flags) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nrow * (nz + 1)) return;
-  const long long row = t / (nz + 1);
+  const long long row = (unsigned)t / (unsigned)(nz + 1);      // cells < 2^31, so rows x (nz + 1) < 2^32
   const int z = (int)(t - row * (nz + 1));
   const int v = cs[row * nz + z] - cs[row * nz];
   if (v > 65535) atomicOr(flags, 64);
