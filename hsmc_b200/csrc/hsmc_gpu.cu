@@ -652,9 +652,9 @@ __global__ void k_trial_points(Grid g, Box sbox, double sf, const double4* __res
 #define RDF_MAX_SMEM_BINS 8192
 __global__ void __launch_bounds__(RDF_T)
 k_rdf_pairs(const double4* __restrict__ pos, int n, Box box, double rmax, double r2_pre, double dr_bin,
-            int nn, int ntile, unsigned long long* __restrict__ hist) {
+            int nn, int ntile, long long b0, unsigned long long* __restrict__ hist) {
   // linear block index -> (ti, tj) with tj >= ti
-  long long b = blockIdx.x;
+  long long b = b0 + blockIdx.x;
   int ti = 0;
   {
     // rows of the upper triangle have ntile - ti entries
@@ -1903,7 +1903,18 @@ extern "C" int hsmc_gpu_rescale(hsmc_gpu* h, double sf, const double new_box[3])
   if (!h || !new_box) return fail("null argument");
   if (!h->have_conf) return fail("no configuration uploaded");
   CU(cudaSetDevice(h->cfg.device));
-  if (h->cfg.world > 1) return fail("rescale: NpT volume moves are not supported in slab mode yet");
+  if (h->cfg.world > 1) {
+    // slab mode: every resident particle (owned + ghosts) is rescaled in place; as long as the
+    // cell COUNT per axis is unchanged the layers a rank owns scale with the box, so ownership
+    // is preserved up to rounding and the ordinary regrid exchange repairs the rest
+    TRY(fresh_ghosts(h));
+    TRY(sync_layout(h));
+    const int onx = h->g.nx, ony = h->g.ny, onz = h->g.nz;
+    if (even_cells(new_box[0], h->cfg.cell_min) != onx || even_cells(new_box[1], h->cfg.cell_min) != ony ||
+        even_cells(new_box[2], h->cfg.cell_min) != onz)
+      return fail("rescale: this volume change alters the cell grid, which needs a redistribution of the slabs; "
+                  "download_owned / upload the configuration (or run NpT on one GPU)");
+  }
   k_rescale<<<nblk(h->n_local, 256), 256, 0, h->st>>>(h->pos[h->cur], (int)h->n_local, sf, new_box[0],
                                                        new_box[1], new_box[2]);
   h->launches++;
@@ -1912,6 +1923,11 @@ extern "C" int hsmc_gpu_rescale(hsmc_gpu* h, double sf, const double new_box[3])
   double sx = h->g.sx / h->g.wx, sy = h->g.sy / h->g.wy, sz = h->g.sz / h->g.wz;
   TRY(setup_grid(h));
   h->g.sx = sx * h->g.wx; h->g.sy = sy * h->g.wy; h->g.sz = sz * h->g.wz;
+  if (h->cfg.world > 1) {
+    h->ghost1_stale = false;
+    TRY(rebuild(h, h->pos[h->cur], 0, 0, 0, true));
+    return sync_layout(h);
+  }
   TRY(rebuild(h, h->pos[h->cur], h->n_local, 0, 0));
   return 0;
 }
@@ -1947,7 +1963,12 @@ extern "C" int hsmc_gpu_widom(hsmc_gpu* h, uint64_t sample_id, int64_t first, in
 }
 
 extern "C" int hsmc_gpu_rdf_counts(hsmc_gpu* h, double dr_bin, int nn, uint64_t* counts) {
+  return hsmc_gpu_rdf_counts_part(h, dr_bin, nn, 0, 1, counts);
+}
+
+extern "C" int hsmc_gpu_rdf_counts_part(hsmc_gpu* h, double dr_bin, int nn, int part, int nparts, uint64_t* counts) {
   if (!h || !counts) return fail("null argument");
+  if (nparts < 1 || part < 0 || part >= nparts) return fail("rdf: bad part/nparts");
   if (!h->have_conf) return fail("no configuration uploaded");
   if (h->cfg.world > 1) return fail("rdf: the all-pairs histogram needs the whole configuration on one GPU (world == 1)");
   if (nn < 1 || nn > SCRATCH_N) return fail("rdf: bin count out of range");
@@ -1961,9 +1982,13 @@ extern "C" int hsmc_gpu_rdf_counts(hsmc_gpu* h, double dr_bin, int nn, uint64_t*
   long long nblocks = (long long)ntile * (ntile + 1) / 2;
   if (nblocks > 0x7fffffffLL) return fail("rdf: system too large for the all-pairs histogram");
   size_t smem = sizeof(double) * 3 * RDF_T + sizeof(unsigned int) * (nn <= RDF_MAX_SMEM_BINS ? nn : 0);
-  k_rdf_pairs<<<(unsigned)nblocks, RDF_T, smem, h->st>>>(h->pos[h->cur], (int)h->N, make_box(g.Lx, g.Ly, g.Lz, 1.0),
-                                                         rmax, r2_pre, dr_bin, nn, ntile, h->d_scratch);
-  h->launches++;
+  // this caller's share of the tile pairs (replicated configuration, pair triangle sharded k ways)
+  const long long b0 = nblocks * part / nparts, b1 = nblocks * (part + 1) / nparts;
+  if (b1 > b0) {
+    k_rdf_pairs<<<(unsigned)(b1 - b0), RDF_T, smem, h->st>>>(h->pos[h->cur], (int)h->N, make_box(g.Lx, g.Ly, g.Lz, 1.0),
+                                                             rmax, r2_pre, dr_bin, nn, ntile, b0, h->d_scratch);
+    h->launches++;
+  }
   CU(cudaGetLastError());
   unsigned long long* hs = (unsigned long long*)h->h_stage;
   CU(cudaMemcpyAsync(hs, h->d_scratch, sizeof(unsigned long long) * nn, cudaMemcpyDeviceToHost, h->st));

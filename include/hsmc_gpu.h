@@ -122,7 +122,8 @@ int hsmc_gpu_sweep_nvt(hsmc_gpu *h, int n_sweeps, double dr_max);
 int hsmc_gpu_overlap_scaled(hsmc_gpu *h, double sf, int *overlap);
 
 /* Accepted volume move (moves.c:129-142): coordinates *= sf, PBC, new box
-   (the host recomputes it with sim_box_init), cell list rebuilt. */
+   (the host recomputes it with sim_box_init), cell list rebuilt.  world > 1: supported while
+   the number of cells per axis does not change (slab ownership then scales with the box). */
 int hsmc_gpu_rescale(hsmc_gpu *h, double sf, const double new_box[3]);
 
 /* widom_insertion() (compute_widom_chem_pot.c:44-71): insertion points
@@ -137,6 +138,12 @@ int hsmc_gpu_widom(hsmc_gpu *h, uint64_t sample_id, int64_t first, int64_t count
 /* rdf_hist_compute() (compute_rdf.c:110-128): pair counts per bin, bin =
    (int)((dr-1.0)/dr_bin) for dr < dr_bin*nn + 1.0.  rdf_hist[k] = 2.0 * counts[k]. */
 int hsmc_gpu_rdf_counts(hsmc_gpu *h, double dr_bin, int nn, uint64_t *counts);
+
+/* The same histogram sharded over GPUs: every process holds the WHOLE configuration
+   (world == 1 handles, replicated upload) and counts the tile pairs of share `part` of `nparts`;
+   the caller sums the nparts results (NCCL / torch.distributed all-reduce).  The sum over all
+   parts equals hsmc_gpu_rdf_counts bin for bin. */
+int hsmc_gpu_rdf_counts_part(hsmc_gpu *h, double dr_bin, int nn, int part, int nparts, uint64_t *counts);
 
 /* pressv_compute_hist() (compute_press.c:123-165): same binning restricted to
    r < dr_bin*nn + 1.0 <= cell edge, through the cell list.  pressv_hist[k] = 2.0*counts[k]. */

@@ -57,12 +57,27 @@ def main():
         h.upload(rows)
         h.sweep_nvt(3, dr_max)
         rows2 = h.download_owned().copy()
+        # third leg: an accepted NpT volume move in slab mode (cell counts unchanged), then more sweeps
+        sf_v = 1.0004
+        h.rescale(sf_v, np.asarray(box) * sf_v)
+        ovl_v = h.overlap_scaled(1.0)
+        h.sweep_nvt(2, dr_max)
+        rows3 = h.download_owned().copy()
         info = h.info()
+        # RDF sharded over the ranks: replicated configuration on a world-1 handle per rank
+        with hsmc_b200.HsmcGpu(N, box, seed=seed, device=lr) as rep:
+            rep.upload(conf)
+            nn_rdf = int((min(box) / 2 - 1.0) / 0.02)
+            rdf_part = torch.from_numpy(rep.rdf_counts_part(0.02, nn_rdf, rank, world).astype(np.int64))
+            dist.all_reduce(rdf_part)
+            rdf_full = rep.rdf_counts(0.02, nn_rdf).astype(np.int64) if rank == 0 else None
     gathered = [None] * world
-    dist.gather_object((rows, rows2, info0["own_x"]), gathered if rank == 0 else None, dst=0)
+    dist.gather_object((rows, rows2, info0["own_x"], rows3), gathered if rank == 0 else None, dst=0)
     if rank == 0:
         allrows = np.concatenate([g[0] for g in gathered])
         allrows2 = np.concatenate([g[1] for g in gathered])
+        allrows3 = np.concatenate([g[3] for g in gathered])
+        multi3 = allrows3[np.argsort(allrows3[:, 0])]
         print("slabs:", [g[2] for g in gathered], "rows:", [len(g[0]) for g in gathered], flush=True)
         ok &= allrows.shape[0] == N and np.array_equal(np.sort(allrows[:, 0]), np.arange(N))
         multi = allrows[np.argsort(allrows[:, 0])]
@@ -84,6 +99,11 @@ def main():
             s.set_sweep_counter(sweeps)
             s.sweep_nvt(3, dr_max)
             checks["reupload_continue"] = np.array_equal(s.download(), multi2)
+            s.rescale(sf_v, np.asarray(box) * sf_v)
+            checks["volume_move_verdict"] = s.overlap_scaled(1.0) == ovl_v
+            s.sweep_nvt(2, dr_max)
+            checks["volume_move_continue"] = np.array_equal(s.download(), multi3)
+            checks["rdf_sharded"] = np.array_equal(rdf_part.numpy(), rdf_full)
         print("nccl calls per rank:", info["nccl_calls"], "acceptance:", cnt[1] / cnt[0], flush=True)
         for k, v in checks.items():
             print(f"{k}: {'ok' if v else 'MISMATCH'}", flush=True)
