@@ -769,6 +769,100 @@ __global__ void k_min_r2(Grid g, Box box, const double4* __restrict__ pos, const
   if ((threadIdx.x & 31) == 0 && best < 1e299) atomicMin(out, (unsigned long long)__double_as_longlong(best));
 }
 
+
+// ----------------------------------------------------------------------------------
+// K8: Steinhardt bond-order parameter q_l (compute_order_parameter.c:84-229), SURVEY 8f #1.
+// One thread per owned particle: bonds = stencil neighbours with r <= rmax (rmax <= cell edge),
+// q_lm(i) = <Y_lm(r_ij)>_bonds, q_l(i) = sqrt(4 pi/(2l+1) sum_m |q_lm|^2) -- |q_l,-m| = |q_l,m|,
+// so m runs over 0..l with weight 2 for m > 0.  Y_lm by the normalised three-term recurrence
+// (coefficients in constant memory), e^{i m phi} by rotation; all in double.  A floating-point
+// observable (3-sigma contract), not on the bit-exact surface; the sum over particles is reduced
+// in a fixed order so results are reproducible run to run.
+// ----------------------------------------------------------------------------------
+#define QL_MAX_L 12
+#define QL_T 128
+__constant__ double c_ql_A[(QL_MAX_L + 1) * (QL_MAX_L + 1)];   // A(k,m) = sqrt((4k^2-1)/(k^2-m^2))
+__constant__ double c_ql_B[(QL_MAX_L + 1) * (QL_MAX_L + 1)];   // B(k,m) = sqrt(((k-1)^2-m^2)/(4(k-1)^2-1))
+__constant__ double c_ql_D[QL_MAX_L + 2];                       // D(m) = sqrt((2m+1)/(2m))
+
+__global__ void __launch_bounds__(QL_T)
+k_order_param(Grid g, Box box, const double4* __restrict__ pos, const int* __restrict__ cs, int first, int n,
+              int l, double rmax, double* __restrict__ partial) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  double q = 0.0;
+  if (t < n) {
+    const double4 p = pos[first + t];
+    const int ll = local_layer(g, axis_cell(p.x, g.sx, g.iwx, g.nx));
+    const int iy = axis_cell(p.y, g.sy, g.iwy, g.ny), iz = axis_cell(p.z, g.sz, g.iwz, g.nz);
+    double re[QL_MAX_L + 1], im[QL_MAX_L + 1];
+    for (int m = 0; m <= l; m++) re[m] = im[m] = 0.0;
+    int bonds = 0;
+    stencil_any(g, cs, ll, iy, iz, [&](int k) {
+      const double4 o = pos[k];
+      if (o.w == p.w) return false;
+      double dx = p.x - o.x, dy = p.y - o.y, dz = p.z - o.z;
+      if (dx > box.hx) dx -= box.Lx; else if (dx < -box.hx) dx += box.Lx;
+      if (dy > box.hy) dy -= box.Ly; else if (dy < -box.hy) dy += box.Ly;
+      if (dz > box.hz) dz -= box.Lz; else if (dz < -box.hz) dz += box.Lz;
+      const double rho2 = dx * dx + dy * dy, dr = sqrt(rho2 + dz * dz);
+      if (dr > rmax) return false;
+      bonds++;
+      const double rho = sqrt(rho2);
+      const double x = dz / dr, sth = rho / dr;
+      const double cph = rho > 0.0 ? dx / rho : 1.0, sph = rho > 0.0 ? dy / rho : 0.0;
+      double pmm = 0.28209479177387814;                  // sqrt(1/(4 pi))
+      double cm = 1.0, sm = 0.0;
+      for (int m = 0; m <= l; m++) {
+        double p0 = 0.0, p1 = pmm;
+        for (int k2 = m + 1; k2 <= l; k2++) {
+          const double p2 = c_ql_A[k2 * (QL_MAX_L + 1) + m] * (x * p1 - c_ql_B[k2 * (QL_MAX_L + 1) + m] * p0);
+          p0 = p1; p1 = p2;
+        }
+        re[m] += p1 * cm;
+        im[m] += p1 * sm;
+        pmm = -c_ql_D[m + 1] * sth * pmm;
+        const double c2 = cm * cph - sm * sph;
+        sm = sm * cph + cm * sph;
+        cm = c2;
+      }
+      return false;
+    });
+    double sum = 0.0;
+    if (bonds) {
+      const double inv = 1.0 / (double)bonds;
+      for (int m = 0; m <= l; m++) {
+        const double a = re[m] * inv, b = im[m] * inv;
+        sum += (m == 0 ? 1.0 : 2.0) * (a * a + b * b);
+      }
+    }
+    q = sqrt(sum * (4.0 * 3.14159265358979323846 / (double)(2 * l + 1)));
+  }
+  // fixed-order block reduction
+  __shared__ double sh[QL_T];
+  sh[threadIdx.x] = q;
+  __syncthreads();
+  for (int o = QL_T / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+
+// sum of the block partials in a fixed order (one block)
+__global__ void __launch_bounds__(256)
+k_sum_partials(const double* __restrict__ partial, int nb, double* __restrict__ out) {
+  __shared__ double sh[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < nb; i += 256) s += partial[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = sh[0];
+}
+
 // ----------------------------------------------------------------------------------
 // K7: accepted volume move (moves.c:135-141): x *= sf, then apply_pbc with the new box
 // ----------------------------------------------------------------------------------
@@ -2021,6 +2115,52 @@ extern "C" int hsmc_gpu_contact_counts(hsmc_gpu* h, double dr_bin, int nn, uint6
   CU(cudaMemcpyAsync(hs, h->d_scratch, sizeof(unsigned long long) * nn, cudaMemcpyDeviceToHost, h->st));
   CU(cudaStreamSynchronize(h->st));
   for (int k = 0; k < nn; k++) counts[k] = hs[k];
+  return 0;
+}
+
+
+extern "C" int hsmc_gpu_order_parameter(hsmc_gpu* h, int l, double rmax, double* ql_ave) {
+  if (!h || !ql_ave) return fail("null argument");
+  if (!h->have_conf) return fail("no configuration uploaded");
+  if (l < 0 || l > QL_MAX_L) return fail("order parameter: order l must be in [0, 12]");
+  CU(cudaSetDevice(h->cfg.device));
+  Grid& g = h->g;
+  if (!(rmax > 0.0) || rmax > std::min(g.wx, std::min(g.wy, g.wz)))
+    return fail("order parameter: the bond cutoff must not exceed the cell edge (27-cell stencil); reduce it to the neighbour-list size as the reference does");
+  TRY(sync_layout(h));
+  static bool coef_ready[64] = {false};
+  if (!coef_ready[h->cfg.device & 63]) {
+    double A[(QL_MAX_L + 1) * (QL_MAX_L + 1)] = {0}, B[(QL_MAX_L + 1) * (QL_MAX_L + 1)] = {0}, D[QL_MAX_L + 2] = {0};
+    for (int k = 1; k <= QL_MAX_L; k++)
+      for (int m = 0; m < k; m++) {
+        A[k * (QL_MAX_L + 1) + m] = sqrt((4.0 * k * k - 1.0) / ((double)k * k - (double)m * m));
+        B[k * (QL_MAX_L + 1) + m] = sqrt((((double)k - 1.0) * (k - 1.0) - (double)m * m) / (4.0 * (k - 1.0) * (k - 1.0) - 1.0));
+      }
+    for (int m = 1; m <= QL_MAX_L + 1; m++) D[m] = sqrt((2.0 * m + 1.0) / (2.0 * m));
+    CU(cudaMemcpyToSymbol(c_ql_A, A, sizeof(A)));
+    CU(cudaMemcpyToSymbol(c_ql_B, B, sizeof(B)));
+    CU(cudaMemcpyToSymbol(c_ql_D, D, sizeof(D)));
+    coef_ready[h->cfg.device & 63] = true;
+  }
+  const int64_t n = h->n_owned;
+  const int nb = nblk(std::max<int64_t>(n, 1), QL_T);
+  // block partials live in the (free) ping-pong table; the final sum goes to the scratch block
+  double* d_partial = reinterpret_cast<double*>(h->pos[h->cur ^ 1]);
+  if ((int64_t)nb * (int64_t)sizeof(double) > h->cap * (int64_t)sizeof(double4)) return fail("order parameter: scratch too small");
+  double* d_out = reinterpret_cast<double*>(h->d_scratch);
+  k_order_param<<<nb, QL_T, 0, h->st>>>(g, make_box(g.Lx, g.Ly, g.Lz, 1.0), h->pos[h->cur], h->cell_start,
+                                        (int)h->own_first, (int)n, l, rmax, d_partial);
+  k_sum_partials<<<1, 256, 0, h->st>>>(d_partial, nb, d_out);
+  h->launches += 2;
+  CU(cudaGetLastError());
+  if (h->cfg.world > 1) {
+    NC(ncclAllReduce(d_out, d_out, 1, ncclDouble, ncclSum, h->comm, h->st));
+    h->nccl_calls++;
+  }
+  double* hs = (double*)h->h_stage;
+  CU(cudaMemcpyAsync(hs, d_out, sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  *ql_ave = hs[0] / (double)h->N;     // compute_order_parameter.c:92-96
   return 0;
 }
 

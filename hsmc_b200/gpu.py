@@ -21,7 +21,7 @@ ABI_SYMBOLS = [
     "hsmc_gpu_destroy", "hsmc_gpu_ipc_export", "hsmc_gpu_ipc_attach", "hsmc_gpu_get_info", "hsmc_gpu_plan", "hsmc_gpu_stream", "hsmc_gpu_sync", "hsmc_gpu_upload",
     "hsmc_gpu_download", "hsmc_gpu_download_owned", "hsmc_gpu_sweep_nvt", "hsmc_gpu_overlap_scaled",
     "hsmc_gpu_rescale", "hsmc_gpu_widom", "hsmc_gpu_rdf_counts", "hsmc_gpu_rdf_counts_part", "hsmc_gpu_contact_counts",
-    "hsmc_gpu_presst_flags", "hsmc_gpu_counters", "hsmc_gpu_reset_counters", "hsmc_gpu_add_vol_move",
+    "hsmc_gpu_presst_flags", "hsmc_gpu_order_parameter", "hsmc_gpu_counters", "hsmc_gpu_reset_counters", "hsmc_gpu_add_vol_move",
     "hsmc_gpu_cell_rejects", "hsmc_gpu_profile", "hsmc_gpu_profile_read", "hsmc_gpu_set_sweep_counter", "hsmc_gpu_trial_verdicts",
     "hsmc_gpu_widom_verdicts", "hsmc_gpu_sweep_nvt_logged", "hsmc_gpu_selftest_u01", "hsmc_gpu_min_dist2",
 ]
@@ -85,6 +85,7 @@ def load_library():
     L.hsmc_gpu_rescale.argtypes = [vp, C.c_double, dp]
     L.hsmc_gpu_widom.argtypes = [vp, C.c_uint64, C.c_int64, C.c_int64, C.c_int, C.POINTER(C.c_int64)]
     L.hsmc_gpu_rdf_counts.argtypes = [vp, C.c_double, C.c_int, vp]
+    L.hsmc_gpu_order_parameter.argtypes = [vp, C.c_int, C.c_double, dp]
     L.hsmc_gpu_rdf_counts_part.argtypes = [vp, C.c_double, C.c_int, C.c_int, C.c_int, vp]
     L.hsmc_gpu_contact_counts.argtypes = [vp, C.c_double, C.c_int, vp]
     L.hsmc_gpu_presst_flags.argtypes = [vp, vp, C.c_int, vp]
@@ -254,6 +255,12 @@ class HsmcGpu:
         c = np.zeros(nn, dtype=np.uint64)
         self._ck(self.L.hsmc_gpu_rdf_counts_part(self.h, float(dr), int(nn), int(part), int(nparts), _ptr(c)))
         return c
+
+    def order_parameter(self, l, rmax):
+        """Average Steinhardt q_l (compute_order_parameter.c:84-229); rmax <= cell edge."""
+        o = C.c_double(0)
+        self._ck(self.L.hsmc_gpu_order_parameter(self.h, int(l), float(rmax), C.byref(o)))
+        return o.value
 
     def contact_counts(self, dr, nn):
         c = np.zeros(nn, dtype=np.uint64)

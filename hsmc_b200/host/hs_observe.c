@@ -178,33 +178,12 @@ void hs_compute_rdf(hs_sim *s, bool init, int sweep) {
   }
 }
 
-/* ---- Steinhardt order parameter q_l (host; SURVEY.md section 8f "next" #1) -----------------
+/* ---- Steinhardt order parameter q_l on the GPU (hsmc_gpu_order_parameter, K8) ---------------
  * q_l(i) = sqrt(4 pi/(2l+1) sum_m |<Y_lm>_bonds|^2), bonds = neighbours within ql_rmax
- * (compute_order_parameter.c:99-229).  Evaluated on the host mirror with a private
- * linked-cell search; normalised associated Legendre functions by recurrence. */
-static double sph_plm(int l, int m, double x) {
-  double pmm = 1.0;
-  if (m > 0) {
-    double s = sqrt((1.0 - x) * (1.0 + x)), f = 1.0;
-    for (int i = 1; i <= m; i++, f += 2.0) pmm *= -f * s;
-  }
-  double p = pmm;
-  if (l > m) {
-    double p1 = x * (2.0 * m + 1.0) * pmm;
-    p = p1;
-    for (int k = m + 2; k <= l; k++) {
-      double pk = (x * (2.0 * k - 1.0) * p1 - (k + m - 1.0) * pmm) / (double)(k - m);
-      pmm = p1; p1 = pk; p = pk;
-    }
-  }
-  double ratio = 1.0;
-  for (int k = l - m + 1; k <= l + m; k++) ratio /= (double)k;
-  return sqrt((2.0 * l + 1.0) / (4.0 * M_PI) * ratio) * p;
-}
-
+ * (compute_order_parameter.c:84-229); the host only keeps the reference's cutoff rule, its
+ * WARNING text and the output file. */
 void hs_compute_op(hs_sim *s, bool init) {
   hs_input *in = &s->in;
-  const int N = s->part.NN, l = in->ql_order;
   const double L[3] = {s->box.lx, s->box.ly, s->box.lz};
   if (init) {
     /* compute_order_parameter.c:29-40: the reference limits the cutoff to the edge of ITS
@@ -222,68 +201,17 @@ void hs_compute_op(hs_sim *s, bool init) {
       printf("WARNING: The cutoff for the order parameter was reduced to %f in order to be consistent with the neighbor list size\n", nl_size);
       in->ql_rmax = nl_size;
     }
-    double lmin = fmin(L[0], fmin(L[1], L[2]));
-    if (in->ql_rmax > lmin / 2.0) in->ql_rmax = lmin / 2.0;
   }
-  hs_gpu_pull(s);
-  int nc[3];
-  for (int a = 0; a < 3; a++) { nc[a] = (int)floor(L[a] / in->ql_rmax); if (nc[a] < 1) nc[a] = 1; }
-  int ncell = nc[0] * nc[1] * nc[2];
-  int *head = malloc(sizeof(int) * (size_t)ncell), *next = malloc(sizeof(int) * (size_t)N);
-  for (int c = 0; c < ncell; c++) head[c] = -1;
-  int ci[3];
-  for (int i = 0; i < N; i++) {
-    for (int a = 0; a < 3; a++) {
-      ci[a] = (int)(s->conf[i][a + 1] / L[a] * nc[a]);
-      if (ci[a] >= nc[a]) ci[a] = nc[a] - 1;
-      if (ci[a] < 0) ci[a] = 0;
-    }
-    int c = (ci[0] * nc[1] + ci[1]) * nc[2] + ci[2];
-    next[i] = head[c]; head[c] = i;
+  /* the GPU cell grid (even cell counts, edge >= neigh_dr) bounds the bond cutoff the same way */
+  hsmc_gpu_info gi;
+  hs_gpu_check(hsmc_gpu_get_info(s->gpu, &gi));
+  double edge = fmin(gi.cell_size[0], fmin(gi.cell_size[1], gi.cell_size[2]));
+  if (edge < in->ql_rmax) {
+    printf("WARNING: The cutoff for the order parameter was reduced to %f in order to be consistent with the neighbor list size\n", edge);
+    in->ql_rmax = edge;
   }
-  double *re = malloc(sizeof(double) * (size_t)(l + 1)), *im = malloc(sizeof(double) * (size_t)(l + 1));
   double ql_ave = 0.0;
-  for (int i = 0; i < N; i++) {
-    for (int m = 0; m <= l; m++) re[m] = im[m] = 0.0;
-    int bonds = 0;
-    for (int a = 0; a < 3; a++) {
-      ci[a] = (int)(s->conf[i][a + 1] / L[a] * nc[a]);
-      if (ci[a] >= nc[a]) ci[a] = nc[a] - 1;
-    }
-    int seen[27], nseen = 0;
-    for (int dx = -1; dx <= 1; dx++) for (int dy = -1; dy <= 1; dy++) for (int dz = -1; dz <= 1; dz++) {
-      int cx = (ci[0] + dx + nc[0]) % nc[0], cy = (ci[1] + dy + nc[1]) % nc[1], cz = (ci[2] + dz + nc[2]) % nc[2];
-      int c = (cx * nc[1] + cy) * nc[2] + cz, dup = 0;
-      for (int q = 0; q < nseen; q++) if (seen[q] == c) dup = 1;
-      if (dup) continue;
-      seen[nseen++] = c;
-      for (int j = head[c]; j >= 0; j = next[j]) {
-        if (j == i) continue;
-        double d[3];
-        for (int a = 0; a < 3; a++) {
-          d[a] = s->conf[i][a + 1] - s->conf[j][a + 1];
-          if (d[a] > L[a] / 2.0) d[a] -= L[a]; else if (d[a] < -L[a] / 2.0) d[a] += L[a];
-        }
-        double dr = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-        if (dr > in->ql_rmax) continue;
-        double phi = atan2(d[1], d[0]);
-        if (phi < 0) phi += 2. * M_PI;
-        bonds++;
-        for (int m = 0; m <= l; m++) {
-          double plm = sph_plm(l, m, d[2] / dr);
-          re[m] += plm * cos(m * phi);
-          im[m] += plm * sin(m * phi);
-        }
-      }
-    }
-    double sum = 0.0;
-    for (int m = 0; m <= l; m++) {
-      double a = bonds ? re[m] / bonds : 0.0, b = bonds ? im[m] / bonds : 0.0;
-      sum += (m == 0 ? 1.0 : 2.0) * (a * a + b * b);   /* |Y_l,-m| = |Y_l,m| */
-    }
-    ql_ave += sqrt(sum * 4 * M_PI / (2 * l + 1)) / N;
-  }
-  free(re); free(im); free(head); free(next);
+  hs_gpu_check(hsmc_gpu_order_parameter(s->gpu, in->ql_order, in->ql_rmax, &ql_ave));
   FILE *f = open_sample_file("order_param.dat", init, "order parameter");
   if (init) {
     fprintf(f, "###############################################################\n");

@@ -149,6 +149,13 @@ int hsmc_gpu_rdf_counts_part(hsmc_gpu *h, double dr_bin, int nn, int part, int n
    r < dr_bin*nn + 1.0 <= cell edge, through the cell list.  pressv_hist[k] = 2.0*counts[k]. */
 int hsmc_gpu_contact_counts(hsmc_gpu *h, double dr_bin, int nn, uint64_t *counts);
 
+/* global_ql_compute() (compute_order_parameter.c:84-97, per particle :99-229): the average over
+   all particles of the Steinhardt bond-order parameter q_l, bonds = neighbours within rmax.
+   rmax must not exceed the cell edge (the reference clips it to its neighbour-list cell size,
+   compute_order_parameter.c:29-40; the host driver does the same before calling).  l <= 12.
+   Floating point (1e-12 relative against the reference); collective over all ranks. */
+int hsmc_gpu_order_parameter(hsmc_gpu *h, int l, double rmax, double *ql_ave);
+
 /* presst_compute_hist() (compute_press.c:239-273): for each scale factor sf[k]
    (host computes pow(1-xi_k, 1./3.) as the reference does) no_overlap[k] = 1 iff the
    compressed system has no overlapping pair.  One pass over the pairs for all k. */

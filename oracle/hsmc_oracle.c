@@ -379,6 +379,58 @@ void orc_pressv_counts(const orc_sys *s, double dr_bin, int nn, uint64_t *counts
   }
 }
 
+/* ---- compute_order_parameter.c:84-229 ----
+ * gsl_sf_legendre_sphPlm restated in gsl_shim/gsl/gsl_sf_legendre.h (GSL is a third-party
+ * dependency absent from the reference tree; not on the bit-exact surface). */
+#include "gsl_shim/gsl/gsl_sf_legendre.h"
+double orc_order_param(const orc_sys *s, int l, double rmax) {
+  const int tlp1 = 2 * l + 1;
+  double *qlm2 = (double *)malloc(sizeof(double) * (size_t)tlp1);
+  const double lx_2 = s->lx / 2.0, ly_2 = s->ly / 2.0, lz_2 = s->lz / 2.0;   /* :108-110 */
+  double ql_ave = 0.0;
+  for (int ref = 0; ref < s->N; ref++) {
+    int cell = orc_cell_of(s, ref);
+    for (int mm = 0; mm < l + 1; mm++) {                                     /* :154-226 */
+      int num_bonds = 0;
+      double qr = 0., qi = 0., qmr = 0., qmi = 0.;
+      for (int ii = 0; ii < 27; ii++) {
+        int nb = s->neigh[(size_t)cell * 27 + ii];
+        const int *row = &s->pc[(size_t)nb * s->max_part];
+        for (int jj = 1; jj <= row[0]; jj++) {
+          int p = row[jj];
+          double dx = X(s, ref) - X(s, p);
+          double dy = Y(s, ref) - Y(s, p);
+          double dz = Z(s, ref) - Z(s, p);
+          if (dx > lx_2) dx -= s->lx; else if (dx < -lx_2) dx += s->lx;
+          if (dy > ly_2) dy -= s->ly; else if (dy < -ly_2) dy += s->ly;
+          if (dz > lz_2) dz -= s->lz; else if (dz < -lz_2) dz += s->lz;
+          double dr = sqrt(dx * dx + dy * dy + dz * dz);
+          if (p != ref && dr <= rmax) {
+            double phi = atan2(dy, dx);
+            if (phi < 0) phi += 2. * M_PI;
+            num_bonds++;
+            double plm = gsl_sf_legendre_sphPlm(l, mm, dz / dr);
+            qr += plm * cos(mm * phi);
+            qi += plm * sin(mm * phi);
+            if (mm % 2 != 0) plm *= -1.0;
+            qmr += plm * cos(-mm * phi);
+            qmi += plm * sin(-mm * phi);
+          }
+        }
+      }
+      if (num_bonds != 0) { qr /= num_bonds; qi /= num_bonds; qmr /= num_bonds; qmi /= num_bonds; }
+      qlm2[l + mm] = qr * qr + qi * qi;
+      qlm2[l - mm] = qmr * qmr + qmi * qmi;
+    }
+    double q = 0.0;                                                          /* :120-126 */
+    for (int jj = 0; jj < tlp1; jj++) q += qlm2[jj];
+    q *= 4 * M_PI / tlp1;
+    ql_ave += sqrt(q) / s->N;                                                /* :92-96 */
+  }
+  free(qlm2);
+  return ql_ave;
+}
+
 /* ---- compute_press.c:211,228-235,250-271 ---- */
 int orc_presst_nn(double dxi, double xi_max) { return (int)(xi_max / dxi); }
 void orc_presst_flags(const orc_sys *s, double dxi, int nn, int *flags, double *sf_out) {

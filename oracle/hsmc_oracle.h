@@ -70,6 +70,9 @@ void orc_pressv_counts(const orc_sys *s, double dr, int nn, uint64_t *counts);  
 int orc_presst_nn(double dxi, double xi_max);                                    /* :211 */
 void orc_presst_flags(const orc_sys *s, double dxi, int nn, int *flags, double *sf_out); /* :250-271 */
 
+/* compute_order_parameter.c:84-229: average Steinhardt q_l, bonds = stencil neighbours within rmax */
+double orc_order_param(const orc_sys *s, int l, double rmax);
+
 /* Philox4x32-10 (Salmon et al., SC'11) -- the device RNG, restated for the checker */
 void orc_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 

@@ -109,6 +109,8 @@ class Port:
             L.orc_presst_nn.argtypes = [C.c_double, C.c_double]
             L.orc_presst_flags.argtypes = [C.c_void_p, C.c_double, C.c_int, _ip, _dp]
             L.orc_philox4x32.argtypes = [_u32p, _u32p, _u32p]
+            L.orc_order_param.argtypes = [C.c_void_p, C.c_int, C.c_double]
+            L.orc_order_param.restype = C.c_double
             L.orc_box_from_lattice.argtypes = [C.c_int] * 4 + [C.c_double, _dp]
             L.orc_lattice_count.argtypes = [C.c_int] * 4
             L.orc_lattice_fill.argtypes = [C.c_int] * 4 + [C.c_double, _dp]
@@ -239,6 +241,10 @@ class Port:
         self.L.orc_pressv_counts(self.h, dr, nn, _p(c, _u64p))
         return c
 
+    def order_param(self, l, rmax):
+        """Average Steinhardt q_l with bond cutoff rmax (<= cell edge of the neighbour list)."""
+        return float(self.L.orc_order_param(self.h, int(l), float(rmax)))
+
     def presst_flags(self, dxi, xi_max):
         nn = self.L.orc_presst_nn(dxi, xi_max)
         f = np.zeros(nn, dtype=np.int32)
@@ -302,6 +308,8 @@ class Ref:
             L.ref_widom_verdicts.argtypes = [C.c_int, _ip]
             L.ref_rdf_hist.argtypes = [C.c_double, C.c_double, _dp, C.c_int]
             L.ref_pressv_hist.argtypes = [C.c_double, _dp, C.c_int]
+            L.ref_order_param.argtypes = [C.c_int, C.c_double]
+            L.ref_order_param.restype = C.c_double
             L.ref_presst_hist.argtypes = [C.c_double, C.c_double, _dp, _dp, C.c_int]
             cls._lib = L
         return cls._lib
@@ -452,6 +460,10 @@ class Ref:
         self.L.ref_widom_verdicts(raw3.shape[0], _p(f, _ip))
         self.script(None)
         return f
+
+    def order_param(self, l, rmax):
+        """global_ql_compute() of the unmodified reference (compute_order_parameter.c:84-97)."""
+        return float(self.L.ref_order_param(int(l), float(rmax)))
 
     def rdf_hist(self, dr, rmax):
         buf = np.zeros(1 << 16)

@@ -7,7 +7,7 @@
  * calls the reference's own routines, and copies results out.  No reference
  * arithmetic is re-implemented here.
  *
- * compute_rdf.c / compute_press.c / compute_widom_chem_pot.c are compiled with
+ * compute_rdf.c / compute_press.c / compute_widom_chem_pot.c / compute_order_parameter.c are compiled with
  * -Dstatic= (oracle/Makefile) so that their histogram arrays are linkable.
  */
 #include <stdio.h>
@@ -43,6 +43,7 @@ extern int presst_hist_nn;
 extern double *presst_xi, *presst_hist;
 extern int wtest;
 extern double mu;
+extern double ql_ave;          /* compute_order_parameter.c:19 */
 
 static int harness_live = 0;
 
@@ -263,3 +264,16 @@ int ref_presst_hist(double dxi, double xi_max, double *hist_out, double *xi_out,
   presst_hist_free();
   return nn;
 }
+
+/* compute_order_parameter.c:84-97: global_ql_compute() = average over particles of the
+   Steinhardt q_l (ql_compute / qlm2_compute, :99-229) with cutoff rmax (the caller keeps it
+   <= the neighbour-list cell edge, as compute_op(init) does at :29-40) */
+double ref_order_param(int l, double rmax) {
+  G_IN.ql_order = l;
+  G_IN.ql_rmax = rmax;
+  ql_alloc();
+  global_ql_compute();
+  ql_free();
+  return ql_ave;
+}
+

@@ -53,6 +53,7 @@ def main():
         ovl = [h.overlap_scaled(sf) for sf in (1.0, 0.9995, 0.98)] if min(h.info()["cell_size"]) * 0.98 >= 1.0 else \
             [h.overlap_scaled(1.0)]
         mind = h.min_dist2()
+        q6 = h.order_parameter(6, min(h.info()["cell_size"]))
         # second leg: re-upload only what this rank owns (the e2e pattern) and continue
         h.upload(rows)
         h.sweep_nvt(3, dr_max)
@@ -91,6 +92,7 @@ def main():
                 "counters": np.array_equal(s.counters(), cnt),
                 "widom": s.widom(3, 200000) == wid,
                 "min_dist2": s.min_dist2() == mind and mind >= 1.0,
+                "order_parameter": abs(s.order_parameter(6, min(s.info()["cell_size"])) - q6) < 1e-12 and 0.0 < q6 <= 1.0,
                 "overlap": [s.overlap_scaled(sf) for sf in ((1.0, 0.9995, 0.98) if len(ovl) == 3 else (1.0,))] == ovl,
             }
             if con is not None:
@@ -104,7 +106,7 @@ def main():
             s.sweep_nvt(2, dr_max)
             checks["volume_move_continue"] = np.array_equal(s.download(), multi3)
             checks["rdf_sharded"] = np.array_equal(rdf_part.numpy(), rdf_full)
-        print("nccl calls per rank:", info["nccl_calls"], "acceptance:", cnt[1] / cnt[0], flush=True)
+        print("nccl calls per rank:", info["nccl_calls"], "acceptance:", cnt[1] / cnt[0], "q6:", q6, flush=True)
         for k, v in checks.items():
             print(f"{k}: {'ok' if v else 'MISMATCH'}", flush=True)
             ok &= bool(v)

@@ -179,3 +179,30 @@ def test_division_free_u01_is_exact_for_all_raw_values(hs):
     with hs.HsmcGpu(500, [8.5, 8.5, 8.5]) as h:
         n_bad, first = h.selftest_u01()
         assert n_bad == 0, f"{n_bad} mismatches, first at raw={first}"
+
+
+@pytest.mark.parametrize("path", GOLDEN_FILES, ids=IDS)
+def test_order_parameter_matches_reference_and_oracle(hs, path, oracle_built):
+    """q_l (compute_order_parameter.c:84-229): GPU value against (i) the committed outputs of the
+    unmodified reference (tests/golden/ql/ql_ref.json, made by tests/golden/make_ql_golden.py) and
+    (ii) the oracle restatement on a configuration the GPU evolved itself.  Floating point:
+    1e-12 relative (different but equivalent summation / recurrence order)."""
+    import json
+    ref = json.load(open(os.path.join(GOLDEN, "ql", "ql_ref.json")))[os.path.basename(path)[:-4]]
+    g = dict(np.load(path))
+    N = g["conf"].shape[0]
+    with hs.HsmcGpu(N, g["box"][:3], seed=3, cell_min=float(g["neigh_dr"])) as h:
+        h.upload(g["conf"])
+        edge = min(h.info()["cell_size"])
+        assert ref["rmax"] <= edge * (1 + 1e-12)
+        for l in (4, 6):
+            assert h.order_parameter(l, ref["rmax"]) == pytest.approx(ref["ql"][str(l)], rel=1e-12, abs=1e-13)
+        h.sweep_nvt(5, float(g["dr_max"]))
+        out = h.download()
+        p = oracle_built.Port(out, g["box"], neigh_dr=float(g["neigh_dr"]), max_part=12)
+        for l in (2, 6, 12):
+            assert h.order_parameter(l, ref["rmax"]) == pytest.approx(p.order_param(l, ref["rmax"]), rel=1e-12, abs=1e-13)
+        with pytest.raises(hs.HsmcError):
+            h.order_parameter(6, edge * 1.01)          # cutoff beyond the 27-cell stencil
+        with pytest.raises(hs.HsmcError):
+            h.order_parameter(13, ref["rmax"])

@@ -10,6 +10,7 @@ import pytest
 from conftest import GOLDEN
 
 GOLDEN_FILES = sorted(glob.glob(os.path.join(GOLDEN, "*.npz")))
+IDS = [os.path.basename(p)[:-4] for p in GOLDEN_FILES]
 
 
 def _load(path):
@@ -184,3 +185,28 @@ def test_port_volume_rescale_equals_reference(ref_mod):
             break
     assert ok
     del p
+
+
+@pytest.mark.parametrize("path", GOLDEN_FILES, ids=IDS)
+def test_order_parameter_port_matches_reference_outputs(path, oracle_built):
+    """orc_order_param (compute_order_parameter.c:84-229 restated) against the committed outputs of
+    the unmodified reference, and against the reference itself where oracle/_ref is present."""
+    import json
+    ref = json.load(open(os.path.join(GOLDEN, "ql", "ql_ref.json")))[os.path.basename(path)[:-4]]
+    g = dict(np.load(path))
+    p = oracle_built.Port(g["conf"], g["box"], neigh_dr=float(g["neigh_dr"]), max_part=12)
+    for l in (4, 6):
+        assert p.order_param(l, ref["rmax"]) == ref["ql"][str(l)]
+    if oracle_built.have_ref():
+        with oracle_built.Ref(conf=g["conf"], box=g["box"], neigh_dr=float(g["neigh_dr"]), max_part=12) as r:
+            for l in (4, 6):
+                assert r.order_param(l, ref["rmax"]) == ref["ql"][str(l)]
+
+
+def test_order_parameter_of_perfect_fcc(oracle_built):
+    """q6 of a perfect fcc lattice with first-shell bonds is 0.574524 (Steinhardt et al. 1983)."""
+    box, conf = oracle_built.Port.lattice(2, 5, 5, 5, 0.9)
+    p = oracle_built.Port(conf, box, neigh_dr=1.2, max_part=12)
+    a = (4 / 0.9) ** (1 / 3)
+    assert p.order_param(6, a / 2 ** 0.5 * 1.05) == pytest.approx(0.574524, abs=2e-6)
+    assert p.order_param(4, a / 2 ** 0.5 * 1.05) == pytest.approx(0.190941, abs=2e-6)
