@@ -1317,8 +1317,10 @@ static void setup_blocks(hsmc_gpu* h) {
       const int per_sm = (int)std::min<size_t>(4, (size_t)(227 * 1024) / (s.smem + 5 * 1024));
       if (per_sm < 1) continue;
       const double interior = (double)s.mx * s.my * s.mz;
-      const double score = std::min(1.0, (double)ctas / (148.0 * 4)) * (interior / (interior + 400.0)) * (per_sm / 4.0) +
-                           1e-9 * interior;
+      // below two waves of CTA slots the ragged last wave costs a whole CTA latency
+      const double waves = (double)ctas / (148.0 * per_sm);
+      const double fill = waves < 2.0 ? waves / std::ceil(waves) : 1.0;
+      const double score = fill * (interior / (interior + 400.0)) * (per_sm / 4.0) + 1e-9 * interior;
       if (score > best_score) { best_score = score; best = s; have = true; }
     }
   }

@@ -54,7 +54,7 @@ struct BlockRow { int gbA, gbB, cntA, off; };
 __device__ __noinline__ bool block_exact_rescan(const double4* pos, const BlockRow* s_row,
                                                 const unsigned short* s_cz, int cz_stride, int nry, int rxc,
                                                 int ryc, int rz, int sel, double xn, double yn, double zn,
-                                                const Box& box) {
+                                                const Box box) {
   for (int dx = -1; dx <= 1; dx++)
     for (int dy = -1; dy <= 1; dy++) {
       const int row = (rxc + dx) * nry + ryc + dy;

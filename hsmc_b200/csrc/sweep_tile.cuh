@@ -48,7 +48,7 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
 }
 
 template <bool LOG>
-__device__ __noinline__ void cell_update_global_noinline(const SweepArgs& a, int phase, double4* __restrict__ pos,
+__device__ __noinline__ void cell_update_global_noinline(const SweepArgs a, int phase, double4* __restrict__ pos,
                                                          float4* __restrict__ rel, const int* __restrict__ cs, int l,
                                                          int iy, int iz, int j0, int j1, int& n_acc, int& n_ov,
                                                          int& n_cell, hsmc_gpu_trial* __restrict__ log,
