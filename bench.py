@@ -200,6 +200,84 @@ def cpu_reference_arm(steps, warmup, cells, sweeps, cores):
     }
 
 
+
+# --------------------------------------------------------------------------------------
+# secondary kernels (insertions/s, pairs/s, particles/s), device-timed
+# --------------------------------------------------------------------------------------
+def _timed(stream, fn, reps=3):
+    """best-of-`reps` device time (ms) of one ABI call, CUDA events on the handle's stream"""
+    import torch
+    fn()                                      # warm-up
+    best = float("inf")
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        fn()
+        b.record(stream)
+        b.synchronize()
+        best = min(best, a.elapsed_time(b))
+    return best
+
+
+def secondary_observables(h, stream, N, nbar, peak, device):
+    """Throughput of the observables' kernels on the benchmark configuration (resident in HBM,
+    larger than L2), each with SURVEY 8(d)'s algorithmic bytes per unit (16 -> 32: double4
+    table) against the same HBM peak.  RDF is O(N^2) on shared-memory tiles (ALU / shared
+    atomics bound): measured on the C2 shape (fcc 20^3, N = 32 000) in pairs/s, no HBM
+    fraction.  q_l is measured on a fcc 64^3 box whose cells are wide enough (1.5) to hold
+    the first neighbour shell, as the reference's `ql` keyword needs."""
+    import torch
+    import hsmc_b200
+    out = {}
+
+    def entry(name, unit, units, ms, bytes_per_unit, what):
+        rate = units / (ms * 1e-3)
+        e = {"value": rate, "unit": unit, "ms": ms, "units_per_call": units, "what": what}
+        if bytes_per_unit:
+            gbs = rate * bytes_per_unit / 1e9
+            e.update(algorithmic_bytes_per_unit=bytes_per_unit, achieved_gbs=gbs, frac_of_hbm_peak=gbs / peak)
+        out[name] = e
+
+    M = 100_000_000
+    ms = _timed(stream, lambda: h.widom(7, M))
+    entry("widom", "insertions/s", M, ms, 32.0 * 27.0 * nbar, "hsmc_gpu_widom, 1e8 insertion points (k_widom)")
+    ms = _timed(stream, lambda: h.overlap_scaled(0.9999))
+    entry("overlap_scaled", "particles/s", N, ms, 32.0 * (27.0 * nbar + 1.0),
+          "hsmc_gpu_overlap_scaled(sf=0.9999): the NpT volume-move verdict (k_overlap_scaled)")
+    sf = (1.0 - 0.0001 * (np.arange(20) + 1.0)) ** (1.0 / 3.0)
+    ms = _timed(stream, lambda: h.presst_flags(sf))
+    entry("presst_flags", "particles/s", N, ms, 32.0 * (27.0 * nbar + 1.0),
+          "hsmc_gpu_presst_flags, 20 compressions in one pass (k_overlap_scaled)")
+    ms = _timed(stream, lambda: h.contact_counts(0.002, 1))
+    entry("contact_counts", "particles/s", N, ms, 32.0 * (27.0 * nbar + 1.0),
+          "hsmc_gpu_contact_counts(dr=0.002, bins up to the cell edge) (k_contact_hist)")
+
+    # RDF on the C2 shape
+    box2, conf2 = fcc_lattice(20, 20, 20, RHO)
+    with hsmc_b200.HsmcGpu(conf2.shape[0], box2, seed=3, device=device) as h2:
+        h2.upload(conf2)
+        h2.sweep_nvt(50, DR_MAX)
+        s2 = torch.cuda.ExternalStream(h2.stream_ptr(), device=torch.device("cuda", device))
+        nn = int((5.0 - 1.0) / 0.01)
+        ms = _timed(s2, lambda: h2.rdf_counts(0.01, nn))
+        n2 = conf2.shape[0]
+        entry("rdf", "pairs/s", n2 * (n2 - 1) // 2, ms, None,
+              "hsmc_gpu_rdf_counts(dr=0.01, rmax=5.0) at N=32000 (k_rdf_pairs); ALU/shared-atomic bound, no HBM fraction")
+    # q_l on cells that hold the first shell
+    box3, conf3 = fcc_lattice(64, 64, 64, RHO)
+    with hsmc_b200.HsmcGpu(conf3.shape[0], box3, seed=4, device=device, cell_min=1.5) as h3:
+        h3.upload(conf3)
+        h3.sweep_nvt(5, DR_MAX)
+        s3 = torch.cuda.ExternalStream(h3.stream_ptr(), device=torch.device("cuda", device))
+        i3 = h3.info()
+        nb3 = conf3.shape[0] / (i3["cells"][0] * i3["cells"][1] * i3["cells"][2])
+        rmax = min(1.5, min(i3["cell_size"]))
+        ms = _timed(s3, lambda: h3.order_parameter(6, rmax))
+        entry("order_parameter", "particles/s", conf3.shape[0], ms, 32.0 * (27.0 * nb3 + 1.0),
+              f"hsmc_gpu_order_parameter(l=6, rmax={rmax:.3f}) at N={conf3.shape[0]}, cells >= 1.5 (k_order_param; fp64 ALU heavy)")
+    return out
+
+
 # --------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -215,6 +293,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep-impl", type=int, default=0)
+    ap.add_argument("--no-secondary", action="store_true", help="skip the observables' kernel timings (N=1 only)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -401,6 +480,23 @@ def main():
     acc = float(cnt[1]) / float(cnt[0])
     min_r2 = h.min_dist2()
     assert min_r2 >= 1.0, f"overlap after benchmark: min r^2 = {min_r2}"
+    # build (cell-list) kernels: one rebuild per sweep, bytes per particle from DESIGN.md K1
+    build_ms, build_groups = prof["build"]
+    secondary = None
+    if world == 1 and not args.no_secondary:
+        secondary = {}
+        if build_groups:
+            rate = N / (build_ms * 1e-3 / build_groups)
+            bpp = 88.0 + 12.0 / nbar
+            secondary["cell_list_build"] = {
+                "value": rate, "unit": "particles/s", "ms": build_ms / build_groups, "units_per_call": N,
+                "algorithmic_bytes_per_unit": bpp, "achieved_gbs": rate * bpp / 1e9,
+                "frac_of_hbm_peak": rate * bpp / 1e9 / peak,
+                "what": "counting-sort rebuild inside the timed sweeps (k_cell_count, k_scan_*, k_cell_scatter, k_cs16)"}
+        try:
+            secondary.update(secondary_observables(h, stream, N, nbar, peak, local_rank))
+        except Exception as e:      # reported, never required for the headline line
+            secondary["error"] = repr(e)
     h.close()
 
     cpu = None
@@ -425,6 +521,8 @@ def main():
                            resident_bytes_per_rank=resident, wall_s_timed_region=t_wall, min_r2_after=min_r2, halo=halo),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         }
+        if secondary is not None:
+            line["secondary"] = secondary
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

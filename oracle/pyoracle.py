@@ -310,6 +310,7 @@ class Ref:
             L.ref_pressv_hist.argtypes = [C.c_double, _dp, C.c_int]
             L.ref_order_param.argtypes = [C.c_int, C.c_double]
             L.ref_order_param.restype = C.c_double
+            L.ref_write_config.argtypes = [C.c_int, C.c_int]
             L.ref_presst_hist.argtypes = [C.c_double, C.c_double, _dp, _dp, C.c_int]
             cls._lib = L
         return cls._lib
@@ -464,6 +465,10 @@ class Ref:
     def order_param(self, l, rmax):
         """global_ql_compute() of the unmodified reference (compute_order_parameter.c:84-97)."""
         return float(self.L.ref_order_param(int(l), float(rmax)))
+
+    def write_config(self, sweep, samples_per_file=1):
+        """write_config() of the unmodified reference (io_config.c:134-191) into the cwd."""
+        self.L.ref_write_config(int(sweep), int(samples_per_file))
 
     def rdf_hist(self, dr, rmax):
         buf = np.zeros(1 << 16)

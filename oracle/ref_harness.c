@@ -277,3 +277,14 @@ double ref_order_param(int l, double rmax) {
   return ql_ave;
 }
 
+
+/* io_config.c:134-191: the reference's own snapshot writer, into the current directory
+   (config_%06d.dat.gz; `samples_per_file` samples are appended to one file).  Pins the
+   byte format the parallel writer of the host driver (hs_fastio.c) must reproduce. */
+#include "io_config.h"
+void ref_write_config(int sweep, int samples_per_file) {
+  G_IN.config_write = 1;
+  G_IN.config_samples = samples_per_file;
+  G_IN.sweep_eq = 1; G_IN.sweep_stat = 1;
+  write_config(sweep);
+}
