@@ -93,6 +93,8 @@ struct BlockCfg {
   int use_tma;
   int force_global;       // ablation: every block takes the global-memory path (same chain)
   int dbg;                // timing ablations (env HSMC_BLOCK_DBG), 0 in production
+  unsigned int* ticket;   // fused launches: CTA ticket counter (never reset; SweepArgs::ticket_base)
+  unsigned int* done;     // fused launches: [nbx][nby][nbz] epoch of the launch that last finished the block
 };
 
 // cfg.sweep_impl: low byte = kernel variant, next byte = virtual world of the x block partition
@@ -161,6 +163,10 @@ struct hsmc_gpu {
   float blk_eps = 0.f;
   std::vector<int> xoff;                 // x block boundaries (local layers), blk.nbx + 1 entries
   int* d_xoff = nullptr;
+  unsigned int* d_fuse = nullptr;      // fused block phases: [0] ticket counter, [64..] completion flags per block
+  int64_t cap_fuse = 0;
+  unsigned int fuse_epoch = 0, fuse_tickets = 0;
+  int fuse_mode = -1;                  // -1: not decided yet; 0 off (HSMC_FUSE=0); 1 on
   int64_t cap_xoff = 0;
   bool xoff_dirty = true;
   hsmc_gpu_trial* d_log = nullptr;
@@ -411,6 +417,9 @@ struct SweepArgs {
   uint32_t sweep_lo, sweep_hi;
   int cx, cy, cz, phase;
   float eps;   // half-width of the fp32 filter's uncertainty band around r^2 = 1
+  // k_sweep_block only: phases [phase, phase + fuse) in one launch (fuse <= 1: just `phase`)
+  int fuse;
+  unsigned int epoch, ticket_base;
 };
 
 // all trials of one active cell straight from global memory (generic path: any grid,
@@ -1551,7 +1560,7 @@ extern "C" int hsmc_gpu_destroy(hsmc_gpu* h) {
   void* ptrs[] = {h->pos[0], h->pos[1], h->rel, h->key, h->rnk, h->cell_count, h->cell_start, h->bsum, h->d_cnt,
                   h->d_scratch, h->d_slot_of_id, h->d_io, h->send_l, h->send_r, h->recv_l, h->recv_r,
                   h->d_halo_cnt, h->d_sfargs, h->d_log, h->key_halo, h->rnk_halo, h->deep_list, h->deep_count, h->d_lay,
-                  h->d_xoff, h->cs16};
+                  h->d_xoff, h->cs16, h->d_fuse};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -1838,14 +1847,41 @@ static int sweep_once(hsmc_gpu* h, double dr_max, bool logged) {
   }
   long long total = (long long)((g.own_hi - g.own_lo) / 2) * (g.ny / 2) * (g.nz / 2);
   const int T = 128;
+  // Fused block phases: phases that need no halo exchange between them go into ONE launch whose
+  // CTAs order themselves by per-block completion flags (see k_sweep_block): all eight on a single
+  // GPU, 0-3 and 4-7 in slab mode.  HSMC_FUSE=0 launches the phases one by one (same chain).
+  int fuse = 1;
+  if (h->blk_ok) {
+    if (h->fuse_mode < 0) { const char* e = getenv("HSMC_FUSE"); h->fuse_mode = (e && atoi(e) == 0) ? 0 : 1; }
+    if (h->fuse_mode == 1 && h->blk.dbg == 0) fuse = (h->cfg.world > 1) ? 4 : 8;
+    if (fuse > 1) {
+      const int64_t need = 64 + (int64_t)h->blk.nbx * h->blk.nby * h->blk.nbz;
+      if (need > h->cap_fuse) {
+        if (h->d_fuse) cudaFree(h->d_fuse);
+        h->cap_fuse = need + 1024;
+        CU(cudaMalloc(&h->d_fuse, sizeof(unsigned int) * (size_t)h->cap_fuse));
+        CU(cudaMemsetAsync(h->d_fuse, 0, sizeof(unsigned int) * (size_t)h->cap_fuse, h->st));
+        h->fuse_tickets = 0;
+      }
+      h->blk.ticket = h->d_fuse;
+      h->blk.done = h->d_fuse + 64;
+    }
+  }
+  a.fuse = fuse; a.epoch = 0; a.ticket_base = 0;
   for (int ph = 0; ph < 8; ph++) {
     a.cx = (ph >> 2) & 1; a.cy = (ph >> 1) & 1; a.cz = ph & 1; a.phase = ph;
-    {
+    if (fuse <= 1 || ph % fuse == 0) {     // else: launched together with phase ph - ph % fuse
     ProfSpan span(h, 0);
     if (h->blk_ok) {
-      // block phase ph: all blocks of block-index parity (cx,cy,cz); each CTA runs the eight
-      // cell colours of its block
-      const int nb = (h->blk.nbx / 2) * (h->blk.nby / 2) * (h->blk.nbz / 2);
+      // block phase ph (or phases ph .. ph+fuse-1): all blocks of block-index parity (cx,cy,cz);
+      // each CTA runs the eight cell colours of its block
+      const int nb = (h->blk.nbx / 2) * (h->blk.nby / 2) * (h->blk.nbz / 2) * fuse;
+      if (fuse > 1) {
+        a.epoch = ++h->fuse_epoch;
+        if (a.epoch == 0) a.epoch = ++h->fuse_epoch;      // 0 means "never finished"
+        a.ticket_base = h->fuse_tickets;
+        h->fuse_tickets += (unsigned int)nb;
+      }
       if (logged)
         k_sweep_block<true><<<nb, BLK_THREADS, h->blk_smem, h->st>>>(a, h->blk, h->d_xoff, h->pos[h->cur], h->rel, h->cell_start,
                                                                       h->cs16, h->d_cnt, h->d_log, h->d_scratch, (long long)h->cap_log);
@@ -1876,8 +1912,8 @@ static int sweep_once(hsmc_gpu* h, double dr_max, bool logged) {
     else
       k_sweep_phase<false><<<nblk(total, T), T, 0, h->st>>>(a, h->pos[h->cur], h->rel, h->cell_start, h->d_cnt, nullptr,
                                                              nullptr, 0);
-    }
     h->launches++;
+    }
     if (h->cfg.world > 1) {
       // ghosts of parity cx are read only by phases of the other parity: one refresh
       // after the last phase of each parity is enough

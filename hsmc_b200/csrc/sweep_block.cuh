@@ -77,6 +77,16 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// block-completion flags of a fused launch (several block phases in one grid, see k_sweep_block)
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // prefetch a master-table entry (32 B) towards L1 for a later iteration of the same thread
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
@@ -127,7 +137,7 @@ k_sweep_block(SweepArgs a, BlockCfg bc, const int* __restrict__ xoff, double4* _
   unsigned int* s_trials = reinterpret_cast<unsigned int*>(s_cz + bc.max_rows * bc.cz_stride);   // [8][tr_cap] trial slots per colour: cell code | j << 16 | n << 20
   __shared__ BlockRow s_row[BLK_MAX_ROWS];
   __shared__ int s_cnt[BLK_MAX_ROWS + 1];
-  __shared__ int s_n[40], s_cbase[40], s_fill[40], s_next[8], s_ntr[8], s_flag;
+  __shared__ int s_n[40], s_cbase[40], s_fill[40], s_next[8], s_ntr[8], s_flag, s_done_idx;
   __shared__ __align__(8) uint64_t s_bar;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = BLK_THREADS / 32;
@@ -135,10 +145,45 @@ k_sweep_block(SweepArgs a, BlockCfg bc, const int* __restrict__ xoff, double4* _
   long long t_mark = clock64();
 
   // ---- which block ------------------------------------------------------------------
-  const int hbz = bc.nbz >> 1, hby = bc.nby >> 1;
-  const int bzi = 2 * (blockIdx.x % hbz) + a.cz;
-  const int byi = 2 * ((blockIdx.x / hbz) % hby) + a.cy;
-  const int bxi = 2 * (blockIdx.x / (hbz * hby)) + a.cx;
+  // a.fuse <= 1: one launch = one block phase (a.phase), CTA = blockIdx.x.
+  // a.fuse  > 1: one launch = the block phases [a.phase, a.phase + a.fuse).  CTAs draw a ticket;
+  // tickets enumerate (phase, block) in phase order, so whenever a CTA holds ticket t, every
+  // ticket < t is held by a CTA that is resident or finished.  A block of phase p only
+  // depends on its (up to 26) neighbouring blocks of EARLIER phases of the launch: it waits
+  // for their completion flags (release/acquire at gpu scope) instead of for a kernel
+  // boundary, so the ragged last wave of one phase overlaps the first wave of the next.
+  // The earliest unfinished phase never waits => no deadlock.  Same chain as separate launches.
+  const int hbz = bc.nbz >> 1, hby = bc.nby >> 1, hbx = bc.nbx >> 1;
+  int ph = a.phase, bid = blockIdx.x;
+  if (a.fuse > 1) {
+    if (tid == 0) s_flag = (int)(atomicAdd(bc.ticket, 1u) - a.ticket_base);
+    __syncthreads();
+    const int per = hbx * hby * hbz, t = s_flag;
+    ph = a.phase + t / per;
+    bid = t - (t / per) * per;
+    __syncthreads();                      // s_flag is reused below
+  }
+  const int pcx = (ph >> 2) & 1, pcy = (ph >> 1) & 1, pcz = ph & 1;
+  const int bzi = 2 * (bid % hbz) + pcz;
+  const int byi = 2 * ((bid / hbz) % hby) + pcy;
+  const int bxi = 2 * (bid / (hbz * hby)) + pcx;
+  if (a.fuse > 1) {
+    if (tid == 0) s_done_idx = (bxi * bc.nby + byi) * bc.nbz + bzi;
+    if (tid < 27 && tid != 13) {
+      int nx = bxi + tid / 9 - 1, ny = byi + (tid / 3) % 3 - 1, nz = bzi + tid % 3 - 1;
+      bool have = true;
+      if (g.wrap_x) { if (nx < 0) nx += bc.nbx; else if (nx >= bc.nbx) nx -= bc.nbx; }
+      else have = nx >= 0 && nx < bc.nbx;          // slab edge: that neighbour lives on another rank (halo exchange)
+      if (ny < 0) ny += bc.nby; else if (ny >= bc.nby) ny -= bc.nby;
+      if (nz < 0) nz += bc.nbz; else if (nz >= bc.nbz) nz -= bc.nbz;
+      const int q = ((nx & 1) << 2) | ((ny & 1) << 1) | (nz & 1);
+      if (have && q >= a.phase && q < ph) {
+        const unsigned int* f = bc.done + ((size_t)nx * bc.nby + ny) * bc.nbz + nz;
+        while (ld_acquire_gpu(f) != a.epoch) __nanosleep(100);
+      }
+    }
+    __syncthreads();
+  }
   const int xa = xoff[bxi], xb = xoff[bxi + 1];                                // local layers [xa, xb)
   const int ya = (int)((long long)byi * g.ny / bc.nby), yb = (int)((long long)(byi + 1) * g.ny / bc.nby);
   const int za = (int)((long long)bzi * g.nz / bc.nbz), zb = (int)((long long)(bzi + 1) * g.nz / bc.nbz);
@@ -496,7 +541,7 @@ k_sweep_block(SweepArgs a, BlockCfg bc, const int* __restrict__ xoff, double4* _
           unsigned long long s = atomicAdd(nlog, 1ull);
           if ((long long)s < logcap) {
             hsmc_gpu_trial tr;
-            tr.seq = ((unsigned long long)(a.phase * 8 + col) << 56) | ((unsigned long long)gcell << 8) | (unsigned)j;
+            tr.seq = ((unsigned long long)(ph * 8 + col) << 56) | ((unsigned long long)gcell << 8) | (unsigned)j;
             tr.id = (int)p.w; tr.verdict = verdict;
             tr.raw[0] = rn.v[0]; tr.raw[1] = rn.v[1]; tr.raw[2] = rn.v[2]; tr.pad = 0;
             log[s] = tr;
@@ -519,7 +564,7 @@ k_sweep_block(SweepArgs a, BlockCfg bc, const int* __restrict__ xoff, double4* _
         const int l = xa + qx, iy = ya + qy, iz = za + qz;
         const int c = (((g.gx0 + l) & 1) << 2) | ((iy & 1) << 1) | (iz & 1);
         if (c == col)
-          cell_update_global_noinline<LOG>(a, a.phase * 8 + col, pos, rel, cs, l, iy, iz, 0, 1 << 30, n_acc, n_ov, n_cell,
+          cell_update_global_noinline<LOG>(a, ph * 8 + col, pos, rel, cs, l, iy, iz, 0, 1 << 30, n_acc, n_ov, n_cell,
                                            log, nlog, logcap);
       }
       __syncthreads();
@@ -535,5 +580,13 @@ k_sweep_block(SweepArgs a, BlockCfg bc, const int* __restrict__ xoff, double4* _
     if (n_acc) atomicAdd(&cnt[CNT_ACC], (unsigned long long)n_acc);
     if (n_ov) atomicAdd(&cnt[CNT_REJ_OVERLAP], (unsigned long long)n_ov);
     if (n_cell) atomicAdd(&cnt[CNT_REJ_CELL], (unsigned long long)n_cell);
+  }
+  if (a.fuse > 1) {
+    // every thread's stores to pos / rel precede the barrier; thread 0 then publishes the block
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      st_release_gpu(bc.done + s_done_idx, a.epoch);
+    }
   }
 }

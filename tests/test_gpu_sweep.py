@@ -166,6 +166,35 @@ def test_kernel_variants_produce_the_same_chain(hs, oracle_built, impls, block, 
     assert cnts[0][0] == 12 * N
 
 
+@pytest.mark.parametrize("block", [None, "2,2,2", "3,2,4", "8,8,24"])
+@pytest.mark.parametrize("impl", [0, 5], ids=["staged", "global"])
+def test_fused_phase_launch_is_the_same_chain(hs, oracle_built, block, impl, monkeypatch):
+    """All eight block phases in ONE launch, ordered by per-block completion flags, against eight
+    separate launches (HSMC_FUSE=0): identical coordinates and counters.  Small blocks give
+    thousands of CTAs per launch (far more than fit the GPU at once), so the ticket / flag protocol is
+    exercised with waiting CTAs; impl 5 reads neighbours straight from global memory, which would
+    expose a stale (non-coherent) read of a block finished earlier in the same launch."""
+    if block is not None:
+        monkeypatch.setenv("HSMC_BLOCK", block)
+    box, conf = oracle_built.Port.lattice(2, 26, 22, 24, 0.88)
+    N = conf.shape[0]
+    outs, cnts = [], []
+    for fuse in ("1", "0", "1"):
+        monkeypatch.setenv("HSMC_FUSE", fuse)
+        with hs.HsmcGpu(N, box[:3], seed=4711, sweep_impl=impl) as h:
+            h.upload(conf)
+            h.sweep_nvt(15, 0.12)
+            outs.append(h.download())
+            cnts.append(h.counters())
+            assert h.min_dist2() >= 1.0
+            launches = h.info()["kernel_launches"]
+        outs[-1] = (outs[-1], launches)
+    (a, la), (b, lb), (c, lc) = outs
+    assert np.array_equal(a, b) and np.array_equal(a, c)
+    assert np.array_equal(cnts[0], cnts[1]) and cnts[0][0] == 15 * N
+    assert lb - la == 15 * 7 and la == lc          # seven launches fewer per sweep
+
+
 def test_interior_fast_path_replays_through_oracle(hs, oracle_built):
     """A 16^3-cell box has interior cells (no minimum-image branches evaluated on the GPU);
     their verdicts must still equal the reference arithmetic, which always evaluates them."""
