@@ -1265,18 +1265,21 @@ static void setup_blocks(hsmc_gpu* h) {
   const double nbar = (double)h->N / ((double)g.nx * g.ny * g.nz);
   if ((long long)g.nz * 16 > 65535) return;        // 16-bit row-relative CSR
   // x slabs of the (virtual) world: [lo, hi) in global layers
-  std::vector<std::pair<int, int>> slabs;
+  // `all_slabs`: every slab of the (virtual) world -- the block SHAPE is chosen from these, so that
+  // it is a function of the grid and the world size only: every rank of a slab run and the single-GPU
+  // run that mimics it (xpart_world) pick the same shape, hence the same chain.  `slabs`: the slabs
+  // whose blocks this handle runs (its own one in slab mode, all of them on a single GPU).
+  std::vector<std::pair<int, int>> slabs, all_slabs;
   {
     const int pairs = g.nx / 2;
     if (Wv > 1 && pairs < 2 * Wv) return;            // cannot honour the requested partition
     for (int r = 0; r < Wv; r++) {
       int x0 = 2 * (int)(((long long)pairs * r) / Wv), x1 = 2 * (int)(((long long)pairs * (r + 1)) / Wv);
+      all_slabs.push_back({x0, x1});
       if (W > 1 && r != h->cfg.rank) continue;
       slabs.push_back({x0, x1});
     }
   }
-  int max_slab = 0;
-  for (auto& sl : slabs) max_slab = std::max(max_slab, sl.second - sl.first);
   double capf = 1.08;
   if (const char* e = getenv("HSMC_BLOCK_CAPF")) capf = atof(e);
   int want[3] = {0, 0, 0};
@@ -1285,7 +1288,7 @@ static void setup_blocks(hsmc_gpu* h) {
   auto eval = [&](int bx, int by, int bz, Shape& s) -> bool {
     // a block and its halo must not cover a cell twice: extent + 2 <= cells of the axis
     int mx = 0;
-    for (auto& sl : slabs) {
+    for (auto& sl : all_slabs) {
       int n = sl.second - sl.first, nb = even_blocks(n, bx);
       if (nb > n) return false;
       mx = std::max(mx, (n + nb - 1) / nb);
@@ -1293,7 +1296,9 @@ static void setup_blocks(hsmc_gpu* h) {
     int nby = even_blocks(g.ny, by), nbz = even_blocks(g.nz, bz);
     if (nby > g.ny || nbz > g.nz) return false;
     int my = (g.ny + nby - 1) / nby, mz = (g.nz + nbz - 1) / nbz;
-    if (mx + 2 > (g.wrap_x ? g.nx : g.nlx) || my + 2 > g.ny || mz + 2 > g.nz) return false;
+    // (x: with Wv > 1 slabs every block is at most its own slab long, and a slab + 2 never exceeds
+    //  the local layer count of a rank nor the box, so only the one-slab case needs the test)
+    if ((Wv == 1 && mx + 2 > g.nx) || my + 2 > g.ny || mz + 2 > g.nz) return false;
     if ((mx + 2) * (my + 2) > std::min(BLK_MAX_ROWS, BLK_THREADS) || mz + 3 > 32 || mx + 2 > 31 || my + 2 > 31) return false;
     double region = (double)(mx + 2) * (my + 2) * (mz + 2);
     int cap = ((int)(region * nbar * capf) + 48 + BLK_PAD + 31) & ~31;
@@ -1320,8 +1325,13 @@ static void setup_blocks(hsmc_gpu* h) {
     for (int bx : cand_xy) for (int by : cand_xy) for (int bz : cand_z) {
       Shape s;
       if (!eval(bx, by, bz, s)) continue;
+      // CTAs of one phase on one GPU: all slabs on a single GPU, the largest slab in a slab run
+      // (the same number for a real and for a mimicked slab run)
       long long ctas = 0;
-      for (auto& sl : slabs) ctas += even_blocks(sl.second - sl.first, bx) / 2;
+      for (auto& sl : all_slabs) {
+        const long long c = even_blocks(sl.second - sl.first, bx) / 2;
+        ctas = (Wv > 1) ? std::max(ctas, c) : ctas + c;
+      }
       ctas *= (long long)(even_blocks(g.ny, by) / 2) * (even_blocks(g.nz, bz) / 2);
       const int per_sm = (int)std::min<size_t>(4, (size_t)(227 * 1024) / (s.smem + 5 * 1024));
       if (per_sm < 1) continue;
