@@ -12,7 +12,9 @@ the same total system is slab-decomposed over N GPUs ("scaling": "strong").
 
 A step = one hsmc_gpu_sweep_nvt() call of --sweeps-per-step sweeps (each sweep = N trial
 moves = 8 checkerboard block phases, each running the 8 cell colours of its blocks inside
-the CTA, + one grid shift / cell-list rebuild).  `value` is
+the CTA, + one grid shift / cell-list rebuild).  The block phases that need no halo exchange
+between them run as ONE k_sweep_block launch (all 8 on one GPU, 0-3 and 4-7 on slabs), so a
+"launch" of the roofline object is a whole sweep (N moves) at N=1 and half a sweep on slabs.  `value` is
 timed on the device (CUDA events on the handle's stream) with the configuration resident
 in HBM; `e2e` is the same call driven from pinned HOST buffers: upload of the {id,x,y,z}
 table, the sweeps, download of the table and the move counters, wall-clock.
@@ -241,9 +243,9 @@ def secondary_observables(h, stream, N, nbar, peak, device):
     M = 100_000_000
     ms = _timed(stream, lambda: h.widom(7, M))
     entry("widom", "insertions/s", M, ms, 32.0 * 27.0 * nbar, "hsmc_gpu_widom, 1e8 insertion points (k_widom)")
-    ms = _timed(stream, lambda: h.overlap_scaled(0.9999))
+    ms = _timed(stream, lambda: h.overlap_scaled(1.0))
     entry("overlap_scaled", "particles/s", N, ms, 32.0 * (27.0 * nbar + 1.0),
-          "hsmc_gpu_overlap_scaled(sf=0.9999): the NpT volume-move verdict (k_overlap_scaled)")
+          "hsmc_gpu_overlap_scaled(sf=1.0, no overlap found = every pair visited): the NpT volume-move verdict (k_overlap_scaled)")
     sf = (1.0 - 0.0001 * (np.arange(20) + 1.0)) ** (1.0 / 3.0)
     ms = _timed(stream, lambda: h.presst_flags(sf))
     entry("presst_flags", "particles/s", N, ms, 32.0 * (27.0 * nbar + 1.0),
@@ -429,7 +431,8 @@ def main():
     assert moves == N * S * args.steps, (moves, N * S * args.steps)
     value = moves / (ms_total * 1e-3)
 
-    # ---- roofline of the dominant kernel (one launch = one block phase = N/8 trial moves) ----
+    # ---- roofline of the dominant kernel (one launch = the fused block phases: N trial moves on one
+    #      GPU, n_owned/2 on a slab; HSMC_FUSE=0 makes it one block phase = N/8) ----
     ncell = info["cells"][0] * info["cells"][1] * info["cells"][2]
     nbar = N / ncell
     b_move = 32.0 * (27.0 * nbar + 2.0)               # double4 slots: 32 B, SURVEY 8(d) with 16 -> 32
@@ -447,8 +450,9 @@ def main():
         "kernel_share_of_step": sweep_ms / ms_local if ms_local > 0 else None,
         "build_share_of_step": prof["build"][0] / ms_local if ms_local > 0 else None,
         "halo_share_of_step": prof["halo"][0] / ms_local if ms_local > 0 else None,
-        "traffic": (traffic or {}).get("dram_bytes_per_launch"),
-        "traffic_source": (traffic or {}).get("source"),
+        # the committed ncu capture is of the single-GPU fused launch; it does not describe slab launches
+        "traffic": (traffic or {}).get("dram_bytes_per_launch") if world == 1 and os.environ.get("HSMC_FUSE", "1") != "0" else None,
+        "traffic_source": (traffic or {}).get("source") if world == 1 else None,
     }
 
     # ---- end to end: host buffers in, host buffers out, every step ----

@@ -148,4 +148,51 @@ __device__ __forceinline__ bool stencil_any(const Grid& g, const int* __restrict
   return false;
 }
 
+// The forward HALF of the stencil: the own cell plus the 13 neighbour cells (dx,dy,dz) that are
+// lexicographically greater than (0,0,0).  With at least four cells per axis a cell and its
+// mirror image are distinct, so looping over all cells visits every unordered pair of particles
+// in adjacent cells exactly once (pairs inside the own cell: the caller orders them, own == true).
+// In slab mode only owned cells loop; a pair across a slab face is seen from the lower-x cell's
+// rank only.  Same contiguous-row trick as stencil_any.  f(k, own) returns true to stop early.
+template <class F>
+__device__ __forceinline__ bool stencil_half(const Grid& g, const int* __restrict__ cs, int l, int iy,
+                                             int iz, F f) {
+  // row (0,0): own cell and its +z neighbour
+  {
+    const long long rb = ((long long)l * g.ny + iy) * g.nz;
+    const int b = cs[rb + iz], m = cs[rb + iz + 1];
+    for (int k = b; k < m; k++)
+      if (f(k, true)) return true;
+    int b2 = m, e2;
+    if (iz + 1 < g.nz) e2 = cs[rb + iz + 2];
+    else { b2 = cs[rb]; e2 = cs[rb + 1]; }
+    for (int k = b2; k < e2; k++)
+      if (f(k, false)) return true;
+  }
+#pragma unroll 1
+  for (int r = 0; r < 4; r++) {            // rows (0,+1), (+1,-1), (+1,0), (+1,+1)
+    const int dx = r == 0 ? 0 : 1, dy = r == 0 ? 1 : r - 2;
+    int ll = l + dx;
+    if (g.wrap_x && ll >= g.nlx) ll -= g.nlx;
+    int yy = iy + dy;
+    if (yy < 0) yy += g.ny; else if (yy >= g.ny) yy -= g.ny;
+    const long long rb = ((long long)ll * g.ny + yy) * g.nz;
+    const int zlo = iz - 1, zhi = iz + 1;
+    if (zlo >= 0 && zhi < g.nz) {
+      const int b = cs[rb + zlo], e = cs[rb + zhi + 1];
+      for (int k = b; k < e; k++)
+        if (f(k, false)) return true;
+    } else {
+      int b1, e1, b2, e2;
+      if (zlo < 0) { b1 = cs[rb + g.nz - 1]; e1 = cs[rb + g.nz]; b2 = cs[rb]; e2 = cs[rb + 2]; }
+      else         { b1 = cs[rb + g.nz - 2]; e1 = cs[rb + g.nz]; b2 = cs[rb]; e2 = cs[rb + 1]; }
+      for (int k = b1; k < e1; k++)
+        if (f(k, false)) return true;
+      for (int k = b2; k < e2; k++)
+        if (f(k, false)) return true;
+    }
+  }
+  return false;
+}
+
 #endif  // __CUDACC__

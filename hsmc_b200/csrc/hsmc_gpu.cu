@@ -540,7 +540,8 @@ k_sweep_phase(SweepArgs a, double4* __restrict__ pos, float4* __restrict__ rel, 
 
 // ----------------------------------------------------------------------------------
 // K3: global scaled-overlap verdict for nsf scale factors in one pass over the pairs.
-// One thread per owned cell; each unordered pair is visited once (id_j > id_i).
+// One thread per owned cell over the forward half of its stencil (stencil_half): each unordered
+// pair is loaded and visited once.
 // A cheap unscaled pre-test skips pairs that cannot overlap under any of the factors
 // (threshold carries a 1e-6 relative margin, far above rounding); pairs that pass are
 // evaluated with the reference's exact scaled arithmetic for every factor.
@@ -569,9 +570,9 @@ k_overlap_scaled(Grid g, Box ubox, const SfArgs* __restrict__ sa, const double4*
   double r2_skip = sa->r2_skip;
   for (int s = beg; s < end; s++) {
     double4 p = pos[s];
-    stencil_any(g, cs, l, iy, iz, [&](int k) {
+    stencil_half(g, cs, l, iy, iz, [&](int k, bool own) {
       double4 q = pos[k];
-      if (!(q.w > p.w)) return false;
+      if (own && !(q.w > p.w)) return false;
       if (pair_r2(p.x, p.y, p.z, q.x, q.y, q.z, ubox) > r2_skip) return false;
       bool all = true;
       for (int m = 0; m < nsf; m++) {
@@ -733,9 +734,9 @@ k_contact_hist(Grid g, Box box, const double4* __restrict__ pos, const int* __re
     double r2_pre = rmax * rmax * (1.0 + 1e-9);
     for (int s = beg; s < end; s++) {
       double4 p = pos[s];
-      stencil_any(g, cs, l, iy, iz, [&](int k) {
+      stencil_half(g, cs, l, iy, iz, [&](int k, bool own) {
         double4 q = pos[k];
-        if (!(q.w > p.w)) return false;
+        if (own && !(q.w > p.w)) return false;
         double r2 = pair_r2(p.x, p.y, p.z, q.x, q.y, q.z, box);
         if (r2 < r2_pre) {
           double dr = sqrt(r2);
