@@ -1,0 +1,92 @@
+/* hs_mp.c -- process-per-GPU plumbing of the host driver (see hs_mp.h). */
+#define _GNU_SOURCE
+#include "hs_mp.h"
+
+#include <pthread.h>
+#include <signal.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/wait.h>
+#include <unistd.h>
+
+struct hs_mp_shared {
+  pthread_barrier_t bar;
+  pid_t pid[HS_MP_MAX_RANKS];
+  unsigned char id[128];
+  unsigned char blob[HS_MP_MAX_RANKS][64];
+  uint64_t scratch[HS_MP_MAX_RANKS][HS_MP_SCRATCH];
+};
+
+int hs_mp_start(hs_mp *mp, int world, int64_t n_rows) {
+  memset(mp, 0, sizeof(*mp));
+  mp->world = world < 1 ? 1 : world;
+  if (mp->world == 1) return 0;
+  if (mp->world > HS_MP_MAX_RANKS) { printf("ERROR: at most %d GPUs\n", HS_MP_MAX_RANKS); exit(EXIT_FAILURE); }
+  size_t bytes = sizeof(struct hs_mp_shared) + (size_t)n_rows * 4 * sizeof(double);
+  void *m = mmap(NULL, bytes, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+  if (m == MAP_FAILED) { perror("Failed allocation of the shared particle table"); exit(EXIT_FAILURE); }
+  mp->sh = m;
+  mp->table = (double (*)[4])((char *)m + sizeof(struct hs_mp_shared));
+  mp->table_rows = n_rows;
+  pthread_barrierattr_t a;
+  pthread_barrierattr_init(&a);
+  pthread_barrierattr_setpshared(&a, PTHREAD_PROCESS_SHARED);
+  pthread_barrier_init(&mp->sh->bar, &a, (unsigned)mp->world);
+  pthread_barrierattr_destroy(&a);
+  fflush(NULL);
+  mp->sh->pid[0] = getpid();
+  for (int r = 1; r < mp->world; r++) {
+    pid_t p = fork();
+    if (p < 0) { perror("fork"); hs_mp_abort(mp); exit(EXIT_FAILURE); }
+    if (p == 0) {
+      mp->rank = r;
+      mp->sh->pid[r] = getpid();
+      /* only rank 0 reports; the others run the same program silently */
+      if (!freopen("/dev/null", "w", stdout)) _exit(EXIT_FAILURE);
+      return r;
+    }
+    mp->sh->pid[r] = p;
+  }
+  return 0;
+}
+
+void hs_mp_barrier(hs_mp *mp) {
+  if (mp->world > 1) pthread_barrier_wait(&mp->sh->bar);
+}
+
+void hs_mp_bcast_id(hs_mp *mp, void *buf, int bytes) {
+  if (mp->world == 1) return;
+  if (mp->rank == 0) memcpy(mp->sh->id, buf, (size_t)bytes);
+  hs_mp_barrier(mp);
+  if (mp->rank != 0) memcpy(buf, mp->sh->id, (size_t)bytes);
+  hs_mp_barrier(mp);
+}
+
+void hs_mp_exchange_blobs(hs_mp *mp, const void *mine, const void **left, const void **right) {
+  memcpy(mp->sh->blob[mp->rank], mine, 64);
+  hs_mp_barrier(mp);
+  *left = mp->sh->blob[(mp->rank + mp->world - 1) % mp->world];
+  *right = mp->sh->blob[(mp->rank + 1) % mp->world];
+}
+
+uint64_t *hs_mp_scratch(hs_mp *mp, int rank) { return mp->sh->scratch[rank]; }
+
+void hs_mp_abort(hs_mp *mp) {
+  if (mp->world == 1 || !mp->sh) return;
+  for (int r = 0; r < mp->world; r++)
+    if (r != mp->rank && mp->sh->pid[r] > 0) kill(mp->sh->pid[r], SIGTERM);
+}
+
+int hs_mp_finish(hs_mp *mp) {
+  if (mp->world == 1) return 0;
+  fflush(NULL);
+  if (mp->rank != 0) _exit(EXIT_SUCCESS);
+  int bad = 0;
+  for (int r = 1; r < mp->world; r++) {
+    int st = 0;
+    if (waitpid(mp->sh->pid[r], &st, 0) < 0 || !WIFEXITED(st) || WEXITSTATUS(st) != 0) bad = 1;
+  }
+  return bad;
+}

@@ -69,6 +69,7 @@ void hs_compute_pressv(hs_sim *s, bool init) {
   for (int i = 0; i < h->nn; i++) h->h[i] = 2.0 * (double)cnt[i];
   free(cnt);
   shell_normalise(h, in->rho, s->part.NN);
+  if (!HS_ROOT(s)) return;
   FILE *f = open_sample_file("press_virial.dat", init, "virial pressure");
   fprintf(f, "######################################\n");
   fprintf(f, "# Bins, volume, number of particles\n");
@@ -96,6 +97,7 @@ void hs_compute_presst(hs_sim *s, bool init) {
   for (int i = 0; i < h->nn; i++) h->h[i] = free_of_overlap[i] ? 1.0 : 0.0;
   free(sf);
   free(free_of_overlap);
+  if (!HS_ROOT(s)) return;
   FILE *f = open_sample_file("press_thermo.dat", init, "thermo pressure");
   fprintf(f, "######################################\n");
   fprintf(f, "# Bins, volume, number of particles\n");
@@ -124,6 +126,7 @@ void hs_compute_mu(hs_sim *s, bool init) {
   int64_t wtest = 0;
   hs_gpu_check(hsmc_gpu_widom(s->gpu, s->mu_samples++, 0, in->mu_insertions, 1, &wtest));
   double mu = (wtest > 0) ? -log((double)wtest / in->mu_insertions) : 0.0;
+  if (!HS_ROOT(s)) return;
   FILE *f = open_sample_file("chem_pot.dat", init, "chemical potential");
   if (init) {
     fprintf(f, "##################################################################################\n");
@@ -153,10 +156,40 @@ void hs_compute_rdf(hs_sim *s, bool init, int sweep) {
   for (int i = 0; i < h->nn; i++) h->x[i] = (i + 1. / 2.) * in->rdf_dr + 1.0;
   in->rdf_rmax = in->rdf_dr * h->nn + 1.0;
   uint64_t *cnt = calloc((size_t)(h->nn > 0 ? h->nn : 1), sizeof(uint64_t));
-  if (h->nn > 0) hs_gpu_check(hsmc_gpu_rdf_counts(s->gpu, in->rdf_dr, h->nn, cnt));
+  if (h->nn > 0 && s->mp.world == 1) {
+    hs_gpu_check(hsmc_gpu_rdf_counts(s->gpu, in->rdf_dr, h->nn, cnt));
+  } else if (h->nn > 0) {
+    /* slab run: the pair histogram is all-pairs, so it is taken on a REPLICA of the configuration
+       (one single-GPU handle per rank), each rank counting its share of the pair-tile triangle
+       (SURVEY 8e); the shares meet in the shared scratch block and rank 0 adds them up */
+    if (h->nn > HS_MP_SCRATCH) hs_die("rdf: more than %d bins in a multi-GPU run", HS_MP_SCRATCH);
+    hs_gpu_pull(s);
+    if (!s->gpu_rep) {
+      hsmc_gpu_config cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      const char *dev = getenv("HSMC_DEVICE");
+      cfg.device = (dev ? atoi(dev) : 0) + s->mp.rank;
+      cfg.world = 1;
+      cfg.seed = (uint64_t)in->seed;
+      cfg.cell_min = in->neigh_dr;
+      double box[3] = {s->box.lx, s->box.ly, s->box.lz};
+      hs_gpu_check(hsmc_gpu_create(&s->gpu_rep, &cfg, s->part.NN, box));
+    }
+    hs_gpu_check(hsmc_gpu_upload(s->gpu_rep, &s->conf[0][0], s->part.NN));
+    hs_gpu_check(hsmc_gpu_rdf_counts_part(s->gpu_rep, in->rdf_dr, h->nn, s->mp.rank, s->mp.world, cnt));
+    memcpy(hs_mp_scratch(&s->mp, s->mp.rank), cnt, sizeof(uint64_t) * (size_t)h->nn);
+    hs_mp_barrier(&s->mp);
+    for (int r = 0; r < s->mp.world; r++) {
+      if (r == s->mp.rank) continue;
+      const uint64_t *o = hs_mp_scratch(&s->mp, r);
+      for (int i = 0; i < h->nn; i++) cnt[i] += o[i];
+    }
+    hs_mp_barrier(&s->mp);
+  }
   for (int i = 0; i < h->nn; i++) h->h[i] = 2.0 * (double)cnt[i];
   free(cnt);
   shell_normalise(h, in->rho, s->part.NN);
+  if (!HS_ROOT(s)) return;
   if (init && (double)(in->sweep_stat + in->sweep_eq) / (in->rdf_sample_int * in->rdf_samples) > 100000)
     printf("ERROR: Too many (> 100000) rdf files will be produced. Consider increasing number of samples per file\n");
   char name[32];
@@ -212,6 +245,7 @@ void hs_compute_op(hs_sim *s, bool init) {
   }
   double ql_ave = 0.0;
   hs_gpu_check(hsmc_gpu_order_parameter(s->gpu, in->ql_order, in->ql_rmax, &ql_ave));
+  if (!HS_ROOT(s)) return;
   FILE *f = open_sample_file("order_param.dat", init, "order parameter");
   if (init) {
     fprintf(f, "###############################################################\n");

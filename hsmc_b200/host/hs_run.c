@@ -172,7 +172,7 @@ static void simulate(hs_sim *s, bool npt) {
   printf("Elapsed time: %f seconds\n", t1 - t0);
   hs_gpu_pull(s);
   hs_gpu_close(s);
-  free(s->conf);
+  if (s->mp.world == 1) free(s->conf);
   s->conf = NULL;
 }
 

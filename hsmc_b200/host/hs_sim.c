@@ -9,8 +9,20 @@
 #include <string.h>
 #include <zlib.h>
 
+static hs_mp *g_mp = NULL;
+void hs_die_hook(hs_mp *mp) { g_mp = mp; }
+
 void hs_die(const char *fmt, ...) {
   va_list ap;
+  if (g_mp && g_mp->rank != 0) {
+    /* the stdout of ranks > 0 is /dev/null: say it on stderr before taking the run down */
+    va_start(ap, fmt);
+    fprintf(stderr, "ERROR (GPU rank %d): ", g_mp->rank);
+    vfprintf(stderr, fmt, ap);
+    fprintf(stderr, "\n");
+    va_end(ap);
+  }
+  if (g_mp) hs_mp_abort(g_mp);
   va_start(ap, fmt);
   printf("ERROR: ");
   vprintf(fmt, ap);
@@ -48,10 +60,30 @@ void hs_box_init(hs_sim *s, int type, int nx, int ny, int nz, double rho) {
   b->cell_type = type;
 }
 
+int64_t hs_plan_particles(const hs_input *in) {
+  if (in->restart_read == 0) return (int64_t)in->nx * in->ny * in->nz * (in->type == 1 ? 1 : 4);
+  /* restart_%d.bin: dr_max, dv_max, box_info, p_info, ... (io_config.c:53-61) */
+  FILE *f = fopen(in->restart_name, "rb");
+  if (!f) { perror("Error while reading restart file"); exit(EXIT_FAILURE); }
+  double d[2];
+  hs_box b;
+  hs_pinfo pi;
+  if (fread(d, sizeof(double), 2, f) != 2 || fread(&b, sizeof(b), 1, f) != 1 || fread(&pi, sizeof(pi), 1, f) != 1)
+    hs_die("restart file %s is truncated", in->restart_name);
+  fclose(f);
+  return pi.NN;
+}
+
 void hs_part_alloc(hs_sim *s) {
   int ppc = particles_per_cell(s->box.cell_type);
   int n = s->box.cell_x * s->box.cell_y * s->box.cell_z * ppc;
-  s->conf = malloc((size_t)n * sizeof(*s->conf));
+  if (s->mp.world > 1) {
+    /* the mirror is the table all ranks share (mapped before the fork) */
+    if (n != s->mp.table_rows) hs_die("internal: shared particle table has %ld rows, the run needs %d", (long)s->mp.table_rows, n);
+    s->conf = s->mp.table;
+  } else {
+    s->conf = malloc((size_t)n * sizeof(*s->conf));
+  }
   if (!s->conf) hs_die("Failed particle allocation");
   s->part.Ncell = ppc;
   s->part.NN = n;
@@ -96,31 +128,74 @@ void hs_gpu_open(hs_sim *s) {
   hsmc_gpu_config cfg;
   memset(&cfg, 0, sizeof(cfg));
   const char *dev = getenv("HSMC_DEVICE");
-  cfg.device = dev ? atoi(dev) : 0;
-  cfg.rank = 0;
-  cfg.world = 1;
+  cfg.device = (dev ? atoi(dev) : 0) + s->mp.rank;
+  cfg.rank = s->mp.rank;
+  cfg.world = s->mp.world;
   cfg.seed = (uint64_t)s->in.seed;
   cfg.cell_min = s->in.neigh_dr;
   cfg.regrid_interval = 1;
+  unsigned char id[HSMC_GPU_NCCL_ID_BYTES];
+  if (s->mp.world > 1) {
+    /* rank 0 draws the communicator id, everybody gets it through the shared block */
+    if (s->mp.rank == 0) hs_gpu_check(hsmc_gpu_nccl_id(id));
+    hs_mp_bcast_id(&s->mp, id, HSMC_GPU_NCCL_ID_BYTES);
+    cfg.nccl_id = id;
+  } else {
+    /* identity checks: a single-GPU run with the block partition of a K-slab run is the K-GPU chain */
+    const char *xp = getenv("HSMC_XPART_WORLD");
+    if (xp && atoi(xp) > 1) cfg.sweep_impl = atoi(xp) << 8;
+  }
   double box[3] = {s->box.lx, s->box.ly, s->box.lz};
   hs_gpu_check(hsmc_gpu_create(&s->gpu, &cfg, s->part.NN, box));
+  if (s->mp.world > 1) {
+    const char *p2p = getenv("HSMC_P2P");
+    if (!p2p || atoi(p2p) != 0) {
+      /* NVLink peer-to-peer halo windows: gather the blobs, attach the two neighbours' */
+      unsigned char blob[HSMC_GPU_IPC_BYTES];
+      const void *left, *right;
+      hs_gpu_check(hsmc_gpu_ipc_export(s->gpu, blob));
+      hs_mp_exchange_blobs(&s->mp, blob, &left, &right);
+      hs_gpu_check(hsmc_gpu_ipc_attach(s->gpu, left, right));
+      hs_mp_barrier(&s->mp);
+    }
+  }
   hs_gpu_check(hsmc_gpu_set_sweep_counter(s->gpu, s->philox_sweeps));
   hs_gpu_push(s);
 }
 
 void hs_gpu_close(hs_sim *s) {
+  if (s->gpu_rep) hsmc_gpu_destroy(s->gpu_rep);
+  s->gpu_rep = NULL;
   if (s->gpu) hsmc_gpu_destroy(s->gpu);
   s->gpu = NULL;
 }
 
 void hs_gpu_push(hs_sim *s) {
+  /* slab mode: every rank hands over the full table and keeps the rows of its slab */
   hs_gpu_check(hsmc_gpu_upload(s->gpu, &s->conf[0][0], s->part.NN));
+  hs_mp_barrier(&s->mp);       /* nobody rewrites the shared table while another rank still reads it */
   s->mirror_current = true;
 }
 
 void hs_gpu_pull(hs_sim *s) {
   if (s->mirror_current) return;
-  hs_gpu_check(hsmc_gpu_download(s->gpu, &s->conf[0][0]));
+  if (s->mp.world == 1) {
+    hs_gpu_check(hsmc_gpu_download(s->gpu, &s->conf[0][0]));
+  } else {
+    /* every rank brings back the rows it owns and files them under their ids in the shared table;
+       first make sure nobody (rank 0 writing a snapshot, say) is still reading the previous contents */
+    hs_mp_barrier(&s->mp);
+    hsmc_gpu_info gi;
+    hs_gpu_check(hsmc_gpu_sync(s->gpu));
+    hs_gpu_check(hsmc_gpu_get_info(s->gpu, &gi));
+    int64_t cap = gi.n_owned + 1024, n = 0;
+    double (*rows)[4] = malloc((size_t)cap * sizeof(*rows));
+    if (!rows) hs_die("Failed allocation of the download buffer");
+    hs_gpu_check(hsmc_gpu_download_owned(s->gpu, &rows[0][0], cap, &n));
+    for (int64_t i = 0; i < n; i++) memcpy(s->conf[(int64_t)rows[i][0]], rows[i], sizeof(*rows));
+    free(rows);
+    hs_mp_barrier(&s->mp);
+  }
   s->mirror_current = true;
 }
 
@@ -136,6 +211,7 @@ void hs_write_restart(hs_sim *s, int sweep) {
   char name[64];
   snprintf(name, sizeof(name), "restart_%0*d.bin", width, sweep);
   hs_gpu_pull(s);
+  if (!HS_ROOT(s)) return;
   FILE *f = fopen(name, "wb");
   if (!f) { perror("Error while creating restart file\n"); exit(EXIT_FAILURE); }
   fwrite(&in->dr_max, sizeof(double), 1, f);
@@ -195,7 +271,9 @@ void hs_write_config(hs_sim *s, int sweep) {
   snprintf(name, sizeof(name), "config_%06d.dat.gz", s->config_file_id);
   const int append = s->config_samples_in_file != 0;
   hs_gpu_pull(s);
-  if (getenv("HSMC_IO_SERIAL")) {
+  if (!HS_ROOT(s)) {
+    /* keep the file counters in step with rank 0 */
+  } else if (getenv("HSMC_IO_SERIAL")) {
     /* the reference's writer, statement for statement (kept for timing comparisons) */
     gzFile f = gzopen(name, append ? "a" : "w");
     if (f == Z_NULL) { perror("Error while creating configuration file"); exit(EXIT_FAILURE); }
@@ -265,12 +343,49 @@ void hs_vol_move(hs_sim *s) {
       in->rho = N / vol_new;
       hs_box_init(s, in->type, in->nx, in->ny, in->nz, in->rho);
       double nb[3] = {s->box.lx, s->box.ly, s->box.lz};
-      hs_gpu_check(hsmc_gpu_rescale(s->gpu, sf, nb));
+      int rc = hsmc_gpu_rescale(s->gpu, sf, nb);
+      if (rc && s->mp.world > 1) {
+        /* the move changed the number of cells per axis: slab ownership has to be redrawn.  Same
+           verdict on every rank (it only depends on the boxes), and the library has not touched the
+           configuration yet: bring the table home, rescale it as the reference does
+           (moves.c:135-139), and hand it to fresh handles on the new grid. */
+        hsmc_gpu_info gi;
+        hs_gpu_check(hsmc_gpu_get_info(s->gpu, &gi));
+        if (HS_ROOT(s) && getenv("HSMC_DEBUG_MP"))
+          fprintf(stderr, "[hsmc_b200] volume move changes the cell grid (box %.4f -> %.4f): slabs redistributed\n", gi.box[0], nb[0]);
+        s->mirror_current = false;
+        hs_gpu_pull(s);
+        if (HS_ROOT(s)) {
+          for (int i = 0; i < N; i++)
+            for (int k = 1; k <= 3; k++) {
+              double v = s->conf[i][k] * sf;
+              if (v > nb[k - 1]) v -= nb[k - 1]; else if (v < 0.0) v += nb[k - 1];
+              s->conf[i][k] = v;
+            }
+        }
+        hs_mp_barrier(&s->mp);
+        int64_t cnt[6];
+        hs_gpu_check(hsmc_gpu_counters(s->gpu, cnt));
+        s->philox_sweeps = gi.sweeps_done;
+        s->carry_moves[0] += cnt[0]; s->carry_moves[1] += cnt[1]; s->carry_moves[2] += cnt[2];
+        s->carry_moves[3] += cnt[3]; s->carry_moves[4] += cnt[4]; s->carry_moves[5] += cnt[5];
+        hs_gpu_close(s);
+        hs_gpu_open(s);
+      } else {
+        hs_gpu_check(rc);
+      }
       s->mirror_current = false;
     }
   }
   hs_gpu_check(hsmc_gpu_add_vol_move(s->gpu, accepted));
 }
 
-void hs_counters(hs_sim *s, int64_t out[6]) { hs_gpu_check(hsmc_gpu_counters(s->gpu, out)); }
-void hs_reset_counters(hs_sim *s) { hs_gpu_check(hsmc_gpu_reset_counters(s->gpu)); }
+/* counters of handles retired by a slab redistribution are carried over */
+void hs_counters(hs_sim *s, int64_t out[6]) {
+  hs_gpu_check(hsmc_gpu_counters(s->gpu, out));
+  for (int k = 0; k < 6; k++) out[k] += s->carry_moves[k];
+}
+void hs_reset_counters(hs_sim *s) {
+  hs_gpu_check(hsmc_gpu_reset_counters(s->gpu));
+  memset(s->carry_moves, 0, sizeof(s->carry_moves));
+}

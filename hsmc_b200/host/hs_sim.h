@@ -15,6 +15,7 @@
 #include "../../include/hsmc_gpu.h"
 #include "hs_input.h"
 #include "hs_rng.h"
+#include "hs_mp.h"
 
 /* on-disk mirror of the reference's box_info / p_info (sim_info.h:6-18): restart files
    are raw struct dumps (io_config.c:53-69) */
@@ -46,7 +47,10 @@ typedef struct hs_sim {
   bool mirror_current;     /* host mirror == device state */
   hs_rng rng;
   hsmc_gpu *gpu;
+  hs_mp mp;                /* process-per-GPU plumbing (`-g K`); world 1 = the plain serial driver */
+  hsmc_gpu *gpu_rep;       /* world > 1: single-GPU handle holding a replica, for the sharded RDF */
   uint64_t philox_sweeps;  /* restart: device RNG sweep counter */
+  int64_t carry_moves[6];  /* move counters of handles retired by a slab redistribution */
   /* observables */
   hs_hist pressv, presst, rdf;
   double pressv_rmax;
@@ -58,6 +62,10 @@ typedef struct hs_sim {
 
 /* fatal error in the reference's style: "ERROR: ..." + exit(EXIT_FAILURE) */
 void hs_die(const char *fmt, ...);
+void hs_die_hook(hs_mp *mp);                 /* so that a fatal error on one rank stops the others */
+#define HS_ROOT(s) ((s)->mp.rank == 0)       /* rank 0 alone writes output files */
+/* particles the run will hold (lattice counts, or the header of the restart file) */
+int64_t hs_plan_particles(const hs_input *in);
 void hs_gpu_check(int rc);
 
 /* box + lattice (sim_info.c:32-71, 99-166) */

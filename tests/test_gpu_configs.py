@@ -69,13 +69,15 @@ out 20
 """
 
 
-def _run(text):
+def _run(text, args=(), env=None):
     d = tempfile.mkdtemp(prefix="hsmc_b200_cfg_")
     with open(os.path.join(d, "in.dat"), "w") as f:
         f.write(text)
-    r = subprocess.run([EXE, "-o", "out.txt"], cwd=d, capture_output=True, text=True, timeout=900)
+    r = subprocess.run([EXE, "-o", "out.txt", *args], cwd=d, capture_output=True, text=True, timeout=900,
+                       env=dict(os.environ, **(env or {})))
     log = open(os.path.join(d, "out.txt")).read() if os.path.exists(os.path.join(d, "out.txt")) else ""
     assert r.returncode == 0 and "Simulation complete!" in log, (r.stdout + r.stderr + log)[-3000:]
+    _run.stderr = r.stderr
     return d, log
 
 
@@ -126,3 +128,69 @@ def test_restart_round_trip():
     text = CONFIG1.replace("opt 1 200 10 0.5 0.5", "opt 0 200 10 0.5 0.5") + f"restart_read 1 {os.path.join(d, rs[-1])}\n"
     d2, log2 = _run(text)
     assert "Reading data from restart file" in log2 and "Number of particles: 1000" in log2
+
+
+CONFIG_SLAB = """# slab-decomposed driver run: every observable, snapshots, a restart file
+rho 0.85
+cells_x 16
+cells_y 8
+cells_z 8
+type 2
+neigh_list 1.05 10
+dr_max 0.12
+opt 1 60 6 0.5 0.5
+press_virial 0.002 10
+press_thermo 0.0001 0.002 10
+rdf 0.02 4.0 20 100
+widom 20000 10
+ql 6 1.5 10
+seed 31
+restart_write 40
+config_write 40 100
+sweep_eq 40
+sweep_stat 60
+out 20
+"""
+
+CONFIG_SLAB_NPT = """# NpT on slabs: volume moves with all-reduced verdicts; Lx starts 0.02 % above 26 cells of 1.1, so the first
+# accepted compressions change the cell grid (26 -> 24 layers) and the slabs have to be redistributed
+npt 8 0.004
+rho 0.6999
+cells_x 16
+cells_y 8
+cells_z 8
+type 2
+neigh_list 1.1 12
+dr_max 0.1
+opt 0 60 6 0.5 0.5
+press_thermo 0.0001 0.002 10
+seed 5
+config_write 50 100
+sweep_eq 50
+sweep_stat 50
+out 25
+"""
+
+
+@pytest.mark.parametrize("text", [CONFIG_SLAB, CONFIG_SLAB_NPT], ids=["nvt", "npt"])
+@pytest.mark.parametrize("halo", ["p2p", "nccl"])
+def test_driver_on_two_gpus_equals_single_gpu_chain(lib_built, text, halo):
+    """`hsmc_b200 -g 2` (one forked process per GPU, x-slabs, rank 0 writes the files) against the
+    single-GPU driver told to use the block partition of a 2-slab run: the same Markov chain, so
+    every output file must be byte-identical (snapshots, restart, histograms, mu, q_l, density)."""
+    if lib_built.load_library().hsmc_gpu_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    d2, log2 = _run(text, args=("-g", "2"), env={"HSMC_P2P": "1" if halo == "p2p" else "0", "HSMC_DEBUG_MP": "1"})
+    if "\nnpt " in text:
+        # the box shrinks through a change of the cell grid: the slabs must have been redistributed
+        assert "slabs redistributed" in _run.stderr, _run.stderr[-2000:]
+    d1, log1 = _run(text, env={"HSMC_XPART_WORLD": "2"})
+    names = sorted(f for f in os.listdir(d1) if f not in ("in.dat", "out.txt"))
+    assert names == sorted(f for f in os.listdir(d2) if f not in ("in.dat", "out.txt")) and len(names) >= 3
+    import gzip
+    for f in names:
+        rd = (lambda p: gzip.open(p).read()) if f.endswith(".gz") else (lambda p: open(p, "rb").read())
+        assert rd(os.path.join(d1, f)) == rd(os.path.join(d2, f)), f
+    # (NCCL announces its version on stdout when NCCL_DEBUG asks for it)
+    strip = lambda log: [ln for ln in log.splitlines() if not ln.startswith(("Elapsed time", "NCCL version"))]
+    assert strip(log1) == strip(log2)
