@@ -511,7 +511,8 @@ def main():
         steps_cpu = max(1, int(args.cpu_seconds / (ncpu * 1.2e-6)))
         try:
             r = cpu_reference_arm(steps_cpu, 1, args.cpu_cells, 1, cores)
-            cpu = {"value": r["value"], "unit": "moves/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+            cpu = {"value": r["value"], "unit": "moves/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+                   "per_core": r["value"] / max(r["cores"], 1)}
         except Exception as e:   # the baseline is reported, never required
             cpu = {"value": None, "unit": "moves/s", "cores": cores, "kind": "unavailable", "sample": repr(e)}
 

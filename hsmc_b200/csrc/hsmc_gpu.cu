@@ -356,13 +356,21 @@ __global__ void k_cell_scatter(Grid g, const double4* __restrict__ in, int n, co
 // shared-memory indices after adding the row's staging offset.
 __global__ void k_cs16(const int* __restrict__ cs, long long nrow, int nz, unsigned short* __restrict__ out,
                        int* __restrict__ flags) {
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nrow * (nz + 1)) return;
-  const long long row = (unsigned)t / (unsigned)(nz + 1);      // cells < 2^31, so rows x (nz + 1) < 2^32
-  const int z = (int)(t - row * (nz + 1));
-  const int v = cs[row * nz + z] - cs[row * nz];
-  if (v > 65535) atomicOr(flags, 64);
-  out[t] = (unsigned short)v;
+  // one warp per (x,y) row: the row's base is one broadcast load, entries are read and written coalesced
+  const int lane = threadIdx.x & 31;
+  const long long nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < nrow; row += nwarp) {
+    const int* src = cs + row * nz;
+    unsigned short* dst = out + row * (nz + 1);
+    const int base = src[0];
+    bool big = false;
+    for (int z = lane; z <= nz; z += 32) {
+      const int v = src[z] - base;
+      big |= v > 65535;
+      dst[z] = (unsigned short)v;
+    }
+    if (big) atomicOr(flags, 64);
+  }
 }
 
 // ----------------------------------------------------------------------------------
@@ -1189,7 +1197,7 @@ static int exclusive_scan(hsmc_gpu* h, const int* in, int64_t n, int* out) {
   h->launches += 3;
   if (h->blk_ok && out == h->cell_start) {
     const long long nrow = (long long)h->g.nlx * h->g.ny;
-    k_cs16<<<nblk(nrow * (h->g.nz + 1), 256), 256, 0, h->st>>>(out, nrow, h->g.nz, h->cs16, h->d_lay + 8);
+    k_cs16<<<(int)std::min<long long>((nrow + 7) / 8, 148LL * 64), 256, 0, h->st>>>(out, nrow, h->g.nz, h->cs16, h->d_lay + 8);
     h->launches++;
   }
   CU(cudaGetLastError());

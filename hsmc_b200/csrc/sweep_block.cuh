@@ -78,9 +78,12 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // block-completion flags of a fused launch (several block phases in one grid, see k_sweep_block)
-__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+// (polled with a relaxed load: an acquire load invalidates the SM's whole L1 each time it is issued
+//  (LDG.STRONG.GPU + CCTL.IVALL), which the co-resident CTAs pay for; the acquire is one fence after
+//  the flag has been seen)
+__device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int* p) {
   unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) {
@@ -150,7 +153,7 @@ k_sweep_block(SweepArgs a, BlockCfg bc, const int* __restrict__ xoff, double4* _
   // tickets enumerate (phase, block) in phase order, so whenever a CTA holds ticket t, every
   // ticket < t is held by a CTA that is resident or finished.  A block of phase p only
   // depends on its (up to 26) neighbouring blocks of EARLIER phases of the launch: it waits
-  // for their completion flags (release/acquire at gpu scope) instead of for a kernel
+  // for their completion flags (release store / relaxed poll + acquire fence at gpu scope) instead of for a kernel
   // boundary, so the ragged last wave of one phase overlaps the first wave of the next.
   // The earliest unfinished phase never waits => no deadlock.  Same chain as separate launches.
   const int hbz = bc.nbz >> 1, hby = bc.nby >> 1, hbx = bc.nbx >> 1;
@@ -179,8 +182,9 @@ k_sweep_block(SweepArgs a, BlockCfg bc, const int* __restrict__ xoff, double4* _
       const int q = ((nx & 1) << 2) | ((ny & 1) << 1) | (nz & 1);
       if (have && q >= a.phase && q < ph) {
         const unsigned int* f = bc.done + ((size_t)nx * bc.nby + ny) * bc.nbz + nz;
-        while (ld_acquire_gpu(f) != a.epoch) __nanosleep(100);
+        while (ld_relaxed_gpu(f) != a.epoch) __nanosleep(100);
       }
+      __threadfence();                     // acquire: everything those blocks wrote is visible from here on
     }
     __syncthreads();
   }
@@ -296,11 +300,22 @@ k_sweep_block(SweepArgs a, BlockCfg bc, const int* __restrict__ xoff, double4* _
     const float wxf = (float)g.wx, wyf = (float)g.wy, wzf = (float)g.wz;
     const float hxr = 0.5f * (float)nrx, hyr = 0.5f * (float)nry, hzr = 0.5f * (float)lenz;
     const int parx = (g.gx0 + x0) & 1, pary = y0 & 1, parz = z0 & 1;    // parity of region cell (0,0,0); grids are even
+    // each staged row is cut into P z-pieces, one (row, piece) item per thread and round; P is the
+    // split that wastes the fewest thread-rounds (100 rows x 2 halves on 128 threads would leave the
+    // second round 44 % empty)
+    int P = 2;
+    {
+      int best = 1 << 30;
+      for (int q = 2; q <= 8; q++) {
+        const int cost = ((q * nrows + BLK_THREADS - 1) / BLK_THREADS) * ((lenz + q - 1) / q + 2);
+        if (cost < best) { best = cost; P = q; }
+      }
+    }
 #pragma unroll 1
-    for (int idx = tid; idx < 2 * nrows; idx += BLK_THREADS) {
-      const int r = idx >> 1, half = idx & 1;
+    for (int idx = tid; idx < P * nrows; idx += BLK_THREADS) {
+      const int r = idx / P, piece = idx - r * P;
       const int rx = r / nry, ry = r - rx * nry;
-      const int zlo = half ? (lenz >> 1) : 0, zhi = half ? lenz : (lenz >> 1);
+      const int zlo = (piece * lenz) / P, zhi = ((piece + 1) * lenz) / P;
       const float cxf = (float)rx - hxr, cyf = (float)ry - hyr;
       const bool rowint = rx >= 1 && rx <= nbx && ry >= 1 && ry <= nby;
       const int colxy = (((parx + rx) & 1) << 2) | (((pary + ry) & 1) << 1);

@@ -1,2 +1,2 @@
 export BENCH_EXTRA="--no-secondary"
-bash scripts/block_sweep.sh "c5.so 8,8,16" "c6.so 8,8,12" "t96c6.so 8,7,12" "t96c6.so 8,7,16"
+bash scripts/block_sweep.sh "default 8,8,24" "v_old.so 8,8,24" "v_halves.so 8,8,24" "v_pipe.so 8,8,24" "v_halves_pipe.so 8,8,24" "default 8,8,24" "v_old.so 8,8,24"
