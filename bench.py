@@ -283,6 +283,13 @@ def secondary_observables(h, stream, N, nbar, peak, device):
 # --------------------------------------------------------------------------------------
 # BASELINE configs[4]: Widom chemical-potential sweep, insertions sharded over the GPUs
 # --------------------------------------------------------------------------------------
+def shard_range(total, rank, world):
+    """[first, first + count) of `rank`: equal shares, the last rank takes the remainder"""
+    share = total // world
+    first = rank * share
+    return first, (share if rank < world - 1 else total - first)
+
+
 def widom_workload(args, rank, world, local_rank):
     """`--workload widom`: the C2 shape (fcc 20^3, N = 32 000) at rho = 0.3 ... 0.9, equilibrated on the
     device; a step = one sample of --insertions (1e8) trial insertions at EACH density.  The
@@ -300,9 +307,7 @@ def widom_workload(args, rank, world, local_rank):
                                 device_id=torch.device("cuda", local_rank))
     rhos = [0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9]
     M = int(args.insertions)
-    share = M // world
-    first = rank * share
-    count = share if rank < world - 1 else M - first
+    first, count = shard_range(M, rank, world)
     handles = []
     for rho in rhos:
         box, conf = fcc_lattice(20, 20, 20, rho)

@@ -7,7 +7,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <errno.h>
 #include <sys/mman.h>
+#include <sys/prctl.h>
 #include <sys/wait.h>
 #include <unistd.h>
 
@@ -18,6 +20,31 @@ struct hs_mp_shared {
   unsigned char blob[HS_MP_MAX_RANKS][64];
   uint64_t scratch[HS_MP_MAX_RANKS][HS_MP_SCRATCH];
 };
+
+/* rank 0 watches its children: a rank that dies (crash, CUDA/NCCL abort, kill) would otherwise leave
+   the others waiting in a barrier or an NCCL call for ever */
+static struct hs_mp_shared *g_sh = NULL;
+static int g_world = 0;
+static volatile sig_atomic_t g_child_ok[HS_MP_MAX_RANKS];
+
+static void on_sigchld(int sig) {
+  (void)sig;
+  int saved = errno, st;
+  pid_t p;
+  while ((p = waitpid(-1, &st, WNOHANG)) > 0) {
+    int r = -1;
+    for (int k = 1; k < g_world; k++)
+      if (g_sh->pid[k] == p) r = k;
+    if (r < 0) continue;
+    if (WIFEXITED(st) && WEXITSTATUS(st) == 0) { g_child_ok[r] = 1; continue; }
+    static const char msg[] = "ERROR: a GPU rank of this run died; stopping the others\n";
+    if (write(STDERR_FILENO, msg, sizeof(msg) - 1) < 0) { /* nothing left to do about it */ }
+    for (int k = 1; k < g_world; k++)
+      if (k != r && !g_child_ok[k] && g_sh->pid[k] > 0) kill(g_sh->pid[k], SIGTERM);
+    _exit(EXIT_FAILURE);
+  }
+  errno = saved;
+}
 
 int hs_mp_start(hs_mp *mp, int world, int64_t n_rows) {
   memset(mp, 0, sizeof(*mp));
@@ -37,10 +64,20 @@ int hs_mp_start(hs_mp *mp, int world, int64_t n_rows) {
   pthread_barrierattr_destroy(&a);
   fflush(NULL);
   mp->sh->pid[0] = getpid();
+  g_sh = mp->sh;
+  g_world = mp->world;
+  struct sigaction sa;
+  memset(&sa, 0, sizeof(sa));
+  sa.sa_handler = on_sigchld;
+  sa.sa_flags = SA_RESTART | SA_NOCLDSTOP;
+  sigaction(SIGCHLD, &sa, NULL);
   for (int r = 1; r < mp->world; r++) {
     pid_t p = fork();
     if (p < 0) { perror("fork"); hs_mp_abort(mp); exit(EXIT_FAILURE); }
     if (p == 0) {
+      signal(SIGCHLD, SIG_DFL);
+      prctl(PR_SET_PDEATHSIG, SIGTERM);      /* no orphans holding a GPU if rank 0 goes away */
+      if (getppid() != mp->sh->pid[0]) _exit(EXIT_FAILURE);
       mp->rank = r;
       mp->sh->pid[r] = getpid();
       /* only rank 0 reports; the others run the same program silently */
@@ -86,7 +123,12 @@ int hs_mp_finish(hs_mp *mp) {
   int bad = 0;
   for (int r = 1; r < mp->world; r++) {
     int st = 0;
-    if (waitpid(mp->sh->pid[r], &st, 0) < 0 || !WIFEXITED(st) || WEXITSTATUS(st) != 0) bad = 1;
+    while (!g_child_ok[r]) {
+      pid_t p = waitpid(mp->sh->pid[r], &st, 0);
+      if (p == mp->sh->pid[r]) { if (!WIFEXITED(st) || WEXITSTATUS(st) != 0) bad = 1; break; }
+      if (p < 0 && errno == ECHILD) { if (!g_child_ok[r]) bad = 1; break; }   /* reaped by the handler */
+      if (p < 0 && errno != EINTR) { bad = 1; break; }
+    }
   }
   return bad;
 }

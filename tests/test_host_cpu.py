@@ -159,6 +159,33 @@ int main(void) {
 """
 
 
+_MP_DEATH_C = r"""
+#include <stdio.h>
+#include <stdlib.h>
+#include <unistd.h>
+#include "hs_mp.h"
+int main(void) {
+  hs_mp mp;
+  int rank = hs_mp_start(&mp, 3, 16);
+  if (rank == 2) { usleep(100000); abort(); }      /* a rank crashes while the others wait for it */
+  hs_mp_barrier(&mp);
+  printf("must not get here\n");
+  return hs_mp_finish(&mp);
+}
+"""
+
+
+def test_a_dying_rank_takes_the_run_down_instead_of_hanging_it(tmp_path):
+    host = os.path.join(ROOT, "hsmc_b200", "host")
+    src = tmp_path / "d.c"
+    src.write_text(_MP_DEATH_C)
+    exe = tmp_path / "d"
+    subprocess.run(["gcc", "-O2", "-std=gnu99", "-I", host, str(src), os.path.join(host, "hs_mp.c"), "-o", str(exe), "-lpthread"],
+                   check=True, capture_output=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=30)
+    assert out.returncode != 0 and "died" in out.stderr and "must not get here" not in out.stdout
+
+
 def test_host_driver_process_per_gpu_plumbing(tmp_path):
     """hs_mp.c (fork before CUDA, shared table, process-shared barrier, id / blob exchange) with
     three ranks on CPU; rank 0 alone reports."""
@@ -170,3 +197,15 @@ def test_host_driver_process_per_gpu_plumbing(tmp_path):
                    check=True, capture_output=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
     assert out.returncode == 0 and out.stdout.strip() == "MP_PLUMBING PASS", out.stdout + out.stderr
+
+
+@pytest.mark.parametrize("total,world", [(100_000_000, 8), (1000, 3), (7, 8), (0, 2)])
+def test_widom_insertion_shares_tile_the_range(total, world):
+    """bench.py --workload widom: the shares of the insertion index range are disjoint and cover it"""
+    from bench import shard_range
+    nxt = 0
+    for r in range(world):
+        first, count = shard_range(total, r, world)
+        assert first == nxt and count >= 0
+        nxt = first + count
+    assert nxt == total
