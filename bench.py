@@ -558,6 +558,13 @@ def main():
         "traffic_source": (traffic or {}).get("source") if world == 1 else None,
     }
 
+    if roofline["traffic"]:
+        # what actually crossed the HBM interface (ncu capture of the same launch), for comparison with the
+        # no-reuse algorithmic figure above: the kernel is latency-bound, not bandwidth-bound
+        roofline["dram_gbs"] = roofline["traffic"] / per_launch_s / 1e9
+        roofline["dram_frac"] = roofline["dram_gbs"] / peak
+        roofline["dram_bytes_per_move"] = roofline["traffic"] / max(roofline["moves_per_launch"], 1)
+
     # ---- end to end: host buffers in, host buffers out, every step ----
     def pull():
         if world > 1:
