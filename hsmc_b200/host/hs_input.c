@@ -76,10 +76,15 @@ void hs_input_defaults(hs_input *in) {
   in->rdf_samples = 100;
 }
 
-static void input_error(int kind, const char *line) {
+/* read_input.c:477-500.  The reference prints its line buffer AFTER strtok(line, " ") has cut it, i.e.
+   the first space-delimited token only (with its newline when the line has no space); same here. */
+static void input_error(int kind, char *line) {
   if (kind == 1) printf("Missing value to key\n");
   else if (kind == 2) printf("Unknown key\n");
   else printf("Name of restart file is too long, maximum 100 characters\n");
+  while (*line == ' ') line++;
+  char *sp = strchr(line, ' ');
+  if (sp) *sp = '\0';
   printf("Last read line in the input file:\n%s\n", line);
   exit(EXIT_FAILURE);
 }

@@ -209,3 +209,60 @@ def test_widom_insertion_shares_tile_the_range(total, world):
         assert first == nxt and count >= 0
         nxt = first + count
     assert nxt == total
+
+
+# ---- the drop-in driver's input handling against the reference executable (no GPU needed) --------
+REF_EXE = os.path.join(ROOT, "oracle", "_ref", "hsmc_ref")
+DRV_EXE = os.path.join(ROOT, "hsmc_b200", "host", "hsmc_b200")
+
+
+@pytest.fixture(scope="module")
+def driver_built(lib_built):
+    from hsmc_b200 import build
+    build.build_host()
+    if not os.path.exists(REF_EXE):
+        pytest.skip("oracle/_ref/hsmc_ref not built on this machine")
+    return DRV_EXE
+
+
+@pytest.mark.parametrize("text", ["rho 0.5\nbogus_key 3\n", "rho\n", "opt 1 1000\n", "neigh_list 1.0\n", "widom 100\n",
+                                  "rho 0.5\nnpt 10\n", "rdf 0.01 5.0 10\n", "restart_read 1 " + "x" * 120 + "\n"],
+                         ids=["unknown_key", "no_value", "opt_short", "neigh_short", "widom_short", "npt_short", "rdf_short",
+                              "restart_name_too_long"])
+def test_driver_rejects_bad_input_exactly_like_the_reference(driver_built, tmp_path, text):
+    """same messages on stdout, same exit code (read_input.c:138-441, 477-500)"""
+    (tmp_path / "in.dat").write_text(text)
+    ref = subprocess.run([REF_EXE, "-i", "in.dat"], cwd=tmp_path, capture_output=True, text=True, timeout=60)
+    mine = subprocess.run([driver_built, "-i", "in.dat"], cwd=tmp_path, capture_output=True, text=True, timeout=60)
+    assert ref.returncode == mine.returncode == 1
+    assert mine.stdout == ref.stdout
+
+
+def test_driver_reads_the_reference_example_and_refuses_to_run_without_a_gpu(driver_built, tmp_path):
+    """The reference's own `-e` example goes through the drop-in parser and set-up (same box and particle
+    lines as the reference prints); on a machine without a CUDA device the run then stops with an ERROR --
+    there is no CPU fallback.  (On the GPU box this test only checks the set-up lines.)"""
+    ex = subprocess.run([REF_EXE, "-e"], capture_output=True, text=True, timeout=60).stdout
+    ex = ex.replace("sweep_eq 1000000", "sweep_eq 2").replace("sweep_stat 1000000", "sweep_stat 2").replace(
+        "opt 1 1000 10 0.5 0.5", "opt 0 1000 10 0.5 0.5").replace("out 10000", "out 1")
+    (tmp_path / "in.dat").write_text(ex)
+    ref = subprocess.run([REF_EXE, "-i", "in.dat"], cwd=tmp_path, capture_output=True, text=True, timeout=120)
+    (tmp_path / "mine").mkdir()
+    (tmp_path / "mine" / "in.dat").write_text(ex)
+    mine = subprocess.run([driver_built, "-i", "in.dat"], cwd=tmp_path / "mine", capture_output=True, text=True, timeout=120)
+    head = lambda out: [ln for ln in out.splitlines() if ln.startswith(("Reading input", "Done", "Simulation box", "Number of particles"))]
+    assert ref.returncode == 0 and head(ref.stdout) == head(mine.stdout) and len(head(ref.stdout)) == 4
+    import hsmc_b200
+    if hsmc_b200.load_library().hsmc_gpu_device_count() < 1:
+        assert mine.returncode == 1 and "ERROR: no CUDA device" in mine.stdout and "no CPU fallback" in mine.stdout
+    else:
+        assert mine.returncode == 0 and "Simulation complete!" in mine.stdout
+
+
+def test_our_example_input_is_accepted_by_the_reference(driver_built, tmp_path):
+    ex = subprocess.run([driver_built, "-e"], capture_output=True, text=True, timeout=60).stdout
+    ex = ex.replace("sweep_eq 1000000", "sweep_eq 2").replace("sweep_stat 1000000", "sweep_stat 2").replace(
+        "opt 1 1000 10 0.5 0.5", "opt 0 1000 10 0.5 0.5").replace("out 10000", "out 1")
+    (tmp_path / "in.dat").write_text(ex)
+    ref = subprocess.run([REF_EXE, "-i", "in.dat"], cwd=tmp_path, capture_output=True, text=True, timeout=120)
+    assert ref.returncode == 0 and "Number of particles: 1000" in ref.stdout and "Production completed." in ref.stdout
