@@ -128,6 +128,16 @@ def test_restart_round_trip():
     text = CONFIG1.replace("opt 1 200 10 0.5 0.5", "opt 0 200 10 0.5 0.5") + f"restart_read 1 {os.path.join(d, rs[-1])}\n"
     d2, log2 = _run(text)
     assert "Reading data from restart file" in log2 and "Number of particles: 1000" in log2
+    # ... and the unmodified reference (CPU) continues from the same file: same byte layout, the trailing
+    # Philox counter is ignored
+    ref_exe = os.path.join(ROOT, "oracle", "_ref", "hsmc_ref")
+    if os.path.exists(ref_exe):
+        d3 = tempfile.mkdtemp(prefix="hsmc_b200_cfg_")
+        short = text.replace("sweep_eq 300", "sweep_eq 20").replace("sweep_stat 400", "sweep_stat 20").replace("out 100", "out 10")
+        with open(os.path.join(d3, "in.dat"), "w") as f:
+            f.write(short)
+        r = subprocess.run([ref_exe, "-i", "in.dat"], cwd=d3, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and "Number of particles: 1000" in r.stdout and "Production completed." in r.stdout, r.stdout[-2000:]
 
 
 CONFIG_SLAB = """# slab-decomposed driver run: every observable, snapshots, a restart file

@@ -266,3 +266,23 @@ def test_our_example_input_is_accepted_by_the_reference(driver_built, tmp_path):
     (tmp_path / "in.dat").write_text(ex)
     ref = subprocess.run([REF_EXE, "-i", "in.dat"], cwd=tmp_path, capture_output=True, text=True, timeout=120)
     assert ref.returncode == 0 and "Number of particles: 1000" in ref.stdout and "Production completed." in ref.stdout
+
+
+def test_driver_reads_a_restart_file_written_by_the_reference(driver_built, tmp_path):
+    """restart_%d.bin of the unmodified reference (io_config.c:28-74: dr_max, dv_max, box_info, p_info, the
+    {id,x,y,z} table, the MT19937 state) is accepted by the drop-in driver: same box, same particle count."""
+    text = ("rho 0.7\ncells_x 4\ncells_y 5\ncells_z 6\ntype 2\nneigh_list 1.0 10\ndr_max 0.1\nopt 0 10 2 0.5 0.5\n"
+            "seed 3\nrestart_write 4\nsweep_eq 4\nsweep_stat 4\nout 2\n")
+    (tmp_path / "in.dat").write_text(text)
+    ref = subprocess.run([REF_EXE, "-i", "in.dat"], cwd=tmp_path, capture_output=True, text=True, timeout=120)
+    assert ref.returncode == 0, ref.stdout[-2000:]
+    rs = sorted(f for f in os.listdir(tmp_path) if f.startswith("restart_"))
+    assert rs and os.path.getsize(tmp_path / rs[-1]) == 16 + 64 + 8 + 480 * 32 + 5000
+    d2 = tmp_path / "again"
+    d2.mkdir()
+    (d2 / "in.dat").write_text(text + f"restart_read 1 {tmp_path / rs[-1]}\n")
+    mine = subprocess.run([driver_built, "-i", "in.dat"], cwd=d2, capture_output=True, text=True, timeout=120)
+    ref2 = subprocess.run([REF_EXE, "-i", "in.dat"], cwd=d2, capture_output=True, text=True, timeout=120)
+    pick = lambda out: [ln for ln in out.splitlines() if ln.startswith(("Reading data from restart", "Simulation box", "Number of particles"))]
+    assert ref2.returncode == 0 and pick(mine.stdout) == pick(ref2.stdout) and len(pick(mine.stdout)) == 3
+    assert "Number of particles: 480" in mine.stdout
