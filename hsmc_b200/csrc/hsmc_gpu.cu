@@ -1723,6 +1723,37 @@ extern "C" int hsmc_gpu_plan(const double box[3], double cell_min, int world, in
   return 0;
 }
 
+extern "C" int hsmc_gpu_plan_blocks(const double box[3], double cell_min, int world, int rank, int xpart_world,
+                                    int64_t n_particles, hsmc_gpu_block_plan* o) {
+  if (!box || !o) return fail("null argument");
+  if (world < 1 || rank < 0 || rank >= world) return fail("invalid rank/world");
+  if (n_particles < 1) return fail("invalid particle count");
+  hsmc_gpu tmp;
+  tmp.cfg.device = 0; tmp.cfg.rank = rank; tmp.cfg.world = world; tmp.cfg.nccl_id = nullptr; tmp.cfg.seed = 0;
+  tmp.cfg.cell_min = cell_min == 0.0 ? 1.0 : cell_min; tmp.cfg.regrid_interval = 1; tmp.cfg.sweep_impl = 0;
+  tmp.impl = IMPL_BLOCK; tmp.xpart_world = (world == 1 && xpart_world > 1) ? xpart_world : 0;
+  if (tmp.cfg.cell_min < 1.0) return fail("cell_min must be >= 1.0 (the particle diameter)");
+  tmp.N = n_particles;
+  tmp.box[0] = box[0]; tmp.box[1] = box[1]; tmp.box[2] = box[2];
+  TRY(setup_grid(&tmp));
+  setup_blocks(&tmp);
+  memset(o, 0, sizeof(*o));
+  o->ok = tmp.blk_ok ? 1 : 0;
+  if (!tmp.blk_ok) return 0;
+  const BlockCfg& b = tmp.blk;
+  o->blocks[0] = b.nbx; o->blocks[1] = b.nby; o->blocks[2] = b.nbz;
+  o->max_extent[0] = b.mbx; o->max_extent[1] = b.mby; o->max_extent[2] = b.mbz;
+  o->ctas_per_phase = (b.nbx / 2) * (b.nby / 2) * (b.nbz / 2);
+  o->staged_capacity = b.cap;
+  o->smem_bytes = (int)tmp.blk_smem;
+  if ((int)tmp.xoff.size() > HSMC_GPU_PLAN_MAX_XCUTS) return fail("plan_blocks: too many x blocks to report");
+  o->n_xcuts = (int)tmp.xoff.size();
+  // local layers -> global layers, counted from the first layer this rank owns (ascending, no wrap)
+  const int x0 = (tmp.g.gx0 + tmp.g.own_lo) % tmp.g.nx;
+  for (int k = 0; k < o->n_xcuts; k++) o->xcuts[k] = x0 + (tmp.xoff[k] - tmp.g.own_lo);
+  return 0;
+}
+
 extern "C" void* hsmc_gpu_stream(hsmc_gpu* h) { return h ? (void*)h->st : nullptr; }
 
 extern "C" int hsmc_gpu_sync(hsmc_gpu* h) {

@@ -18,7 +18,7 @@ NCCL_ID_BYTES = 128
 # every symbol include/hsmc_gpu.h declares
 ABI_SYMBOLS = [
     "hsmc_gpu_last_error", "hsmc_gpu_device_count", "hsmc_gpu_nccl_id", "hsmc_gpu_create",
-    "hsmc_gpu_destroy", "hsmc_gpu_ipc_export", "hsmc_gpu_ipc_attach", "hsmc_gpu_get_info", "hsmc_gpu_plan", "hsmc_gpu_stream", "hsmc_gpu_sync", "hsmc_gpu_upload",
+    "hsmc_gpu_destroy", "hsmc_gpu_ipc_export", "hsmc_gpu_ipc_attach", "hsmc_gpu_get_info", "hsmc_gpu_plan", "hsmc_gpu_plan_blocks", "hsmc_gpu_stream", "hsmc_gpu_sync", "hsmc_gpu_upload",
     "hsmc_gpu_download", "hsmc_gpu_download_owned", "hsmc_gpu_sweep_nvt", "hsmc_gpu_overlap_scaled",
     "hsmc_gpu_rescale", "hsmc_gpu_widom", "hsmc_gpu_rdf_counts", "hsmc_gpu_rdf_counts_part", "hsmc_gpu_contact_counts",
     "hsmc_gpu_presst_flags", "hsmc_gpu_order_parameter", "hsmc_gpu_counters", "hsmc_gpu_reset_counters", "hsmc_gpu_add_vol_move",
@@ -42,6 +42,15 @@ class _Info(C.Structure):
                 ("n_owned", C.c_int64), ("n_local", C.c_int64), ("cells", C.c_int * 3), ("own_x0", C.c_int),
                 ("own_x1", C.c_int), ("cell_size", C.c_double * 3), ("box", C.c_double * 3),
                 ("sweeps_done", C.c_uint64), ("kernel_launches", C.c_uint64), ("nccl_calls", C.c_uint64)]
+
+
+PLAN_MAX_XCUTS = 512
+
+
+class _BlockPlan(C.Structure):
+    _fields_ = [("ok", C.c_int), ("blocks", C.c_int * 3), ("max_extent", C.c_int * 3), ("ctas_per_phase", C.c_int),
+                ("staged_capacity", C.c_int), ("smem_bytes", C.c_int), ("n_xcuts", C.c_int),
+                ("xcuts", C.c_int * PLAN_MAX_XCUTS)]
 
 
 class Trial(C.Structure):
@@ -74,6 +83,7 @@ def load_library():
     L.hsmc_gpu_ipc_attach.argtypes = [vp, vp, vp]
     L.hsmc_gpu_get_info.argtypes = [vp, C.POINTER(_Info)]
     L.hsmc_gpu_plan.argtypes = [dp, C.c_double, C.c_int, C.c_int, C.POINTER(_Info)]
+    L.hsmc_gpu_plan_blocks.argtypes = [dp, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int64, C.POINTER(_BlockPlan)]
     L.hsmc_gpu_stream.restype = vp
     L.hsmc_gpu_stream.argtypes = [vp]
     L.hsmc_gpu_sync.argtypes = [vp]
@@ -122,6 +132,18 @@ def plan(box, cell_min=1.0, world=1, rank=0):
         raise HsmcError(L.hsmc_gpu_last_error().decode())
     return {"cells": tuple(i.cells), "cell_size": tuple(i.cell_size), "own_x": (i.own_x0, i.own_x1),
             "rank": i.rank, "world": i.world}
+
+
+def plan_blocks(box, n_particles, cell_min=1.0, world=1, rank=0, xpart_world=0):
+    """Block partition of the two-level checkerboard for this box (host only, no GPU needed)."""
+    L = load_library()
+    b = (C.c_double * 3)(*[float(x) for x in box[:3]])
+    o = _BlockPlan()
+    if L.hsmc_gpu_plan_blocks(b, float(cell_min), int(world), int(rank), int(xpart_world), int(n_particles), C.byref(o)):
+        raise HsmcError(L.hsmc_gpu_last_error().decode())
+    return {"ok": bool(o.ok), "blocks": tuple(o.blocks), "max_extent": tuple(o.max_extent),
+            "ctas_per_phase": o.ctas_per_phase, "staged_capacity": o.staged_capacity, "smem_bytes": o.smem_bytes,
+            "xcuts": list(o.xcuts[: o.n_xcuts])}
 
 
 def _ptr(a):

@@ -92,6 +92,25 @@ int hsmc_gpu_get_info(hsmc_gpu *h, hsmc_gpu_info *out);
    rank, world.  Lets launchers and CPU tests reason about the decomposition. */
 int hsmc_gpu_plan(const double box[3], double cell_min, int world, int rank, hsmc_gpu_info *out);
 
+/* Host-only (no CUDA call): the two-level checkerboard's block partition hsmc_gpu_sweep_nvt would use
+   for this box / particle count on rank `rank` of `world` (xpart_world > 1: a single-GPU handle told to
+   mimic that many slabs, hsmc_gpu_config.sweep_impl bits 8..15).  The block SHAPE must be the same on
+   every rank of a run and on the single-GPU run that mimics it -- it is part of the chain's definition;
+   CPU tests check exactly that. */
+#define HSMC_GPU_PLAN_MAX_XCUTS 512
+typedef struct hsmc_gpu_block_plan {
+  int ok;                 /* 0: the block-resident kernel cannot be used on this grid (generic kernel instead) */
+  int blocks[3];          /* blocks per axis (even); x counts the blocks of this rank's layers */
+  int max_extent[3];      /* largest block extent per axis, in cells */
+  int ctas_per_phase;
+  int staged_capacity;    /* particles (pad included) one CTA can stage */
+  int smem_bytes;         /* dynamic shared memory per CTA */
+  int n_xcuts;            /* blocks[0] + 1 */
+  int xcuts[HSMC_GPU_PLAN_MAX_XCUTS];  /* global x-layer boundaries of this rank's blocks, ascending */
+} hsmc_gpu_block_plan;
+int hsmc_gpu_plan_blocks(const double box[3], double cell_min, int world, int rank, int xpart_world,
+                         int64_t n_particles, hsmc_gpu_block_plan *out);
+
 /* CUDA stream (cudaStream_t) all work of this handle is enqueued on. */
 void *hsmc_gpu_stream(hsmc_gpu *h);
 

@@ -286,3 +286,47 @@ def test_driver_reads_a_restart_file_written_by_the_reference(driver_built, tmp_
     pick = lambda out: [ln for ln in out.splitlines() if ln.startswith(("Reading data from restart", "Simulation box", "Number of particles"))]
     assert ref2.returncode == 0 and pick(mine.stdout) == pick(ref2.stdout) and len(pick(mine.stdout)) == 3
     assert "Number of particles: 480" in mine.stdout
+
+
+# ---- block partition of the two-level checkerboard: the same on every rank (host-only planning) -------
+def _fcc_box(nx, ny, nz, rho):
+    a = (4.0 / rho) ** (1.0 / 3.0)
+    return [nx * a, ny * a, nz * a], 4 * nx * ny * nz
+
+
+@pytest.mark.parametrize("cells,rho", [((256, 128, 128), 0.9), ((40, 10, 12), 0.85), ((24, 10, 12), 0.85), ((64, 64, 64), 0.9),
+                                       ((30, 30, 30), 0.94), ((100, 8, 6), 0.5), ((37, 11, 9), 0.7)])
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+def test_block_shape_is_the_same_on_every_rank_and_on_the_single_gpu_mimic(lib_built, cells, rho, world):
+    """The block shape is part of the chain's definition.  Choosing it from the rank's own slab (slabs differ
+    by two layers) once made a 4-GPU run a different chain from the single-GPU run; it must be a function of
+    the grid and the world size only, and the x cuts of the ranks must tile the single-GPU partition."""
+    from hsmc_b200 import gpu as G
+    box, n = _fcc_box(*cells, rho)
+    try:
+        plans = [G.plan_blocks(box, n, world=world, rank=r) for r in range(world)]
+    except G.HsmcError as e:
+        assert "too few cell layers" in str(e)
+        return
+    single = G.plan_blocks(box, n, xpart_world=world)
+    assert all(p["ok"] for p in plans) and single["ok"]
+    assert len({(p["max_extent"], p["blocks"][1:], p["staged_capacity"], p["smem_bytes"]) for p in plans}) == 1
+    assert plans[0]["max_extent"] == single["max_extent"] and plans[0]["blocks"][1:] == single["blocks"][1:]
+    cuts = []
+    for r, p in enumerate(plans):
+        own = G.plan(box, 1.0, world, r)["own_x"]
+        assert p["xcuts"][0] == own[0] and p["xcuts"][-1] == own[1] and p["blocks"][0] % 2 == 0
+        assert all(b > a for a, b in zip(p["xcuts"], p["xcuts"][1:]))
+        cuts += p["xcuts"][:-1]
+    assert cuts + [plans[-1]["xcuts"][-1]] == single["xcuts"]
+    # every block with its one-cell halo fits the staging limits the kernel was compiled with
+    mx, my, mz = single["max_extent"]
+    assert (mx + 2) * (my + 2) <= 128 and mz + 3 <= 32 and single["smem_bytes"] <= 100 * 1024
+
+
+def test_block_plan_of_the_benchmark_box(lib_built):
+    from hsmc_b200 import gpu as G
+    box, n = _fcc_box(256, 128, 128, 0.9)
+    p = G.plan_blocks(box, n)
+    assert p["blocks"] == (54, 28, 10) and p["max_extent"] == (8, 8, 21) and p["ctas_per_phase"] == 1890
+    assert p["xcuts"][0] == 0 and p["xcuts"][-1] == 420
