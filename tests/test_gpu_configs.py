@@ -204,3 +204,35 @@ def test_driver_on_two_gpus_equals_single_gpu_chain(lib_built, text, halo):
     # (NCCL announces its version on stdout when NCCL_DEBUG asks for it)
     strip = lambda log: [ln for ln in log.splitlines() if not ln.startswith(("Elapsed time", "NCCL version"))]
     assert strip(log1) == strip(log2)
+
+
+PATCHED_REF = os.path.join(ROOT, "oracle", "_ref", "hsmc_gpu_patched")
+
+
+@pytest.mark.skipif(os.environ.get("HSMC_TEST_PATCHED_REF") != "1" or not os.path.exists(PATCHED_REF),
+                    reason="opt-in (HSMC_TEST_PATCHED_REF=1): needs oracle/_ref/hsmc_gpu_patched, built where the reference is")
+@pytest.mark.parametrize("text", [CONFIG_SLAB, CONFIG3.replace("cells_x 30", "cells_x 12").replace("cells_y 30", "cells_y 12")
+                                  .replace("cells_z 30", "cells_z 12")], ids=["nvt_all_observables", "npt"])
+def test_patched_reference_and_drop_in_driver_write_the_same_files(text):
+    """The reference's OWN drivers, optimizer and output writers on top of libhsmc_gpu.so (the seam patch of
+    INTEGRATION.md, integration/patch_reference.py) against this repository's host driver: same seed, same
+    library, hence the same chain -- every output file must carry the same bytes (snapshots after gunzip,
+    restart files up to the trailing Philox counter)."""
+    import gzip
+    d_mine, _ = _run(text)
+    d_ref = tempfile.mkdtemp(prefix="hsmc_b200_patched_")
+    with open(os.path.join(d_ref, "in.dat"), "w") as f:
+        f.write(text)
+    r = subprocess.run([PATCHED_REF, "-i", "in.dat"], cwd=d_ref, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "Simulation complete!" in r.stdout, (r.stdout + r.stderr)[-3000:]
+    names = sorted(f for f in os.listdir(d_ref) if f != "in.dat")
+    assert names == sorted(f for f in os.listdir(d_mine) if f not in ("in.dat", "out.txt")) and names
+    for f in names:
+        a, b = os.path.join(d_ref, f), os.path.join(d_mine, f)
+        if f.endswith(".gz"):
+            assert gzip.open(a).read() == gzip.open(b).read(), f
+        elif f.startswith("restart_"):
+            ra, rb = open(a, "rb").read(), open(b, "rb").read()
+            assert rb[: len(ra)] == ra and len(rb) == len(ra) + 16, f
+        else:
+            assert open(a, "rb").read() == open(b, "rb").read(), f
