@@ -53,17 +53,27 @@ BODIES = {
   /* host-side cell geometry stays available to get_cell_list_info() users */
   compute_cell_list_info(true);
   (void)alloc;
-  /* one handle per configuration upload: the box may have changed since the last call (NpT restart
-     from the lattice after the optimizer, npt.c:54-61) */
-  if (G_GPU) { hsmc_gpu_destroy(G_GPU); G_GPU = NULL; }
-  hsmc_gpu_config cfg = {0};
-  cfg.world = 1;
-  cfg.seed = G_IN.seed;
-  cfg.cell_min = G_IN.neigh_dr;
-  cfg.regrid_interval = 1;
   box_info b = sim_box_info_get();
   double L[3] = {b.lx, b.ly, b.lz};
-  gpu_check(hsmc_gpu_create(&G_GPU, &cfg, part_info_get().NN, L));
+  /* Same box as the live handle (the NVT restart from the lattice after the optimizer, nvt.c:58-62):
+     keep the handle, so the device Philox sweep counter runs on as in the drop-in driver.  A different
+     box (first call; NpT restart after the optimizer, npt.c:54-61) needs a fresh handle. */
+  if (G_GPU) {
+    hsmc_gpu_info gi;
+    gpu_check(hsmc_gpu_get_info(G_GPU, &gi));
+    if (gi.box[0] != L[0] || gi.box[1] != L[1] || gi.box[2] != L[2] || gi.n_total != part_info_get().NN) {
+      hsmc_gpu_destroy(G_GPU);
+      G_GPU = NULL;
+    }
+  }
+  if (!G_GPU) {
+    hsmc_gpu_config cfg = {0};
+    cfg.world = 1;
+    cfg.seed = G_IN.seed;
+    cfg.cell_min = G_IN.neigh_dr;
+    cfg.regrid_interval = 1;
+    gpu_check(hsmc_gpu_create(&G_GPU, &cfg, part_info_get().NN, L));
+  }
   gpu_check(hsmc_gpu_upload(G_GPU, &part_config_get()[0][0], part_info_get().NN));
 """,
     ("cell_list.c", "cell_list_free"): r"""
