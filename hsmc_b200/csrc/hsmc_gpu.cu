@@ -948,9 +948,25 @@ __global__ void k_flag_post(volatile uint32_t* flag_a, volatile uint32_t* flag_b
   if (flag_b) *flag_b = seq;
   __threadfence_system();
 }
+// A wait is bounded: a neighbour that never delivers (its process died, say) must turn into a loud CUDA
+// error on this rank, not into a GPU that spins for ever.  HSMC_SPIN_LIMIT_NS is far beyond any legitimate
+// delay (a rank writing a 16.8M-particle snapshot keeps its neighbours waiting for seconds).
+#define HSMC_SPIN_LIMIT_NS (300ull * 1000000000ull)
+__device__ __forceinline__ void hsmc_wait_flag(volatile uint32_t* flag, uint32_t seq) {
+  unsigned long long t0 = 0;
+  unsigned int spins = 0;
+  while ((int32_t)(*flag - seq) < 0) {
+    __nanosleep(200);
+    if ((++spins & 4095u) == 0) {
+      const unsigned long long t = hsmc_globaltimer_ns();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > HSMC_SPIN_LIMIT_NS) __trap();
+    }
+  }
+}
 __global__ void k_flag_wait(volatile uint32_t* flag_a, volatile uint32_t* flag_b, uint32_t seq) {
-  if (flag_a) while ((int32_t)(*flag_a - seq) < 0) __nanosleep(200);
-  if (flag_b) while ((int32_t)(*flag_b - seq) < 0) __nanosleep(200);
+  if (flag_a) hsmc_wait_flag(flag_a, seq);
+  if (flag_b) hsmc_wait_flag(flag_b, seq);
   __threadfence_system();
 }
 

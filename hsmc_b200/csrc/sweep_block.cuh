@@ -77,6 +77,13 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// nanosecond wall clock of the device (bounds the spin waits below and in the halo flag kernels)
+__device__ __forceinline__ unsigned long long hsmc_globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 // block-completion flags of a fused launch (several block phases in one grid, see k_sweep_block)
 // (polled with a relaxed load: an acquire load invalidates the SM's whole L1 each time it is issued
 //  (LDG.STRONG.GPU + CCTL.IVALL), which the co-resident CTAs pay for; the acquire is one fence after
@@ -182,7 +189,18 @@ k_sweep_block(SweepArgs a, BlockCfg bc, const int* __restrict__ xoff, double4* _
       const int q = ((nx & 1) << 2) | ((ny & 1) << 1) | (nz & 1);
       if (have && q >= a.phase && q < ph) {
         const unsigned int* f = bc.done + ((size_t)nx * bc.nby + ny) * bc.nbz + nz;
-        while (ld_relaxed_gpu(f) != a.epoch) __nanosleep(100);
+        // (bounded: a protocol error must surface as a CUDA error, not as a GPU that spins for ever;
+        //  a whole launch lasts milliseconds, the limit is a minute)
+        unsigned long long t0 = 0;
+        unsigned int spins = 0;
+        while (ld_relaxed_gpu(f) != a.epoch) {
+          __nanosleep(100);
+          if ((++spins & 4095u) == 0) {
+            const unsigned long long t = hsmc_globaltimer_ns();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 60ull * 1000000000ull) __trap();
+          }
+        }
       }
       __threadfence();                     // acquire: everything those blocks wrote is visible from here on
     }
