@@ -257,3 +257,30 @@ def test_fp32_filter_without_error_band_is_caught(hs, oracle_built):
                 mismatch = True
                 break
         assert mismatch
+
+
+def test_logged_trial_draws_are_philox_of_cell_trial_and_sweep(hs, oracle_built):
+    """The device RNG contract (BASELINE north star: Philox keyed by sweep, colour/cell): the three raw draws
+    of every logged trial are Philox4x32-10(counter = (global cell, stream 0 | trial index in the cell, sweep),
+    key = seed), recomputed here with the oracle's independent Philox; per sweep every particle has exactly one
+    trial, the trials of a cell are numbered 0..n-1 in ascending particle id, and (cell, trial) is unique."""
+    g = dict(np.load(os.path.join(GOLDEN, "fcc6_rho09.npz")))
+    N = g["conf"].shape[0]
+    seed = 0x1234ABCD5
+    key = [seed & 0xFFFFFFFF, seed >> 32]
+    with hs.HsmcGpu(N, g["box"][:3], seed=seed) as h:
+        h.upload(g["conf"])
+        for sweep in range(3):
+            assert h.info()["sweeps_done"] == sweep
+            log = h.sweep_nvt_logged(0.1)
+            assert log.shape[0] == N and np.array_equal(np.sort(log["id"]), np.arange(N))
+            gcell = (log["seq"] >> np.uint64(8)) & np.uint64((1 << 48) - 1)
+            j = (log["seq"] & np.uint64(0xFF)).astype(np.int64)
+            assert np.unique(log["seq"] & np.uint64((1 << 56) - 1)).shape[0] == N
+            for c in np.unique(gcell):
+                sel = np.flatnonzero(gcell == c)
+                o = sel[np.argsort(j[sel])]
+                assert np.array_equal(j[o], np.arange(o.shape[0])) and np.all(np.diff(log["id"][o]) > 0)
+            for k in range(0, N, 7):                          # every 7th trial, all three draws
+                r = oracle_built.Port.philox([int(gcell[k]) & 0xFFFFFFFF, int(j[k]), sweep & 0xFFFFFFFF, sweep >> 32], key)
+                assert tuple(int(x) for x in r[:3]) == tuple(int(x) for x in log["raw"][k]), (sweep, k)
