@@ -14,3 +14,7 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:'k_c
 ls -la gpurun_out | tail -8
 # multi-GPU (separate calls, charged N x):  gpurun --gpus 2 -- 'python -m pytest tests/test_gpu_multi.py tests/test_gpu_configs.py -q -k "2- or two_gpus"'
 #                                           gpurun --gpus 8 -- 'bash scripts/bench2.sh 8 -'
+# experiment prepared in round 1: the split colour barrier
+#   scripts/build_variant.sh v_split "-DBLK_SPLIT_BARRIER"      (here, before the call)
+#   gpurun -- 'HSMC_GPU_LIB=$PWD/hsmc_b200/csrc/variants/v_split.so python -m pytest tests/test_gpu_sweep.py -x -q -m gpu | tail -3;
+#              BENCH_EXTRA=--no-secondary bash scripts/block_sweep.sh "default 8,8,24" "v_split.so 8,8,24"'
