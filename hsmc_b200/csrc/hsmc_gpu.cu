@@ -5,14 +5,19 @@
 //   pos[2][cap]   double4 {x, y, z, id}, cell-ordered (counting sort), ping-pong
 //   cell_start    int[ncell_local + 1]   CSR offsets into pos
 //   key, rnk      int[cap]               scratch of the counting sort
-// Kernels ("new kernel" table):
-//   K1  k_cell_count / k_scan_* / k_cell_scatter   cell_list_new   (cell_list.c:142-175)
-//   K2  k_sweep_phase        part_move + check_overlap             (moves.c:27-80,157-212)
-//   K3  k_overlap_scaled     vol_move / presst verdict             (moves.c:106-112)
-//   K4  k_widom              widom_insertion                       (compute_widom_chem_pot.c:44-71)
-//   K5  k_rdf_pairs          rdf_hist_compute                      (compute_rdf.c:110-128)
-//   K6  k_contact_hist       pressv_compute_hist                   (compute_press.c:123-165)
-//   K7  k_rescale            accepted volume move                  (moves.c:135-142)
+// One translation unit; the kernels live in the headers included below, this file keeps the handle, the
+// host-side orchestration and the ABI entry points ("new kernel" table):
+//   cell_list.cuh      K1  k_cell_count / k_scan_* / k_cell_scatter / k_cs16   cell_list_new (cell_list.c:142-175)
+//   sweep_generic.cuh  K2  k_sweep_phase (global memory)  part_move + check_overlap (moves.c:27-80,157-212)
+//   sweep_tile.cuh     K2' k_sweep_tile + k_sweep_deep    one launch per cell colour, TMA-staged tiles
+//   sweep_block.cuh    K2  k_sweep_block                  the default: block-resident, fused block phases
+//   observables.cuh    K3  k_overlap_scaled   vol_move / presst verdict   (moves.c:106-112)
+//                      K4  k_widom            widom_insertion             (compute_widom_chem_pot.c:44-71)
+//                      K5  k_rdf_pairs        rdf_hist_compute            (compute_rdf.c:110-128)
+//                      K6  k_contact_hist     pressv_compute_hist         (compute_press.c:123-165)
+//                      K7  k_rescale          accepted volume move        (moves.c:135-142)
+//                      K8  k_order_param      global_ql_compute           (compute_order_parameter.c:84-229)
+//   slab.cuh           slab decomposition: classification, halo messages, flags (world > 1)
 #include <cuda_runtime.h>
 #include <nccl.h>
 #include <math.h>
@@ -200,914 +205,13 @@ struct ProfSpan {
 
 static inline int nblk(int64_t n, int t) { return (int)((n + t - 1) / t); }
 
-// ----------------------------------------------------------------------------------
-// K1: cell list = counting sort
-// ----------------------------------------------------------------------------------
-// pass 1: cell key of every particle, rank inside its cell by atomic counter
-__global__ void k_cell_count(Grid g, const double4* __restrict__ in, int n, int* __restrict__ key,
-                             int* __restrict__ rnk, int* __restrict__ count) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  double4 p = in[i];
-  long long c = local_cell(g, p.x, p.y, p.z);
-  key[i] = (int)c;
-  if (c >= 0) rnk[i] = atomicAdd(&count[c], 1);
-}
-
-// exclusive scan of count[0..n) into out[0..n], out[n] = total: three small kernels
-#define SCAN_T 512
-#define SCAN_V 8
-#define SCAN_CHUNK (SCAN_T * SCAN_V)
-
-__device__ __forceinline__ int block_exclusive_scan(int v, int* total) {
-  __shared__ int wsum[SCAN_T / 32];
-  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  int inc = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += t;
-  }
-  if (lane == 31) wsum[w] = inc;
-  __syncthreads();
-  if (w == 0) {
-    int s = (lane < SCAN_T / 32) ? wsum[lane] : 0;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int t = __shfl_up_sync(0xffffffffu, s, o);
-      if (lane >= o) s += t;
-    }
-    if (lane < SCAN_T / 32) wsum[lane] = s;
-  }
-  __syncthreads();
-  int base = (w > 0) ? wsum[w - 1] : 0;
-  *total = wsum[SCAN_T / 32 - 1];
-  __syncthreads();
-  return base + inc - v;
-}
-
-__global__ void k_scan_blocksum(const int* __restrict__ in, long long n, int* __restrict__ bsum) {
-  long long base = (long long)blockIdx.x * SCAN_CHUNK;
-  int s = 0;
-  if (base + SCAN_CHUNK <= n) {
-    const int4* p4 = reinterpret_cast<const int4*>(in + base);
-#pragma unroll
-    for (int j = 0; j < SCAN_V / 4; j++) {
-      const int4 a = p4[j * SCAN_T + threadIdx.x];
-      s += a.x + a.y + a.z + a.w;
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < SCAN_V; j++) {
-      long long i = base + (long long)j * SCAN_T + threadIdx.x;
-      if (i < n) s += in[i];
-    }
-  }
-  int tot;
-  block_exclusive_scan(s, &tot);
-  if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
-}
-
-__global__ void k_scan_top(int* bsum, int nb) {
-  // single block; sequential over chunks of SCAN_T with a running carry
-  __shared__ int carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  for (int b0 = 0; b0 < nb; b0 += SCAN_T) {
-    int i = b0 + threadIdx.x;
-    int v = (i < nb) ? bsum[i] : 0;
-    int tot;
-    int ex = block_exclusive_scan(v, &tot);
-    if (i < nb) bsum[i] = carry + ex;
-    __syncthreads();
-    if (threadIdx.x == 0) carry += tot;
-    __syncthreads();
-  }
-}
-
-// last pass of the scan; cells found to hold >= 3 particles are appended to the per-colour
-// deep lists on the way (owned layers only)
-__global__ void k_scan_final(const int* __restrict__ in, long long n, const int* __restrict__ bsum,
-                             int* __restrict__ out, Grid g, int* __restrict__ deep_list,
-                             int* __restrict__ deep_count, int list_stride) {
-  long long base = (long long)blockIdx.x * SCAN_CHUNK + (long long)threadIdx.x * SCAN_V;
-  int v[SCAN_V];
-  int s = 0;
-  static_assert(SCAN_V == 8, "two int4 per thread");
-  if (base + SCAN_V <= n) {                       // 32-byte vector path (cudaMalloc'd arrays, base % 8 == 0)
-    const int4 a0 = reinterpret_cast<const int4*>(in + base)[0], a1 = reinterpret_cast<const int4*>(in + base)[1];
-    v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
-  } else {
-#pragma unroll
-    for (int j = 0; j < SCAN_V; j++) v[j] = (base + j < n) ? in[base + j] : 0;
-  }
-#pragma unroll
-  for (int j = 0; j < SCAN_V; j++) s += v[j];
-  int tot;
-  int ex = block_exclusive_scan(s, &tot) + bsum[blockIdx.x];
-  int o[SCAN_V];
-#pragma unroll
-  for (int j = 0; j < SCAN_V; j++) { o[j] = ex; ex += v[j]; }
-  if (base + SCAN_V <= n) {
-    reinterpret_cast<int4*>(out + base)[0] = make_int4(o[0], o[1], o[2], o[3]);
-    reinterpret_cast<int4*>(out + base)[1] = make_int4(o[4], o[5], o[6], o[7]);
-    if (base + SCAN_V == n) out[n] = ex;
-  } else {
-#pragma unroll
-    for (int j = 0; j < SCAN_V; j++) {
-      if (base + j < n) out[base + j] = o[j];
-      if (base + j == n - 1) out[n] = o[j] + v[j];
-    }
-  }
-  if (deep_list) {
-#pragma unroll
-    for (int j = 0; j < SCAN_V; j++) {
-      const long long i = base + j;
-      if (i < n && v[j] >= 3) {
-        int iz = (int)(i % g.nz);
-        long long r = i / g.nz;
-        int iy = (int)(r % g.ny), l = (int)(r / g.ny);
-        if (l >= g.own_lo && l < g.own_hi) {
-          int colour = (((g.gx0 + l) & 1) << 2) | ((iy & 1) << 1) | (iz & 1);
-          int slot = atomicAdd(&deep_count[colour], 1);
-          if (slot < list_stride) deep_list[(long long)colour * list_stride + slot] = (int)i;
-        }
-      }
-    }
-  }
-}
-
-// pass 3: scatter into cell order
-__global__ void k_cell_scatter(Grid g, const double4* __restrict__ in, int n, const int* __restrict__ key,
-                               const int* __restrict__ rnk, const int* __restrict__ cs,
-                               double4* __restrict__ out, float4* __restrict__ rel) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int c = key[i];
-  if (c < 0) return;
-  double4 p = in[i];
-  int d = cs[c] + rnk[i];
-  out[d] = p;
-  rel[d] = make_rel_cell(g, c, p);
-}
-
-// 16-bit row-relative copy of the CSR offsets: cs16[row][z] = cs[row*nz + z] - cs[row*nz], z = 0..nz
-// (entry nz = population of the row).  Half the bytes to stage, and directly usable as
-// shared-memory indices after adding the row's staging offset.
-__global__ void k_cs16(const int* __restrict__ cs, long long nrow, int nz, unsigned short* __restrict__ out,
-                       int* __restrict__ flags) {
-  // one warp per (x,y) row: the row's base is one broadcast load, entries are read and written coalesced
-  const int lane = threadIdx.x & 31;
-  const long long nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < nrow; row += nwarp) {
-    const int* src = cs + row * nz;
-    unsigned short* dst = out + row * (nz + 1);
-    const int base = src[0];
-    bool big = false;
-    for (int z = lane; z <= nz; z += 32) {
-      const int v = src[z] - base;
-      big |= v > 65535;
-      dst[z] = (unsigned short)v;
-    }
-    if (big) atomicOr(flags, 64);
-  }
-}
-
-// ----------------------------------------------------------------------------------
-// host <-> device table conversion ({id,x,y,z} rows <-> {x,y,z,id} slots)
-// ----------------------------------------------------------------------------------
-__global__ void k_unpack_rows(const double* __restrict__ rows, int n, double4* __restrict__ out) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const double4 r = reinterpret_cast<const double4*>(rows)[i];
-  out[i] = make_double4(r.y, r.z, r.w, r.x);
-}
-
-__global__ void k_pack_by_id(const double4* __restrict__ pos, int first, int n, double* __restrict__ out) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  double4 p = pos[first + i];
-  long long id = (long long)p.w;
-  reinterpret_cast<double4*>(out)[id] = make_double4(p.w, p.x, p.y, p.z);
-}
-
-__global__ void k_pack_rows(const double4* __restrict__ pos, int first, int n, double* __restrict__ out) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  double4 p = pos[first + i];
-  reinterpret_cast<double4*>(out)[i] = make_double4(p.w, p.x, p.y, p.z);
-}
-
-__global__ void k_slot_of_id(const double4* __restrict__ pos, int n, int* __restrict__ slot) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  slot[(long long)pos[i].w] = i;
-}
-
-// ----------------------------------------------------------------------------------
-// K2: one colour phase of the checkerboard sweep.
-//
-// Cells are coloured by the parity of their (global) indices, 2x2x2 = 8 colours.  Two
-// cells of one colour are separated by a full cell (edge >= 1.0 = sigma), so particles
-// in different active cells can never overlap whatever moves they make inside their
-// cells: all active cells are independent and are processed concurrently, one thread
-// per active cell, the particles of a cell sequentially in ascending-id order.  A trial
-// that would leave its cell is rejected (membership is static within a sweep); the grid
-// origin is redrawn between sweeps so that walls move (Anderson et al., J. Comput. Phys.
-// 254 (2013) 27).  Each trial is the reference's part_move(): three uniforms,
-// x += (u - 0.5)*dr_max, apply_pbc, accept iff check_overlap is false.
-// ----------------------------------------------------------------------------------
-struct SweepArgs {
-  Grid g;
-  Box box;
-  double dr_max;
-  uint32_t key0, key1;
-  uint32_t sweep_lo, sweep_hi;
-  int cx, cy, cz, phase;
-  float eps;   // half-width of the fp32 filter's uncertainty band around r^2 = 1
-  // k_sweep_block only: phases [phase, phase + fuse) in one launch (fuse <= 1: just `phase`)
-  int fuse;
-  unsigned int epoch, ticket_base;
-};
-
-// all trials of one active cell straight from global memory (generic path: any grid,
-// minimum image always evaluated)
-template <bool LOG>
-__device__ __forceinline__ void cell_update_global(const SweepArgs& a, int phase, double4* __restrict__ pos,
-                                                   float4* __restrict__ rel, const int* __restrict__ cs, int l,
-                                                   int iy, int iz, int j0, int j1, int& n_acc,
-                                                   int& n_ov, int& n_cell, hsmc_gpu_trial* __restrict__ log,
-                                                   unsigned long long* __restrict__ nlog, long long logcap) {
-  const Grid& g = a.g;
-  long long c = ((long long)l * g.ny + iy) * g.nz + iz;
-  int beg = cs[c], end = cs[c + 1];
-  if (beg == end) return;
-  if (j0 < 0) {                        // tile-kernel fallback: deep cells are not its business
-    if (end - beg > j1) return;
-    j0 = 0;
-  }
-  const int gx = (g.gx0 + l >= g.nx) ? g.gx0 + l - g.nx : g.gx0 + l;
-  long long gcell = ((long long)gx * g.ny + iy) * g.nz + iz;
-  double last_id = -1.0;
-  for (int j = 0; j < end - beg; j++) {
-    // next particle of this cell in ascending-id order (order is then independent of
-    // how the counting sort happened to place them)
-    int sel = beg;
-    double best = 1e300;
-    for (int k = beg; k < end; k++) {
-      double id = pos[k].w;
-      if (id > last_id && id < best) { best = id; sel = k; }
-    }
-    last_id = best;
-    if (j < j0) continue;      // trials below j0 belong to the tile kernel
-    if (j >= j1) break;
-    double4 p = pos[sel];
-    Philox4 rn = philox4x32_10((uint32_t)gcell, (HSMC_STREAM_MOVE << 24) | (uint32_t)j, a.sweep_lo, a.sweep_hi,
-                               a.key0, a.key1);
-    // moves.c:52-54
-    double xn = p.x + (hsmc_u01(rn.v[0]) - 0.5) * a.dr_max;
-    double yn = p.y + (hsmc_u01(rn.v[1]) - 0.5) * a.dr_max;
-    double zn = p.z + (hsmc_u01(rn.v[2]) - 0.5) * a.dr_max;
-    // moves.c:215-226
-    if (xn > g.Lx) xn -= g.Lx; else if (xn < 0.0) xn += g.Lx;
-    if (yn > g.Ly) yn -= g.Ly; else if (yn < 0.0) yn += g.Ly;
-    if (zn > g.Lz) zn -= g.Lz; else if (zn < 0.0) zn += g.Lz;
-    int verdict;
-    if (axis_cell(xn, g.sx, g.iwx, g.nx) != gx || axis_cell(yn, g.sy, g.iwy, g.ny) != iy ||
-        axis_cell(zn, g.sz, g.iwz, g.nz) != iz) {
-      verdict = 2;
-      n_cell++;
-    } else {
-      const Box& b = a.box;
-      bool ov = stencil_any(g, cs, l, iy, iz, [&](int k) {
-        if (k == sel) return false;
-        double4 q = pos[k];
-        return pair_r2(xn, yn, zn, q.x, q.y, q.z, b) < 1.0;
-      });
-      if (ov) { verdict = 1; n_ov++; }
-      else {
-        verdict = 0; n_acc++;
-        pos[sel] = make_double4(xn, yn, zn, p.w);
-        rel[sel] = make_rel(g, gx, iy, iz, xn, yn, zn, p.w);
-      }
-    }
-    if (LOG) {
-      unsigned long long s = atomicAdd(nlog, 1ull);
-      if ((long long)s < logcap) {
-        hsmc_gpu_trial tr;
-        tr.seq = ((unsigned long long)phase << 56) | ((unsigned long long)gcell << 8) | (unsigned)j;
-        tr.id = (int)p.w; tr.verdict = verdict;
-        tr.raw[0] = rn.v[0]; tr.raw[1] = rn.v[1]; tr.raw[2] = rn.v[2]; tr.pad = 0;
-        log[s] = tr;
-      }
-    }
-  }
-}
-
-// generic kernel: one thread per active cell, everything from global memory
-template <bool LOG>
-__global__ void __launch_bounds__(128)
-k_sweep_phase(SweepArgs a, double4* __restrict__ pos, float4* __restrict__ rel, const int* __restrict__ cs,
-              unsigned long long* __restrict__ cnt, hsmc_gpu_trial* __restrict__ log,
-              unsigned long long* __restrict__ nlog, long long logcap) {
-  const Grid& g = a.g;
-  const int hx = (g.own_hi - g.own_lo) >> 1, hy = g.ny >> 1, hz = g.nz >> 1;
-  const long long total = (long long)hx * hy * hz;
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  int n_acc = 0, n_ov = 0, n_cell = 0;
-  if (t < total) {
-    int az = (int)(t % hz);
-    long long r = t / hz;
-    int ay = (int)(r % hy), ax = (int)(r / hy);
-    int par0 = (g.gx0 + g.own_lo) & 1;
-    int l = g.own_lo + 2 * ax + ((a.cx - par0) & 1);
-    int iy = 2 * ay + a.cy, iz = 2 * az + a.cz;
-    cell_update_global<LOG>(a, a.phase, pos, rel, cs, l, iy, iz, 0, 1 << 30, n_acc, n_ov, n_cell, log, nlog, logcap);
-  }
-  // block-aggregated counters
-  __shared__ int s_cnt[3];
-  if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
-  __syncthreads();
-  if (n_acc) atomicAdd(&s_cnt[0], n_acc);
-  if (n_ov) atomicAdd(&s_cnt[1], n_ov);
-  if (n_cell) atomicAdd(&s_cnt[2], n_cell);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int tot = s_cnt[0] + s_cnt[1] + s_cnt[2];
-    if (tot) {
-      atomicAdd(&cnt[CNT_TRIALS], (unsigned long long)tot);
-      if (s_cnt[0]) atomicAdd(&cnt[CNT_ACC], (unsigned long long)s_cnt[0]);
-      if (s_cnt[1]) atomicAdd(&cnt[CNT_REJ_OVERLAP], (unsigned long long)s_cnt[1]);
-      if (s_cnt[2]) atomicAdd(&cnt[CNT_REJ_CELL], (unsigned long long)s_cnt[2]);
-    }
-  }
-}
-
+#include "cell_list.cuh"
+#include "sweep_generic.cuh"
 #include "sweep_tile.cuh"
 #include "sweep_block.cuh"
 
-// ----------------------------------------------------------------------------------
-// K3: global scaled-overlap verdict for nsf scale factors in one pass over the pairs.
-// One thread per owned cell over the forward half of its stencil (stencil_half): each unordered
-// pair is loaded and visited once.
-// A cheap unscaled pre-test skips pairs that cannot overlap under any of the factors
-// (threshold carries a 1e-6 relative margin, far above rounding); pairs that pass are
-// evaluated with the reference's exact scaled arithmetic for every factor.
-// ----------------------------------------------------------------------------------
-#define MAX_SF 64
-struct SfArgs {
-  int n;
-  double r2_skip;       // unscaled r2 above which no factor can give an overlap
-  double sf[MAX_SF];
-  Box box[MAX_SF];
-};
-
-__global__ void __launch_bounds__(128)
-k_overlap_scaled(Grid g, Box ubox, const SfArgs* __restrict__ sa, const double4* __restrict__ pos,
-                 const int* __restrict__ cs, int* __restrict__ flags) {
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)(g.own_hi - g.own_lo) * g.ny * g.nz;
-  if (t >= total) return;
-  int nsf = sa->n;
-  if (nsf == 1 && flags[0]) return;   // verdict already known
-  int iz = (int)(t % g.nz);
-  long long r = t / g.nz;
-  int iy = (int)(r % g.ny), l = g.own_lo + (int)(r / g.ny);
-  long long c = ((long long)l * g.ny + iy) * g.nz + iz;
-  int beg = cs[c], end = cs[c + 1];
-  double r2_skip = sa->r2_skip;
-  for (int s = beg; s < end; s++) {
-    double4 p = pos[s];
-    stencil_half(g, cs, l, iy, iz, [&](int k, bool own) {
-      double4 q = pos[k];
-      if (own && !(q.w > p.w)) return false;
-      if (pair_r2(p.x, p.y, p.z, q.x, q.y, q.z, ubox) > r2_skip) return false;
-      bool all = true;
-      for (int m = 0; m < nsf; m++) {
-        if (pair_r2_scaled(p.x, p.y, p.z, q.x, q.y, q.z, sa->sf[m], sa->box[m]) < 1.0) flags[m] = 1;
-        else all = false;
-      }
-      return nsf == 1 && all;
-    });
-  }
-}
-
-// ----------------------------------------------------------------------------------
-// K4: Widom insertions.  One thread per insertion point; the point is
-// r = u * L (compute_widom_chem_pot.c:73-80) with u from Philox(sample, index).
-// ----------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_widom(Grid g, Box box, const double4* __restrict__ pos, const int* __restrict__ cs, uint32_t key0,
-        uint32_t key1, uint32_t sample_lo, uint32_t sample_hi, long long first, long long count,
-        unsigned long long* __restrict__ accepted) {
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  int ok = 0;
-  if (t < count) {
-    unsigned long long m = (unsigned long long)(first + t);
-    Philox4 rn = philox4x32_10((uint32_t)m, (HSMC_STREAM_WIDOM << 24) | (uint32_t)(m >> 32), sample_lo,
-                               sample_hi, key0, key1);
-    double rx = hsmc_u01(rn.v[0]) * g.Lx, ry = hsmc_u01(rn.v[1]) * g.Ly, rz = hsmc_u01(rn.v[2]) * g.Lz;
-    int l = local_layer(g, axis_cell(rx, g.sx, g.iwx, g.nx));
-    if (l >= g.own_lo && l < g.own_hi) {
-      int iy = axis_cell(ry, g.sy, g.iwy, g.ny), iz = axis_cell(rz, g.sz, g.iwz, g.nz);
-      bool ov = stencil_any(g, cs, l, iy, iz, [&](int k) {
-        double4 q = pos[k];
-        return pair_r2(rx, ry, rz, q.x, q.y, q.z, box) < 1.0;
-      });
-      ok = ov ? 0 : 1;
-    }
-  }
-  unsigned m = __ballot_sync(0xffffffffu, ok);
-  __shared__ int s_ok;
-  if (threadIdx.x == 0) s_ok = 0;
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0 && m) atomicAdd(&s_ok, __popc(m));
-  __syncthreads();
-  if (threadIdx.x == 0 && s_ok) atomicAdd(accepted, (unsigned long long)s_ok);
-}
-
-// explicit points (parity entry point)
-__global__ void k_widom_points(Grid g, Box box, const double4* __restrict__ pos, const int* __restrict__ cs,
-                               const double* __restrict__ xyz, int n, int* __restrict__ flags) {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n) return;
-  double rx = xyz[3 * t], ry = xyz[3 * t + 1], rz = xyz[3 * t + 2];
-  int l = local_layer(g, axis_cell(rx, g.sx, g.iwx, g.nx));
-  int iy = axis_cell(ry, g.sy, g.iwy, g.ny), iz = axis_cell(rz, g.sz, g.iwz, g.nz);
-  bool ov = stencil_any(g, cs, l, iy, iz, [&](int k) {
-    double4 q = pos[k];
-    return pair_r2(rx, ry, rz, q.x, q.y, q.z, box) < 1.0;
-  });
-  flags[t] = ov ? 1 : 0;
-}
-
-// explicit trial moves (parity entry point): verdict of check_overlap for particle
-// idx placed at xyz with everything else fixed
-__global__ void k_trial_points(Grid g, Box sbox, double sf, const double4* __restrict__ pos,
-                               const int* __restrict__ cs, const int* __restrict__ idx,
-                               const double* __restrict__ xyz, int n, int* __restrict__ flags) {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n) return;
-  double rx = xyz[3 * t], ry = xyz[3 * t + 1], rz = xyz[3 * t + 2];
-  double id = (double)idx[t];
-  int l = local_layer(g, axis_cell(rx, g.sx, g.iwx, g.nx));
-  int iy = axis_cell(ry, g.sy, g.iwy, g.ny), iz = axis_cell(rz, g.sz, g.iwz, g.nz);
-  bool ov = stencil_any(g, cs, l, iy, iz, [&](int k) {
-    double4 q = pos[k];
-    if (q.w == id) return false;
-    return pair_r2_scaled(rx, ry, rz, q.x, q.y, q.z, sf, sbox) < 1.0;
-  });
-  flags[t] = ov ? 1 : 0;
-}
-
-// ----------------------------------------------------------------------------------
-// K5: RDF pair histogram, all pairs (compute_rdf.c:110-128), shared-memory privatised.
-// Tiles of RDF_T x RDF_T pairs; the j tile is staged in shared memory; the square root
-// and the division (needed for a bit-exact bin index) are only evaluated for pairs that
-// pass a conservative r2 pre-test.
-// ----------------------------------------------------------------------------------
-#define RDF_T 256
-#define RDF_MAX_SMEM_BINS 8192
-__global__ void __launch_bounds__(RDF_T)
-k_rdf_pairs(const double4* __restrict__ pos, int n, Box box, double rmax, double r2_pre, double dr_bin,
-            int nn, int ntile, long long b0, unsigned long long* __restrict__ hist) {
-  // linear block index -> (ti, tj) with tj >= ti
-  long long b = b0 + blockIdx.x;
-  int ti = 0;
-  {
-    // rows of the upper triangle have ntile - ti entries
-    double nt = (double)ntile;
-    ti = (int)floor(((2.0 * nt + 1.0) - sqrt((2.0 * nt + 1.0) * (2.0 * nt + 1.0) - 8.0 * (double)b)) * 0.5);
-    while ((long long)ti * (2LL * ntile - ti + 1) / 2 > b) ti--;
-    while ((long long)(ti + 1) * (2LL * ntile - ti) / 2 <= b) ti++;
-  }
-  int tj = ti + (int)(b - (long long)ti * (2LL * ntile - ti + 1) / 2);
-  extern __shared__ unsigned char smem_raw[];
-  double* sx = reinterpret_cast<double*>(smem_raw);
-  double* sy = sx + RDF_T;
-  double* sz = sy + RDF_T;
-  unsigned int* sh = reinterpret_cast<unsigned int*>(sz + RDF_T);
-  bool use_sh = nn <= RDF_MAX_SMEM_BINS;
-  if (use_sh)
-    for (int k = threadIdx.x; k < nn; k += RDF_T) sh[k] = 0;
-  int j0 = tj * RDF_T;
-  int jn = min(RDF_T, n - j0);
-  if ((int)threadIdx.x < jn) {
-    double4 q = pos[j0 + threadIdx.x];
-    sx[threadIdx.x] = q.x; sy[threadIdx.x] = q.y; sz[threadIdx.x] = q.z;
-  }
-  __syncthreads();
-  int i = ti * RDF_T + threadIdx.x;
-  if (i < n) {
-    double4 p = pos[i];
-    int jb = (ti == tj) ? (int)threadIdx.x + 1 : 0;
-    for (int j = jb; j < jn; j++) {
-      double r2 = pair_r2(p.x, p.y, p.z, sx[j], sy[j], sz[j], box);
-      if (r2 < r2_pre) {
-        double dr = sqrt(r2);
-        if (dr < rmax) {
-          int bin = (int)((dr - 1.0) / dr_bin);
-          if (bin >= 0 && bin < nn) {
-            if (use_sh) atomicAdd(&sh[bin], 1u);
-            else atomicAdd(&hist[bin], 1ull);
-          }
-        }
-      }
-    }
-  }
-  __syncthreads();
-  if (use_sh)
-    for (int k = threadIdx.x; k < nn; k += RDF_T)
-      if (sh[k]) atomicAdd(&hist[k], (unsigned long long)sh[k]);
-}
-
-// ----------------------------------------------------------------------------------
-// K6: near-contact pair histogram through the cell list (compute_press.c:123-165).
-// ----------------------------------------------------------------------------------
-#define CONTACT_MAX_BINS 1024
-__global__ void __launch_bounds__(128)
-k_contact_hist(Grid g, Box box, const double4* __restrict__ pos, const int* __restrict__ cs, double rmax,
-               double dr_bin, int nn, unsigned long long* __restrict__ hist) {
-  __shared__ unsigned int sh[CONTACT_MAX_BINS];
-  for (int k = threadIdx.x; k < nn; k += blockDim.x) sh[k] = 0;
-  __syncthreads();
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)(g.own_hi - g.own_lo) * g.ny * g.nz;
-  if (t < total) {
-    int iz = (int)(t % g.nz);
-    long long r = t / g.nz;
-    int iy = (int)(r % g.ny), l = g.own_lo + (int)(r / g.ny);
-    long long c = ((long long)l * g.ny + iy) * g.nz + iz;
-    int beg = cs[c], end = cs[c + 1];
-    double r2_pre = rmax * rmax * (1.0 + 1e-9);
-    for (int s = beg; s < end; s++) {
-      double4 p = pos[s];
-      stencil_half(g, cs, l, iy, iz, [&](int k, bool own) {
-        double4 q = pos[k];
-        if (own && !(q.w > p.w)) return false;
-        double r2 = pair_r2(p.x, p.y, p.z, q.x, q.y, q.z, box);
-        if (r2 < r2_pre) {
-          double dr = sqrt(r2);
-          if (dr < rmax) {
-            int bin = (int)((dr - 1.0) / dr_bin);
-            if (bin >= 0 && bin < nn) atomicAdd(&sh[bin], 1u);
-          }
-        }
-        return false;
-      });
-    }
-  }
-  __syncthreads();
-  for (int k = threadIdx.x; k < nn; k += blockDim.x)
-    if (sh[k]) atomicAdd(&hist[k], (unsigned long long)sh[k]);
-}
-
-// min pair r2 over the stencil (invariant check: never below 1.0 in a valid run)
-__global__ void k_min_r2(Grid g, Box box, const double4* __restrict__ pos, const int* __restrict__ cs,
-                         unsigned long long* __restrict__ out) {
-  long long total = (long long)(g.own_hi - g.own_lo) * g.ny * g.nz;
-  double best = 1e300;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    int iz = (int)(t % g.nz);
-    long long r = t / g.nz;
-    int iy = (int)(r % g.ny), l = g.own_lo + (int)(r / g.ny);
-    long long c = ((long long)l * g.ny + iy) * g.nz + iz;
-    int beg = cs[c], end = cs[c + 1];
-    for (int s = beg; s < end; s++) {
-      double4 p = pos[s];
-      stencil_any(g, cs, l, iy, iz, [&](int k) {
-        double4 q = pos[k];
-        if (q.w > p.w) best = fmin(best, pair_r2(p.x, p.y, p.z, q.x, q.y, q.z, box));
-        return false;
-      });
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) best = fmin(best, __shfl_xor_sync(0xffffffffu, best, o));
-  if ((threadIdx.x & 31) == 0 && best < 1e299) atomicMin(out, (unsigned long long)__double_as_longlong(best));
-}
-
-
-// ----------------------------------------------------------------------------------
-// K8: Steinhardt bond-order parameter q_l (compute_order_parameter.c:84-229), SURVEY 8f #1.
-// One thread per owned particle: bonds = stencil neighbours with r <= rmax (rmax <= cell edge),
-// q_lm(i) = <Y_lm(r_ij)>_bonds, q_l(i) = sqrt(4 pi/(2l+1) sum_m |q_lm|^2) -- |q_l,-m| = |q_l,m|,
-// so m runs over 0..l with weight 2 for m > 0.  Y_lm by the normalised three-term recurrence
-// (coefficients in constant memory), e^{i m phi} by rotation; all in double.  A floating-point
-// observable (3-sigma contract), not on the bit-exact surface; the sum over particles is reduced
-// in a fixed order so results are reproducible run to run.
-// ----------------------------------------------------------------------------------
-#define QL_MAX_L 12
-#define QL_T 128
-__constant__ double c_ql_A[(QL_MAX_L + 1) * (QL_MAX_L + 1)];   // A(k,m) = sqrt((4k^2-1)/(k^2-m^2))
-__constant__ double c_ql_B[(QL_MAX_L + 1) * (QL_MAX_L + 1)];   // B(k,m) = sqrt(((k-1)^2-m^2)/(4(k-1)^2-1))
-__constant__ double c_ql_D[QL_MAX_L + 2];                       // D(m) = sqrt((2m+1)/(2m))
-
-__global__ void __launch_bounds__(QL_T)
-k_order_param(Grid g, Box box, const double4* __restrict__ pos, const int* __restrict__ cs, int first, int n,
-              int l, double rmax, double* __restrict__ partial) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  double q = 0.0;
-  if (t < n) {
-    const double4 p = pos[first + t];
-    const int ll = local_layer(g, axis_cell(p.x, g.sx, g.iwx, g.nx));
-    const int iy = axis_cell(p.y, g.sy, g.iwy, g.ny), iz = axis_cell(p.z, g.sz, g.iwz, g.nz);
-    double re[QL_MAX_L + 1], im[QL_MAX_L + 1];
-    for (int m = 0; m <= l; m++) re[m] = im[m] = 0.0;
-    int bonds = 0;
-    stencil_any(g, cs, ll, iy, iz, [&](int k) {
-      const double4 o = pos[k];
-      if (o.w == p.w) return false;
-      double dx = p.x - o.x, dy = p.y - o.y, dz = p.z - o.z;
-      if (dx > box.hx) dx -= box.Lx; else if (dx < -box.hx) dx += box.Lx;
-      if (dy > box.hy) dy -= box.Ly; else if (dy < -box.hy) dy += box.Ly;
-      if (dz > box.hz) dz -= box.Lz; else if (dz < -box.hz) dz += box.Lz;
-      const double rho2 = dx * dx + dy * dy, dr = sqrt(rho2 + dz * dz);
-      if (dr > rmax) return false;
-      bonds++;
-      const double rho = sqrt(rho2);
-      const double x = dz / dr, sth = rho / dr;
-      const double cph = rho > 0.0 ? dx / rho : 1.0, sph = rho > 0.0 ? dy / rho : 0.0;
-      double pmm = 0.28209479177387814;                  // sqrt(1/(4 pi))
-      double cm = 1.0, sm = 0.0;
-      for (int m = 0; m <= l; m++) {
-        double p0 = 0.0, p1 = pmm;
-        for (int k2 = m + 1; k2 <= l; k2++) {
-          const double p2 = c_ql_A[k2 * (QL_MAX_L + 1) + m] * (x * p1 - c_ql_B[k2 * (QL_MAX_L + 1) + m] * p0);
-          p0 = p1; p1 = p2;
-        }
-        re[m] += p1 * cm;
-        im[m] += p1 * sm;
-        pmm = -c_ql_D[m + 1] * sth * pmm;
-        const double c2 = cm * cph - sm * sph;
-        sm = sm * cph + cm * sph;
-        cm = c2;
-      }
-      return false;
-    });
-    double sum = 0.0;
-    if (bonds) {
-      const double inv = 1.0 / (double)bonds;
-      for (int m = 0; m <= l; m++) {
-        const double a = re[m] * inv, b = im[m] * inv;
-        sum += (m == 0 ? 1.0 : 2.0) * (a * a + b * b);
-      }
-    }
-    q = sqrt(sum * (4.0 * 3.14159265358979323846 / (double)(2 * l + 1)));
-  }
-  // fixed-order block reduction
-  __shared__ double sh[QL_T];
-  sh[threadIdx.x] = q;
-  __syncthreads();
-  for (int o = QL_T / 2; o > 0; o >>= 1) {
-    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
-}
-
-// sum of the block partials in a fixed order (one block)
-__global__ void __launch_bounds__(256)
-k_sum_partials(const double* __restrict__ partial, int nb, double* __restrict__ out) {
-  __shared__ double sh[256];
-  double s = 0.0;
-  for (int i = threadIdx.x; i < nb; i += 256) s += partial[i];
-  sh[threadIdx.x] = s;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) out[0] = sh[0];
-}
-
-// ----------------------------------------------------------------------------------
-// K7: accepted volume move (moves.c:135-141): x *= sf, then apply_pbc with the new box
-// ----------------------------------------------------------------------------------
-__global__ void k_rescale(double4* __restrict__ pos, int n, double sf, double lx, double ly, double lz) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  double4 p = pos[i];
-  p.x *= sf; p.y *= sf; p.z *= sf;
-  if (p.x > lx) p.x -= lx; else if (p.x < 0.0) p.x += lx;
-  if (p.y > ly) p.y -= ly; else if (p.y < 0.0) p.y += ly;
-  if (p.z > lz) p.z -= lz; else if (p.z < 0.0) p.z += lz;
-  pos[i] = p;
-}
-
-// ----------------------------------------------------------------------------------
-// slab decomposition (world > 1): classify + halo buffers
-// ----------------------------------------------------------------------------------
-// Source particles are this rank's previously owned ones (or, for an upload, arbitrary
-// rows).  Each is keyed into the local cell grid and, when it lies in one of the two
-// layers at either end of the slab, also appended to the buffer bound for that
-// neighbour: layers {0,1} -> left, {nlx-2,nlx-1} -> right (migrants + fresh ghosts in one
-// message).  upload_mode keeps only owned layers and sends only boundary layers.
-__global__ void k_slab_classify(Grid g, const double4* __restrict__ in, int n, int rows_layout,
-                                int upload_mode, int* __restrict__ key, int* __restrict__ rnk,
-                                int* __restrict__ count, double4* __restrict__ send_l,
-                                double4* __restrict__ send_r, int* __restrict__ halo_cnt, int cap_halo,
-                                const int* __restrict__ d_lay) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (d_lay) {                       // source = the previously owned slot range, known on the device only
-    n = d_lay[4] - d_lay[1];
-    in += d_lay[1];
-  }
-  if (i >= n) return;
-  double4 p = in[i];
-  if (rows_layout) p = make_double4(p.y, p.z, p.w, p.x);
-  long long c = local_cell(g, p.x, p.y, p.z);
-  int lyr = (c >= 0) ? (int)(c / ((long long)g.ny * g.nz)) : -1;
-  bool keep, to_l, to_r;
-  if (upload_mode) {
-    keep = lyr >= g.own_lo && lyr < g.own_hi;
-    to_l = lyr == g.own_lo;
-    to_r = lyr == g.own_hi - 1;
-  } else {
-    if (c < 0) atomicOr(&halo_cnt[2], 1);   // moved more than one layer: impossible by construction
-    keep = c >= 0;
-    to_l = keep && lyr <= 1;
-    to_r = keep && lyr >= g.nlx - 2;
-  }
-  key[i] = keep ? (int)c : -1;
-  if (keep) rnk[i] = atomicAdd(&count[c], 1);
-  if (to_l) {
-    int s = atomicAdd(&halo_cnt[0], 1);
-    if (s + 1 < cap_halo) send_l[s + 1] = p; else atomicOr(&halo_cnt[2], 2);
-  }
-  if (to_r) {
-    int s = atomicAdd(&halo_cnt[1], 1);
-    if (s + 1 < cap_halo) send_r[s + 1] = p; else atomicOr(&halo_cnt[2], 2);
-  }
-}
-
-// p2p: publish "message seq is complete" to a neighbour's window / wait for a neighbour's
-__global__ void k_flag_post(volatile uint32_t* flag_a, volatile uint32_t* flag_b, uint32_t seq) {
-  __threadfence_system();
-  if (flag_a) *flag_a = seq;
-  if (flag_b) *flag_b = seq;
-  __threadfence_system();
-}
-// A wait is bounded: a neighbour that never delivers (its process died, say) must turn into a loud CUDA
-// error on this rank, not into a GPU that spins for ever.  HSMC_SPIN_LIMIT_NS is far beyond any legitimate
-// delay (a rank writing a 16.8M-particle snapshot keeps its neighbours waiting for seconds).
-#define HSMC_SPIN_LIMIT_NS (300ull * 1000000000ull)
-__device__ __forceinline__ void hsmc_wait_flag(volatile uint32_t* flag, uint32_t seq) {
-  unsigned long long t0 = 0;
-  unsigned int spins = 0;
-  while ((int32_t)(*flag - seq) < 0) {
-    __nanosleep(200);
-    if ((++spins & 4095u) == 0) {
-      const unsigned long long t = hsmc_globaltimer_ns();
-      if (t0 == 0) t0 = t;
-      else if (t - t0 > HSMC_SPIN_LIMIT_NS) __trap();
-    }
-  }
-}
-__global__ void k_flag_wait(volatile uint32_t* flag_a, volatile uint32_t* flag_b, uint32_t seq) {
-  if (flag_a) hsmc_wait_flag(flag_a, seq);
-  if (flag_b) hsmc_wait_flag(flag_b, seq);
-  __threadfence_system();
-}
-
-__global__ void k_halo_headers(double4* send_l, double4* send_r, const int* halo_cnt) {
-  send_l[0] = make_double4((double)halo_cnt[0], 0, 0, 0);
-  send_r[0] = make_double4((double)halo_cnt[1], 0, 0, 0);
-}
-
-// key the received particles (count in the header slot)
-__global__ void k_recv_count(Grid g, const double4* __restrict__ buf0, const double4* __restrict__ buf1,
-                             int cap_halo, int* __restrict__ key, int* __restrict__ rnk, int* __restrict__ count,
-                             int* __restrict__ halo_cnt) {
-  const double4* buf = blockIdx.y ? buf1 : buf0;
-  key += (size_t)blockIdx.y * cap_halo;
-  rnk += (size_t)blockIdx.y * cap_halo;
-  int n = (int)buf[0].x;
-  if (n > cap_halo - 1) n = cap_halo - 1;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    double4 p = buf[i + 1];
-    long long c = local_cell(g, p.x, p.y, p.z);
-    key[i] = (int)c;
-    if (c >= 0) rnk[i] = atomicAdd(&count[c], 1);
-    else atomicOr(&halo_cnt[2], 4);
-  }
-}
-
-__global__ void k_recv_scatter(Grid g, const double4* __restrict__ buf0, const double4* __restrict__ buf1,
-                               int cap_halo, const int* __restrict__ key, const int* __restrict__ rnk,
-                               const int* __restrict__ cs, double4* __restrict__ out, float4* __restrict__ rel,
-                               int cap, int* __restrict__ flags) {
-  const double4* buf = blockIdx.y ? buf1 : buf0;
-  key += (size_t)blockIdx.y * cap_halo;
-  rnk += (size_t)blockIdx.y * cap_halo;
-  int n = (int)buf[0].x;
-  if (n > cap_halo - 1) n = cap_halo - 1;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    int c = key[i];
-    if (c >= 0) {
-      double4 p = buf[i + 1];
-      int d = cs[c] + rnk[i];
-      if (d >= cap) { atomicOr(flags, 32); continue; }
-      out[d] = p;
-      rel[d] = make_rel_cell(g, c, p);
-    }
-  }
-}
-
-// boundary layer -> message buffer (count in the header slot); the slot range of the layer
-// is only known on the device
-__global__ void k_halo_pack(Grid g, const double4* __restrict__ pos, const int* __restrict__ cs, int layer,
-                            double4* __restrict__ buf, int cap_msg, int* __restrict__ flags) {
-  long long per = (long long)g.ny * g.nz;
-  int b = cs[(long long)layer * per], e = cs[(long long)(layer + 1) * per];
-  int n = e - b;
-  if (n > cap_msg - 1) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(flags, 2); n = cap_msg - 1; }
-  if (blockIdx.x == 0 && threadIdx.x == 0) buf[0] = make_double4((double)n, 0, 0, 0);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) buf[1 + i] = pos[b + i];
-}
-
-// message buffer -> ghost layer, slot for slot (both sides keep these layers id-sorted),
-// plus the fp32 shadow of the refreshed slots
-__global__ void k_halo_unpack(Grid g, double4* __restrict__ pos, float4* __restrict__ rel, const int* __restrict__ cs,
-                              int layer, const double4* __restrict__ buf, int* __restrict__ flags) {
-  long long per = (long long)g.ny * g.nz;
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  int b0 = cs[(long long)layer * per];
-  if (t == 0 && (int)buf[0].x != cs[(long long)(layer + 1) * per] - b0) atomicOr(flags, 16);
-  if (t >= per) return;
-  long long c = (long long)layer * per + t;
-  for (int i = cs[c]; i < cs[c + 1]; i++) {
-    double4 p = buf[1 + (i - b0)];
-    pos[i] = p;
-    rel[i] = make_rel_cell(g, c, p);
-  }
-}
-
-__global__ void k_scatter_layout(Grid g, const double4* __restrict__ in, int n, int rows_layout,
-                                 const int* __restrict__ key, const int* __restrict__ rnk,
-                                 const int* __restrict__ cs, double4* __restrict__ out, float4* __restrict__ rel,
-                                 const int* __restrict__ d_lay, int cap, int* __restrict__ flags) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (d_lay) {
-    n = d_lay[4] - d_lay[1];
-    in += d_lay[1];
-  }
-  if (i >= n) return;
-  int c = key[i];
-  if (c < 0) return;
-  double4 p = in[i];
-  if (rows_layout) p = make_double4(p.y, p.z, p.w, p.x);
-  int d = cs[c] + rnk[i];
-  if (d >= cap) { atomicOr(flags, 32); return; }
-  out[d] = p;
-  rel[d] = make_rel_cell(g, c, p);
-}
-
-// canonical (ascending id) slot order inside every cell of the given layers, so that a
-// boundary layer and its ghost copy on the neighbour are slot-for-slot identical
-__global__ void k_sort_cells_by_id(Grid g, double4* __restrict__ pos, float4* __restrict__ rel,
-                                   const int* __restrict__ cs, int layer_a, int layer_b) {
-  long long per = (long long)g.ny * g.nz;
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= 2 * per) return;
-  if (blockIdx.y) { layer_a = g.nlx - 2; layer_b = g.nlx - 1; }     // second pair of layers
-  long long c = (t < per) ? (long long)layer_a * per + t : (long long)layer_b * per + (t - per);
-  int beg = cs[c], end = cs[c + 1];
-  for (int i = beg + 1; i < end; i++) {
-    double4 v = pos[i];
-    int j = i - 1;
-    while (j >= beg && pos[j].w > v.w) { pos[j + 1] = pos[j]; j--; }
-    pos[j + 1] = v;
-  }
-  for (int i = beg; i < end; i++) rel[i] = make_rel_cell(g, c, pos[i]);
-}
-
-// shadow of one cell layer recomputed from the master table (ghost layers after a halo refresh)
-__global__ void k_rel_layer(Grid g, const double4* __restrict__ pos, float4* __restrict__ rel,
-                            const int* __restrict__ cs, int layer) {
-  long long per = (long long)g.ny * g.nz;
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= per) return;
-  long long c = (long long)layer * per + t;
-  for (int i = cs[c]; i < cs[c + 1]; i++) rel[i] = make_rel_cell(g, c, pos[i]);
-}
-
-// slab mode: the six layer offsets and the error flags in one staging vector (one D2H copy)
-__global__ void k_gather_layout(Grid g, const int* __restrict__ cs, const int* __restrict__ halo_cnt,
-                                int* __restrict__ out) {
-  long long per = (long long)g.ny * g.nz;
-  int k = threadIdx.x;
-  if (k < 6) {
-    long long offs = (k == 0) ? 0 : (k == 1) ? per : (k == 2) ? 2 * per : (k == 3) ? (long long)(g.nlx - 2) * per
-                   : (k == 4) ? (long long)(g.nlx - 1) * per : (long long)g.nlx * per;
-    out[k] = cs[offs];
-  } else if (k < 8) {
-    out[k] = halo_cnt[k - 6];
-  } else if (k == 8) {
-    out[8] |= halo_cnt[2];           // error bits are sticky until the host reads them
-  }
-}
-
+#include "observables.cuh"
+#include "slab.cuh"
 // ----------------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------------
