@@ -373,7 +373,7 @@ def widom_workload(args, rank, world, local_rank):
             "mu_ex": {f"{r:.1f}": float(m) for r, m in zip(rhos, mu)},
             "accepted_fraction": {f"{r:.1f}": float(f) for r, f in zip(rhos, frac_acc)},
         }
-        print(json.dumps(line))
+        args.emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -404,6 +404,18 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: whatever native libraries print on fd 1 while the benchmark runs
+    # (NCCL's version banner under NCCL_DEBUG=VERSION, say) is sent to stderr; emit() restores fd 1 for the line
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line))
+        sys.stdout.flush()
+    args.emit = emit
     if args.workload == "widom" and args.impl == "b200":
         return widom_workload(args, rank, world, local_rank)
     nx, ny, nz = args.cells
@@ -430,7 +442,7 @@ def main():
             "e2e": {"value": res["value"], "unit": "moves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch
@@ -638,7 +650,7 @@ def main():
         }
         if secondary is not None:
             line["secondary"] = secondary
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -50,6 +50,9 @@ int hs_mp_start(hs_mp *mp, int world, int64_t n_rows) {
   memset(mp, 0, sizeof(*mp));
   mp->world = world < 1 ? 1 : world;
   if (mp->world == 1) return 0;
+  /* stdout is the reference's report: NCCL's own messages (version banner under NCCL_DEBUG=VERSION, ...)
+     go to stderr unless the user chose a file for them */
+  setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
   if (mp->world > HS_MP_MAX_RANKS) { printf("ERROR: at most %d GPUs\n", HS_MP_MAX_RANKS); exit(EXIT_FAILURE); }
   size_t bytes = sizeof(struct hs_mp_shared) + (size_t)n_rows * 4 * sizeof(double);
   void *m = mmap(NULL, bytes, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
