@@ -112,3 +112,21 @@ def test_unwritable_path_reports_failure(fastio, tmp_path):
     rc = fastio.hs_fastio_write_config(os.fsencode(str(tmp_path / "no" / "such" / "dir.gz")), 0, 0, 4, b,
                                        C.c_void_p(conf.ctypes.data), 2)
     assert rc != 0
+
+
+def test_fmt_f8_property(fastio):
+    """hypothesis: any finite double formats exactly as printf("%.8f") does (CPython's repr-exact formatting
+    is correctly rounded, ties to even, like glibc's)."""
+    from hypothesis import given, settings, strategies as st
+    buf = C.create_string_buffer(512)
+
+    @settings(max_examples=3000, deadline=None)
+    @given(st.one_of(st.floats(allow_nan=False, allow_infinity=False, width=64),
+                     st.floats(min_value=0.0, max_value=500.0),
+                     st.integers(min_value=0, max_value=10 ** 11).map(lambda k: k / 2.0 ** 9),       # k/512: ties
+                     st.integers(min_value=0, max_value=10 ** 12).map(lambda k: (2 * k + 1) * 5e-9)))  # near ...5e-9
+    def check(x):
+        n = fastio.hs_fmt_f8(buf, float(x))
+        assert buf.raw[:n].decode() == "%.8f" % x
+
+    check()
