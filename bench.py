@@ -223,8 +223,9 @@ def _timed(stream, fn, reps=3):
 
 def secondary_observables(h, stream, N, nbar, peak, device):
     """Throughput of the observables' kernels on the benchmark configuration (resident in HBM,
-    larger than L2), each with SURVEY 8(d)'s algorithmic bytes per unit (16 -> 32: double4
-    table) against the same HBM peak.  RDF is O(N^2) on shared-memory tiles (ALU / shared
+    larger than L2), each with SURVEY 8(d)'s algorithmic bytes per unit (16 -> 32: these kernels
+    read the double4 table; the pair kernels walk the forward HALF stencil, own cell + 13
+    neighbours, so 14 cells per particle, not 27) against the same HBM peak.  RDF is O(N^2) on shared-memory tiles (ALU / shared
     atomics bound): measured on the C2 shape (fcc 20^3, N = 32 000) in pairs/s, no HBM
     fraction.  q_l is measured on a fcc 64^3 box whose cells are wide enough (1.5) to hold
     the first neighbour shell, as the reference's `ql` keyword needs."""
@@ -244,14 +245,14 @@ def secondary_observables(h, stream, N, nbar, peak, device):
     ms = _timed(stream, lambda: h.widom(7, M))
     entry("widom", "insertions/s", M, ms, 32.0 * 27.0 * nbar, "hsmc_gpu_widom, 1e8 insertion points (k_widom)")
     ms = _timed(stream, lambda: h.overlap_scaled(1.0))
-    entry("overlap_scaled", "particles/s", N, ms, 32.0 * (27.0 * nbar + 1.0),
+    entry("overlap_scaled", "particles/s", N, ms, 32.0 * (14.0 * nbar + 1.0),
           "hsmc_gpu_overlap_scaled(sf=1.0, no overlap found = every pair visited): the NpT volume-move verdict (k_overlap_scaled)")
     sf = (1.0 - 0.0001 * (np.arange(20) + 1.0)) ** (1.0 / 3.0)
     ms = _timed(stream, lambda: h.presst_flags(sf))
-    entry("presst_flags", "particles/s", N, ms, 32.0 * (27.0 * nbar + 1.0),
+    entry("presst_flags", "particles/s", N, ms, 32.0 * (14.0 * nbar + 1.0),
           "hsmc_gpu_presst_flags, 20 compressions in one pass (k_overlap_scaled)")
     ms = _timed(stream, lambda: h.contact_counts(0.002, 1))
-    entry("contact_counts", "particles/s", N, ms, 32.0 * (27.0 * nbar + 1.0),
+    entry("contact_counts", "particles/s", N, ms, 32.0 * (14.0 * nbar + 1.0),
           "hsmc_gpu_contact_counts(dr=0.002, bins up to the cell edge) (k_contact_hist)")
 
     # RDF on the C2 shape
