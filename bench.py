@@ -564,7 +564,7 @@ def main():
     peak, peak_src = measured_peak()
     traffic = ncu_traffic()
     roofline = {
-        "bound": "hbm", "kernel": "k_sweep_block" if (args.sweep_impl & 0xff) in (0, 3, 5, 6) else "k_sweep_tile+k_sweep_deep", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "bound": "hbm", "kernel": {0: "k_sweep_lean", 3: "k_sweep_lean", 5: "k_sweep_lean(global path)", 6: "k_sweep_block"}.get(args.sweep_impl & 0xff, "k_sweep_phase"), "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "peak_source": peak_src,
         "algorithmic_bytes_per_move": b_move, "nbar": nbar, "moves_per_launch": moves_local / max(sweep_groups, 1),
         "algorithmic_bytes_definition": "16*27*nbar (stencil from the fp32 shadow) + 32 (own double4 read) + 48 (double4 + float4 write-back), no reuse",

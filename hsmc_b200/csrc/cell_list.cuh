@@ -87,11 +87,9 @@ __global__ void k_scan_top(int* bsum, int nb) {
   }
 }
 
-// last pass of the scan; cells found to hold >= 3 particles are appended to the per-colour
-// deep lists on the way (owned layers only)
+// last pass of the scan
 __global__ void k_scan_final(const int* __restrict__ in, long long n, const int* __restrict__ bsum,
-                             int* __restrict__ out, Grid g, int* __restrict__ deep_list,
-                             int* __restrict__ deep_count, int list_stride) {
+                             int* __restrict__ out) {
   long long base = (long long)blockIdx.x * SCAN_CHUNK + (long long)threadIdx.x * SCAN_V;
   int v[SCAN_V];
   int s = 0;
@@ -119,22 +117,6 @@ __global__ void k_scan_final(const int* __restrict__ in, long long n, const int*
     for (int j = 0; j < SCAN_V; j++) {
       if (base + j < n) out[base + j] = o[j];
       if (base + j == n - 1) out[n] = o[j] + v[j];
-    }
-  }
-  if (deep_list) {
-#pragma unroll
-    for (int j = 0; j < SCAN_V; j++) {
-      const long long i = base + j;
-      if (i < n && v[j] >= 3) {
-        int iz = (int)(i % g.nz);
-        long long r = i / g.nz;
-        int iy = (int)(r % g.ny), l = (int)(r / g.ny);
-        if (l >= g.own_lo && l < g.own_hi) {
-          int colour = (((g.gx0 + l) & 1) << 2) | ((iy & 1) << 1) | (iz & 1);
-          int slot = atomicAdd(&deep_count[colour], 1);
-          if (slot < list_stride) deep_list[(long long)colour * list_stride + slot] = (int)i;
-        }
-      }
     }
   }
 }

@@ -9,8 +9,9 @@
 // host-side orchestration and the ABI entry points ("new kernel" table):
 //   cell_list.cuh      K1  k_cell_count / k_scan_* / k_cell_scatter / k_cs16   cell_list_new (cell_list.c:142-175)
 //   sweep_generic.cuh  K2  k_sweep_phase (global memory)  part_move + check_overlap (moves.c:27-80,157-212)
-//   sweep_tile.cuh     K2' k_sweep_tile + k_sweep_deep    one launch per cell colour, TMA-staged tiles
-//   sweep_block.cuh    K2  k_sweep_block                  the default: block-resident, fused block phases
+//   sweep_lean.cuh     K2  k_block_plan + k_sweep_lean    the default: proposals + per-block plan up front, block-resident
+//                                                         fp32x2 stencil filter, fused block phases
+//   sweep_block.cuh    K2' k_sweep_block                  round-1 block kernel (in-kernel generation), kept as an ablation
 //   observables.cuh    K3  k_overlap_scaled   vol_move / presst verdict   (moves.c:106-112)
 //                      K4  k_widom            widom_insertion             (compute_widom_chem_pot.c:44-71)
 //                      K5  k_rdf_pairs        rdf_hist_compute            (compute_rdf.c:110-128)
@@ -71,21 +72,7 @@ extern "C" const char* hsmc_gpu_last_error(void) { return g_err.c_str(); }
 // ----------------------------------------------------------------------------------
 enum { CNT_TRIALS = 0, CNT_ACC = 1, CNT_REJ_OVERLAP = 2, CNT_REJ_CELL = 3, CNT_N = 8 };
 
-#define TILE_MAX_A 4          // active cells per tile along x and y (max)
-#define TILE_MAX_AZ 12        // along z (max)
-#define TILE_THREADS 96
-#define TILE_MAX_ROWS ((2 * TILE_MAX_A + 1) * (2 * TILE_MAX_A + 1))
-#define TILE_MAX_CELLS (TILE_MAX_A * TILE_MAX_A * TILE_MAX_AZ)
-
-struct TileCfg {
-  int ax, ay, az;          // active cells per tile
-  int ntx, nty, ntz;       // tiles per axis of the active-cell lattice
-  int cap;                 // staged shadow capacity (entries of 16 B)
-  int use_tma;
-  int cs_stride;           // ints per staged CSR row
-};
-
-// block-resident sweep (sweep_block.cuh)
+// block-resident sweeps (sweep_lean.cuh, sweep_block.cuh)
 struct BlockCfg {
   int nbx, nby, nbz;      // blocks per axis (even); x: over the layers this rank owns
   int mbx, mby, mbz;      // largest block extent per axis (cells)
@@ -95,6 +82,7 @@ struct BlockCfg {
   int max_rows;           // (mbx+2)*(mby+2)
   int max_cells;          // mbx*mby*mbz
   int tr_cap;             // trial slots per colour (multiple of 32)
+  int desc_cap;           // k_block_plan: trial descriptors per block (8 colours, each padded to a multiple of 32)
   int use_tma;
   int force_global;       // ablation: every block takes the global-memory path (same chain)
   int dbg;                // timing ablations (env HSMC_BLOCK_DBG), 0 in production
@@ -102,9 +90,29 @@ struct BlockCfg {
   unsigned int* done;     // fused launches: [nbx][nby][nbz] epoch of the launch that last finished the block
 };
 
+// per-row staging record: global slots of the row's one or two pieces, staged offset
+struct BlockRow { int gbA, gbB, cntA, off; };
+
+// header of a block's plan: ints [0] staged particles, [1..8] trials per cell colour, [9] flags, [10] first trial slot
+enum { PLAN_TOTAL = 0, PLAN_NTR = 1, PLAN_FLAGS = 9, PLAN_TBASE = 10, PLAN_HDR_INTS = 16 };
+enum { PLAN_BAD = 1, PLAN_DEEP = 2 };
+
+struct LeanPlan {
+  int* hdr;                   // [blocks][PLAN_HDR_INTS]
+  BlockRow* row;              // [blocks][max_rows]
+  unsigned short* cz;         // [blocks][max_rows * cz_stride]   staged index of the first particle of each region cell
+  uint4* trial;               // [cap_trials] {fp32 shadow of the proposed position (cell-relative), code}
+  uint4* raw;                 // [cap_trials] logged sweeps only: {raw draws 0..2, id}
+  unsigned int* cursor;       // trial-slot allocator (reset before every plan launch)
+  long long cap_trials;
+};
+
 // cfg.sweep_impl: low byte = kernel variant, next byte = virtual world of the x block partition
-enum { IMPL_BLOCK = 0, IMPL_CELL_GLOBAL = 1, IMPL_TILE_LDG = 2, IMPL_EPS0 = 3, IMPL_TILE_TMA = 4,
-       IMPL_BLOCK_GLOBAL = 5, IMPL_BLOCK_TMA = 6 };
+// 0 default (k_block_plan + k_sweep_lean); 1 one thread per cell from global memory, one launch per CELL colour
+// (a different, equally valid update order); 3 the default with the filter's error band forced to zero (negative
+// control of the parity tests); 5 the default's update order evaluated all in double from global memory;
+// 6 the round-1 block kernel (same chain as 0 and 5)
+enum { IMPL_LEAN = 0, IMPL_CELL_GLOBAL = 1, IMPL_EPS0 = 3, IMPL_BLOCK_GLOBAL = 5, IMPL_BLOCK_R1 = 6 };
 
 struct hsmc_gpu {
   hsmc_gpu_config cfg;
@@ -120,7 +128,7 @@ struct hsmc_gpu {
   int64_t ncell = 0;       // local cells
   int64_t cap_cells = 0;
   cudaStream_t st = nullptr;
-  cudaStream_t st2 = nullptr;            // deep-cell kernel runs beside the tile kernel
+  cudaStream_t st2 = nullptr;            // copy stream (chunked upload / download)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   double4* pos[2] = {nullptr, nullptr};
   float4* rel = nullptr;                 // fp32 shadow {cell-relative offset, id} of pos[cur]
@@ -156,15 +164,13 @@ struct hsmc_gpu {
   bool p2p = false;
   uint32_t seqA = 0, seqB = 0, seqC = 0; // exchanges issued so far (same on every rank)             // left ghost layer not refreshed since the last odd-x phases
   void* d_sfargs = nullptr;
-  TileCfg tile;
-  int* deep_list = nullptr;              // [8][deep_stride] cells with >= 3 particles, per colour
-  int* deep_count = nullptr;             // [8]
-  int64_t deep_stride = 0;
-  size_t tile_smem = 0;
-  bool tile_ok = false;
   BlockCfg blk;
-  size_t blk_smem = 0;
-  bool blk_ok = false;
+  size_t blk_smem = 0;                   // dynamic shared memory of the kernel in use (lean or round-1 block)
+  size_t plan_smem = 0;                  // ... of k_block_plan
+  bool blk_ok = false;                   // a block-resident kernel runs the sweeps
+  bool lean = false;                     // ... and it is k_block_plan + k_sweep_lean
+  LeanPlan plan = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+  int64_t plan_blocks = 0, plan_rows = 0, plan_czs = 0;   // what the plan arrays were sized for
   float blk_eps = 0.f;
   std::vector<int> xoff;                 // x block boundaries (local layers), blk.nbx + 1 entries
   int* d_xoff = nullptr;
@@ -206,9 +212,10 @@ struct ProfSpan {
 static inline int nblk(int64_t n, int t) { return (int)((n + t - 1) / t); }
 
 #include "cell_list.cuh"
+#include "async_copy.cuh"
 #include "sweep_generic.cuh"
-#include "sweep_tile.cuh"
 #include "sweep_block.cuh"
+#include "sweep_lean.cuh"
 
 #include "observables.cuh"
 #include "slab.cuh"
@@ -223,7 +230,6 @@ static int even_cells(double L, double cell_min) {
   return n;
 }
 
-static void setup_tiles(hsmc_gpu* h);
 static void setup_blocks(hsmc_gpu* h);
 static int sync_layout(hsmc_gpu* h);
 
@@ -254,7 +260,6 @@ static int setup_grid(hsmc_gpu* h) {
   }
   h->ncell = (int64_t)g.nlx * g.ny * g.nz;
   if (h->ncell + 1 > (int64_t)INT32_MAX) return fail("too many cells for 32-bit cell indices");
-  setup_tiles(h);
   setup_blocks(h);
   return 0;
 }
@@ -271,10 +276,6 @@ static int ensure_cell_arrays(hsmc_gpu* h) {
   if (h->cs16) cudaFree(h->cs16);
   // rows x (nz + 1) <= cells + rows <= 2 x cells; tail padding for the 16-byte TMA granules
   CU(cudaMalloc(&h->cs16, sizeof(unsigned short) * (size_t)(2 * h->cap_cells + 64)));
-  if (h->deep_list) cudaFree(h->deep_list);
-  h->deep_stride = h->cap_cells / 8 + 64;
-  CU(cudaMalloc(&h->deep_list, sizeof(int) * (size_t)(8 * h->deep_stride)));
-  if (!h->deep_count) CU(cudaMalloc(&h->deep_count, sizeof(int) * 8));
   return 0;
 }
 
@@ -309,71 +310,17 @@ static void draw_shift(hsmc_gpu* h) {
 
 static int exclusive_scan(hsmc_gpu* h, const int* in, int64_t n, int* out) {
   int nb = (int)((n + SCAN_CHUNK - 1) / SCAN_CHUNK);
-  CU(cudaMemsetAsync(h->deep_count, 0, sizeof(int) * 8, h->st));
   k_scan_blocksum<<<nb, SCAN_T, 0, h->st>>>(in, n, h->bsum);
   k_scan_top<<<1, SCAN_T, 0, h->st>>>(h->bsum, nb);
-  k_scan_final<<<nb, SCAN_T, 0, h->st>>>(in, n, h->bsum, out, h->g, h->tile_ok ? h->deep_list : nullptr, h->deep_count,
-                                         (int)h->deep_stride);
+  k_scan_final<<<nb, SCAN_T, 0, h->st>>>(in, n, h->bsum, out);
   h->launches += 3;
-  if (h->blk_ok && out == h->cell_start) {
+  if (h->blk_ok && !h->lean && out == h->cell_start) {      // (only the round-1 block kernel stages the 16-bit CSR)
     const long long nrow = (long long)h->g.nlx * h->g.ny;
     k_cs16<<<(int)std::min<long long>((nrow + 7) / 8, 148LL * 64), 256, 0, h->st>>>(out, nrow, h->g.nz, h->cs16, h->d_lay + 8);
     h->launches++;
   }
   CU(cudaGetLastError());
   return 0;
-}
-
-// tile shape of the staged sweep kernel for the current grid / density
-// Tile shape of the staged sweep kernel for the current grid / density: among the shapes
-// that fit shared memory, the one with the fewest "CTA waves x (fixed prologue + cells)"
-// over the 148 SMs -- keeps partial tiles and a ragged last wave from wasting the machine
-// when a rank's slab is small.
-static void setup_tiles(hsmc_gpu* h) {
-  Grid& g = h->g;
-  TileCfg& t = h->tile;
-  const int hx = (g.own_hi - g.own_lo) / 2, hy = g.ny / 2, hz = g.nz / 2;
-  const double nbar = (double)h->N / ((double)g.nx * g.ny * g.nz);
-  double capf = 1.05;   // head-room over the mean region population; a denser tile takes the global-memory path
-  int az_max = TILE_MAX_AZ, force_az = 0;
-  if (const char* e = getenv("HSMC_TILE_AZ")) { force_az = std::max(1, std::min(TILE_MAX_AZ, atoi(e))); }   // tuning knobs
-  if (const char* e = getenv("HSMC_TILE_CAPF")) capf = atof(e);
-  auto lim = [](int amax, int n_cells, int half) {       // region (2a+1 cells) must not wrap onto itself
-    int a = std::min(amax, std::max(1, (n_cells - 1) / 2));
-    return std::min(a, std::max(1, half));
-  };
-  const int ax_max = lim(TILE_MAX_A, g.wrap_x ? g.nx : g.nlx, hx), ay_max = lim(TILE_MAX_A, g.ny, hy);
-  az_max = lim(az_max, g.nz, hz);
-  const int cap_max = 2240;
-  double best_cost = 1e300;
-  int bx = 1, by = 1, bz = 1, bcap = 256;
-  for (int ax = 1; ax <= ax_max; ax++)
-    for (int ay = 1; ay <= ay_max; ay++)
-      for (int az = (force_az ? std::min(force_az, az_max) : 1); az <= (force_az ? std::min(force_az, az_max) : az_max); az++) {
-        double region = (2.0 * ax + 1) * (2.0 * ay + 1) * (2.0 * az + 1);
-        int cap = ((int)(region * nbar * capf) + 64 + 31) & ~31;
-        if (cap > cap_max) continue;
-        cap = std::max(cap, 256);
-        size_t smem = (size_t)cap * 16 + (size_t)(2 * ax + 1) * (2 * ay + 1) * (((2 * az + 2 + 3 + 3) & ~3)) * 4 + 3072 + 1024;
-        int per_sm = std::max(1, std::min(5, (int)((size_t)227 * 1024 / smem)));
-        long long tiles = (long long)((hx + ax - 1) / ax) * ((hy + ay - 1) / ay) * ((hz + az - 1) / az);
-        long long waves = (tiles + 148LL * per_sm - 1) / (148LL * per_sm);
-        // time of one CTA ~ fixed prologue (about 100 cell-equivalents) + its cells, shared by the
-        // per_sm CTAs of an SM
-        double cost = (double)waves * (100.0 + (double)ax * ay * az) * per_sm / 5.0;
-        // the largest shape is the measured optimum on big grids: smaller ones must beat it by 10 %
-        if (!(ax == ax_max && ay == ay_max && az == az_max)) cost *= 1.1;
-        if (cost < best_cost) { best_cost = cost; bx = ax; by = ay; bz = az; bcap = cap; }
-      }
-  t.ax = bx; t.ay = by; t.az = bz; t.cap = bcap;
-  t.ntx = (hx + t.ax - 1) / t.ax; t.nty = (hy + t.ay - 1) / t.ay; t.ntz = (hz + t.az - 1) / t.az;
-  t.use_tma = (h->impl == IMPL_TILE_LDG) ? 0 : 1;
-  t.cs_stride = (2 * t.az + 2 + 3 + 3) & ~3;
-  h->tile_smem = (size_t)t.cap * 16 + (size_t)(2 * t.ax + 1) * (2 * t.ay + 1) * t.cs_stride * sizeof(int);
-  h->tile_ok = (h->impl == IMPL_TILE_LDG || h->impl == IMPL_TILE_TMA) && t.cap * 1 <= 65535;
-  if (getenv("HSMC_DEBUG_TILES"))
-    fprintf(stderr, "[hsmc_gpu] rank %d: active lattice %dx%dx%d, tile %dx%dx%d, %d tiles/phase, cap %d, smem %zu B\n", h->cfg.rank,
-            hx, hy, hz, t.ax, t.ay, t.az, t.ntx * t.nty * t.ntz, t.cap, h->tile_smem);
 }
 
 
@@ -413,7 +360,8 @@ static void setup_blocks(hsmc_gpu* h) {
   if (const char* e = getenv("HSMC_BLOCK_CAPF")) capf = atof(e);
   int want[3] = {0, 0, 0};
   if (const char* e = getenv("HSMC_BLOCK")) sscanf(e, "%d,%d,%d", &want[0], &want[1], &want[2]);
-  struct Shape { int bx, by, bz, mx, my, mz, cap, tr_cap; size_t smem; };
+  struct Shape { int bx, by, bz, mx, my, mz, cap, tr_cap; size_t smem, smem_r1, smem_plan; };
+  const bool r1 = h->impl == IMPL_BLOCK_R1;
   auto eval = [&](int bx, int by, int bz, Shape& s) -> bool {
     // a block and its halo must not cover a cell twice: extent + 2 <= cells of the axis
     int mx = 0;
@@ -428,17 +376,23 @@ static void setup_blocks(hsmc_gpu* h) {
     // (x: with Wv > 1 slabs every block is at most its own slab long, and a slab + 2 never exceeds
     //  the local layer count of a rank nor the box, so only the one-slab case needs the test)
     if ((Wv == 1 && mx + 2 > g.nx) || my + 2 > g.ny || mz + 2 > g.nz) return false;
-    if ((mx + 2) * (my + 2) > std::min(BLK_MAX_ROWS, BLK_THREADS) || mz + 3 > 32 || mx + 2 > 31 || my + 2 > 31) return false;
+    // trial code of the lean kernel: 4-bit row coordinates, 5-bit z, 12-bit staged index
+    if ((mx + 2) * (my + 2) > LEAN_MAX_ROWS || mz + 2 > 32 || mx + 2 > 16 || my + 2 > 16) return false;
+    // the round-1 kernel stages one row per thread
+    if (r1 && ((mx + 2) * (my + 2) > std::min(BLK_MAX_ROWS, BLK_THREADS) || mz + 3 > 32)) return false;
     double region = (double)(mx + 2) * (my + 2) * (mz + 2);
-    int cap = ((int)(region * nbar * capf) + 48 + BLK_PAD + 31) & ~31;
-    if (cap > 8192) return false;
+    int cap = ((int)(region * nbar * capf) + 48 + LEAN_PAD + 31) & ~31;
+    if (cap > 4096) return false;
     int cz_stride = (mz + 3 + 7) & ~7;
     double per_colour = (double)((mx + 1) / 2) * ((my + 1) / 2) * ((mz + 1) / 2);
     int tr_cap = ((int)(per_colour * std::max(nbar, 0.2) * 1.4) + 48 + 31) & ~31;
-    size_t smem = (size_t)cap * 16 + (size_t)(mx + 2) * (my + 2) * cz_stride * 2 + (size_t)8 * tr_cap * 4;
-    smem = (smem + 15) & ~(size_t)15;
-    if (smem > 100 * 1024) return false;
-    s = {bx, by, bz, mx, my, mz, cap, tr_cap, smem};
+    const size_t rows = (size_t)(mx + 2) * (my + 2);
+    size_t smem = (size_t)cap * 12 + rows * cz_stride * 2 + rows * 16 + PLAN_HDR_INTS * 4;
+    size_t smem_r1 = (size_t)cap * 16 + rows * cz_stride * 2 + (size_t)8 * tr_cap * 4;
+    size_t smem_plan = rows * cz_stride * 2 + (size_t)8 * tr_cap * 4;
+    smem = (smem + 15) & ~(size_t)15; smem_r1 = (smem_r1 + 15) & ~(size_t)15; smem_plan = (smem_plan + 15) & ~(size_t)15;
+    if ((r1 ? smem_r1 : smem) > 100 * 1024 || smem_plan > 100 * 1024) return false;
+    s = {bx, by, bz, mx, my, mz, cap, tr_cap, smem, smem_r1, smem_plan};
     return true;
   };
   Shape best{};
@@ -462,7 +416,7 @@ static void setup_blocks(hsmc_gpu* h) {
         ctas = (Wv > 1) ? std::max(ctas, c) : ctas + c;
       }
       ctas *= (long long)(even_blocks(g.ny, by) / 2) * (even_blocks(g.nz, bz) / 2);
-      const int per_sm = (int)std::min<size_t>(4, (size_t)(227 * 1024) / (s.smem + 5 * 1024));
+      const int per_sm = (int)std::min<size_t>(4, (size_t)(227 * 1024) / (s.smem_r1 + 5 * 1024));   // (round-1 measure, kept: the shape is part of the chain)
       if (per_sm < 1) continue;
       const double interior = (double)s.mx * s.my * s.mz;
       // below two waves of CTA slots the ragged last wave costs a whole CTA latency
@@ -478,7 +432,8 @@ static void setup_blocks(hsmc_gpu* h) {
   b.cs_stride = 0; b.cz_stride = (best.mz + 3 + 7) & ~7;
   b.max_rows = (best.mx + 2) * (best.my + 2);
   b.max_cells = best.mx * best.my * best.mz; b.tr_cap = best.tr_cap;
-  b.use_tma = (h->impl == IMPL_BLOCK_TMA) ? 1 : 0;
+  b.desc_cap = 8 * best.tr_cap;
+  b.use_tma = 0;
   b.force_global = (h->impl == IMPL_BLOCK_GLOBAL) ? 1 : 0;
   b.dbg = getenv("HSMC_BLOCK_DBG") ? atoi(getenv("HSMC_BLOCK_DBG")) : 0;
   h->xoff.clear();
@@ -489,7 +444,9 @@ static void setup_blocks(hsmc_gpu* h) {
   }
   h->xoff.push_back((W > 1) ? g.own_hi : g.nx);
   b.nbx = (int)h->xoff.size() - 1;
-  h->blk_smem = best.smem;
+  h->lean = !r1;
+  h->blk_smem = r1 ? best.smem_r1 : best.smem;
+  h->plan_smem = best.smem_plan;
   if (const char* e = getenv("HSMC_BLOCK_PADSMEM")) h->blk_smem += (size_t)atoi(e);    // occupancy experiments
   // fp32 filter error bound: staged coordinates are block-relative,
   // |X| <= (m/2 + 2) cells; per pair and axis: two final roundings at that magnitude, the
@@ -502,7 +459,7 @@ static void setup_blocks(hsmc_gpu* h) {
   for (int k = 0; k < 3; k++) sum += 2.0 * half_ulp(mag[k]) + 2.0 * wv[k] * ldexp(1.0, -24) + 2.0 * wv[k] * ldexp(1.0, -25);
   double r2err = 2.0 * 1.01 * sum + 8.0 * ldexp(1.0, -24);
   h->blk_eps = (float)(2.0 * r2err);
-  h->blk_ok = (h->impl == IMPL_BLOCK || h->impl == IMPL_EPS0 || h->impl == IMPL_BLOCK_GLOBAL || h->impl == IMPL_BLOCK_TMA);
+  h->blk_ok = (h->impl == IMPL_LEAN || h->impl == IMPL_EPS0 || h->impl == IMPL_BLOCK_GLOBAL || h->impl == IMPL_BLOCK_R1);
   if (getenv("HSMC_DEBUG_TILES"))
     fprintf(stderr, "[hsmc_gpu] rank %d: blocks %dx%dx%d of up to %dx%dx%d cells, %d CTAs/phase, cap %d, smem %zu B, eps %.3g\n",
             h->cfg.rank, b.nbx, b.nby, b.nbz, b.mbx, b.mby, b.mbz, (b.nbx / 2) * (b.nby / 2) * (b.nbz / 2), b.cap,
@@ -698,8 +655,8 @@ extern "C" int hsmc_gpu_destroy(hsmc_gpu* h) {
   if (h->comm) ncclCommDestroy(h->comm);
   void* ptrs[] = {h->pos[0], h->pos[1], h->rel, h->key, h->rnk, h->cell_count, h->cell_start, h->bsum, h->d_cnt,
                   h->d_scratch, h->d_slot_of_id, h->d_io, h->send_l, h->send_r, h->recv_l, h->recv_r,
-                  h->d_halo_cnt, h->d_sfargs, h->d_log, h->key_halo, h->rnk_halo, h->deep_list, h->deep_count, h->d_lay,
-                  h->d_xoff, h->cs16, h->d_fuse};
+                  h->d_halo_cnt, h->d_sfargs, h->d_log, h->key_halo, h->rnk_halo, h->d_lay,
+                  h->d_xoff, h->cs16, h->d_fuse, h->plan.hdr, h->plan.row, h->plan.cz, h->plan.trial, h->plan.raw, h->plan.cursor};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -728,7 +685,8 @@ extern "C" int hsmc_gpu_create(hsmc_gpu** out, const hsmc_gpu_config* cfg, int64
   h->cfg = *cfg;
   h->impl = cfg->sweep_impl & 0xff;
   h->xpart_world = (cfg->sweep_impl >> 8) & 0xff;
-  if (h->impl > IMPL_BLOCK_TMA) { delete h; return fail("unknown sweep_impl variant"); }
+  if (h->impl != IMPL_LEAN && h->impl != IMPL_CELL_GLOBAL && h->impl != IMPL_EPS0 && h->impl != IMPL_BLOCK_GLOBAL &&
+      h->impl != IMPL_BLOCK_R1) { delete h; return fail("unknown sweep_impl variant"); }
   if (h->cfg.cell_min == 0.0) h->cfg.cell_min = 1.0;
   if (h->cfg.cell_min < 1.0) { delete h; return fail("cell_min must be >= 1.0 (the particle diameter)"); }
   if (h->cfg.regrid_interval <= 0) h->cfg.regrid_interval = 1;
@@ -778,8 +736,11 @@ extern "C" int hsmc_gpu_create(hsmc_gpu** out, const hsmc_gpu_config* cfg, int64
   CUD(cudaMemset(h->d_lay, 0, sizeof(int) * 16));
   CUD(cudaMallocHost(&h->h_stage, sizeof(unsigned long long) * SCRATCH_N));
   if (ensure_cell_arrays(h)) { hsmc_gpu_destroy(h); return 1; }
-  CUD(cudaFuncSetAttribute(k_sweep_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-  CUD(cudaFuncSetAttribute(k_sweep_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+  CUD(cudaFuncSetAttribute(k_sweep_lean<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+  CUD(cudaFuncSetAttribute(k_sweep_lean<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+  CUD(cudaFuncSetAttribute(k_sweep_lean<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  CUD(cudaFuncSetAttribute(k_block_plan<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+  CUD(cudaFuncSetAttribute(k_block_plan<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
   CUD(cudaFuncSetAttribute(k_sweep_block<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
   CUD(cudaFuncSetAttribute(k_sweep_block<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
   if (W > 1) {
@@ -851,7 +812,7 @@ extern "C" int hsmc_gpu_plan_blocks(const double box[3], double cell_min, int wo
   hsmc_gpu tmp;
   tmp.cfg.device = 0; tmp.cfg.rank = rank; tmp.cfg.world = world; tmp.cfg.nccl_id = nullptr; tmp.cfg.seed = 0;
   tmp.cfg.cell_min = cell_min == 0.0 ? 1.0 : cell_min; tmp.cfg.regrid_interval = 1; tmp.cfg.sweep_impl = 0;
-  tmp.impl = IMPL_BLOCK; tmp.xpart_world = (world == 1 && xpart_world > 1) ? xpart_world : 0;
+  tmp.impl = IMPL_LEAN; tmp.xpart_world = (world == 1 && xpart_world > 1) ? xpart_world : 0;
   if (tmp.cfg.cell_min < 1.0) return fail("cell_min must be >= 1.0 (the particle diameter)");
   tmp.N = n_particles;
   tmp.box[0] = box[0]; tmp.box[1] = box[1]; tmp.box[2] = box[2];
@@ -991,6 +952,37 @@ static int do_regrid(hsmc_gpu* h) {
   return rebuild(h, h->pos[h->cur], h->N, 0, 0);
 }
 
+// plan arrays of the lean sweep: sized for the current block partition
+static int ensure_plan(hsmc_gpu* h, bool logged) {
+  const BlockCfg& b = h->blk;
+  const int64_t nblocks = (int64_t)b.nbx * b.nby * b.nbz;
+  LeanPlan& p = h->plan;
+  if (nblocks > h->plan_blocks || b.max_rows > h->plan_rows || b.cz_stride > h->plan_czs) {
+    if (p.hdr) cudaFree(p.hdr);
+    if (p.row) cudaFree(p.row);
+    if (p.cz) cudaFree(p.cz);
+    p.hdr = nullptr; p.row = nullptr; p.cz = nullptr;
+    h->plan_blocks = nblocks + nblocks / 8 + 64; h->plan_rows = b.max_rows; h->plan_czs = b.cz_stride;
+    CU(cudaMalloc(&p.hdr, sizeof(int) * PLAN_HDR_INTS * (size_t)h->plan_blocks));
+    CU(cudaMalloc(&p.row, sizeof(BlockRow) * (size_t)h->plan_rows * (size_t)h->plan_blocks));
+    CU(cudaMalloc(&p.cz, sizeof(unsigned short) * (size_t)h->plan_rows * (size_t)h->plan_czs * (size_t)h->plan_blocks));
+  }
+  // every colour list of a block is padded to a multiple of 32 trial slots
+  // (+ the slots skipped so that no cell straddles a chunk: a few per cent at most)
+  const long long need = (long long)h->cap + h->cap / 8 + 256LL * nblocks + 1024;
+  if (need > p.cap_trials) {
+    if (p.trial) cudaFree(p.trial);
+    if (p.raw) { cudaFree(p.raw); p.raw = nullptr; }
+    p.cap_trials = need + need / 16;
+    CU(cudaMalloc(&p.trial, sizeof(uint4) * (size_t)p.cap_trials));
+  }
+  if (logged && !p.raw) CU(cudaMalloc(&p.raw, sizeof(uint4) * (size_t)p.cap_trials));
+  if (!p.cursor) {
+    CU(cudaMalloc(&p.cursor, sizeof(unsigned int) * 4));
+  }
+  return 0;
+}
+
 static int sweep_once(hsmc_gpu* h, double dr_max, bool logged) {
   if (h->since_regrid % h->cfg.regrid_interval == 0) TRY(do_regrid(h));
   h->since_regrid++;
@@ -1038,6 +1030,21 @@ static int sweep_once(hsmc_gpu* h, double dr_max, bool logged) {
     }
   }
   a.fuse = fuse; a.epoch = 0; a.ticket_base = 0;
+  a.cx = a.cy = a.cz = a.phase = 0;
+  if (h->blk_ok && h->lean) {
+    // proposals of the whole sweep + the per-block plan (static while cell membership is): one launch, all blocks
+    ProfSpan span(h, 3);
+    TRY(ensure_plan(h, logged));
+    const int nblocks = h->blk.nbx * h->blk.nby * h->blk.nbz;
+    CU(cudaMemsetAsync(h->plan.cursor, 0, sizeof(unsigned int), h->st));
+    if (logged)
+      k_block_plan<true><<<nblocks, PLAN_THREADS, h->plan_smem, h->st>>>(a, h->blk, h->plan, h->d_xoff, h->pos[h->cur], h->cell_start,
+                                                                        h->pos[h->cur ^ 1]);
+    else
+      k_block_plan<false><<<nblocks, PLAN_THREADS, h->plan_smem, h->st>>>(a, h->blk, h->plan, h->d_xoff, h->pos[h->cur], h->cell_start,
+                                                                         h->pos[h->cur ^ 1]);
+    h->launches++;
+  }
   for (int ph = 0; ph < 8; ph++) {
     a.cx = (ph >> 2) & 1; a.cy = (ph >> 1) & 1; a.cz = ph & 1; a.phase = ph;
     if (fuse <= 1 || ph % fuse == 0) {     // else: launched together with phase ph - ph % fuse
@@ -1052,30 +1059,21 @@ static int sweep_once(hsmc_gpu* h, double dr_max, bool logged) {
         a.ticket_base = h->fuse_tickets;
         h->fuse_tickets += (unsigned int)nb;
       }
-      if (logged)
+      if (h->lean) {
+        if (logged)
+          k_sweep_lean<true><<<nb, LEAN_THREADS, h->blk_smem, h->st>>>(a, h->blk, h->plan, h->d_xoff, h->pos[h->cur], h->rel,
+                                                                       h->pos[h->cur ^ 1], h->cell_start, h->d_cnt, h->d_log,
+                                                                       h->d_scratch, (long long)h->cap_log);
+        else
+          k_sweep_lean<false><<<nb, LEAN_THREADS, h->blk_smem, h->st>>>(a, h->blk, h->plan, h->d_xoff, h->pos[h->cur], h->rel,
+                                                                        h->pos[h->cur ^ 1], h->cell_start, h->d_cnt, nullptr,
+                                                                        nullptr, 0);
+      } else if (logged)
         k_sweep_block<true><<<nb, BLK_THREADS, h->blk_smem, h->st>>>(a, h->blk, h->d_xoff, h->pos[h->cur], h->rel, h->cell_start,
                                                                       h->cs16, h->d_cnt, h->d_log, h->d_scratch, (long long)h->cap_log);
       else
         k_sweep_block<false><<<nb, BLK_THREADS, h->blk_smem, h->st>>>(a, h->blk, h->d_xoff, h->pos[h->cur], h->rel, h->cell_start,
                                                                        h->cs16, h->d_cnt, nullptr, nullptr, 0);
-    } else if (h->tile_ok) {
-      int nb = h->tile.ntx * h->tile.nty * h->tile.ntz;
-      int gb = 148 * 4;
-      if (logged)
-        k_sweep_tile<true><<<nb, TILE_THREADS, h->tile_smem, h->st>>>(a, h->tile, h->pos[h->cur], h->rel, h->cell_start, h->d_cnt,
-                                                                      h->d_log, h->d_scratch, (long long)h->cap_log);
-      else
-        k_sweep_tile<false><<<nb, TILE_THREADS, h->tile_smem, h->st>>>(a, h->tile, h->pos[h->cur], h->rel, h->cell_start, h->d_cnt,
-                                                                       nullptr, nullptr, 0);
-      h->launches++;
-      // third and later trials of the (2-3 %) cells holding >= 3 particles
-      if (logged)
-        k_sweep_deep<true><<<gb, 256, 0, h->st>>>(a, h->deep_list, h->deep_count, ph, (int)h->deep_stride, h->pos[h->cur],
-                                                  h->rel, h->cell_start, h->d_cnt, h->d_log, h->d_scratch,
-                                                  (long long)h->cap_log);
-      else
-        k_sweep_deep<false><<<gb, 256, 0, h->st>>>(a, h->deep_list, h->deep_count, ph, (int)h->deep_stride, h->pos[h->cur],
-                                                   h->rel, h->cell_start, h->d_cnt, nullptr, nullptr, 0);
     } else if (logged)
       k_sweep_phase<true><<<nblk(total, T), T, 0, h->st>>>(a, h->pos[h->cur], h->rel, h->cell_start, h->d_cnt, h->d_log,
                                                             h->d_scratch, (long long)h->cap_log);

@@ -45,8 +45,7 @@
 
 // BlockCfg: see hsmc_gpu.cu (the handle keeps one)
 
-// per-row staging record: global slots of the row's one or two pieces, staged offset
-struct BlockRow { int gbA, gbB, cntA, off; };
+// BlockRow: see hsmc_gpu.cu
 
 // exact re-evaluation of a whole stencil from the master table (moves.c:157-212, 400-431)
 // (`pos` deliberately not const __restrict__: entries of this block were written earlier in this
@@ -71,34 +70,6 @@ __device__ __noinline__ bool block_exact_rescan(const double4* pos, const BlockR
     }
   return false;
 }
-
-__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-// nanosecond wall clock of the device (bounds the spin waits below and in the halo flag kernels)
-__device__ __forceinline__ unsigned long long hsmc_globaltimer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-
-// block-completion flags of a fused launch (several block phases in one grid, see k_sweep_block)
-// (polled with a relaxed load: an acquire load invalidates the SM's whole L1 each time it is issued
-//  (LDG.STRONG.GPU + CCTL.IVALL), which the co-resident CTAs pay for; the acquire is one fence after
-//  the flag has been seen)
-__device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-// prefetch a master-table entry (32 B) towards L1 for a later iteration of the same thread
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // One (x,y) row of a trial's stencil: the three z-cells are one contiguous staged range,
 // scanned in groups of BLK_SLOTS entries at fixed offsets, unmasked (see the file header).
@@ -443,172 +414,6 @@ k_sweep_block(SweepArgs a, BlockCfg bc, const int* __restrict__ xoff, double4* _
       }
       return u;
     };
-#ifdef BLK_SPLIT_BARRIER
-    // ---- EXPERIMENT (not in the default build; scripts/build_variant.sh x "-DBLK_SPLIT_BARRIER") ----------
-    // Split colour barrier.  Everything up to the trial point of a chunk (slot lookup, master load, Philox,
-    // double arithmetic, cell test) depends on the trial particle alone, never on what other cells did in
-    // the current colour.  So a warp that has finished its chunks of colour c ARRIVES at the colour barrier
-    // (mbarrier), generates its first chunk of colour c+1 while the slower warps finish, and only then WAITS;
-    // hide + scan + verdict follow the wait.  Same trials, same order of dependent updates: same chain.
-    struct Gen { Slot u; double4 p; double xn, yn, zn; float4 nrel; float tx, ty, tz; Philox4 rn; bool act; };
-    auto generate = [&](const Slot& u) {
-      Gen q;
-      q.u = u; q.p = make_double4(0, 0, 0, 0); q.xn = q.yn = q.zn = 0.0; q.nrel = make_float4(0.f, 0.f, 0.f, 0.f);
-      q.tx = q.ty = q.tz = 0.f; q.act = false; q.rn.v[0] = q.rn.v[1] = q.rn.v[2] = q.rn.v[3] = 0u;
-      if (u.code >= 0) {
-        const int j = u.code & 15;
-        const int rxc = u.cell >> 11, ryc = (u.cell >> 6) & 31, rz = u.cell & 63;
-        const int iy = y0 + ryc, iz = z0 + rz;
-        const int gxl = g.gx0 + x0 + rxc;
-        const int gx = (gxl >= g.nx) ? gxl - g.nx : gxl;
-        const long long gcell = ((long long)gx * g.ny + iy) * g.nz + iz;
-        q.p = pos[u.gs];
-        q.rn = philox4x32_10((uint32_t)gcell, (HSMC_STREAM_MOVE << 24) | (uint32_t)j, a.sweep_lo, a.sweep_hi, a.key0, a.key1);
-        double xn = q.p.x + (hsmc_u01(q.rn.v[0]) - 0.5) * a.dr_max;
-        double yn = q.p.y + (hsmc_u01(q.rn.v[1]) - 0.5) * a.dr_max;
-        double zn = q.p.z + (hsmc_u01(q.rn.v[2]) - 0.5) * a.dr_max;
-        if (xn > g.Lx) xn -= g.Lx; else if (xn < 0.0) xn += g.Lx;
-        if (yn > g.Ly) yn -= g.Ly; else if (yn < 0.0) yn += g.Ly;
-        if (zn > g.Lz) zn -= g.Lz; else if (zn < 0.0) zn += g.Lz;
-        q.xn = xn; q.yn = yn; q.zn = zn;
-        q.act = axis_cell(xn, g.sx, g.iwx, g.nx) == gx && axis_cell(yn, g.sy, g.iwy, g.ny) == iy &&
-                axis_cell(zn, g.sz, g.iwz, g.nz) == iz;
-        if (q.act) {
-          q.nrel = make_rel(g, gx, iy, iz, xn, yn, zn, q.p.w);
-          q.tx = __fmaf_rn((float)rxc - hxr, wxf, q.nrel.x);
-          q.ty = __fmaf_rn((float)ryc - hyr, wyf, q.nrel.y);
-          q.tz = __fmaf_rn((float)rz - hzr, wzf, q.nrel.z);
-        } else n_cell++;
-      }
-      return q;
-    };
-    __shared__ __align__(8) uint64_t s_cbar;
-    if (tid == 0) mbar_init(&s_cbar, BLK_THREADS);
-    __syncthreads();
-    uint32_t cpar = 0;
-    Gen cur;
-    cur.u.code = -1;
-    if (warp * 32 < s_ntr[0]) cur = generate(stage_a(0, warp));
-#pragma unroll 1
-    for (int col = 0; col < 8; col++) {
-      const int ntr = s_ntr[col];
-      int chunk = warp;
-#pragma unroll 1
-      while (chunk * 32 < ntr) {                     // cur = the generated trials of `chunk`
-        const Slot u = cur.u;
-        const bool valid = u.code >= 0, act = cur.act;
-        const int j = u.code & 15, n = valid ? (u.code >> 4) : 0;
-        const double4 p = cur.p;
-        const double xn = cur.xn, yn = cur.yn, zn = cur.zn;
-        const float tx = cur.tx, ty = cur.ty, tz = cur.tz;
-        const float4 nrel = cur.nrel;
-        int nxt = 0;
-        if (lane == 0) nxt = atomicAdd(&s_next[col], 1);
-        nxt = __shfl_sync(FULL, nxt, 0);
-        Slot nx;
-        nx.code = -1; nx.cell = 0; nx.sel = 0; nx.gs = 0;
-        const bool more = nxt * 32 < ntr;
-        if (more) nx = stage_a(col, nxt);
-        const int rxc = u.cell >> 11, ryc = (u.cell >> 6) & 31, rz = u.cell & 63;
-        float4 keep = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid) {
-          keep = s_rel[u.sel];
-          s_rel[u.sel] = make_float4(BLK_FAR, BLK_FAR, BLK_FAR, keep.w);
-        }
-        __syncwarp();
-        float r2min = 3.0e38f;
-        if (act) {
-          const unsigned short* cp0 = s_cz + ((rxc - 1) * nry + ryc - 1) * czs + rz;
-          bool deep = false;
-#pragma unroll
-          for (int r = 0; r < 9; r++) {
-            const unsigned short* cp = cp0 + ((r / 3) * nry + (r % 3)) * czs;
-            const int b = cp[-1];
-            deep |= (int)cp[2] - b > BLK_SLOTS;
-            const float4* q = s_rel + b;
-#pragma unroll
-            for (int s2 = 0; s2 < BLK_SLOTS; s2++) {
-              const float4 qv = q[s2];
-              const float ddx = tx - qv.x, ddy = ty - qv.y, ddz = tz - qv.z;
-              r2min = fminf(r2min, __fmaf_rn(ddz, ddz, __fmaf_rn(ddy, ddy, ddx * ddx)));
-            }
-          }
-          if (deep) {
-#pragma unroll 1
-            for (int r = 0; r < 9; r++) {
-              const unsigned short* cp = cp0 + ((r / 3) * nry + (r % 3)) * czs;
-              const int e = cp[2];
-#pragma unroll 1
-              for (int k0 = cp[-1] + BLK_SLOTS; k0 < e; k0 += BLK_SLOTS) {
-                const float4* q = s_rel + k0;
-#pragma unroll
-                for (int s2 = 0; s2 < BLK_SLOTS; s2++) {
-                  const float4 qv = q[s2];
-                  const float ddx = tx - qv.x, ddy = ty - qv.y, ddz = tz - qv.z;
-                  r2min = fminf(r2min, __fmaf_rn(ddz, ddz, __fmaf_rn(ddy, ddy, ddx * ddx)));
-                }
-              }
-            }
-          }
-        }
-        const int maxn = __reduce_max_sync(FULL, n);
-        const int gb = lane - j;
-        bool mate_ov = false;
-        for (int s2 = 1; s2 < maxn; s2++) {
-          const int src = (gb + s2) & 31;
-          const double qx = __shfl_sync(FULL, p.x, src), qy = __shfl_sync(FULL, p.y, src), qz = __shfl_sync(FULL, p.z, src);
-          if (act && j < s2 && s2 < n && !mate_ov) mate_ov = pair_r2(xn, yn, zn, qx, qy, qz, a.box) < 1.0;
-        }
-        double cx = p.x, cy = p.y, cz = p.z;
-        int verdict = 2;
-        for (int s2 = 0; s2 < maxn; s2++) {
-          if (valid && j == s2) {
-            bool acc = false;
-            if (act) {
-              bool ov = mate_ov || r2min < lo;
-              if (!ov && r2min <= hi)
-                ov = block_exact_rescan(pos, s_row, s_cz, czs, nry, rxc, ryc, rz, u.sel, xn, yn, zn, a.box);
-              if (ov) { verdict = 1; n_ov++; }
-              else {
-                verdict = 0; n_acc++; acc = true;
-                cx = xn; cy = yn; cz = zn;
-                rel[u.gs] = nrel;
-                pos[u.gs] = make_double4(xn, yn, zn, p.w);
-              }
-            }
-            s_rel[u.sel] = acc ? make_float4(tx, ty, tz, keep.w) : keep;
-          }
-          if (s2 + 1 < maxn) {
-            __syncwarp();
-            const int src = (gb + s2) & 31;
-            const double qx = __shfl_sync(FULL, cx, src), qy = __shfl_sync(FULL, cy, src), qz = __shfl_sync(FULL, cz, src);
-            if (act && j > s2 && !mate_ov) mate_ov = pair_r2(xn, yn, zn, qx, qy, qz, a.box) < 1.0;
-          }
-        }
-        if (LOG && valid) {
-          const int iy = y0 + ryc, iz = z0 + rz;
-          const int gxl = g.gx0 + x0 + rxc;
-          const int gx = (gxl >= g.nx) ? gxl - g.nx : gxl;
-          const long long gcell = ((long long)gx * g.ny + iy) * g.nz + iz;
-          unsigned long long sl = atomicAdd(nlog, 1ull);
-          if ((long long)sl < logcap) {
-            hsmc_gpu_trial tr;
-            tr.seq = ((unsigned long long)(ph * 8 + col) << 56) | ((unsigned long long)gcell << 8) | (unsigned)j;
-            tr.id = (int)p.w; tr.verdict = verdict;
-            tr.raw[0] = cur.rn.v[0]; tr.raw[1] = cur.rn.v[1]; tr.raw[2] = cur.rn.v[2]; tr.pad = 0;
-            log[sl] = tr;
-          }
-        }
-        if (more) cur = generate(nx);
-        chunk = nxt;
-      }
-      // this warp is done with colour `col`: arrive, pre-generate, wait
-      mbar_arrive(&s_cbar);
-      if (col < 7 && warp * 32 < s_ntr[col + 1]) cur = generate(stage_a(col + 1, warp));
-      mbar_wait(&s_cbar, cpar);
-      cpar ^= 1u;
-    }
-#else
 #pragma unroll 1
     for (int col = 0; col < 8; col++) {
       const int ntr = s_ntr[col];
@@ -752,7 +557,6 @@ k_sweep_block(SweepArgs a, BlockCfg bc, const int* __restrict__ xoff, double4* _
       __syncthreads();
       BLK_MARK(7)     // waiting for the other warps at the colour barrier
     }
-#endif
   } else {
     // ---- staging capacity exceeded (unusually dense block) or ablation: global-memory path,
     //      same order of updates ------------------------------------------------------------

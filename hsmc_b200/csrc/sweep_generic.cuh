@@ -141,3 +141,13 @@ k_sweep_phase(SweepArgs a, double4* __restrict__ pos, float4* __restrict__ rel, 
   }
 }
 
+
+// out-of-line copy for the staged kernels' fallback path (blocks that do not fit the staged scheme)
+template <bool LOG>
+__device__ __noinline__ void cell_update_global_noinline(const SweepArgs a, int phase, double4* __restrict__ pos,
+                                                         float4* __restrict__ rel, const int* __restrict__ cs, int l,
+                                                         int iy, int iz, int j0, int j1, int& n_acc, int& n_ov,
+                                                         int& n_cell, hsmc_gpu_trial* __restrict__ log,
+                                                         unsigned long long* __restrict__ nlog, long long logcap) {
+  cell_update_global<LOG>(a, phase, pos, rel, cs, l, iy, iz, j0, j1, n_acc, n_ov, n_cell, log, nlog, logcap);
+}

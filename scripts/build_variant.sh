@@ -6,4 +6,5 @@ cd "$(dirname "$0")/.."
 mkdir -p hsmc_b200/csrc/variants
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false -DHSMC_FAST_U01 --extended-lambda \
   -Xcompiler -fPIC -shared $2 -Xptxas=-v -o hsmc_b200/csrc/variants/$1.so hsmc_b200/csrc/hsmc_gpu.cu -lnccl 2>&1 \
-  | grep -A1 "k_sweep_blockILb0" | grep -E "registers|spill" | head -2
+  | grep -A2 "k_sweep_leanILb0" | grep -E "registers|spill" | tr '\n' ' '
+echo " <- $1 ($2)"
