@@ -10,14 +10,19 @@ Workload (config.workload): NVT hard spheres, fcc start, rho = 0.9, N = 16 777 2
 configs[3] -- the configuration the headline metric is quoted on; it fits one B200, and
 the same total system is slab-decomposed over N GPUs ("scaling": "strong").
 
-A step = one hsmc_gpu_sweep_nvt() call of --sweeps-per-step sweeps (each sweep = N trial
-moves = 8 checkerboard block phases, each running the 8 cell colours of its blocks inside
-the CTA, + one grid shift / cell-list rebuild).  The block phases that need no halo exchange
-between them run as ONE k_sweep_block launch (all 8 on one GPU, 0-3 and 4-7 on slabs), so a
-"launch" of the roofline object is a whole sweep (N moves) at N=1 and half a sweep on slabs.  `value` is
-timed on the device (CUDA events on the handle's stream) with the configuration resident
-in HBM; `e2e` is the same call driven from pinned HOST buffers: upload of the {id,x,y,z}
-table, the sweeps, download of the table and the move counters, wall-clock.
+A step = one hsmc_gpu_sweep_nvt() call of S sweeps (each sweep = one grid shift + cell-list
+rebuild, one k_block_plan launch that generates the sweep's proposals and the per-block plan,
+and N trial moves = 8 checkerboard block phases, each running the 8 cell colours of its blocks
+inside the CTA).  The block phases that need no halo exchange between them run as ONE
+k_sweep_lean launch (all 8 on one GPU, 0-3 and 4-7 on slabs), so a "launch" of the roofline
+object is a whole sweep (N moves) at N=1 and half a sweep on slabs.  S (--sweeps-per-step,
+default: chosen after the warm-up so that the timed region lasts >= 2.5 s) is reported in
+config.  `value` is timed on the device (CUDA events on the handle's stream) with the
+configuration resident in HBM; `e2e` is the same call driven from pinned HOST buffers: upload
+of the {id,x,y,z} table, the sweeps, download of the table and the move counters, wall-clock.
+At N > 1 the line also carries `chain_identical`: after the timed region the slabs' state is
+gathered, rank 0 runs the same sweeps on ONE GPU (told to use the N-slab block partition) and
+the coordinates (checksum of every row) and counters must be equal.
 """
 from __future__ import annotations
 
@@ -132,23 +137,26 @@ def ncu_traffic():
 # CPU arm: the reference's own sweep_nvt()/part_move() on host cores
 # --------------------------------------------------------------------------------------
 def _cpu_worker(args):
-    """One replica: reference lattice of `cells`^3 fcc cells, `sweeps` sweeps per step."""
-    kind, cells, seed, steps, warmup, sweeps, conn = args
+    """One replica: the reference's own lattice generator + cell list for a cubic fcc `cells`^3 box, then
+    `moves` part_move() calls per step (sweep_nvt() is N of them, nvt.c:201-209)."""
+    kind, cells, seed, steps, warmup, moves, conn = args
     from oracle import pyoracle
     if kind == "reference":
         r = pyoracle.Ref(lattice=(2, cells, cells, cells, RHO), neigh_dr=1.0, max_part=10, seed=seed)
         r.set_moves(dr_max=DR_MAX)
-        run = lambda: r.sweep_nvt(sweeps)
+        run = lambda: r.part_moves(moves)
         n = r.N
     else:
         box, conf = pyoracle.Port.lattice(2, cells, cells, cells, RHO)
         p = pyoracle.Port(conf, box, neigh_dr=1.0, max_part=10)
+        n = conf.shape[0]
         state = {"k": 0}
 
         def run():
-            p.sweep_nvt(sweeps, DR_MAX, seed + state["k"])
+            # the restatement only exposes whole sweeps: scale the count afterwards
+            p.sweep_nvt(max(1, int(round(moves / n))), DR_MAX, seed + state["k"])
             state["k"] += 1
-        n = conf.shape[0]
+        moves = max(1, int(round(moves / n))) * n
     times = []
     for s in range(warmup + steps):
         conn.send("ready")
@@ -156,12 +164,33 @@ def _cpu_worker(args):
         t0 = time.perf_counter()
         run()
         times.append(time.perf_counter() - t0)
-    conn.send(("done", n, times[warmup:]))
+    conn.send(("done", n, times[warmup:], moves))
 
 
-def cpu_reference_arm(steps, warmup, cells, sweeps, cores):
-    """K steps, each = every replica (one per host core) runs `sweeps` sweeps of a
-    `cells`^3 fcc box at rho 0.9 through the reference's own sweep_nvt()."""
+def cpu_replicas_that_fit(cells, cores):
+    """Replicas of the reference that fit the host's memory: its cell matrices cost ~250 bytes per particle at
+    rho 0.9 / neigh_list 1.0 (one malloc per cell row, cell_list.c:33-58), 4.2 GB at N = 17 M."""
+    need = 4 * cells ** 3 * 260.0
+    avail = None
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable:"):
+                avail = float(ln.split()[1]) * 1024.0
+        for pth in ("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory/memory.limit_in_bytes"):
+            if os.path.exists(pth):
+                v = open(pth).read().strip()
+                if v.isdigit():
+                    avail = min(avail, float(v)) if avail else float(v)
+    except Exception:
+        pass
+    if not avail:
+        return max(1, min(cores, 4))
+    return int(max(1, min(cores, (0.4 * avail) // need)))
+
+
+def cpu_reference_arm(steps, warmup, cells, moves_per_step, replicas):
+    """K steps; in each, every replica (one per host core used) makes `moves_per_step` trial moves on its own
+    cubic fcc `cells`^3 box at rho 0.9 through the reference's own part_move()."""
     import multiprocessing as mp
     from oracle import pyoracle
     kind = "reference" if pyoracle.have_ref() else "port"
@@ -169,38 +198,31 @@ def cpu_reference_arm(steps, warmup, cells, sweeps, cores):
         pyoracle.build()
     ctx = mp.get_context("spawn")
     procs, conns = [], []
-    for c in range(cores):
+    for c in range(replicas):
         a, b = ctx.Pipe()
-        p = ctx.Process(target=_cpu_worker, args=((kind, cells, 1000 + c, steps, warmup, sweeps, b),))
+        p = ctx.Process(target=_cpu_worker, args=((kind, cells, 1000 + c, steps, warmup, moves_per_step, b),))
         p.start()
         procs.append(p); conns.append(a)
-    step_times = []
     for s in range(warmup + steps):
         for c in conns:
             assert c.recv() == "ready"
-        t0 = time.perf_counter()
         for c in conns:
             c.send("go")
-        # next "ready" (or "done") arrives when the replica finished this step
-        if s < warmup + steps - 1:
-            pass
-        step_times.append(t0)
     results = [c.recv() for c in conns]
     for p in procs:
         p.join()
-    n = results[0][1]
+    n, moves = results[0][1], results[0][3]
     per_step = np.max(np.array([r[2] for r in results]), axis=0)   # slowest replica per step
-    moves_per_step = n * sweeps * cores
     total = float(per_step.sum())
     return {
-        "value": moves_per_step * steps / total, "ms_per_step": 1e3 * total / steps, "kind": kind, "cores": cores,
-        "sample": (f"{cores} independent replicas (one per host core) x {sweeps} sweep(s) of a cubic fcc {cells}^3 "
-                   f"box, N={n}, rho={RHO}, dr_max={DR_MAX}, neigh_list 1.0, through the reference's own "
-                   f"sweep_nvt()/part_move() ({'unmodified sources, oracle/_ref' if kind == 'reference' else 'oracle C restatement'}); "
-                   "the reference cannot index the non-cubic 16.8M box (SURVEY 0.6) and a smaller box is cache-friendlier, "
-                   "so this over-states the CPU"),
+        "value": moves * replicas * steps / total, "ms_per_step": 1e3 * total / steps, "kind": kind, "cores": replicas,
+        "N": n, "moves_per_step_per_replica": moves,
+        "sample": (f"{replicas} independent replica(s), one per host core, each {moves} part_move() calls per step "
+                   f"({moves / n:.3g} sweep) on a cubic fcc {cells}^3 box, N={n}, rho={RHO}, dr_max={DR_MAX}, neigh_list 1.0, "
+                   f"through the reference's own part_move()/check_overlap() "
+                   f"({'unmodified sources, oracle/_ref' if kind == 'reference' else 'oracle C restatement'}); "
+                   f"{steps} timed step(s) after {warmup} warm-up step(s), slowest replica per step"),
     }
-
 
 
 # --------------------------------------------------------------------------------------
@@ -386,12 +408,16 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--sweeps-per-step", type=int, default=10)
-    ap.add_argument("--cells", type=int, nargs=3, default=[256, 128, 128], help="fcc unit cells (x is the slab axis)")
+    ap.add_argument("--sweeps-per-step", type=int, default=0, help="0: chosen so that the timed region lasts >= --min-seconds")
+    ap.add_argument("--min-seconds", type=float, default=2.5)
+    ap.add_argument("--chain-check-sweeps", type=int, default=8, help="N > 1: sweeps of the 1-GPU identity check (0 = skip)")
+    ap.add_argument("--cells", type=int, nargs=3, default=[162, 162, 162],
+                    help="fcc unit cells (x is the slab axis); the default cubic 162^3 (N = 17 006 112) is the C4 shape the reference can run too (SURVEY 8d)")
     ap.add_argument("--regrid", type=int, default=1)
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-cells", type=int, default=64)
-    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--cpu-cells", type=int, default=64, help="CPU arm box when --cells is not cubic (the reference mis-indexes non-cubic boxes)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--cpu-moves-per-step", type=int, default=200000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep-impl", type=int, default=0)
     ap.add_argument("--no-secondary", action="store_true", help="skip the observables' kernel timings (N=1 only)")
@@ -432,12 +458,28 @@ def main():
         if rank != 0:
             return
         cores = len(os.sched_getaffinity(0))
-        res = cpu_reference_arm(args.steps, args.warmup, args.cpu_cells, 1, cores)
+        same = nx == ny == nz
+        ccells = nx if same else args.cpu_cells
+        reps = cpu_replicas_that_fit(ccells, cores)
+        res = cpu_reference_arm(args.steps, args.warmup, ccells, args.cpu_moves_per_step, reps)
+        cfg = dict(workload, same_config=same, replicas=reps, host_cores=cores,
+                   moves_per_step_per_replica=res["moves_per_step_per_replica"])
+        for k in ("positions", "sweeps_per_step", "regrid_interval"):
+            cfg.pop(k, None)
+        if same:
+            cfg["workload"] += (f" -- reference arm: {reps} independent replica(s) of this same system, one per host core "
+                                f"(as many as fit the host memory), {res['moves_per_step_per_replica']} part_move() calls each per step")
+        else:
+            # the reference mis-indexes non-cubic boxes: say what is run instead
+            cfg["b200_arm_workload"] = workload["workload"]
+            cfg["workload"] = (f"NVT hard spheres, {reps} independent replicas of a CUBIC fcc {ccells}^3 start, N={res['N']} each, "
+                               f"rho={RHO}, dr_max={DR_MAX}, neigh_list 1.0 (NOT the b200 arm's non-cubic box)")
+            cfg["N"] = res["N"]
         line = {
             "impl": "reference", "metric": "hard_sphere_trial_moves_per_sec", "value": res["value"], "unit": "moves/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload,
+            "config": cfg,
             "cpu_baseline": {"value": res["value"], "unit": "moves/s", "cores": res["cores"], "kind": res["kind"],
                              "sample": res["sample"]},
             "e2e": {"value": res["value"], "unit": "moves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -480,6 +522,12 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t[0])
 
+    def allsum_u64(x, dist, torch):
+        """sum modulo 2^64 over the ranks"""
+        parts = [None] * world
+        dist.all_gather_object(parts, int(x))
+        return sum(parts) % (1 << 64)
+
     box, conf = fcc_lattice(nx, ny, nz, RHO)
     h = hsmc_b200.HsmcGpu(N, box, seed=20261017, device=local_rank, rank=rank, world=world, nccl_id=nccl_id,
                           cell_min=1.0, regrid_interval=args.regrid, sweep_impl=args.sweep_impl)
@@ -502,6 +550,17 @@ def main():
     host = torch.empty((cap_rows, 4), dtype=torch.float64, pin_memory=True)
     stream = torch.cuda.ExternalStream(h.stream_ptr(), device=torch.device("cuda", local_rank))
     S = args.sweeps_per_step
+    if S <= 0:
+        # sweeps per step: long enough a timed region for the clock sampler (>= 20 samples at 100 ms) at every N
+        h.sweep_nvt(5, DR_MAX)
+        h.sync()
+        barrier()
+        t0 = time.perf_counter()
+        h.sweep_nvt(10, DR_MAX)
+        h.sync()
+        t_sweep = allmax(time.perf_counter() - t0) / 10.0
+        S = int(min(5000, max(10, np.ceil(args.min_seconds / (args.steps * t_sweep)))))
+    workload["sweeps_per_step"] = S
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -551,32 +610,47 @@ def main():
     #      GPU, n_owned/2 on a slab; HSMC_FUSE=0 makes it one block phase = N/8) ----
     ncell = info["cells"][0] * info["cells"][1] * info["cells"][2]
     nbar = N / ncell
-    # Algorithmic bytes per trial move, no reuse credit, for THIS data layout: the 27-cell stencil
-    # is gathered from the 16-byte fp32 shadow (float4), the trial particle's own master entry is a 32-byte
-    # double4 read, and an accepted move writes master + shadow back (32 + 16; counted for every move, as the
-    # BASELINE.md formula counts its write).  BASELINE.md's all-float4 figure 16*(27*nbar + 2) is reported too.
-    b_move = 16.0 * 27.0 * nbar + 32.0 + 48.0
-    b_move_baseline_md = 16.0 * (27.0 * nbar + 2.0)
+    # Algorithmic bytes per trial move, no reuse credit: SURVEY 8(d)'s figure, 16*(27*nbar + 2) (full 27-cell
+    # stencil gather of 16-byte entries + own read + own write) -- the headline `frac`.  What this layout moves
+    # per move without reuse credit is reported beside it: the stencil is gathered from 12-byte fp32 pair-records,
+    # the trial slot is a 16-byte record, an accepted move copies a 32-byte proposal into the master table
+    # (24 bytes written) and 12 bytes of shadow.
+    b_move = 16.0 * (27.0 * nbar + 2.0)
+    acc_now = float(cnt[1]) / float(cnt[0])
+    b_move_layout = 12.0 * 27.0 * nbar + 16.0 + acc_now * (32.0 + 24.0 + 12.0)
     sweep_ms, sweep_groups = prof["sweep"]
+    plan_ms, plan_groups = prof["other"]
     moves_local = info["n_owned"] * S * args.steps     # this rank's trial moves (N/world up to migration)
     per_launch_s = (sweep_ms * 1e-3) / max(sweep_groups, 1)
     achieved = (moves_local / max(sweep_groups, 1)) * b_move / per_launch_s / 1e9
     peak, peak_src = measured_peak()
     traffic = ncu_traffic()
+    kname = {0: "k_sweep_lean", 3: "k_sweep_lean", 5: "k_sweep_lean (global-memory path)", 6: "k_sweep_block (round 1)"}.get(args.sweep_impl & 0xff, "k_sweep_phase")
     roofline = {
-        "bound": "hbm", "kernel": {0: "k_sweep_lean", 3: "k_sweep_lean", 5: "k_sweep_lean(global path)", 6: "k_sweep_block"}.get(args.sweep_impl & 0xff, "k_sweep_phase"), "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "peak_source": peak_src,
         "algorithmic_bytes_per_move": b_move, "nbar": nbar, "moves_per_launch": moves_local / max(sweep_groups, 1),
-        "algorithmic_bytes_definition": "16*27*nbar (stencil from the fp32 shadow) + 32 (own double4 read) + 48 (double4 + float4 write-back), no reuse",
-        "frac_with_baseline_md_bytes": achieved / b_move * b_move_baseline_md / peak,
+        "algorithmic_bytes_definition": "SURVEY 8(d): 16*(27*nbar + 2), no reuse credit",
+        "layout_bytes_per_move": b_move_layout,
+        "layout_bytes_definition": "12*27*nbar (stencil from fp32 pair-records) + 16 (trial record) + acceptance*(32 proposal read + 24 master + 12 shadow written)",
+        "frac_with_layout_bytes": achieved / b_move * b_move_layout / peak,
+        # the whole step (rebuild + plan + sweep + halo) against the same figure: value * bytes / (n_gpus * peak)
+        "step_frac": value * b_move / 1e9 / (world * peak),
         "avg_launch_ms": per_launch_s * 1e3, "launches_timed": sweep_groups,
         "kernel_share_of_step": sweep_ms / ms_local if ms_local > 0 else None,
+        "plan_share_of_step": plan_ms / ms_local if ms_local > 0 else None,
         "build_share_of_step": prof["build"][0] / ms_local if ms_local > 0 else None,
         "halo_share_of_step": prof["halo"][0] / ms_local if ms_local > 0 else None,
-        # the committed ncu capture is of the single-GPU fused launch; it does not describe slab launches
-        "traffic": (traffic or {}).get("dram_bytes_per_launch") if world == 1 and os.environ.get("HSMC_FUSE", "1") != "0" else None,
-        "traffic_source": (traffic or {}).get("source") if world == 1 else None,
+        "traffic": None, "traffic_source": None,
     }
+    if traffic and world == 1 and os.environ.get("HSMC_FUSE", "1") != "0":
+        # dram__bytes of one launch of the same kernel from the committed ncu capture; marked stale when the capture
+        # is of another kernel than the one timed here
+        if traffic.get("kernel", "") == kname.split(" ")[0]:
+            roofline["traffic"] = traffic.get("dram_bytes_per_launch")
+            roofline["traffic_source"] = traffic.get("source")
+        else:
+            roofline["traffic_source"] = "stale: committed capture is of " + str(traffic.get("kernel", "k_sweep_block (round 1)"))
 
     if roofline["traffic"]:
         # what actually crossed the HBM interface (ncu capture of the same launch), for comparison with the
@@ -611,7 +685,54 @@ def main():
            "d2h_bytes_per_step": int(allsum(d2h) / args.e2e_steps), "steps": args.e2e_steps,
            "ms_per_step": 1e3 * t_e2e / args.e2e_steps,
            "what": "hsmc_gpu_upload(pinned host rows) + hsmc_gpu_sweep_nvt + hsmc_gpu_download + hsmc_gpu_counters per step"}
-    acc = float(cnt[1]) / float(cnt[0])
+    # ---- N > 1: is the slab run the same Markov chain as one GPU?  (the Philox draws are keyed by global
+    #      cell, the block partition is that of the N-slab run.)  The slabs' table is gathered on rank 0, which runs
+    #      the same sweeps on ONE GPU; every row (order-independent 64-bit checksum) and the counters must agree.
+    chain = None
+    if world > 1 and args.chain_check_sweeps > 0:
+        C_ = args.chain_check_sweeps
+        K64 = np.array([0x9E3779B97F4A7C15, 0xC2B2AE3D27D4EB4F, 0x165667B19E3779F9, 0x27D4EB2F165667C5], dtype=np.uint64)
+
+        def checksum(rows):
+            with np.errstate(over="ignore"):
+                return int((rows.view(np.uint64).reshape(-1, 4) * K64[None, :]).sum(dtype=np.uint64))
+        n_rows = pull()
+        mine = host[:n_rows].numpy()
+        counts = [None] * world
+        dist.all_gather_object(counts, int(n_rows))
+        mx = max(counts)
+        pad = torch.zeros((mx, 4), dtype=torch.float64)
+        pad[:n_rows] = host[:n_rows]
+        gathered = [torch.empty((mx, 4), dtype=torch.float64) for _ in range(world)] if rank == 0 else None
+        dist.gather(pad, gathered, dst=0)
+        sweeps_done = h.info()["sweeps_done"]
+        h.upload_ptr(host.data_ptr(), n_rows)            # (both sides restart their regrid phase from an upload)
+        h.reset_counters()
+        h.sweep_nvt(C_, DR_MAX)
+        n_rows = pull()
+        cs_slabs = int(allsum_u64(checksum(host[:n_rows].numpy()), dist, torch))
+        cnt_slabs = [int(x) for x in h.counters()]
+        ok = None
+        if rank == 0:
+            table = np.empty((N, 4))
+            for r_ in range(world):
+                rows = gathered[r_][:counts[r_]].numpy()
+                table[rows[:, 0].astype(np.int64)] = rows
+            del gathered
+            with hsmc_b200.HsmcGpu(N, box, seed=20261017, device=local_rank, cell_min=1.0, regrid_interval=args.regrid,
+                                   sweep_impl=args.sweep_impl, xpart_world=world) as m1:
+                m1.upload(table)
+                m1.set_sweep_counter(sweeps_done)
+                m1.sweep_nvt(C_, DR_MAX)
+                out1 = m1.download()
+                cnt1 = [int(x) for x in m1.counters()]
+            cs1 = checksum(out1)
+            ok = bool(cs1 == cs_slabs and cnt1 == cnt_slabs)
+            chain = {"identical": ok, "sweeps": C_, "rows_checksum_slabs": f"{cs_slabs:016x}", "rows_checksum_one_gpu": f"{cs1:016x}",
+                     "counters_slabs": cnt_slabs[:3], "counters_one_gpu": cnt1[:3],
+                     "what": f"{C_} sweeps from the state after the timed region: {world} slabs vs one GPU with the {world}-slab block partition"}
+        barrier()
+    acc = acc_now
     min_r2 = h.min_dist2()
     assert min_r2 >= 1.0, f"overlap after benchmark: min r^2 = {min_r2}"
     # build (cell-list) kernels: one rebuild per sweep, bytes per particle from DESIGN.md K1
@@ -636,13 +757,23 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = len(os.sched_getaffinity(0))
-        # bounded sample: ~cpu_seconds of CPU work per replica (about 1.1 us per move per core)
-        ncpu = 4 * args.cpu_cells ** 3
-        steps_cpu = max(1, int(args.cpu_seconds / (ncpu * 1.2e-6)))
+        same = nx == ny == nz
+        ccells = nx if same else args.cpu_cells
+        # bounded sample: ~cpu_seconds of CPU work per replica (6.5 us per move per core at N = 17 M, 1.1 us at N = 1 M)
+        per_move = 7.0e-6 if ccells > 100 else 1.2e-6
+        steps_cpu = max(2, int(args.cpu_seconds / (args.cpu_moves_per_step * per_move)))
         try:
-            r = cpu_reference_arm(steps_cpu, 1, args.cpu_cells, 1, cores)
+            reps = cpu_replicas_that_fit(ccells, cores)
+            r = cpu_reference_arm(steps_cpu, 1, ccells, args.cpu_moves_per_step, reps)
             cpu = {"value": r["value"], "unit": "moves/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
-                   "per_core": r["value"] / max(r["cores"], 1)}
+                   "per_core": r["value"] / max(r["cores"], 1), "same_config": same, "host_cores": cores}
+            if same and reps > 1:
+                # one replica alone (no contention for the host's memory bandwidth): the serial reference as its
+                # author runs it, on the same system as the GPU arm
+                r1 = cpu_reference_arm(max(2, steps_cpu // 2), 1, ccells, args.cpu_moves_per_step, 1)
+                cpu["c4_cubic_1core"] = {"value": r1["value"], "unit": "moves/s", "cores": 1, "kind": r1["kind"],
+                                         "sample": r1["sample"], "same_config": True,
+                                         "sweep_seconds_extrapolated": r1["N"] / r1["value"]}
         except Exception as e:   # the baseline is reported, never required
             cpu = {"value": None, "unit": "moves/s", "cores": cores, "kind": "unavailable", "sample": repr(e)}
 
@@ -656,6 +787,9 @@ def main():
                            resident_bytes_per_rank=resident, wall_s_timed_region=t_wall, min_r2_after=min_r2, halo=halo),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         }
+        if chain is not None:
+            line["chain_identical"] = chain["identical"]
+            line["chain_check"] = chain
         if secondary is not None:
             line["secondary"] = secondary
         emit(line)

@@ -1150,8 +1150,13 @@ static int overlap_flags(hsmc_gpu* h, const double* sf, int nn, int* flags_out) 
     sfmin = std::min(sfmin, sf[k]);
   }
   double wmin = std::min(g.wx, std::min(g.wy, g.wz));
-  if (wmin * sfmin < 1.0)
-    return fail("scaled overlap: cell size too small for this compression (cell*sf < 1); increase neigh_list");
+  // cell * sf < 1: pairs two cells apart can overlap after the compression -- wider stencil (the reference
+  // would silently miss them, moves.c:108); exact as long as two compressed cells still span a diameter
+  const bool wide = wmin * sfmin < 1.0;
+  if (wide && h->cfg.world > 1)
+    return fail("scaled overlap: cell size too small for this compression on slabs (cell*sf < 1, one ghost layer); increase neigh_list");
+  if (wide && 2.0 * wmin * sfmin < 1.0)
+    return fail("scaled overlap: compression by more than a factor of two of the cell edge is not supported");
   sa.r2_skip = (1.0 / (sfmin * sfmin)) * (1.0 + 1e-6);
   SfArgs* hsa = (SfArgs*)h->h_stage;
   *hsa = sa;
@@ -1159,8 +1164,12 @@ static int overlap_flags(hsmc_gpu* h, const double* sf, int nn, int* flags_out) 
   int* d_flags = (int*)h->d_scratch;
   CU(cudaMemsetAsync(d_flags, 0, sizeof(int) * MAX_SF, h->st));
   long long total = (long long)(g.own_hi - g.own_lo) * g.ny * g.nz;
-  k_overlap_scaled<<<nblk(total, 128), 128, 0, h->st>>>(g, make_box(g.Lx, g.Ly, g.Lz, 1.0), (const SfArgs*)h->d_sfargs,
-                                                         h->pos[h->cur], h->cell_start, d_flags);
+  if (wide)
+    k_overlap_scaled_wide<<<nblk(total, 128), 128, 0, h->st>>>(g, make_box(g.Lx, g.Ly, g.Lz, 1.0), (const SfArgs*)h->d_sfargs,
+                                                                h->pos[h->cur], h->cell_start, 2, d_flags);
+  else
+    k_overlap_scaled<<<nblk(total, 128), 128, 0, h->st>>>(g, make_box(g.Lx, g.Ly, g.Lz, 1.0), (const SfArgs*)h->d_sfargs,
+                                                           h->pos[h->cur], h->cell_start, d_flags);
   h->launches++;
   CU(cudaGetLastError());
   if (h->cfg.world > 1) {

@@ -48,6 +48,43 @@ k_overlap_scaled(Grid g, Box ubox, const SfArgs* __restrict__ sa, const double4*
   }
 }
 
+// The same verdict when a factor compresses the cells below the particle diameter (cell * sf < 1): pairs two
+// cells apart can then overlap, which the 27-cell stencil cannot see (the reference scans its unscaled
+// 27-stencil there and misses them, moves.c:108 / SURVEY section 7; it then exits in cell_list.c:127 if such
+// a move is accepted).  Rare path (a compression proposal while the cell edge is within dv of 1.0): one thread
+// per owned cell over the full (2R+1)^3 stencil, each unordered pair taken from the lower-id side.  Single
+// GPU only (a slab keeps one ghost layer).
+__global__ void __launch_bounds__(128)
+k_overlap_scaled_wide(Grid g, Box ubox, const SfArgs* __restrict__ sa, const double4* __restrict__ pos,
+                      const int* __restrict__ cs, int R, int* __restrict__ flags) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)g.nlx * g.ny * g.nz;
+  if (t >= total) return;
+  const int nsf = sa->n;
+  int iz = (int)(t % g.nz);
+  long long r = t / g.nz;
+  int iy = (int)(r % g.ny), l = (int)(r / g.ny);
+  const int beg = cs[t], end = cs[t + 1];
+  const double r2_skip = sa->r2_skip;
+  for (int s = beg; s < end; s++) {
+    const double4 p = pos[s];
+    for (int dx = -R; dx <= R; dx++)
+      for (int dy = -R; dy <= R; dy++)
+        for (int dz = -R; dz <= R; dz++) {
+          const int ll = ((l + dx) % g.nlx + g.nlx) % g.nlx, yy = ((iy + dy) % g.ny + g.ny) % g.ny,
+                    zz = ((iz + dz) % g.nz + g.nz) % g.nz;
+          const long long c2 = ((long long)ll * g.ny + yy) * g.nz + zz;
+          for (int k = cs[c2]; k < cs[c2 + 1]; k++) {
+            const double4 q = pos[k];
+            if (!(q.w > p.w)) continue;
+            if (pair_r2(p.x, p.y, p.z, q.x, q.y, q.z, ubox) > r2_skip) continue;
+            for (int m = 0; m < nsf; m++)
+              if (pair_r2_scaled(p.x, p.y, p.z, q.x, q.y, q.z, sa->sf[m], sa->box[m]) < 1.0) flags[m] = 1;
+          }
+        }
+  }
+}
+
 // ----------------------------------------------------------------------------------
 // K4: Widom insertions.  One thread per insertion point; the point is
 // r = u * L (compute_widom_chem_pot.c:73-80) with u from Philox(sample, index).

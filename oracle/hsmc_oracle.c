@@ -251,6 +251,12 @@ int orc_part_move_raw(orc_sys *s, int idx, uint32_t rx, uint32_t ry, uint32_t rz
   return acc;
 }
 
+/* the same, for a whole list of trials (test harness convenience: one call per logged sweep) */
+void orc_replay_moves(orc_sys *s, int n, const int *ids, const uint32_t *raw3, double dr_max, int *accepted) {
+  for (int k = 0; k < n; k++)
+    accepted[k] = orc_part_move_raw(s, ids[k], raw3[3 * k], raw3[3 * k + 1], raw3[3 * k + 2], dr_max);
+}
+
 void orc_counters(const orc_sys *s, int64_t *o) {
   o[0] = s->pm; o[1] = s->apm; o[2] = s->rpm; o[3] = s->vm; o[4] = s->avm; o[5] = s->rvm;
 }

@@ -46,6 +46,7 @@ void orc_overlap_all(const orc_sys *s, double sf, int *flags);
 int orc_any_overlap(const orc_sys *s, double sf);                                /* :106-112 */
 /* part_move (:27-80) driven by explicit raw 32-bit draws: returns 1 accepted, 0 rejected */
 int orc_part_move_raw(orc_sys *s, int idx, uint32_t rx, uint32_t ry, uint32_t rz, double dr_max);
+void orc_replay_moves(orc_sys *s, int n, const int *ids, const uint32_t *raw3, double dr_max, int *accepted);
 void orc_counters(const orc_sys *s, int64_t *out6);
 void orc_reset_counters(orc_sys *s);
 /* rescale after an accepted volume move (:129-142); new box passed in */

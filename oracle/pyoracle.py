@@ -87,6 +87,8 @@ class Port:
             L.orc_overlap_all.argtypes = [C.c_void_p, C.c_double, _ip]
             L.orc_any_overlap.argtypes = [C.c_void_p, C.c_double]
             L.orc_part_move_raw.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double]
+            L.orc_replay_moves.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+            L.orc_replay_moves.restype = None
             L.orc_counters.argtypes = [C.c_void_p, _i64p]
             L.orc_reset_counters.argtypes = [C.c_void_p]
             L.orc_rescale.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double]
@@ -195,11 +197,10 @@ class Port:
 
     def replay_moves(self, ids, raw, dr_max):
         """Drive part_move with explicit (id, rx, ry, rz) draws; returns accept flags."""
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        raw = np.ascontiguousarray(raw, dtype=np.uint32).reshape(-1, 3)
         out = np.zeros(len(ids), dtype=np.int32)
-        f = self.L.orc_part_move_raw
-        h = self.h
-        for k in range(len(ids)):
-            out[k] = f(h, int(ids[k]), int(raw[k, 0]), int(raw[k, 1]), int(raw[k, 2]), dr_max)
+        self.L.orc_replay_moves(self.h, len(ids), ids.ctypes.data, raw.ctypes.data, float(dr_max), out.ctypes.data)
         return out
 
     def counters(self):

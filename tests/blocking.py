@@ -35,3 +35,13 @@ def agree(a, b, nsigma=3.0):
     ma, mb = float(np.mean(a)), float(np.mean(b))
     se = np.hypot(std_error(a), std_error(b))
     return abs(ma - mb) <= nsigma * se, ma, mb, se
+
+
+def family_nsigma(m, nsigma=3.0):
+    """Per-comparison threshold that keeps the FAMILY-WISE two-sided false-alarm probability of m independent
+    comparisons at the level of one nsigma test (Sidak): 1 - (1 - p)^(1/m) with p = erfc(nsigma / sqrt 2).
+    m = 1 gives nsigma back; m = 8 gives 3.59 for nsigma = 3."""
+    from scipy.special import erfc, erfcinv
+    p = erfc(nsigma / np.sqrt(2.0))
+    pk = 1.0 - (1.0 - p) ** (1.0 / m)
+    return float(np.sqrt(2.0) * erfcinv(pk))

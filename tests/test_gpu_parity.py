@@ -90,6 +90,70 @@ def test_global_overlap_verdict(hs, path, oracle_built):
 
 
 @pytest.mark.parametrize("path", GOLDEN_FILES, ids=IDS)
+def test_accepted_volume_move_rescales_like_the_reference(hs, path, oracle_built):
+    """K7 `hsmc_gpu_rescale` = the accepted branch of vol_move (moves.c:135-142): every coordinate times sf,
+    new box, cell list rebuilt.  Coordinates bit for bit against the oracle's rescale (itself checked against
+    the unmodified reference, test_oracle_cpu.py), for an expansion, a compression and a factor that changes the
+    number of cells per axis; the rebuilt cell list must give the oracle's verdicts afterwards."""
+    g = dict(np.load(path))
+    box = np.array(g["box"][:3], dtype=np.float64)
+    N = g["conf"].shape[0]
+    for sf in (1.0 + 3.0e-4, pow(1.0 - 1.0e-3, 1.0 / 3.0), 1.13):
+        p = oracle_built.Port(g["conf"], g["box"], neigh_dr=1.0, max_part=16)
+        new_box = np.array([box[0] * sf, box[1] * sf, box[2] * sf])      # moves.c:129-131 order: edge * sf
+        with _gpu(hs, g) as h:
+            cells0 = h.info()["cells"]
+            h.rescale(sf, new_box)
+            p.rescale(sf, new_box)
+            out = h.download()
+            assert np.array_equal(out, p.get_conf()), f"sf={sf}"
+            assert np.allclose(h.info()["box"], new_box, rtol=0, atol=0)
+            if sf == 1.13:
+                assert h.info()["cells"] != cells0
+            # the rebuilt device cell list answers like the oracle on the rescaled configuration
+            rng = np.random.default_rng(5)
+            idx = rng.integers(0, N, 2000).astype(np.int32)
+            xyz = (out[idx, 1:] + (rng.random((2000, 3)) - 0.5) * 0.4) % new_box[None, :]
+            q = oracle_built.Port(out, new_box, neigh_dr=1.0, max_part=16)
+            assert np.array_equal(h.trial_verdicts(idx, xyz), q.trial_verdicts(idx, xyz))
+            assert h.overlap_scaled(1.0) == q.any_overlap(1.0)
+            # and sweeps go on from there as the same chain the oracle replays
+            log = h.sweep_nvt_logged(0.1)
+            keep = log[log["verdict"] != 2]
+            acc = q.replay_moves(keep["id"], keep["raw"], 0.1)
+            assert np.array_equal(acc, (keep["verdict"] == 0).astype(np.int32))
+            assert np.array_equal(h.download(), q.get_conf())
+
+
+def test_compression_below_the_cell_edge_is_evaluated_not_refused(hs, oracle_built):
+    """with the reference default `neigh_list 1.0` the cell edge L/n can sit anywhere above 1.0, and a
+    volume-move or press_thermo compression with cell*sf < 1 used to be refused (the host driver died).  The
+    verdict is now evaluated over a two-cell stencil; checked against brute-force all-pairs arithmetic in the
+    reference's operation order (the reference's own 27-cell scan misses such pairs, moves.c:108)."""
+    box, conf = oracle_built.Port.lattice(2, 6, 6, 6, 0.9)
+    L = float(box[0])
+    N = conf.shape[0]
+    with hs.HsmcGpu(N, box[:3], seed=11, cell_min=1.0) as h:
+        h.upload(conf)
+        h.sweep_nvt(30, 0.1)
+        out = h.download()
+        w = min(h.info()["cell_size"])
+        # smallest pair distance decides which compressions overlap
+        d = out[:, None, 1:] - out[None, :, 1:]
+        d -= L * np.round(d / L)
+        r = np.sqrt((d ** 2).sum(-1))
+        r[np.arange(N), np.arange(N)] = 9.0
+        rmin = r.min()
+        for sf in (0.999 / w, 0.97 / w, 0.8):
+            assert w * sf < 1.0
+            assert abs(rmin * sf - 1.0) > 1e-9          # (no verdict within rounding of the threshold)
+            assert h.overlap_scaled(sf) == int(rmin * sf < 1.0)
+        sfs = np.array([1.0, 0.9999, 0.999 / w, 0.9 / w])
+        f = h.presst_flags(sfs)
+        assert list(f) == [int(not (rmin * s < 1.0)) for s in sfs]
+
+
+@pytest.mark.parametrize("path", GOLDEN_FILES, ids=IDS)
 def test_widom_verdicts_and_counts(hs, path, oracle_built):
     g = dict(np.load(path))
     box = g["box"]

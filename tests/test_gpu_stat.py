@@ -15,7 +15,7 @@ import pytest
 
 from conftest import GOLDEN, ROOT
 from hsmc_outputs import collect
-from blocking import agree, std_error
+from blocking import agree, family_nsigma, std_error
 
 pytestmark = pytest.mark.gpu
 STAT = os.path.join(GOLDEN, "stat")
@@ -79,15 +79,19 @@ def test_widom_chemical_potential(runs):
     # README table / Adams: mu_ex(rho=0.5) = 3.83-3.86
     assert abs(-np.log(ma) - 3.85) < 0.1
     m1, r1, _ = runs["S1_nvt_rho08"]
-    _check("widom accepted fraction rho=0.8", m1["widom_frac"], r1["widom_frac"], nsigma=4.0)
+    _check("widom accepted fraction rho=0.8", m1["widom_frac"], r1["widom_frac"])
 
 
 def test_radial_distribution_function(runs):
     mine, ref, _ = runs["S1_nvt_rho08"]
     assert np.allclose(mine["rdf_rr"], ref["rdf_rr"])
-    # per-bin 3 sigma near contact (8 bins with per-sample series on both sides)
+    # near contact, bin by bin (8 bins with per-sample series on both sides).  Eight comparisons are one test
+    # here: the per-bin threshold is the Sidak-corrected one that keeps the family-wise false-alarm probability
+    # at that of a single 3 sigma comparison (3.59 sigma per bin)
+    ns = family_nsigma(8, 3.0)
+    assert 3.5 < ns < 3.7
     for k in range(8):
-        _check(f"g(r) bin {k}", mine["rdf_g"][:, k], ref["rdf_g_samples_first8"][:, k], nsigma=3.5)
+        _check(f"g(r) bin {k}", mine["rdf_g"][:, k], ref["rdf_g_samples_first8"][:, k], nsigma=ns)
     # the whole curve: mean absolute deviation of the sample means
     assert np.abs(mine["rdf_g"].mean(axis=0) - ref["rdf_g_mean"]).mean() < 0.01
 

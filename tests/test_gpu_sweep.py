@@ -55,6 +55,31 @@ def test_every_trial_verdict_replays_through_oracle(hs, path, impl, oracle_built
         assert h.cell_rejects() == c[0] - p.counters()[0]
 
 
+@pytest.mark.parametrize("name,lat,rho,neigh,dr_max", [
+    ("C2", (2, 20, 20, 20), 0.9, 1.05, 0.1),        # BASELINE configs[1]: N = 32 000, rho 0.9
+    ("C3", (2, 30, 30, 30), 0.94, 1.1, 0.06),       # BASELINE configs[2]: N = 108 000, rho 0.94 (NpT start)
+])
+def test_replay_at_baseline_sizes(hs, oracle_built, name, lat, rho, neigh, dr_max):
+    """Every trial of three sweeps at the sizes BASELINE.json names for configs 2 and 3, replayed through the
+    oracle's part_move (one C call per sweep): verdicts and final coordinates bit for bit.  At these sizes a
+    box holds several blocks per axis, so interior blocks, wrapped blocks and the fused-phase protocol are all
+    on the path (the small fixtures have two blocks per axis)."""
+    box, conf = oracle_built.Port.lattice(*lat, rho)
+    N = conf.shape[0]
+    p = oracle_built.Port(conf, box, neigh_dr=neigh, max_part=16)
+    with hs.HsmcGpu(N, box[:3], seed=424242, cell_min=neigh) as h:
+        h.upload(conf)
+        h.sweep_nvt(5, dr_max)                       # leave the perfect lattice first
+        p.set_conf(h.download())
+        for sweep in range(3):
+            log = h.sweep_nvt_logged(dr_max)
+            assert len(log) == N and np.array_equal(np.sort(log["id"]), np.arange(N))
+            keep, acc = _replay(p, log, dr_max)
+            assert np.array_equal(acc, (keep["verdict"] == 0).astype(np.int32)), name
+            assert np.array_equal(h.download(), p.get_conf()), name
+        assert h.min_dist2() >= 1.0
+
+
 def test_replay_through_unmodified_reference(hs, oracle_built):
     """Same replay, but through the reference's own part_move() (oracle/_ref)."""
     if not oracle_built.have_ref():
