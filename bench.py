@@ -402,6 +402,154 @@ def widom_workload(args, rank, world, local_rank):
 
 
 # --------------------------------------------------------------------------------------
+# BASELINE configs[1] / configs[2]: whole runs of the input file through the host driver (and, as the reference arm,
+# through the reference executable on the IDENTICAL file): moves/s by the reference's own accounting
+# (`Particle moves` / `Elapsed time`, nvt.c:65-95), sampling hooks included
+# --------------------------------------------------------------------------------------
+CONFIG_INPUTS = {
+    "c2": ("NVT rho=0.9, N=32000 (fcc 20^3), pressure (virial + thermodynamic), RDF and Widom sampling", """rho 0.9
+cells_x 20
+cells_y 20
+cells_z 20
+type 2
+neigh_list 1.05 10
+dr_max 0.1
+opt 1 100 10 0.5 0.5
+press_virial 0.002 20
+press_thermo 0.0001 0.002 20
+rdf 0.01 5.0 50 100
+widom 1000 20
+seed 7
+sweep_eq 100
+sweep_stat 200
+out 50
+"""),
+    "c3": ("NpT P=10 from rho=0.94, N=108000 (fcc 30^3), optimizer-tuned moves, thermodynamic pressure sampling", """npt 10 0.001
+rho 0.94
+cells_x 30
+cells_y 30
+cells_z 30
+type 2
+neigh_list 1.1 12
+dr_max 0.05
+opt 1 100 10 0.5 0.5
+press_thermo 0.0001 0.002 20
+seed 99
+sweep_eq 60
+sweep_stat 100
+out 20
+"""),
+}
+
+
+def _run_driver(exe, text, extra=()):
+    import tempfile
+    d = tempfile.mkdtemp(prefix="hsmc_bench_cfg_")
+    with open(os.path.join(d, "in.dat"), "w") as f:
+        f.write(text)
+    t0 = time.perf_counter()
+    r = subprocess.run([exe, "-o", "out.txt", *extra], cwd=d, capture_output=True, text=True, timeout=1800,
+                       env=dict(os.environ, HSMC_REPORT_LAUNCHES="1"))
+    wall = time.perf_counter() - t0
+    log = open(os.path.join(d, "out.txt")).read() if os.path.exists(os.path.join(d, "out.txt")) else ""
+    if r.returncode != 0 or "Simulation complete!" not in log:
+        raise RuntimeError((r.stdout + r.stderr + log)[-1500:])
+    moves = float(log.split("-- Particle moves:")[1].split()[0])
+    elapsed = float(log.split("Elapsed time:")[1].split()[0])
+    return moves, elapsed, wall, log + r.stderr
+
+
+def config_workload(args, rank, world, local_rank):
+    if rank != 0:
+        return
+    name, text = CONFIG_INPUTS[args.workload]
+    cfg = {"workload": f"BASELINE configs[{1 if args.workload == 'c2' else 2}]: {name}; whole run of the input file below, sampling hooks at "
+                       "the input's intervals", "input": text, "same_config": True}
+    ref_exe = os.path.join(ROOT, "oracle", "_ref", "hsmc_ref")
+    if args.impl == "reference":
+        if not os.path.exists(ref_exe):
+            args.emit({"impl": "reference", "unavailable": "oracle/_ref/hsmc_ref not built (no /root/reference on this box and no prebuilt copy)"})
+            return
+        moves, elapsed, wall, _ = _run_driver(ref_exe, text)
+        args.emit({"impl": "reference", "metric": "hard_sphere_trial_moves_per_sec", "value": moves / elapsed, "unit": "moves/s",
+                   "n_gpus": args.gpus, "steps": 1, "warmup": 0, "ms_per_step": 1e3 * elapsed, "higher_is_better": True,
+                   "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+                   "cpu_baseline": {"value": moves / elapsed, "unit": "moves/s", "cores": 1, "kind": "reference",
+                                    "sample": "the unmodified reference executable (oracle/_ref/hsmc_ref, serial) on the identical input, once"},
+                   "e2e": {"value": moves / wall, "unit": "moves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                   "gpu_launches": 0})
+        return
+    from hsmc_b200 import build
+    exe = build.build_host()
+    extra = ("-g", str(args.gpus)) if args.gpus > 1 else ()
+    sampler = ClockSampler(local_rank)
+    for _ in range(max(1, args.warmup // 3)):
+        _run_driver(exe, text, extra)
+    sampler.start()
+    runs = [_run_driver(exe, text, extra) for _ in range(args.steps)]
+    clocks = sampler.stop()
+    moves = runs[0][0]
+    el = sum(r[1] for r in runs) / len(runs)
+    wall = sum(r[2] for r in runs) / len(runs)
+    launches = None
+    for ln in runs[-1][3].splitlines():
+        if "kernel launches" in ln.lower():
+            launches = int(float(ln.split()[-1]))
+    cpu = None
+    if not args.no_cpu_baseline and os.path.exists(ref_exe):
+        m_r, e_r, w_r, _ = _run_driver(ref_exe, text)
+        cpu = {"value": m_r / e_r, "unit": "moves/s", "cores": 1, "kind": "reference", "same_config": True,
+               "sample": "the unmodified reference executable (oracle/_ref/hsmc_ref, serial) on the identical input file, once",
+               "elapsed_s": e_r, "moves": m_r}
+    # the sweep kernels at this shape, timed in-process (launch-latency-bound at these sizes)
+    roofline = config_roofline(args, text, local_rank)
+    args.emit({"metric": "hard_sphere_trial_moves_per_sec", "value": moves / el, "unit": "moves/s", "n_gpus": args.gpus,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el, "higher_is_better": True, "scaling": "strong",
+               "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": dict(cfg, value_is="Particle moves / Elapsed time as the driver prints them (equilibration + production, "
+                                            "sampling and output files included; the reference's own accounting)"),
+               "clocks": clocks,
+               "e2e": {"value": moves / wall, "unit": "moves/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+                       "what": "the same run by the wall clock of the whole process (CUDA context, upload, output files)",
+                       "wall_s": wall},
+               "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu})
+
+
+def config_roofline(args, text, device):
+    """Sweep path at the shape of a config input, in-process: ms per sweep by profile bucket and the SURVEY 8(d) figure."""
+    try:
+        import hsmc_b200
+        kv = dict(ln.split(None, 1) for ln in text.splitlines() if ln.strip() and not ln.startswith("#"))
+        nx = int(kv["cells_x"]); rho = float(kv["rho"]); cell_min = float(kv["neigh_list"].split()[0]); dr = float(kv["dr_max"])
+        box, conf = fcc_lattice(nx, nx, nx, rho)
+        N = conf.shape[0]
+        with hsmc_b200.HsmcGpu(N, box, seed=1, device=device, cell_min=cell_min) as h:
+            h.upload(conf)
+            h.sweep_nvt(200, dr)
+            h.sync()
+            h.profile(True); h.profile_read()
+            S = 2000
+            t0 = time.perf_counter()
+            h.sweep_nvt(S, dr)
+            h.sync()
+            wall = time.perf_counter() - t0
+            p = h.profile_read()
+            info = h.info()
+        nbar = N / (info["cells"][0] * info["cells"][1] * info["cells"][2])
+        b_move = 16.0 * (27.0 * nbar + 2.0)
+        peak, peak_src = measured_peak()
+        k_ms = p["sweep"][0] / S
+        return {"bound": "hbm (launch latency at this size: the whole table fits L2)", "kernel": "k_sweep_lean",
+                "achieved": N * b_move / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": N * b_move / (k_ms * 1e-3) / 1e9 / peak,
+                "peak_source": peak_src, "algorithmic_bytes_per_move": b_move, "nbar": nbar, "traffic": None,
+                "ms_per_sweep": {k: v[0] / S for k, v in p.items()}, "wall_ms_per_sweep": 1e3 * wall / S,
+                "moves_per_s_sweeps_only": N * S / wall,
+                "what": f"{S} plain sweeps of the same shape (N={N}) after 200 warm-up sweeps, CUDA events per launch group"}
+    except Exception as e:      # reported, never required
+        return {"error": repr(e)}
+
+
+# --------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -421,8 +569,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep-impl", type=int, default=0)
     ap.add_argument("--no-secondary", action="store_true", help="skip the observables' kernel timings (N=1 only)")
-    ap.add_argument("--workload", default="sweep", choices=["sweep", "widom"],
-                    help="sweep: the headline metric (default); widom: BASELINE configs[4], insertions sharded over the GPUs")
+    ap.add_argument("--workload", default="sweep", choices=["sweep", "widom", "c2", "c3"],
+                    help="sweep: the headline metric (default, BASELINE configs[3]); widom: configs[4], insertions sharded over the "
+                         "GPUs; c2 / c3: configs[1] / configs[2] run through the drop-in host driver on their input files "
+                         "(the reference arm runs the reference executable on the identical file)")
     ap.add_argument("--insertions", type=float, default=1e8, help="--workload widom: insertions per sample and density")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -445,6 +595,8 @@ def main():
     args.emit = emit
     if args.workload == "widom" and args.impl == "b200":
         return widom_workload(args, rank, world, local_rank)
+    if args.workload in ("c2", "c3"):
+        return config_workload(args, rank, world, local_rank)
     nx, ny, nz = args.cells
     N = 4 * nx * ny * nz
     workload = {

@@ -93,8 +93,9 @@ struct BlockCfg {
 // per-row staging record: global slots of the row's one or two pieces, staged offset
 struct BlockRow { int gbA, gbB, cntA, off; };
 
-// header of a block's plan: ints [0] staged particles, [1..8] trials per cell colour, [9] flags, [10] first trial slot
-enum { PLAN_TOTAL = 0, PLAN_NTR = 1, PLAN_FLAGS = 9, PLAN_TBASE = 10, PLAN_HDR_INTS = 16 };
+// header of a block's plan: ints [0] staged particles, [1..8] trial slots per cell colour, [9] flags, [10] first trial slot,
+// [11] pair-records per stencil row the sweep's straight-line scan must cover
+enum { PLAN_TOTAL = 0, PLAN_NTR = 1, PLAN_FLAGS = 9, PLAN_TBASE = 10, PLAN_NPAIRS = 11, PLAN_HDR_INTS = 16 };
 enum { PLAN_BAD = 1, PLAN_DEEP = 2 };
 
 struct LeanPlan {
@@ -389,7 +390,7 @@ static void setup_blocks(hsmc_gpu* h) {
     const size_t rows = (size_t)(mx + 2) * (my + 2);
     size_t smem = (size_t)cap * 12 + rows * cz_stride * 2 + rows * 16 + PLAN_HDR_INTS * 4;
     size_t smem_r1 = (size_t)cap * 16 + rows * cz_stride * 2 + (size_t)8 * tr_cap * 4;
-    size_t smem_plan = rows * cz_stride * 2 + (size_t)8 * tr_cap * 4;
+    size_t smem_plan = rows * cz_stride * 2 + (size_t)8 * tr_cap * 4 + (size_t)mx * my * 32 * 2;
     smem = (smem + 15) & ~(size_t)15; smem_r1 = (smem_r1 + 15) & ~(size_t)15; smem_plan = (smem_plan + 15) & ~(size_t)15;
     if ((r1 ? smem_r1 : smem) > 100 * 1024 || smem_plan > 100 * 1024) return false;
     s = {bx, by, bz, mx, my, mz, cap, tr_cap, smem, smem_r1, smem_plan};

@@ -35,7 +35,8 @@
 #ifndef LEAN_MIN_CTAS
 #define LEAN_MIN_CTAS 5
 #endif
-#define LEAN_NP 4               // pair-records (8 entries) scanned per stencil row before the deep loop
+#define LEAN_NP_MIN 3           // pair-records (2 entries each) scanned per stencil row in straight-line code:
+#define LEAN_NP_MAX 5           //   chosen per block by k_block_plan from its longest stencil row; beyond MAX: deep loop
 #define LEAN_PAD 10             // far-away entries after the last staged particle (covers the over-scan)
 #define LEAN_FAR 1.0e15f
 #define LEAN_MAX_OCC 8          // most particles per cell (3-bit trial index)
@@ -96,22 +97,24 @@ k_block_plan(SweepArgs a, BlockCfg bc, LeanPlan pl, const int* __restrict__ xoff
              const int* __restrict__ cs, double4* __restrict__ prop) {
   const Grid& g = a.g;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  unsigned short* s_cz = reinterpret_cast<unsigned short*>(smem_raw);                       // [max_rows][cz_stride]
+  unsigned short* s_cz = reinterpret_cast<unsigned short*>(smem_raw);                          // [max_rows][cz_stride]
   unsigned int* s_desc = reinterpret_cast<unsigned int*>(s_cz + bc.max_rows * bc.cz_stride);   // [desc_cap]
+  unsigned short* s_pre = reinterpret_cast<unsigned short*>(s_desc + bc.desc_cap);             // [interior rows][32]
   __shared__ BlockRow s_row[LEAN_MAX_ROWS];
   __shared__ int s_cnt[LEAN_MAX_ROWS + 1];
   __shared__ int s_grow[LEAN_MAX_ROWS];
-  __shared__ int s_rc[2 * LEAN_MAX_ROWS];      // per interior row and z parity (a "run"): offset of the run in its colour's list
-  __shared__ unsigned long long s_occ[2 * LEAN_MAX_ROWS];
-  __shared__ int s_ntr[8], s_cbase[9], s_flags, s_tbase;
-  const int tid = threadIdx.x;
+  __shared__ int s_rc[2 * LEAN_MAX_ROWS];      // per interior row and z parity (a "run"): trials, then offset in its colour's list
+  __shared__ int s_ntr[8], s_cbase[9], s_flags, s_need, s_tbase;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NWP = PLAN_THREADS / 32;
   const int czs = bc.cz_stride;
+  const unsigned FULL = 0xffffffffu;
 
   const int bl = blockIdx.x;
   const int bzi = bl % bc.nbz, byi = (bl / bc.nbz) % bc.nby, bxi = bl / (bc.nbz * bc.nby);
   const BlkGeom q = blk_geom(g, bc, xoff, bxi, byi, bzi);
   const int nrows = q.nrows, nry = q.nry, lenz = q.lenz;
-  if (tid == 0) s_flags = 0;
+  if (tid == 0) { s_flags = 0; s_need = 0; }
 
   // ---- staging rows: one or two contiguous slot ranges of the cell-ordered table each ----------------
   for (int r = tid; r < nrows; r += PLAN_THREADS) {
@@ -133,92 +136,111 @@ k_block_plan(SweepArgs a, BlockCfg bc, LeanPlan pl, const int* __restrict__ xoff
       int inc = v;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        const int t = __shfl_up_sync(FULL, inc, o);
         if (tid >= o) inc += t;
       }
-      if (r < nrows) s_cnt[r] = carry + inc - v;
-      carry += __shfl_sync(0xffffffffu, inc, 31);
+      if (r < nrows) s_row[r].off = carry + inc - v;
+      carry += __shfl_sync(FULL, inc, 31);
     }
-    if (tid == 0) s_cnt[nrows] = carry;
+    if (tid == 0) {
+      s_cnt[nrows] = carry;
+      if (carry + LEAN_PAD > bc.cap) atomicOr(&s_flags, PLAN_BAD);
+    }
   }
   __syncthreads();
   const int total = s_cnt[nrows];
-  for (int r = tid; r < nrows; r += PLAN_THREADS) s_row[r].off = s_cnt[r];
-  if (tid == 0 && total + LEAN_PAD > bc.cap) atomicOr(&s_flags, PLAN_BAD);
-  __syncthreads();
 
-  // ---- staged index of the first particle of every region cell ----------------------------------------
-  for (int idx = tid; idx < nrows * (lenz + 1); idx += PLAN_THREADS) {
-    const int r = idx / (lenz + 1), zi = idx - r * (lenz + 1);
+  // ---- one warp per staged row, one lane per cell of the row (at most 32): staged index of the first particle
+  //      of every cell; longest stencil row; for interior rows the trials of each z parity ("run") and every
+  //      cell's offset inside its run ----------------------------------------------------------------------
+  const int parx = (g.gx0 + q.x0) & 1, pary = q.y0 & 1, parz = q.z0 & 1;   // parity of region cell (0,0,0); grids are even
+  unsigned short* gcz = pl.cz + (size_t)bl * bc.max_rows * czs;
+  for (int r = warp; r < nrows; r += NWP) {
+    const int rx = r / nry, ry = r - rx * nry;
     const long long rbase = (long long)s_grow[r] * g.nz;
     const BlockRow rw = s_row[r];
-    const int z = q.zs + zi;
-    const int v = (z <= g.nz) ? rw.off + (cs[rbase + z] - rw.gbA) : rw.off + rw.cntA + (cs[rbase + (z - g.nz)] - rw.gbB);
-    s_cz[r * czs + zi] = (unsigned short)v;
-  }
-  __syncthreads();
-
-  // ---- trials per (interior row, z parity); cells deeper than the scheme handles ---------------------------
-  const int parx = (g.gx0 + q.x0) & 1, pary = q.y0 & 1, parz = q.z0 & 1;   // parity of region cell (0,0,0); grids are even
-  const int nint = q.ex * q.ey;
-  for (int idx = tid; idx < 2 * nint; idx += PLAN_THREADS) {
-    const int ri = idx >> 1, p = idx & 1;
-    const int rx = ri / q.ey + 1, ry = ri - (rx - 1) * q.ey + 1;
-    const unsigned short* cz = s_cz + (rx * nry + ry) * czs;
-    unsigned long long occ = 0;                 // occupancy of the run's cells, one nibble each (<= 15 cells of <= 8)
-    bool deep = false;
-    int sh = 0;
-    for (int zi = 1 + ((parz + 1 + p) & 1); zi <= q.ez; zi += 2, sh += 4) {     // cells with (parz + zi) & 1 == p
-      const int n = (int)cz[zi + 1] - (int)cz[zi];
-      deep |= n > LEAN_MAX_OCC;
-      occ |= (unsigned long long)(n & 15) << sh;
+    const int zi = lane, z = q.zs + zi;
+    int v = 0;
+    if (zi <= lenz) {
+      v = (z <= g.nz) ? rw.off + (cs[rbase + z] - rw.gbA) : rw.off + rw.cntA + (cs[rbase + (z - g.nz)] - rw.gbB);
+      s_cz[r * czs + zi] = (unsigned short)v;
+      gcz[r * czs + zi] = (unsigned short)v;
     }
-    s_occ[idx] = occ;
-    if (deep) atomicOr(&s_flags, PLAN_BAD);
-  }
-  // stencil rows longer than the straight-line scan covers (block-uniform flag: the sweep then runs its deep loop)
-  for (int idx = tid; idx < nrows * q.ez; idx += PLAN_THREADS) {
-    const int r = idx / q.ez, zi = idx - r * q.ez + 1;
-    const unsigned short* cz = s_cz + r * czs;
-    const int b = cz[zi - 1], e = cz[zi + 2];
-    if (e - (b & ~1) > 2 * LEAN_NP) atomicOr(&s_flags, PLAN_DEEP);
+    const int vn = __shfl_down_sync(FULL, v, 1), vb = __shfl_up_sync(FULL, v, 1), ve = __shfl_down_sync(FULL, v, 2);
+    const bool zint = zi >= 1 && zi <= q.ez;
+    const int n = zint ? vn - v : 0;
+    // entries a trial in cell zi scans in this row, from the pair-aligned start of cell zi-1 to the end of cell zi+1
+    const int need = __reduce_max_sync(FULL, zint ? ve - (vb & ~1) : 0);
+    if (lane == 0) atomicMax(&s_need, need);
+    if (rx >= 1 && rx <= q.ex && ry >= 1 && ry <= q.ey) {
+      const int ri = (rx - 1) * q.ey + (ry - 1);
+      if (__any_sync(FULL, n > LEAN_MAX_OCC) && lane == 0) atomicOr(&s_flags, PLAN_BAD);
+      const int par = (parz + zi) & 1;
+      int inc = par ? (n << 16) : n;                 // both parities in one scan
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += t;
+      }
+      const int tot = __shfl_sync(FULL, inc, 31);
+      const int pre = par ? (inc >> 16) - n : (inc & 0xffff) - n;
+      if (zint) s_pre[ri * 32 + zi] = (unsigned short)pre;
+      if (lane == 0) { s_rc[2 * ri] = tot & 0xffff; s_rc[2 * ri + 1] = tot >> 16; }
+    }
   }
   __syncthreads();
-  // per colour: offset of every run in the colour's list, rows in (rx, ry) order.  The trials of one cell never
-  // straddle a 32-slot chunk (chunks of a colour run concurrently on different warps; the trials of a cell are
-  // ordered): a cell that would is moved to the next chunk boundary, the gap holds invalid slots.
+  // ---- per colour (one thread each): place the runs, rows in (rx, ry) order, in the colour's list.  A colour's
+  //      trials are split evenly over its chunks (each chunk is one warp's work between two colour barriers), and
+  //      the trials of one cell never straddle a chunk (chunks of a colour run concurrently, the trials of a cell
+  //      are ordered): a cell that would is moved to the start of the next chunk; skipped slots stay invalid.
   if (tid < 8) {
-    int run = 0;
-    for (int ri = 0; ri < nint; ri++) {
-      const int rx = ri / q.ey + 1, ry = ri - (rx - 1) * q.ey + 1;
-      const int colxy = (((parx + rx) & 1) << 2) | (((pary + ry) & 1) << 1);
-      if (colxy == (tid & 6)) {
-        s_rc[2 * ri + (tid & 1)] = run;
-        for (unsigned long long occ = s_occ[2 * ri + (tid & 1)]; occ; occ >>= 4) {
-          const int n = (int)(occ & 15);
-          if ((run & 31) + n > 32) run = (run + 31) & ~31;
-          run += n;
+    const int p = tid & 1;
+    int sum = 0;
+    for (int rx = 1, ri = 0; rx <= q.ex; rx++)
+      for (int ry = 1; ry <= q.ey; ry++, ri++)
+        if (((((parx + rx) & 1) << 2) | (((pary + ry) & 1) << 1)) == (tid & 6)) sum += s_rc[2 * ri + p];
+    const int nch = max(1, (sum + 31) >> 5);
+    const int ccap = min(32, (sum + nch - 1) / nch + 2);        // chunk capacity (+2: room for the moved cells)
+    int at = 0;
+    for (int rx = 1, ri = 0; rx <= q.ex; rx++)
+      for (int ry = 1; ry <= q.ey; ry++, ri++) {
+        if (((((parx + rx) & 1) << 2) | (((pary + ry) & 1) << 1)) != (tid & 6)) continue;
+        const int len = s_rc[2 * ri + p];
+        if ((at & 31) >= ccap) at = (at + 31) & ~31;
+        s_rc[2 * ri + p] = at;
+        if ((at & 31) + len <= ccap) { at += len; continue; }
+        // the run crosses a chunk boundary: walk its cells
+        const unsigned short* cz = s_cz + (rx * nry + ry) * czs;
+        unsigned short* pre = s_pre + ri * 32;
+        const int start = at;
+        for (int zi = 1 + ((parz + 1 + p) & 1); zi <= q.ez; zi += 2) {
+          const int n = (int)cz[zi + 1] - (int)cz[zi];
+          if (n == 0) continue;
+          if ((at & 31) + n > ccap) at = (at + 31) & ~31;
+          pre[zi] = (unsigned short)(at - start);
+          at += n;
         }
       }
-    }
-    s_ntr[tid] = run;
+    s_ntr[tid] = at;
   }
   __syncthreads();
   if (tid == 0) {
     int base = 0;
     for (int c = 0; c < 8; c++) { s_cbase[c] = base; base += (s_ntr[c] + 31) & ~31; }
     s_cbase[8] = base;
-    if (base > bc.desc_cap) s_flags |= PLAN_BAD;
+    if (base > bc.desc_cap) atomicOr(&s_flags, PLAN_BAD);
     unsigned int tb = 0;
     if (!(s_flags & PLAN_BAD)) {
       tb = atomicAdd(pl.cursor, (unsigned int)base);
-      if ((long long)tb + base > pl.cap_trials) s_flags |= PLAN_BAD;
+      if ((long long)tb + base > pl.cap_trials) atomicOr(&s_flags, PLAN_BAD);
     }
     s_tbase = (int)tb;
+    // pair-records the straight-line scan must cover; beyond LEAN_NP_MAX the sweep runs its deep loop too
+    if (s_need > 2 * LEAN_NP_MAX) atomicOr(&s_flags, PLAN_DEEP);
   }
   __syncthreads();
   const int flags = s_flags;
-  // ---- the plan goes to global memory ---------------------------------------------------------------------
+  // ---- header and rows go to global memory (the cell indices went out above) ---------------------------------
   {
     int* hdr = pl.hdr + (size_t)bl * PLAN_HDR_INTS;
     if (tid < PLAN_HDR_INTS) {
@@ -227,84 +249,74 @@ k_block_plan(SweepArgs a, BlockCfg bc, LeanPlan pl, const int* __restrict__ xoff
       else if (tid >= PLAN_NTR && tid < PLAN_NTR + 8) v = s_ntr[tid - PLAN_NTR];
       else if (tid == PLAN_FLAGS) v = flags;
       else if (tid == PLAN_TBASE) v = s_tbase;
+      else if (tid == PLAN_NPAIRS) v = min(LEAN_NP_MAX, max(LEAN_NP_MIN, (s_need + 1) >> 1));
       hdr[tid] = v;
     }
     int4* grow = reinterpret_cast<int4*>(pl.row + (size_t)bl * bc.max_rows);
     for (int r = tid; r < nrows; r += PLAN_THREADS) grow[r] = reinterpret_cast<const int4*>(s_row)[r];
-    // (rows of 8 ushorts = 16 bytes; cz_stride is a multiple of 8)
-    uint4* gcz = reinterpret_cast<uint4*>(pl.cz + (size_t)bl * bc.max_rows * czs);
-    const uint4* scz4 = reinterpret_cast<const uint4*>(s_cz);
-    for (int i = tid; i < nrows * (czs >> 3); i += PLAN_THREADS) gcz[i] = scz4[i];
   }
   if (flags & PLAN_BAD) return;              // the sweep runs this block from global memory (no proposals needed)
 
-  // ---- trial descriptors, per colour in (row, z, trial index) order ------------------------------------------
-  for (int idx = tid; idx < 2 * nint; idx += PLAN_THREADS) {
-    const int ri = idx >> 1, p = idx & 1;
+  // ---- trial descriptors ----------------------------------------------------------------------------------
+  const int nslots = s_cbase[8];
+  for (int u = tid; u < nslots; u += PLAN_THREADS) s_desc[u] = LEAN_INVALID;
+  __syncthreads();
+  for (int ri = warp; ri < q.ex * q.ey; ri += NWP) {
     const int rx = ri / q.ey + 1, ry = ri - (rx - 1) * q.ey + 1;
-    const int col = (((parx + rx) & 1) << 2) | (((pary + ry) & 1) << 1) | p;
-    const unsigned short* cz = s_cz + (rx * nry + ry) * czs;
-    unsigned int* out = s_desc + s_cbase[col];
-    int at = s_rc[idx];
-    for (int zi = 1 + ((parz + 1 + p) & 1); zi <= q.ez; zi += 2) {
+    const int zi = lane;
+    if (zi >= 1 && zi <= q.ez) {
+      const int p = (parz + zi) & 1;
+      const int col = (((parx + rx) & 1) << 2) | (((pary + ry) & 1) << 1) | p;
+      const unsigned short* cz = s_cz + (rx * nry + ry) * czs;
       const int b = cz[zi], n = (int)cz[zi + 1] - b;
-      if ((at & 31) + n > 32)
-        for (const int to = (at + 31) & ~31; at < to; at++) out[at] = LEAN_INVALID;
-      for (int j = 0; j < n; j++) out[at++] = LEAN_CODE(b, rx, ry, zi, j, n - 1);
+      unsigned int* out = s_desc + s_cbase[col] + s_rc[2 * ri + p] + s_pre[ri * 32 + zi];
+      for (int j = 0; j < n; j++) out[j] = LEAN_CODE(b, rx, ry, zi, j, n - 1);
     }
   }
   __syncthreads();
 
   // ---- proposals: the reference's trial point (moves.c:52-57), apply_pbc (moves.c:215-226), cell test ---------
   const long long tbase = s_tbase;
-#pragma unroll 1
-  for (int col = 0; col < 8; col++) {
-    const int ntr = s_ntr[col], cb = s_cbase[col];
-#pragma unroll 1
-    for (int t = tid; t < ntr; t += PLAN_THREADS) {
-      const unsigned int d = s_desc[cb + t];
-      if (d == LEAN_INVALID) { pl.trial[tbase + cb + t] = make_uint4(0u, 0u, 0u, LEAN_INVALID); continue; }
-      const int ob = d & 0xfff, rx = (d >> 12) & 15, ry = (d >> 16) & 15, rz = (d >> 20) & 31;
-      const int j = (d >> 25) & 7, n1 = (d >> 28) & 7;
-      const BlockRow rw = s_row[rx * nry + ry];
-      const int o = ob - rw.off;
-      const int gs0 = (o < rw.cntA) ? rw.gbA + o : rw.gbB + o - rw.cntA;
-      // the particle with exactly j smaller ids in its cell
-      int k = 0;
-      if (n1 > 0) {
-        double ids[LEAN_MAX_OCC];
-#pragma unroll
-        for (int m = 0; m < LEAN_MAX_OCC; m++) ids[m] = (m <= n1) ? pos[gs0 + m].w : 1e300;
-#pragma unroll
-        for (int m = 0; m < LEAN_MAX_OCC; m++) {
-          int c2 = 0;
-#pragma unroll
-          for (int m2 = 0; m2 < LEAN_MAX_OCC; m2++) c2 += ids[m2] < ids[m];
-          if (m <= n1 && c2 == j) k = m;
-        }
+#pragma unroll 2
+  for (int u = tid; u < nslots; u += PLAN_THREADS) {
+    const unsigned int d = s_desc[u];
+    if (d == LEAN_INVALID) { pl.trial[tbase + u] = make_uint4(0u, 0u, 0u, LEAN_INVALID); continue; }
+    const int ob = d & 0xfff, rx = (d >> 12) & 15, ry = (d >> 16) & 15, rz = (d >> 20) & 31;
+    const int j = (d >> 25) & 7, n1 = (d >> 28) & 7;
+    const BlockRow rw = s_row[rx * nry + ry];
+    const int o = ob - rw.off;
+    const int gs0 = (o < rw.cntA) ? rw.gbA + o : rw.gbB + o - rw.cntA;
+    // the particle with exactly j smaller ids in its cell (cells rarely hold more than three)
+    int k = 0;
+    if (n1 > 0) {
+      for (int m = 0; m <= n1; m++) {
+        const double idm = pos[gs0 + m].w;
+        int c2 = 0;
+        for (int m2 = 0; m2 <= n1; m2++) c2 += pos[gs0 + m2].w < idm;
+        if (c2 == j) k = m;
       }
-      const int gs = gs0 + k;
-      const double4 p = pos[gs];
-      const int iy = q.y0 + ry, iz = q.z0 + rz;
-      const int gxl = g.gx0 + q.x0 + rx;
-      const int gx = (gxl >= g.nx) ? gxl - g.nx : gxl;          // interior cells never wrap inside the block
-      const long long gcell = ((long long)gx * g.ny + iy) * g.nz + iz;
-      const Philox4 rn = philox4x32_10((uint32_t)gcell, (HSMC_STREAM_MOVE << 24) | (uint32_t)j, a.sweep_lo, a.sweep_hi, a.key0, a.key1);
-      double xn = p.x + (hsmc_u01(rn.v[0]) - 0.5) * a.dr_max;
-      double yn = p.y + (hsmc_u01(rn.v[1]) - 0.5) * a.dr_max;
-      double zn = p.z + (hsmc_u01(rn.v[2]) - 0.5) * a.dr_max;
-      if (xn > g.Lx) xn -= g.Lx; else if (xn < 0.0) xn += g.Lx;
-      if (yn > g.Ly) yn -= g.Ly; else if (yn < 0.0) yn += g.Ly;
-      if (zn > g.Lz) zn -= g.Lz; else if (zn < 0.0) zn += g.Lz;
-      const bool act = axis_cell(xn, g.sx, g.iwx, g.nx) == gx && axis_cell(yn, g.sy, g.iwy, g.ny) == iy &&
-                       axis_cell(zn, g.sz, g.iwz, g.nz) == iz;
-      float4 nrel = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (act) nrel = make_rel(g, gx, iy, iz, xn, yn, zn, p.w);
-      const unsigned int code = LEAN_CODE(ob + k, rx, ry, rz, j, n1) | (act ? 0x80000000u : 0u);
-      pl.trial[tbase + cb + t] = make_uint4(__float_as_uint(nrel.x), __float_as_uint(nrel.y), __float_as_uint(nrel.z), code);
-      prop[gs] = make_double4(xn, yn, zn, p.w);
-      if (LOG) pl.raw[tbase + cb + t] = make_uint4(rn.v[0], rn.v[1], rn.v[2], (unsigned int)(int)p.w);
     }
+    const int gs = gs0 + k;
+    const double4 p = pos[gs];
+    const int iy = q.y0 + ry, iz = q.z0 + rz;
+    const int gxl = g.gx0 + q.x0 + rx;
+    const int gx = (gxl >= g.nx) ? gxl - g.nx : gxl;          // interior cells never wrap inside the block
+    const long long gcell = ((long long)gx * g.ny + iy) * g.nz + iz;
+    const Philox4 rn = philox4x32_10((uint32_t)gcell, (HSMC_STREAM_MOVE << 24) | (uint32_t)j, a.sweep_lo, a.sweep_hi, a.key0, a.key1);
+    double xn = p.x + (hsmc_u01(rn.v[0]) - 0.5) * a.dr_max;
+    double yn = p.y + (hsmc_u01(rn.v[1]) - 0.5) * a.dr_max;
+    double zn = p.z + (hsmc_u01(rn.v[2]) - 0.5) * a.dr_max;
+    if (xn > g.Lx) xn -= g.Lx; else if (xn < 0.0) xn += g.Lx;
+    if (yn > g.Ly) yn -= g.Ly; else if (yn < 0.0) yn += g.Ly;
+    if (zn > g.Lz) zn -= g.Lz; else if (zn < 0.0) zn += g.Lz;
+    const bool act = axis_cell(xn, g.sx, g.iwx, g.nx) == gx && axis_cell(yn, g.sy, g.iwy, g.ny) == iy &&
+                     axis_cell(zn, g.sz, g.iwz, g.nz) == iz;
+    float4 nrel = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (act) nrel = make_rel(g, gx, iy, iz, xn, yn, zn, p.w);
+    const unsigned int code = LEAN_CODE(ob + k, rx, ry, rz, j, n1) | (act ? 0x80000000u : 0u);
+    pl.trial[tbase + u] = make_uint4(__float_as_uint(nrel.x), __float_as_uint(nrel.y), __float_as_uint(nrel.z), code);
+    prop[gs] = make_double4(xn, yn, zn, p.w);
+    if (LOG) pl.raw[tbase + u] = make_uint4(rn.v[0], rn.v[1], rn.v[2], (unsigned int)(int)p.w);
   }
 }
 
@@ -349,6 +361,26 @@ __device__ __forceinline__ float lean_pair(const ulonglong2 xy, const unsigned l
   float lo, hi;
   f2_unpack(r2, lo, hi);
   return f_min3(r2min, lo, hi);
+}
+
+// the fp32 filter over the 27-cell stencil of one trial: nine (x,y) rows, NP pair-records each, read at fixed offsets
+// from the pair-aligned start of cell rz-1, unmasked (entries past the row's three cells are real particles farther
+// along -- true positions, so harmless -- or the far-away pad after the last staged particle)
+template <int NP>
+__device__ __forceinline__ float lean_scan(const ulonglong2* __restrict__ s_xy, const unsigned long long* __restrict__ s_z2,
+                                           const unsigned short* __restrict__ cp0, int nry, int czs, float tx, float ty,
+                                           float tz) {
+  const unsigned long long TX = f2_pack(tx, tx), TY = f2_pack(ty, ty), TZ = f2_pack(tz, tz);
+  float r2min = 3.0e38f;
+#pragma unroll
+  for (int r = 0; r < 9; r++) {
+    const int p0 = (int)cp0[((r / 3) * nry + (r % 3)) * czs] >> 1;
+    const ulonglong2* pxy = s_xy + p0;
+    const unsigned long long* pz = s_z2 + p0;
+#pragma unroll
+    for (int s = 0; s < NP; s++) r2min = lean_pair(pxy[s], pz[s], TX, TY, TZ, r2min);
+  }
+  return r2min;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -436,36 +468,43 @@ k_sweep_lean(SweepArgs a, BlockCfg bc, LeanPlan pl, const int* __restrict__ xoff
 
   int n_acc = 0, n_ov = 0, n_cell = 0;
   if (!(pflags & PLAN_BAD) && !bc.force_global) {
-    // ---- stage the fp32 shadow: block-relative x and y now, z after the barrier (it needs the cell) -------------
+    // ---- stage the fp32 shadow as block-relative coordinates fma(cell index - centre, edge, offset) -----------------
     const float wxf = (float)g.wx, wyf = (float)g.wy, wzf = (float)g.wz;
     const float hxr = 0.5f * (float)q.nrx, hyr = 0.5f * (float)nry, hzr = 0.5f * (float)lenz;
     {
-      // each staged row is cut into P runs, one (row, run) item per thread and round
-      int P = 1;
-      {
-        int best = 1 << 30;
-        for (int c = 1; c <= 4; c++) {
-          const int cost = ((c * nrows + LEAN_THREADS - 1) / LEAN_THREADS) * ((lenz + c - 1) / c + 2);
-          if (cost < best) { best = cost; P = c; }
-        }
-      }
+      // each staged row is cut into P runs of particles, one (row, run) item per thread and round; a thread first
+      // issues all the loads of a batch, then converts them (the cell of a particle follows from the row's cell index)
+      const int P = (2 * nrows <= LEAN_THREADS) ? 2 : 1;
 #pragma unroll 1
       for (int idx = tid; idx < P * nrows; idx += LEAN_THREADS) {
-        const int r = idx / P, piece = idx - r * P;
+        const int r = (P == 2) ? idx >> 1 : idx, piece = (P == 2) ? idx & 1 : 0;
         const BlockRow rw = s_row[r];
         const int cntr = ((r + 1 < nrows) ? s_row[r + 1].off : total) - rw.off;
         const int k0 = (cntr * piece) / P, k1 = (cntr * (piece + 1)) / P;
         const int rx = r / nry, ry = r - rx * nry;
         const float cxw = ((float)rx - hxr), cyw = ((float)ry - hyr);
-#pragma unroll 4
-        for (int k = k0; k < k1; k++) {
-          const int gsrc = (k < rw.cntA) ? rw.gbA + k : rw.gbB + (k - rw.cntA);
-          const float4 v = __ldcg(rel + gsrc);      // L2: neighbours' blocks wrote these earlier in this launch
-          const int i = rw.off + k;
-          float* xy = s_xyf + ((i >> 1) << 2) + (i & 1);
-          xy[0] = __fmaf_rn(cxw, wxf, v.x);
-          xy[2] = __fmaf_rn(cyw, wyf, v.y);
-          s_zf[i] = v.z;
+        const unsigned short* cz = s_cz + r * czs;
+        int zi = 0, nextb = cz[1];                       // cell of the particle being converted; start of the next cell
+#pragma unroll 1
+        for (int kb = k0; kb < k1; kb += 8) {
+          float4 v[8];
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            const int k = kb + u;
+            if (k < k1) v[u] = __ldcg(rel + ((k < rw.cntA) ? rw.gbA + k : rw.gbB + (k - rw.cntA)));   // L2: neighbours' blocks wrote these earlier in this launch
+          }
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            const int k = kb + u;
+            if (k < k1) {
+              const int i = rw.off + k;
+              while (i >= nextb && zi < lenz - 1) { zi++; nextb = cz[zi + 1]; }
+              float* xy = s_xyf + ((i >> 1) << 2) + (i & 1);
+              xy[0] = __fmaf_rn(cxw, wxf, v[u].x);
+              xy[2] = __fmaf_rn(cyw, wyf, v[u].y);
+              s_zf[i] = __fmaf_rn((float)zi - hzr, wzf, v[u].z);
+            }
+          }
         }
       }
       if (tid < LEAN_PAD) {
@@ -475,20 +514,12 @@ k_sweep_lean(SweepArgs a, BlockCfg bc, LeanPlan pl, const int* __restrict__ xoff
       }
     }
     __syncthreads();
-#pragma unroll 1
-    for (int idx = tid; idx < nrows * lenz; idx += LEAN_THREADS) {
-      const int r = idx / lenz, zi = idx - r * lenz;
-      const unsigned short* cz = s_cz + r * czs;
-      const int b = cz[zi], e = cz[zi + 1];
-      const float czw = (float)zi - hzr;
-      for (int k = b; k < e; k++) s_zf[k] = __fmaf_rn(czw, wzf, s_zf[k]);
-    }
-    __syncthreads();
 
     // ---- trials -----------------------------------------------------------------------------------------------
     const unsigned FULL = 0xffffffffu;
     const float lo = 1.0f - a.eps, hi = 1.0f + a.eps;
     const bool deep_rows = (pflags & PLAN_DEEP) != 0;
+    const int npairs = s_hdr[PLAN_NPAIRS];
     int cbase = 0;
 #pragma unroll 1
     for (int col = 0; col < 8; col++) {
@@ -503,7 +534,7 @@ k_sweep_lean(SweepArgs a, BlockCfg bc, LeanPlan pl, const int* __restrict__ xoff
         {
           const bool same = (chunk + NW) * 32 < ntr;
           const long long nt = same ? (long long)cbase + t + NW * 32 : (long long)cbase + ((ntr + 31) & ~31) + warp * 32 + lane;
-          if (same || col < 7) prefetch_l2(pl.trial + tbase + nt);
+          if (same || col < 7) prefetch_l1(pl.trial + tbase + nt);
         }
         const unsigned int code = rec.w;
         valid = valid && code != LEAN_INVALID;
@@ -513,6 +544,11 @@ k_sweep_lean(SweepArgs a, BlockCfg bc, LeanPlan pl, const int* __restrict__ xoff
         // mates: the trials of a cell sit in adjacent lanes of one chunk (k_block_plan never lets a cell straddle)
         const int nprev = valid ? j : 0;
         const int nnext = valid ? n1 - j : 0;
+        if (act) {                                 // the proposal an accepted trial copies: towards L1 now
+          const BlockRow rwc = s_row[rxc * nry + ryc];
+          const int ro = sel - rwc.off;
+          prefetch_l1(prop + ((ro < rwc.cntA) ? rwc.gbA + ro : rwc.gbB + ro - rwc.cntA));
+        }
         // trial point, block-relative
         const float tx = __fmaf_rn((float)rxc - hxr, wxf, __uint_as_float(rec.x));
         const float ty = __fmaf_rn((float)ryc - hyr, wyf, __uint_as_float(rec.y));
@@ -527,23 +563,18 @@ k_sweep_lean(SweepArgs a, BlockCfg bc, LeanPlan pl, const int* __restrict__ xoff
         __syncwarp();
         float r2min = 3.0e38f;
         if (act) {
-          const unsigned long long TX = f2_pack(tx, tx), TY = f2_pack(ty, ty), TZ = f2_pack(tz, tz);
           const unsigned short* cp0 = s_cz + ((rxc - 1) * nry + ryc - 1) * czs + rz - 1;
-#pragma unroll
-          for (int r = 0; r < 9; r++) {
-            const int p0 = (int)cp0[((r / 3) * nry + (r % 3)) * czs] >> 1;
-            const ulonglong2* pxy = s_xy + p0;
-            const unsigned long long* pz = s_z2 + p0;
-#pragma unroll
-            for (int s = 0; s < LEAN_NP; s++) r2min = lean_pair(pxy[s], pz[s], TX, TY, TZ, r2min);
-          }
-          if (deep_rows) {
+          if (npairs <= 3) r2min = lean_scan<3>(s_xy, s_z2, cp0, nry, czs, tx, ty, tz);
+          else if (npairs == 4) r2min = lean_scan<4>(s_xy, s_z2, cp0, nry, czs, tx, ty, tz);
+          else r2min = lean_scan<5>(s_xy, s_z2, cp0, nry, czs, tx, ty, tz);
+          if (deep_rows) {                         // some stencil row of this block is longer than the straight-line scan
+            const unsigned long long TX = f2_pack(tx, tx), TY = f2_pack(ty, ty), TZ = f2_pack(tz, tz);
 #pragma unroll 1
             for (int r = 0; r < 9; r++) {
               const unsigned short* cp = cp0 + ((r / 3) * nry + (r % 3)) * czs;
               const int e = cp[3];
 #pragma unroll 1
-              for (int p = ((int)cp[0] >> 1) + LEAN_NP; 2 * p < e; p++) r2min = lean_pair(s_xy[p], s_z2[p], TX, TY, TZ, r2min);
+              for (int p = ((int)cp[0] >> 1) + LEAN_NP_MAX; 2 * p < e; p++) r2min = lean_pair(s_xy[p], s_z2[p], TX, TY, TZ, r2min);
             }
           }
         }

@@ -170,6 +170,11 @@ static void simulate(hs_sim *s, bool npt) {
     printf("   Rejection percentage: %f\n", (double)c[5] / (double)c[3]);
   }
   printf("Elapsed time: %f seconds\n", t1 - t0);
+  if (getenv("HSMC_REPORT_LAUNCHES")) {       /* bench.py: kernels this handle launched (stderr: stdout is the reference's format) */
+    hsmc_gpu_info gi;
+    hs_gpu_check(hsmc_gpu_get_info(s->gpu, &gi));
+    fprintf(stderr, "[hsmc_b200] kernel launches: %llu\n", (unsigned long long)gi.kernel_launches);
+  }
   hs_gpu_pull(s);
   hs_gpu_close(s);
   if (s->mp.world == 1) free(s->conf);
