@@ -11,7 +11,7 @@ configs[3] -- the configuration the headline metric is quoted on; it fits one B2
 the same total system is slab-decomposed over N GPUs ("scaling": "strong").
 
 A step = one hsmc_gpu_sweep_nvt() call of S sweeps (each sweep = one grid shift + cell-list
-rebuild, one k_block_plan launch that generates the sweep's proposals and the per-block plan,
+rebuild, one k_propose launch that generates the sweep's proposals,
 and N trial moves = 8 checkerboard block phases, each running the 8 cell colours of its blocks
 inside the CTA).  The block phases that need no halo exchange between them run as ONE
 k_sweep_lean launch (all 8 on one GPU, 0-3 and 4-7 on slabs), so a "launch" of the roofline
@@ -777,7 +777,7 @@ def main():
     achieved = (moves_local / max(sweep_groups, 1)) * b_move / per_launch_s / 1e9
     peak, peak_src = measured_peak()
     traffic = ncu_traffic()
-    kname = {0: "k_sweep_lean", 3: "k_sweep_lean", 5: "k_sweep_lean (global-memory path)", 6: "k_sweep_block (round 1)"}.get(args.sweep_impl & 0xff, "k_sweep_phase")
+    kname = {0: "k_sweep_lean", 3: "k_sweep_lean", 5: "k_sweep_lean (global-memory path)"}.get(args.sweep_impl & 0xff, "k_sweep_phase")
     roofline = {
         "bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "peak_source": peak_src,

@@ -1,4 +1,4 @@
-// cell_list.cuh -- K1: counting-sort cell list (count / scan / scatter / 16-bit row CSR) and the host <-> device table conversion kernels
+// cell_list.cuh -- K1: counting-sort cell list (count / scan / scatter) and the host <-> device table conversion kernels
 // (part of the single translation unit hsmc_gpu.cu; included there, in this order)
 #pragma once
 
@@ -133,28 +133,6 @@ __global__ void k_cell_scatter(Grid g, const double4* __restrict__ in, int n, co
   int d = cs[c] + rnk[i];
   out[d] = p;
   rel[d] = make_rel_cell(g, c, p);
-}
-
-// 16-bit row-relative copy of the CSR offsets: cs16[row][z] = cs[row*nz + z] - cs[row*nz], z = 0..nz
-// (entry nz = population of the row).  Half the bytes to stage, and directly usable as
-// shared-memory indices after adding the row's staging offset.
-__global__ void k_cs16(const int* __restrict__ cs, long long nrow, int nz, unsigned short* __restrict__ out,
-                       int* __restrict__ flags) {
-  // one warp per (x,y) row: the row's base is one broadcast load, entries are read and written coalesced
-  const int lane = threadIdx.x & 31;
-  const long long nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < nrow; row += nwarp) {
-    const int* src = cs + row * nz;
-    unsigned short* dst = out + row * (nz + 1);
-    const int base = src[0];
-    bool big = false;
-    for (int z = lane; z <= nz; z += 32) {
-      const int v = src[z] - base;
-      big |= v > 65535;
-      dst[z] = (unsigned short)v;
-    }
-    if (big) atomicOr(flags, 64);
-  }
 }
 
 // ----------------------------------------------------------------------------------

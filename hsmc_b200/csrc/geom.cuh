@@ -70,15 +70,15 @@ __host__ __device__ inline long long global_cell_of_local(const Grid& g, int l, 
 #if defined(__CUDACC__)
 
 // float4 shadow entry of a particle: offset from the origin of its own cell (gx,iy,iz)
-// and its id.  The cell of index n-1 straddles the periodic box edge when the grid is
+// and, in the fourth word, the z index of that cell (what the staging pass of k_sweep_lean needs to
+// turn the offset into a block-relative coordinate).  The cell of index n-1 straddles the periodic box edge when the grid is
 // shifted, hence the +-L repair.  Offsets lie in [0, edge]: fp32 keeps ~1e-7 absolute.
-__device__ __forceinline__ float4 make_rel(const Grid& g, int gx, int iy, int iz, double x, double y, double z,
-                                           double idw) {
+__device__ __forceinline__ float4 make_rel(const Grid& g, int gx, int iy, int iz, double x, double y, double z) {
   double ox = x - (g.sx + gx * g.wx), oy = y - (g.sy + iy * g.wy), oz = z - (g.sz + iz * g.wz);
   if (ox < -0.5 * g.wx) ox += g.Lx; else if (ox > 1.5 * g.wx) ox -= g.Lx;
   if (oy < -0.5 * g.wy) oy += g.Ly; else if (oy > 1.5 * g.wy) oy -= g.Ly;
   if (oz < -0.5 * g.wz) oz += g.Lz; else if (oz > 1.5 * g.wz) oz -= g.Lz;
-  return make_float4((float)ox, (float)oy, (float)oz, __int_as_float((int)idw));
+  return make_float4((float)ox, (float)oy, (float)oz, __int_as_float(iz));
 }
 
 // shadow entry from a local cell index
@@ -88,7 +88,7 @@ __device__ __forceinline__ float4 make_rel_cell(const Grid& g, long long c, cons
   int iy = (int)(r % g.ny), l = (int)(r / g.ny);
   int gx = g.gx0 + l;
   if (gx >= g.nx) gx -= g.nx;
-  return make_rel(g, gx, iy, iz, p.x, p.y, p.z, p.w);
+  return make_rel(g, gx, iy, iz, p.x, p.y, p.z);
 }
 
 // unscaled squared distance, minimum image

@@ -7,11 +7,10 @@
 //   key, rnk      int[cap]               scratch of the counting sort
 // One translation unit; the kernels live in the headers included below, this file keeps the handle, the
 // host-side orchestration and the ABI entry points ("new kernel" table):
-//   cell_list.cuh      K1  k_cell_count / k_scan_* / k_cell_scatter / k_cs16   cell_list_new (cell_list.c:142-175)
+//   cell_list.cuh      K1  k_cell_count / k_scan_* / k_cell_scatter   cell_list_new (cell_list.c:142-175)
 //   sweep_generic.cuh  K2  k_sweep_phase (global memory)  part_move + check_overlap (moves.c:27-80,157-212)
-//   sweep_lean.cuh     K2  k_block_plan + k_sweep_lean    the default: proposals + per-block plan up front, block-resident
+//   sweep_lean.cuh     K2  k_propose + k_sweep_lean       the default: all proposals of a sweep up front, block-resident
 //                                                         fp32x2 stencil filter, fused block phases
-//   sweep_block.cuh    K2' k_sweep_block                  round-1 block kernel (in-kernel generation), kept as an ablation
 //   observables.cuh    K3  k_overlap_scaled   vol_move / presst verdict   (moves.c:106-112)
 //                      K4  k_widom            widom_insertion             (compute_widom_chem_pot.c:44-71)
 //                      K5  k_rdf_pairs        rdf_hist_compute            (compute_rdf.c:110-128)
@@ -72,7 +71,7 @@ extern "C" const char* hsmc_gpu_last_error(void) { return g_err.c_str(); }
 // ----------------------------------------------------------------------------------
 enum { CNT_TRIALS = 0, CNT_ACC = 1, CNT_REJ_OVERLAP = 2, CNT_REJ_CELL = 3, CNT_N = 8 };
 
-// block-resident sweeps (sweep_lean.cuh, sweep_block.cuh)
+// block-resident sweep (sweep_lean.cuh)
 struct BlockCfg {
   int nbx, nby, nbz;      // blocks per axis (even); x: over the layers this rank owns
   int mbx, mby, mbz;      // largest block extent per axis (cells)
@@ -81,8 +80,6 @@ struct BlockCfg {
   int cz_stride;          // ushorts per staged CSR row (multiple of 8: rows are TMA destinations)
   int max_rows;           // (mbx+2)*(mby+2)
   int max_cells;          // mbx*mby*mbz
-  int tr_cap;             // trial slots per colour (multiple of 32)
-  int desc_cap;           // k_block_plan: trial descriptors per block (8 colours, each padded to a multiple of 32)
   int use_tma;
   int force_global;       // ablation: every block takes the global-memory path (same chain)
   int dbg;                // timing ablations (env HSMC_BLOCK_DBG), 0 in production
@@ -93,27 +90,11 @@ struct BlockCfg {
 // per-row staging record: global slots of the row's one or two pieces, staged offset
 struct BlockRow { int gbA, gbB, cntA, off; };
 
-// header of a block's plan: ints [0] staged particles, [1..8] trial slots per cell colour, [9] flags, [10] first trial slot,
-// [11] pair-records per stencil row the sweep's straight-line scan must cover
-enum { PLAN_TOTAL = 0, PLAN_NTR = 1, PLAN_FLAGS = 9, PLAN_TBASE = 10, PLAN_NPAIRS = 11, PLAN_HDR_INTS = 16 };
-enum { PLAN_BAD = 1, PLAN_DEEP = 2 };
-
-struct LeanPlan {
-  int* hdr;                   // [blocks][PLAN_HDR_INTS]
-  BlockRow* row;              // [blocks][max_rows]
-  unsigned short* cz;         // [blocks][max_rows * cz_stride]   staged index of the first particle of each region cell
-  uint4* trial;               // [cap_trials] {fp32 shadow of the proposed position (cell-relative), code}
-  uint4* raw;                 // [cap_trials] logged sweeps only: {raw draws 0..2, id}
-  unsigned int* cursor;       // trial-slot allocator (reset before every plan launch)
-  long long cap_trials;
-};
-
 // cfg.sweep_impl: low byte = kernel variant, next byte = virtual world of the x block partition
-// 0 default (k_block_plan + k_sweep_lean); 1 one thread per cell from global memory, one launch per CELL colour
+// 0 default (k_propose + k_sweep_lean); 1 one thread per cell from global memory, one launch per CELL colour
 // (a different, equally valid update order); 3 the default with the filter's error band forced to zero (negative
-// control of the parity tests); 5 the default's update order evaluated all in double from global memory;
-// 6 the round-1 block kernel (same chain as 0 and 5)
-enum { IMPL_LEAN = 0, IMPL_CELL_GLOBAL = 1, IMPL_EPS0 = 3, IMPL_BLOCK_GLOBAL = 5, IMPL_BLOCK_R1 = 6 };
+// control of the parity tests); 5 the default's update order evaluated all in double from global memory
+enum { IMPL_LEAN = 0, IMPL_CELL_GLOBAL = 1, IMPL_EPS0 = 3, IMPL_BLOCK_GLOBAL = 5 };
 
 struct hsmc_gpu {
   hsmc_gpu_config cfg;
@@ -138,7 +119,6 @@ struct hsmc_gpu {
   int64_t cap_keys = 0;
   int *key_halo = nullptr, *rnk_halo = nullptr;   // [2*cap_halo]
   int *cell_count = nullptr, *cell_start = nullptr, *bsum = nullptr;
-  unsigned short* cs16 = nullptr;        // 16-bit row-relative CSR: [(x,y) row][nz + 1], what the block kernel stages
   unsigned long long* d_cnt = nullptr;       // CNT_N counters
   unsigned long long* d_scratch = nullptr;   // SCRATCH_N x u64 general scratch (flags, hist, min)
   int* d_slot_of_id = nullptr;           // parity entry points only
@@ -166,12 +146,10 @@ struct hsmc_gpu {
   uint32_t seqA = 0, seqB = 0, seqC = 0; // exchanges issued so far (same on every rank)             // left ghost layer not refreshed since the last odd-x phases
   void* d_sfargs = nullptr;
   BlockCfg blk;
-  size_t blk_smem = 0;                   // dynamic shared memory of the kernel in use (lean or round-1 block)
-  size_t plan_smem = 0;                  // ... of k_block_plan
-  bool blk_ok = false;                   // a block-resident kernel runs the sweeps
-  bool lean = false;                     // ... and it is k_block_plan + k_sweep_lean
-  LeanPlan plan = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
-  int64_t plan_blocks = 0, plan_rows = 0, plan_czs = 0;   // what the plan arrays were sized for
+  size_t blk_smem = 0;                   // dynamic shared memory of k_sweep_lean
+  bool blk_ok = false;                   // the block-resident kernel runs the sweeps
+  uint4* trec = nullptr;                 // [cap] trial records of the current sweep, trial order inside each cell (k_propose)
+  uint4* traw = nullptr;                 // [cap] logged sweeps only: {raw draws, id}
   float blk_eps = 0.f;
   std::vector<int> xoff;                 // x block boundaries (local layers), blk.nbx + 1 entries
   int* d_xoff = nullptr;
@@ -215,7 +193,6 @@ static inline int nblk(int64_t n, int t) { return (int)((n + t - 1) / t); }
 #include "cell_list.cuh"
 #include "async_copy.cuh"
 #include "sweep_generic.cuh"
-#include "sweep_block.cuh"
 #include "sweep_lean.cuh"
 
 #include "observables.cuh"
@@ -274,9 +251,6 @@ static int ensure_cell_arrays(hsmc_gpu* h) {
   CU(cudaMalloc(&h->cell_start, sizeof(int) * (size_t)h->cap_cells));
   CU(cudaMalloc(&h->cell_count, sizeof(int) * (size_t)h->cap_cells));
   CU(cudaMalloc(&h->bsum, sizeof(int) * (size_t)((h->cap_cells + SCAN_CHUNK - 1) / SCAN_CHUNK + 1)));
-  if (h->cs16) cudaFree(h->cs16);
-  // rows x (nz + 1) <= cells + rows <= 2 x cells; tail padding for the 16-byte TMA granules
-  CU(cudaMalloc(&h->cs16, sizeof(unsigned short) * (size_t)(2 * h->cap_cells + 64)));
   return 0;
 }
 
@@ -315,11 +289,6 @@ static int exclusive_scan(hsmc_gpu* h, const int* in, int64_t n, int* out) {
   k_scan_top<<<1, SCAN_T, 0, h->st>>>(h->bsum, nb);
   k_scan_final<<<nb, SCAN_T, 0, h->st>>>(in, n, h->bsum, out);
   h->launches += 3;
-  if (h->blk_ok && !h->lean && out == h->cell_start) {      // (only the round-1 block kernel stages the 16-bit CSR)
-    const long long nrow = (long long)h->g.nlx * h->g.ny;
-    k_cs16<<<(int)std::min<long long>((nrow + 7) / 8, 148LL * 64), 256, 0, h->st>>>(out, nrow, h->g.nz, h->cs16, h->d_lay + 8);
-    h->launches++;
-  }
   CU(cudaGetLastError());
   return 0;
 }
@@ -361,8 +330,7 @@ static void setup_blocks(hsmc_gpu* h) {
   if (const char* e = getenv("HSMC_BLOCK_CAPF")) capf = atof(e);
   int want[3] = {0, 0, 0};
   if (const char* e = getenv("HSMC_BLOCK")) sscanf(e, "%d,%d,%d", &want[0], &want[1], &want[2]);
-  struct Shape { int bx, by, bz, mx, my, mz, cap, tr_cap; size_t smem, smem_r1, smem_plan; };
-  const bool r1 = h->impl == IMPL_BLOCK_R1;
+  struct Shape { int bx, by, bz, mx, my, mz, cap; size_t smem; };
   auto eval = [&](int bx, int by, int bz, Shape& s) -> bool {
     // a block and its halo must not cover a cell twice: extent + 2 <= cells of the axis
     int mx = 0;
@@ -377,23 +345,17 @@ static void setup_blocks(hsmc_gpu* h) {
     // (x: with Wv > 1 slabs every block is at most its own slab long, and a slab + 2 never exceeds
     //  the local layer count of a rank nor the box, so only the one-slab case needs the test)
     if ((Wv == 1 && mx + 2 > g.nx) || my + 2 > g.ny || mz + 2 > g.nz) return false;
-    // trial code of the lean kernel: 4-bit row coordinates, 5-bit z, 12-bit staged index
-    if ((mx + 2) * (my + 2) > LEAN_MAX_ROWS || mz + 2 > 32 || mx + 2 > 16 || my + 2 > 16) return false;
-    // the round-1 kernel stages one row per thread
-    if (r1 && ((mx + 2) * (my + 2) > std::min(BLK_MAX_ROWS, BLK_THREADS) || mz + 3 > 32)) return false;
+    // k_sweep_lean: 4-bit row coordinates, one lane per cell of a staged row (mz + 3 entries), 12-bit staged index
+    if ((mx + 2) * (my + 2) > LEAN_MAX_ROWS || mz + 3 > 32 || mx + 2 > 16 || my + 2 > 16) return false;
     double region = (double)(mx + 2) * (my + 2) * (mz + 2);
     int cap = ((int)(region * nbar * capf) + 48 + LEAN_PAD + 31) & ~31;
     if (cap > 4096) return false;
     int cz_stride = (mz + 3 + 7) & ~7;
-    double per_colour = (double)((mx + 1) / 2) * ((my + 1) / 2) * ((mz + 1) / 2);
-    int tr_cap = ((int)(per_colour * std::max(nbar, 0.2) * 1.4) + 48 + 31) & ~31;
     const size_t rows = (size_t)(mx + 2) * (my + 2);
-    size_t smem = (size_t)cap * 12 + rows * cz_stride * 2 + rows * 16 + PLAN_HDR_INTS * 4;
-    size_t smem_r1 = (size_t)cap * 16 + rows * cz_stride * 2 + (size_t)8 * tr_cap * 4;
-    size_t smem_plan = rows * cz_stride * 2 + (size_t)8 * tr_cap * 4 + (size_t)mx * my * 32 * 2;
-    smem = (smem + 15) & ~(size_t)15; smem_r1 = (smem_r1 + 15) & ~(size_t)15; smem_plan = (smem_plan + 15) & ~(size_t)15;
-    if ((r1 ? smem_r1 : smem) > 100 * 1024 || smem_plan > 100 * 1024) return false;
-    s = {bx, by, bz, mx, my, mz, cap, tr_cap, smem, smem_r1, smem_plan};
+    size_t smem = (size_t)cap * 12 + rows * cz_stride * 2 + (LEAN_THREADS / 32) * 32 * 4 + 8 * (LEAN_MAX_CHUNKS + 1) * 2;
+    smem = (smem + 15) & ~(size_t)15;
+    if (smem > 100 * 1024) return false;
+    s = {bx, by, bz, mx, my, mz, cap, smem};
     return true;
   };
   Shape best{};
@@ -417,7 +379,9 @@ static void setup_blocks(hsmc_gpu* h) {
         ctas = (Wv > 1) ? std::max(ctas, c) : ctas + c;
       }
       ctas *= (long long)(even_blocks(g.ny, by) / 2) * (even_blocks(g.nz, bz) / 2);
-      const int per_sm = (int)std::min<size_t>(4, (size_t)(227 * 1024) / (s.smem_r1 + 5 * 1024));   // (round-1 measure, kept: the shape is part of the chain)
+      // (the round-1 kernel staged 16 bytes per particle plus its trial slots; its measure of residency is kept:
+      //  the block shape is part of the chain's definition)
+      const int per_sm = (int)std::min<size_t>(4, (size_t)(227 * 1024) / ((size_t)s.cap * 16 + 16 * 1024));
       if (per_sm < 1) continue;
       const double interior = (double)s.mx * s.my * s.mz;
       // below two waves of CTA slots the ragged last wave costs a whole CTA latency
@@ -432,8 +396,7 @@ static void setup_blocks(hsmc_gpu* h) {
   b.nby = even_blocks(g.ny, best.by); b.nbz = even_blocks(g.nz, best.bz);
   b.cs_stride = 0; b.cz_stride = (best.mz + 3 + 7) & ~7;
   b.max_rows = (best.mx + 2) * (best.my + 2);
-  b.max_cells = best.mx * best.my * best.mz; b.tr_cap = best.tr_cap;
-  b.desc_cap = 8 * best.tr_cap;
+  b.max_cells = best.mx * best.my * best.mz;
   b.use_tma = 0;
   b.force_global = (h->impl == IMPL_BLOCK_GLOBAL) ? 1 : 0;
   b.dbg = getenv("HSMC_BLOCK_DBG") ? atoi(getenv("HSMC_BLOCK_DBG")) : 0;
@@ -445,9 +408,7 @@ static void setup_blocks(hsmc_gpu* h) {
   }
   h->xoff.push_back((W > 1) ? g.own_hi : g.nx);
   b.nbx = (int)h->xoff.size() - 1;
-  h->lean = !r1;
-  h->blk_smem = r1 ? best.smem_r1 : best.smem;
-  h->plan_smem = best.smem_plan;
+  h->blk_smem = best.smem;
   if (const char* e = getenv("HSMC_BLOCK_PADSMEM")) h->blk_smem += (size_t)atoi(e);    // occupancy experiments
   // fp32 filter error bound: staged coordinates are block-relative,
   // |X| <= (m/2 + 2) cells; per pair and axis: two final roundings at that magnitude, the
@@ -460,7 +421,7 @@ static void setup_blocks(hsmc_gpu* h) {
   for (int k = 0; k < 3; k++) sum += 2.0 * half_ulp(mag[k]) + 2.0 * wv[k] * ldexp(1.0, -24) + 2.0 * wv[k] * ldexp(1.0, -25);
   double r2err = 2.0 * 1.01 * sum + 8.0 * ldexp(1.0, -24);
   h->blk_eps = (float)(2.0 * r2err);
-  h->blk_ok = (h->impl == IMPL_LEAN || h->impl == IMPL_EPS0 || h->impl == IMPL_BLOCK_GLOBAL || h->impl == IMPL_BLOCK_R1);
+  h->blk_ok = (h->impl == IMPL_LEAN || h->impl == IMPL_EPS0 || h->impl == IMPL_BLOCK_GLOBAL);
   if (getenv("HSMC_DEBUG_TILES"))
     fprintf(stderr, "[hsmc_gpu] rank %d: blocks %dx%dx%d of up to %dx%dx%d cells, %d CTAs/phase, cap %d, smem %zu B, eps %.3g\n",
             h->cfg.rank, b.nbx, b.nby, b.nbz, b.mbx, b.mby, b.mbz, (b.nbx / 2) * (b.nby / 2) * (b.nbz / 2), b.cap,
@@ -657,7 +618,7 @@ extern "C" int hsmc_gpu_destroy(hsmc_gpu* h) {
   void* ptrs[] = {h->pos[0], h->pos[1], h->rel, h->key, h->rnk, h->cell_count, h->cell_start, h->bsum, h->d_cnt,
                   h->d_scratch, h->d_slot_of_id, h->d_io, h->send_l, h->send_r, h->recv_l, h->recv_r,
                   h->d_halo_cnt, h->d_sfargs, h->d_log, h->key_halo, h->rnk_halo, h->d_lay,
-                  h->d_xoff, h->cs16, h->d_fuse, h->plan.hdr, h->plan.row, h->plan.cz, h->plan.trial, h->plan.raw, h->plan.cursor};
+                  h->d_xoff, h->d_fuse, h->trec, h->traw};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -686,8 +647,10 @@ extern "C" int hsmc_gpu_create(hsmc_gpu** out, const hsmc_gpu_config* cfg, int64
   h->cfg = *cfg;
   h->impl = cfg->sweep_impl & 0xff;
   h->xpart_world = (cfg->sweep_impl >> 8) & 0xff;
-  if (h->impl != IMPL_LEAN && h->impl != IMPL_CELL_GLOBAL && h->impl != IMPL_EPS0 && h->impl != IMPL_BLOCK_GLOBAL &&
-      h->impl != IMPL_BLOCK_R1) { delete h; return fail("unknown sweep_impl variant"); }
+  if (h->impl != IMPL_LEAN && h->impl != IMPL_CELL_GLOBAL && h->impl != IMPL_EPS0 && h->impl != IMPL_BLOCK_GLOBAL) {
+    delete h;
+    return fail("unknown sweep_impl variant");
+  }
   if (h->cfg.cell_min == 0.0) h->cfg.cell_min = 1.0;
   if (h->cfg.cell_min < 1.0) { delete h; return fail("cell_min must be >= 1.0 (the particle diameter)"); }
   if (h->cfg.regrid_interval <= 0) h->cfg.regrid_interval = 1;
@@ -740,10 +703,6 @@ extern "C" int hsmc_gpu_create(hsmc_gpu** out, const hsmc_gpu_config* cfg, int64
   CUD(cudaFuncSetAttribute(k_sweep_lean<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
   CUD(cudaFuncSetAttribute(k_sweep_lean<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
   CUD(cudaFuncSetAttribute(k_sweep_lean<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  CUD(cudaFuncSetAttribute(k_block_plan<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-  CUD(cudaFuncSetAttribute(k_block_plan<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-  CUD(cudaFuncSetAttribute(k_sweep_block<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-  CUD(cudaFuncSetAttribute(k_sweep_block<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
   if (W > 1) {
     CUD(cudaMalloc(&h->send_l, sizeof(double4) * (size_t)h->cap_halo));
     CUD(cudaMalloc(&h->send_r, sizeof(double4) * (size_t)h->cap_halo));
@@ -953,34 +912,10 @@ static int do_regrid(hsmc_gpu* h) {
   return rebuild(h, h->pos[h->cur], h->N, 0, 0);
 }
 
-// plan arrays of the lean sweep: sized for the current block partition
-static int ensure_plan(hsmc_gpu* h, bool logged) {
-  const BlockCfg& b = h->blk;
-  const int64_t nblocks = (int64_t)b.nbx * b.nby * b.nbz;
-  LeanPlan& p = h->plan;
-  if (nblocks > h->plan_blocks || b.max_rows > h->plan_rows || b.cz_stride > h->plan_czs) {
-    if (p.hdr) cudaFree(p.hdr);
-    if (p.row) cudaFree(p.row);
-    if (p.cz) cudaFree(p.cz);
-    p.hdr = nullptr; p.row = nullptr; p.cz = nullptr;
-    h->plan_blocks = nblocks + nblocks / 8 + 64; h->plan_rows = b.max_rows; h->plan_czs = b.cz_stride;
-    CU(cudaMalloc(&p.hdr, sizeof(int) * PLAN_HDR_INTS * (size_t)h->plan_blocks));
-    CU(cudaMalloc(&p.row, sizeof(BlockRow) * (size_t)h->plan_rows * (size_t)h->plan_blocks));
-    CU(cudaMalloc(&p.cz, sizeof(unsigned short) * (size_t)h->plan_rows * (size_t)h->plan_czs * (size_t)h->plan_blocks));
-  }
-  // every colour list of a block is padded to a multiple of 32 trial slots
-  // (+ the slots skipped so that no cell straddles a chunk: a few per cent at most)
-  const long long need = (long long)h->cap + h->cap / 8 + 256LL * nblocks + 1024;
-  if (need > p.cap_trials) {
-    if (p.trial) cudaFree(p.trial);
-    if (p.raw) { cudaFree(p.raw); p.raw = nullptr; }
-    p.cap_trials = need + need / 16;
-    CU(cudaMalloc(&p.trial, sizeof(uint4) * (size_t)p.cap_trials));
-  }
-  if (logged && !p.raw) CU(cudaMalloc(&p.raw, sizeof(uint4) * (size_t)p.cap_trials));
-  if (!p.cursor) {
-    CU(cudaMalloc(&p.cursor, sizeof(unsigned int) * 4));
-  }
+// trial tables of k_propose: one 16-byte record per particle slot
+static int ensure_trial_tables(hsmc_gpu* h, bool logged) {
+  if (!h->trec) CU(cudaMalloc(&h->trec, sizeof(uint4) * (size_t)h->cap));
+  if (logged && !h->traw) CU(cudaMalloc(&h->traw, sizeof(uint4) * (size_t)h->cap));
   return 0;
 }
 
@@ -1032,18 +967,16 @@ static int sweep_once(hsmc_gpu* h, double dr_max, bool logged) {
   }
   a.fuse = fuse; a.epoch = 0; a.ticket_base = 0;
   a.cx = a.cy = a.cz = a.phase = 0;
-  if (h->blk_ok && h->lean) {
-    // proposals of the whole sweep + the per-block plan (static while cell membership is): one launch, all blocks
+  if (h->blk_ok) {
+    // all proposals of the sweep, element-wise (they only depend on the particles' own positions at this point)
     ProfSpan span(h, 3);
-    TRY(ensure_plan(h, logged));
-    const int nblocks = h->blk.nbx * h->blk.nby * h->blk.nbz;
-    CU(cudaMemsetAsync(h->plan.cursor, 0, sizeof(unsigned int), h->st));
+    TRY(ensure_trial_tables(h, logged));
     if (logged)
-      k_block_plan<true><<<nblocks, PLAN_THREADS, h->plan_smem, h->st>>>(a, h->blk, h->plan, h->d_xoff, h->pos[h->cur], h->cell_start,
-                                                                        h->pos[h->cur ^ 1]);
+      k_propose<true><<<nblk(h->cap, PROPOSE_THREADS), PROPOSE_THREADS, 0, h->st>>>(a, h->pos[h->cur], h->cell_start, h->ncell,
+                                                                                   h->pos[h->cur ^ 1], h->trec, h->traw);
     else
-      k_block_plan<false><<<nblocks, PLAN_THREADS, h->plan_smem, h->st>>>(a, h->blk, h->plan, h->d_xoff, h->pos[h->cur], h->cell_start,
-                                                                         h->pos[h->cur ^ 1]);
+      k_propose<false><<<nblk(h->cap, PROPOSE_THREADS), PROPOSE_THREADS, 0, h->st>>>(a, h->pos[h->cur], h->cell_start, h->ncell,
+                                                                                    h->pos[h->cur ^ 1], h->trec, nullptr);
     h->launches++;
   }
   for (int ph = 0; ph < 8; ph++) {
@@ -1060,21 +993,13 @@ static int sweep_once(hsmc_gpu* h, double dr_max, bool logged) {
         a.ticket_base = h->fuse_tickets;
         h->fuse_tickets += (unsigned int)nb;
       }
-      if (h->lean) {
-        if (logged)
-          k_sweep_lean<true><<<nb, LEAN_THREADS, h->blk_smem, h->st>>>(a, h->blk, h->plan, h->d_xoff, h->pos[h->cur], h->rel,
-                                                                       h->pos[h->cur ^ 1], h->cell_start, h->d_cnt, h->d_log,
-                                                                       h->d_scratch, (long long)h->cap_log);
-        else
-          k_sweep_lean<false><<<nb, LEAN_THREADS, h->blk_smem, h->st>>>(a, h->blk, h->plan, h->d_xoff, h->pos[h->cur], h->rel,
-                                                                        h->pos[h->cur ^ 1], h->cell_start, h->d_cnt, nullptr,
-                                                                        nullptr, 0);
-      } else if (logged)
-        k_sweep_block<true><<<nb, BLK_THREADS, h->blk_smem, h->st>>>(a, h->blk, h->d_xoff, h->pos[h->cur], h->rel, h->cell_start,
-                                                                      h->cs16, h->d_cnt, h->d_log, h->d_scratch, (long long)h->cap_log);
+      if (logged)
+        k_sweep_lean<true><<<nb, LEAN_THREADS, h->blk_smem, h->st>>>(a, h->blk, h->d_xoff, h->pos[h->cur], h->rel, h->pos[h->cur ^ 1],
+                                                                     h->trec, h->traw, h->cell_start, h->d_cnt, h->d_log,
+                                                                     h->d_scratch, (long long)h->cap_log);
       else
-        k_sweep_block<false><<<nb, BLK_THREADS, h->blk_smem, h->st>>>(a, h->blk, h->d_xoff, h->pos[h->cur], h->rel, h->cell_start,
-                                                                       h->cs16, h->d_cnt, nullptr, nullptr, 0);
+        k_sweep_lean<false><<<nb, LEAN_THREADS, h->blk_smem, h->st>>>(a, h->blk, h->d_xoff, h->pos[h->cur], h->rel, h->pos[h->cur ^ 1],
+                                                                      h->trec, nullptr, h->cell_start, h->d_cnt, nullptr, nullptr, 0);
     } else if (logged)
       k_sweep_phase<true><<<nblk(total, T), T, 0, h->st>>>(a, h->pos[h->cur], h->rel, h->cell_start, h->d_cnt, h->d_log,
                                                             h->d_scratch, (long long)h->cap_log);
@@ -1481,18 +1406,6 @@ extern "C" int hsmc_gpu_profile_read(hsmc_gpu* h, double ms[HSMC_GPU_PROFILE_BUC
     ms[k] = h->prof_ms[k]; groups[k] = h->prof_n[k];
     h->prof_ms[k] = 0; h->prof_n[k] = 0;
   }
-  return 0;
-}
-
-// tuning aid (not part of the drop-in surface): per-stage cycle totals of the block kernel
-// collected when HSMC_BLOCK_DBG=10; reading resets them
-extern "C" int hsmc_gpu_debug_block_cycles(hsmc_gpu* h, uint64_t out[16]) {
-  if (!h || !out) return fail("null argument");
-  CU(cudaSetDevice(h->cfg.device));
-  CU(cudaStreamSynchronize(h->st));
-  unsigned long long z[16] = {0};
-  CU(cudaMemcpyFromSymbol(out, g_blk_t, sizeof(z)));
-  CU(cudaMemcpyToSymbol(g_blk_t, z, sizeof(z)));
   return 0;
 }
 

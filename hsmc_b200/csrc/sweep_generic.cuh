@@ -1,4 +1,4 @@
-// sweep_generic.cuh -- K2 (generic form): SweepArgs and the one-thread-per-cell sweep from global memory; the staged kernels are sweep_tile.cuh / sweep_block.cuh
+// sweep_generic.cuh -- K2 (generic form): SweepArgs and the one-thread-per-cell sweep from global memory; the staged kernel is sweep_lean.cuh
 // (part of the single translation unit hsmc_gpu.cu; included there, in this order)
 #pragma once
 
@@ -86,7 +86,7 @@ __device__ __forceinline__ void cell_update_global(const SweepArgs& a, int phase
       else {
         verdict = 0; n_acc++;
         pos[sel] = make_double4(xn, yn, zn, p.w);
-        rel[sel] = make_rel(g, gx, iy, iz, xn, yn, zn, p.w);
+        rel[sel] = make_rel(g, gx, iy, iz, xn, yn, zn);
       }
     }
     if (LOG) {

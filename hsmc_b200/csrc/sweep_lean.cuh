@@ -1,32 +1,31 @@
-// sweep_lean.cuh -- K2, the default sweep: k_block_plan (trial planning + proposals) and k_sweep_lean
-// (block-resident fp32x2 stencil filter).  Same two-level checkerboard and the same Markov chain as
-// k_sweep_block (sweep_block.cuh, kept as an ablation) and as the all-double global-memory evaluation
-// (sweep_impl 5): every particle gets one trial per sweep, each trial is the reference's part_move()
-// (moves.c:27-80), a trial that leaves its cell is rejected.
+// sweep_lean.cuh -- K2, the default sweep: k_propose (all proposals of a sweep, up front) and k_sweep_lean
+// (block-resident packed-fp32 stencil filter).  Two-level checkerboard, same Markov chain as the all-double
+// global-memory evaluation (sweep_impl 5): every particle gets one trial per sweep, each trial is the reference's
+// part_move() (moves.c:27-80), a trial that leaves its cell is rejected.
 //
-// What moved out of the latency-critical kernel, and why (profiles/r01_ncu_k_sweep_block_fused.txt: 128
-// registers, 16 warps/SM, 38 % issue, 55 % shared-memory bank conflicts, prologue 31 % of warp time):
+// Design notes (profiles/r01_ncu_k_sweep_block_fused.txt: the round-1 kernel generated, staged, scanned and committed
+// in one 128-register kernel: 16 warps/SM, 38 % issue, 55 % shared-memory bank conflicts, prologue 31 % of warp time;
+// profiles/r02_ncu_k_block_plan_v1.txt: a per-block "plan" kernel that pre-built the trial lists cost as many
+// instructions as the sweep itself -- dropped):
 //
-//  * A trial point depends on nothing but the particle's own position at the start of the sweep (a particle
-//    only ever moves by its own trial) and on Philox(global cell, trial index, sweep).  So all proposals of a
-//    sweep are generated up front by k_block_plan, a throughput kernel: new position in double
-//    (moves.c:52-57, 215-226) into the idle half of the ping-pong master table, cell test, fp32 shadow of the
-//    new position.  k_sweep_lean has no Philox and no double arithmetic on its hot path.
-//  * k_block_plan also lays out, per block, everything that is static during a sweep (cell membership is):
-//    the staging rows, the staged index of every region cell, and per cell colour the list of trials in
-//    (row, z, trial index) order.  The sweep kernel's prologue is three bulk-TMA copies plus one pass that
-//    stages the shadow coordinates; its trial slots are read coalesced, 16 B per lane.
-//  * Staged coordinates are block-relative fp32, stored as PAIRS {x0,x1,y0,y1} + {z0,z1}, so the stencil
-//    filter runs on packed fp32x2 instructions (FADD2 / FMUL2 / FFMA2 + FMNMX3: 7 math instructions and two
-//    loads per two neighbours instead of 14 + 2).  Consecutive lanes of a warp hold consecutive trials along
-//    z of one (x,y) row: their stencil rows start at monotonically increasing shared-memory addresses about
-//    one pair-record apart, which is (nearly) conflict-free for the 16-byte and the 8-byte loads alike.
+//  * A trial point depends on nothing but the particle's own position at the start of the sweep (a particle only ever
+//    moves by its own trial) and on Philox(global cell, trial index, sweep).  k_propose, an element-wise throughput
+//    kernel (one thread per particle), generates them all: new position in double (moves.c:52-57, 215-226) into the
+//    idle half of the ping-pong master table, the cell test, and a 16-byte trial record {fp32 shadow of the new
+//    position, slot | accept-able}, both stored in TRIAL ORDER inside the cell's slot range (ascending particle id).
+//    k_sweep_lean has no Philox and no double arithmetic on its hot path: 64 registers, 30 warps per SM.
+//  * The sweep kernel derives everything else itself: one warp per staged (x,y) row reads the row's CSR entries
+//    (lane = cell), a warp scan places the rows, the fp32 shadow is staged as block-relative coordinates in PAIRS
+//    {x0,x1,y0,y1} + {z0,z1}, so the stencil filter runs on packed fp32x2 instructions (FADD2 / FMUL2 / FFMA2 +
+//    FMNMX3: 7 math instructions and two loads per two neighbours instead of 14 + 2).
+//  * Per cell colour each warp owns a contiguous group of the colour's cells (lane = cell, z fastest, so that the
+//    stencil rows of neighbouring lanes start at nearby shared-memory addresses); the cells' trials are compacted with
+//    a warp scan into lane-slots.  The trials of one cell are always handled by one warp, in order.
 //
-// Exactness is unchanged: the fp32 minimum r^2 is a filter with a rigorous error bound eps
-// (setup_blocks); min < 1 - eps is a certain overlap, min > 1 + eps a certain miss, anything in between is
-// re-evaluated from the master table with the reference's double arithmetic (moves.c:400-431).  Trials of
-// one cell that fall into the same 32-lane chunk are ordered with warp shuffles: a later trial sees its
-// earlier mates at the positions their own trials left them in.
+// Exactness is unchanged: the fp32 minimum r^2 is a filter with a rigorous error bound eps (setup_blocks); min < 1 - eps
+// is a certain overlap, min > 1 + eps a certain miss, anything in between is re-evaluated from the master table with
+// the reference's double arithmetic (moves.c:400-431).  Trials of one cell that fall into the same 32-lane chunk are
+// ordered with warp shuffles: a later trial sees its earlier mates at the positions their own trials left them in.
 #pragma once
 
 #ifndef LEAN_THREADS
@@ -36,18 +35,19 @@
 #define LEAN_MIN_CTAS 5
 #endif
 #define LEAN_NP_MIN 3           // pair-records (2 entries each) scanned per stencil row in straight-line code:
-#define LEAN_NP_MAX 5           //   chosen per block by k_block_plan from its longest stencil row; beyond MAX: deep loop
-#define LEAN_PAD 10             // far-away entries after the last staged particle (covers the over-scan)
+#define LEAN_NP_MAX 5           //   chosen per block from its longest stencil row; beyond MAX: deep loop
+#define LEAN_PAD 12             // far-away entries after the last staged particle (covers the over-scan)
 #define LEAN_FAR 1.0e15f
-#define LEAN_MAX_OCC 8          // most particles per cell (3-bit trial index)
+#define LEAN_MAX_OCC 8          // most particles per cell on the staged path (3-bit trial index)
 #define LEAN_MAX_ROWS 256       // (mbx+2)*(mby+2)
-#define PLAN_THREADS 256
+#define LEAN_MAX_CHUNKS 30       // chunks per cell colour of a block
+#define PROPOSE_THREADS 256
 
-// LeanPlan and the plan header layout: see hsmc_gpu.cu
+// trial record code: slot of the particle inside its cell (4 bits) | bit 4: the trial stays inside its cell
+#define TREC_ACT 16u
 
-// trial code: sel (staged index) 12 | rx 4 | ry 4 | rz 5 | j 3 | n-1 3 | act 1
-#define LEAN_INVALID 0xffffffffu     // (rx = 15 never occurs: at most 16 staged rows along x, the last one halo)
-#define LEAN_CODE(sel, rx, ry, rz, j, n1) ((unsigned)(sel) | ((unsigned)(rx) << 12) | ((unsigned)(ry) << 16) | ((unsigned)(rz) << 20) | ((unsigned)(j) << 25) | ((unsigned)(n1) << 28))
+// item of a warp's trial queue: first staged index of the cell 12 | rx 4 | ry 4 | rz 5 | j 3 | n-1 3
+#define LEAN_ITEM(ob, rx, ry, rz, j, n1) ((unsigned)(ob) | ((unsigned)(rx) << 12) | ((unsigned)(ry) << 16) | ((unsigned)(rz) << 20) | ((unsigned)(j) << 25) | ((unsigned)(n1) << 28))
 
 struct BlkGeom {
   int xa, ya, za;            // first interior cell (local x layer, y, z)
@@ -63,7 +63,7 @@ __device__ __forceinline__ BlkGeom blk_geom(const Grid& g, const BlockCfg& bc, c
   BlkGeom q;
   q.xa = xoff[bxi];
   const int xb = xoff[bxi + 1];
-  // (32-bit: block index x cells per axis stays far below 2^31; same values as the 64-bit form)
+  // (32-bit: block index x cells per axis stays far below 2^31)
   q.ya = (byi * g.ny) / bc.nby;
   const int yb = ((byi + 1) * g.ny) / bc.nby;
   q.za = (bzi * g.nz) / bc.nbz;
@@ -77,9 +77,8 @@ __device__ __forceinline__ BlkGeom blk_geom(const Grid& g, const BlockCfg& bc, c
   return q;
 }
 
-// global (x,y) row index of staged row r
-__device__ __forceinline__ long long blk_global_row(const Grid& g, const BlkGeom& q, int r) {
-  const int rx = r / q.nry, ry = r - rx * q.nry;
+// global (x,y) row index of staged row (rx, ry)
+__device__ __forceinline__ long long blk_global_row(const Grid& g, const BlkGeom& q, int rx, int ry) {
   int lx = q.x0 + rx;
   if (g.wrap_x) { if (lx < 0) lx += g.nlx; else if (lx >= g.nlx) lx -= g.nlx; }
   int y = q.y0 + ry;
@@ -87,237 +86,67 @@ __device__ __forceinline__ long long blk_global_row(const Grid& g, const BlkGeom
   return (long long)lx * g.ny + y;
 }
 
+// exact re-evaluation of a whole stencil from the master table (moves.c:157-212, 400-431)
+// (`pos` deliberately not const __restrict__: entries of this block were written earlier in this
+// launch by other threads of the CTA, so the loads must not take the non-coherent path)
+__device__ __noinline__ bool block_exact_rescan(const double4* pos, const BlockRow* s_row,
+                                                const unsigned short* s_cz, int cz_stride, int nry, int rxc,
+                                                int ryc, int rz, int sel, double xn, double yn, double zn,
+                                                const Box box) {
+  for (int dx = -1; dx <= 1; dx++)
+    for (int dy = -1; dy <= 1; dy++) {
+      const int row = (rxc + dx) * nry + ryc + dy;
+      const BlockRow rw = s_row[row];
+      const unsigned short* cp = s_cz + row * cz_stride + rz;
+      const int b = cp[-1], e = cp[2];
+      for (int k = b; k < e; k++) {
+        if (k == sel) continue;
+        const int o = k - rw.off;
+        const int gs = (o < rw.cntA) ? rw.gbA + o : rw.gbB + o - rw.cntA;
+        const double4 q = pos[gs];
+        if (pair_r2(xn, yn, zn, q.x, q.y, q.z, box) < 1.0) return true;
+      }
+    }
+  return false;
+}
+
 // ---------------------------------------------------------------------------------------------------
-// k_block_plan: one CTA per block (all eight block phases at once; nothing here depends on the order
-// of the updates).  Writes the block's plan and generates the proposals of its interior particles.
+// k_propose: one thread per resident particle.  Trial index j = number of particles of the same cell with a
+// smaller id; the proposal and the trial record are stored at slot (cell start + j), i.e. in trial order.
 // ---------------------------------------------------------------------------------------------------
 template <bool LOG>
-__global__ void __launch_bounds__(PLAN_THREADS)
-k_block_plan(SweepArgs a, BlockCfg bc, LeanPlan pl, const int* __restrict__ xoff, const double4* __restrict__ pos,
-             const int* __restrict__ cs, double4* __restrict__ prop) {
+__global__ void __launch_bounds__(PROPOSE_THREADS)
+k_propose(SweepArgs a, const double4* __restrict__ pos, const int* __restrict__ cs, long long ncell,
+          double4* __restrict__ prop, uint4* __restrict__ trec, uint4* __restrict__ traw) {
   const Grid& g = a.g;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  unsigned short* s_cz = reinterpret_cast<unsigned short*>(smem_raw);                          // [max_rows][cz_stride]
-  unsigned int* s_desc = reinterpret_cast<unsigned int*>(s_cz + bc.max_rows * bc.cz_stride);   // [desc_cap]
-  unsigned short* s_pre = reinterpret_cast<unsigned short*>(s_desc + bc.desc_cap);             // [interior rows][32]
-  __shared__ BlockRow s_row[LEAN_MAX_ROWS];
-  __shared__ int s_cnt[LEAN_MAX_ROWS + 1];
-  __shared__ int s_grow[LEAN_MAX_ROWS];
-  __shared__ int s_rc[2 * LEAN_MAX_ROWS];      // per interior row and z parity (a "run"): trials, then offset in its colour's list
-  __shared__ int s_ntr[8], s_cbase[9], s_flags, s_need, s_tbase;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int NWP = PLAN_THREADS / 32;
-  const int czs = bc.cz_stride;
-  const unsigned FULL = 0xffffffffu;
-
-  const int bl = blockIdx.x;
-  const int bzi = bl % bc.nbz, byi = (bl / bc.nbz) % bc.nby, bxi = bl / (bc.nbz * bc.nby);
-  const BlkGeom q = blk_geom(g, bc, xoff, bxi, byi, bzi);
-  const int nrows = q.nrows, nry = q.nry, lenz = q.lenz;
-  if (tid == 0) { s_flags = 0; s_need = 0; }
-
-  // ---- staging rows: one or two contiguous slot ranges of the cell-ordered table each ----------------
-  for (int r = tid; r < nrows; r += PLAN_THREADS) {
-    const long long grow = blk_global_row(g, q, r);
-    const long long rbase = grow * g.nz;
-    const int gbA = cs[rbase + q.zs], geA = cs[rbase + min(q.zs + lenz, g.nz)];
-    int gbB = 0, geB = 0;
-    if (q.zwrap) { gbB = cs[rbase]; geB = cs[rbase + (q.zs + lenz - g.nz)]; }
-    s_grow[r] = (int)grow;
-    s_row[r].gbA = gbA; s_row[r].gbB = gbB; s_row[r].cntA = geA - gbA;
-    s_cnt[r] = (geA - gbA) + (geB - gbB);
-  }
-  __syncthreads();
-  if (tid < 32) {                               // exclusive scan of the row populations
-    int carry = 0;
-    for (int base = 0; base < nrows; base += 32) {
-      const int r = base + tid;
-      const int v = (r < nrows) ? s_cnt[r] : 0;
-      int inc = v;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(FULL, inc, o);
-        if (tid >= o) inc += t;
-      }
-      if (r < nrows) s_row[r].off = carry + inc - v;
-      carry += __shfl_sync(FULL, inc, 31);
-    }
-    if (tid == 0) {
-      s_cnt[nrows] = carry;
-      if (carry + LEAN_PAD > bc.cap) atomicOr(&s_flags, PLAN_BAD);
-    }
-  }
-  __syncthreads();
-  const int total = s_cnt[nrows];
-
-  // ---- one warp per staged row, one lane per cell of the row (at most 32): staged index of the first particle
-  //      of every cell; longest stencil row; for interior rows the trials of each z parity ("run") and every
-  //      cell's offset inside its run ----------------------------------------------------------------------
-  const int parx = (g.gx0 + q.x0) & 1, pary = q.y0 & 1, parz = q.z0 & 1;   // parity of region cell (0,0,0); grids are even
-  unsigned short* gcz = pl.cz + (size_t)bl * bc.max_rows * czs;
-  for (int r = warp; r < nrows; r += NWP) {
-    const int rx = r / nry, ry = r - rx * nry;
-    const long long rbase = (long long)s_grow[r] * g.nz;
-    const BlockRow rw = s_row[r];
-    const int zi = lane, z = q.zs + zi;
-    int v = 0;
-    if (zi <= lenz) {
-      v = (z <= g.nz) ? rw.off + (cs[rbase + z] - rw.gbA) : rw.off + rw.cntA + (cs[rbase + (z - g.nz)] - rw.gbB);
-      s_cz[r * czs + zi] = (unsigned short)v;
-      gcz[r * czs + zi] = (unsigned short)v;
-    }
-    const int vn = __shfl_down_sync(FULL, v, 1), vb = __shfl_up_sync(FULL, v, 1), ve = __shfl_down_sync(FULL, v, 2);
-    const bool zint = zi >= 1 && zi <= q.ez;
-    const int n = zint ? vn - v : 0;
-    // entries a trial in cell zi scans in this row, from the pair-aligned start of cell zi-1 to the end of cell zi+1
-    const int need = __reduce_max_sync(FULL, zint ? ve - (vb & ~1) : 0);
-    if (lane == 0) atomicMax(&s_need, need);
-    if (rx >= 1 && rx <= q.ex && ry >= 1 && ry <= q.ey) {
-      const int ri = (rx - 1) * q.ey + (ry - 1);
-      if (__any_sync(FULL, n > LEAN_MAX_OCC) && lane == 0) atomicOr(&s_flags, PLAN_BAD);
-      const int par = (parz + zi) & 1;
-      int inc = par ? (n << 16) : n;                 // both parities in one scan
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(FULL, inc, o);
-        if (lane >= o) inc += t;
-      }
-      const int tot = __shfl_sync(FULL, inc, 31);
-      const int pre = par ? (inc >> 16) - n : (inc & 0xffff) - n;
-      if (zint) s_pre[ri * 32 + zi] = (unsigned short)pre;
-      if (lane == 0) { s_rc[2 * ri] = tot & 0xffff; s_rc[2 * ri + 1] = tot >> 16; }
-    }
-  }
-  __syncthreads();
-  // ---- per colour (one thread each): place the runs, rows in (rx, ry) order, in the colour's list.  A colour's
-  //      trials are split evenly over its chunks (each chunk is one warp's work between two colour barriers), and
-  //      the trials of one cell never straddle a chunk (chunks of a colour run concurrently, the trials of a cell
-  //      are ordered): a cell that would is moved to the start of the next chunk; skipped slots stay invalid.
-  if (tid < 8) {
-    const int p = tid & 1;
-    int sum = 0;
-    for (int rx = 1, ri = 0; rx <= q.ex; rx++)
-      for (int ry = 1; ry <= q.ey; ry++, ri++)
-        if (((((parx + rx) & 1) << 2) | (((pary + ry) & 1) << 1)) == (tid & 6)) sum += s_rc[2 * ri + p];
-    const int nch = max(1, (sum + 31) >> 5);
-    const int ccap = min(32, (sum + nch - 1) / nch + 2);        // chunk capacity (+2: room for the moved cells)
-    int at = 0;
-    for (int rx = 1, ri = 0; rx <= q.ex; rx++)
-      for (int ry = 1; ry <= q.ey; ry++, ri++) {
-        if (((((parx + rx) & 1) << 2) | (((pary + ry) & 1) << 1)) != (tid & 6)) continue;
-        const int len = s_rc[2 * ri + p];
-        if ((at & 31) >= ccap) at = (at + 31) & ~31;
-        s_rc[2 * ri + p] = at;
-        if ((at & 31) + len <= ccap) { at += len; continue; }
-        // the run crosses a chunk boundary: walk its cells
-        const unsigned short* cz = s_cz + (rx * nry + ry) * czs;
-        unsigned short* pre = s_pre + ri * 32;
-        const int start = at;
-        for (int zi = 1 + ((parz + 1 + p) & 1); zi <= q.ez; zi += 2) {
-          const int n = (int)cz[zi + 1] - (int)cz[zi];
-          if (n == 0) continue;
-          if ((at & 31) + n > ccap) at = (at + 31) & ~31;
-          pre[zi] = (unsigned short)(at - start);
-          at += n;
-        }
-      }
-    s_ntr[tid] = at;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    int base = 0;
-    for (int c = 0; c < 8; c++) { s_cbase[c] = base; base += (s_ntr[c] + 31) & ~31; }
-    s_cbase[8] = base;
-    if (base > bc.desc_cap) atomicOr(&s_flags, PLAN_BAD);
-    unsigned int tb = 0;
-    if (!(s_flags & PLAN_BAD)) {
-      tb = atomicAdd(pl.cursor, (unsigned int)base);
-      if ((long long)tb + base > pl.cap_trials) atomicOr(&s_flags, PLAN_BAD);
-    }
-    s_tbase = (int)tb;
-    // pair-records the straight-line scan must cover; beyond LEAN_NP_MAX the sweep runs its deep loop too
-    if (s_need > 2 * LEAN_NP_MAX) atomicOr(&s_flags, PLAN_DEEP);
-  }
-  __syncthreads();
-  const int flags = s_flags;
-  // ---- header and rows go to global memory (the cell indices went out above) ---------------------------------
-  {
-    int* hdr = pl.hdr + (size_t)bl * PLAN_HDR_INTS;
-    if (tid < PLAN_HDR_INTS) {
-      int v = 0;
-      if (tid == PLAN_TOTAL) v = total;
-      else if (tid >= PLAN_NTR && tid < PLAN_NTR + 8) v = s_ntr[tid - PLAN_NTR];
-      else if (tid == PLAN_FLAGS) v = flags;
-      else if (tid == PLAN_TBASE) v = s_tbase;
-      else if (tid == PLAN_NPAIRS) v = min(LEAN_NP_MAX, max(LEAN_NP_MIN, (s_need + 1) >> 1));
-      hdr[tid] = v;
-    }
-    int4* grow = reinterpret_cast<int4*>(pl.row + (size_t)bl * bc.max_rows);
-    for (int r = tid; r < nrows; r += PLAN_THREADS) grow[r] = reinterpret_cast<const int4*>(s_row)[r];
-  }
-  if (flags & PLAN_BAD) return;              // the sweep runs this block from global memory (no proposals needed)
-
-  // ---- trial descriptors ----------------------------------------------------------------------------------
-  const int nslots = s_cbase[8];
-  for (int u = tid; u < nslots; u += PLAN_THREADS) s_desc[u] = LEAN_INVALID;
-  __syncthreads();
-  for (int ri = warp; ri < q.ex * q.ey; ri += NWP) {
-    const int rx = ri / q.ey + 1, ry = ri - (rx - 1) * q.ey + 1;
-    const int zi = lane;
-    if (zi >= 1 && zi <= q.ez) {
-      const int p = (parz + zi) & 1;
-      const int col = (((parx + rx) & 1) << 2) | (((pary + ry) & 1) << 1) | p;
-      const unsigned short* cz = s_cz + (rx * nry + ry) * czs;
-      const int b = cz[zi], n = (int)cz[zi + 1] - b;
-      unsigned int* out = s_desc + s_cbase[col] + s_rc[2 * ri + p] + s_pre[ri * 32 + zi];
-      for (int j = 0; j < n; j++) out[j] = LEAN_CODE(b, rx, ry, zi, j, n - 1);
-    }
-  }
-  __syncthreads();
-
-  // ---- proposals: the reference's trial point (moves.c:52-57), apply_pbc (moves.c:215-226), cell test ---------
-  const long long tbase = s_tbase;
-#pragma unroll 2
-  for (int u = tid; u < nslots; u += PLAN_THREADS) {
-    const unsigned int d = s_desc[u];
-    if (d == LEAN_INVALID) { pl.trial[tbase + u] = make_uint4(0u, 0u, 0u, LEAN_INVALID); continue; }
-    const int ob = d & 0xfff, rx = (d >> 12) & 15, ry = (d >> 16) & 15, rz = (d >> 20) & 31;
-    const int j = (d >> 25) & 7, n1 = (d >> 28) & 7;
-    const BlockRow rw = s_row[rx * nry + ry];
-    const int o = ob - rw.off;
-    const int gs0 = (o < rw.cntA) ? rw.gbA + o : rw.gbB + o - rw.cntA;
-    // the particle with exactly j smaller ids in its cell (cells rarely hold more than three)
-    int k = 0;
-    if (n1 > 0) {
-      for (int m = 0; m <= n1; m++) {
-        const double idm = pos[gs0 + m].w;
-        int c2 = 0;
-        for (int m2 = 0; m2 <= n1; m2++) c2 += pos[gs0 + m2].w < idm;
-        if (c2 == j) k = m;
-      }
-    }
-    const int gs = gs0 + k;
-    const double4 p = pos[gs];
-    const int iy = q.y0 + ry, iz = q.z0 + rz;
-    const int gxl = g.gx0 + q.x0 + rx;
-    const int gx = (gxl >= g.nx) ? gxl - g.nx : gxl;          // interior cells never wrap inside the block
-    const long long gcell = ((long long)gx * g.ny + iy) * g.nz + iz;
-    const Philox4 rn = philox4x32_10((uint32_t)gcell, (HSMC_STREAM_MOVE << 24) | (uint32_t)j, a.sweep_lo, a.sweep_hi, a.key0, a.key1);
-    double xn = p.x + (hsmc_u01(rn.v[0]) - 0.5) * a.dr_max;
-    double yn = p.y + (hsmc_u01(rn.v[1]) - 0.5) * a.dr_max;
-    double zn = p.z + (hsmc_u01(rn.v[2]) - 0.5) * a.dr_max;
-    if (xn > g.Lx) xn -= g.Lx; else if (xn < 0.0) xn += g.Lx;
-    if (yn > g.Ly) yn -= g.Ly; else if (yn < 0.0) yn += g.Ly;
-    if (zn > g.Lz) zn -= g.Lz; else if (zn < 0.0) zn += g.Lz;
-    const bool act = axis_cell(xn, g.sx, g.iwx, g.nx) == gx && axis_cell(yn, g.sy, g.iwy, g.ny) == iy &&
-                     axis_cell(zn, g.sz, g.iwz, g.nz) == iz;
-    float4 nrel = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (act) nrel = make_rel(g, gx, iy, iz, xn, yn, zn, p.w);
-    const unsigned int code = LEAN_CODE(ob + k, rx, ry, rz, j, n1) | (act ? 0x80000000u : 0u);
-    pl.trial[tbase + u] = make_uint4(__float_as_uint(nrel.x), __float_as_uint(nrel.y), __float_as_uint(nrel.z), code);
-    prop[gs] = make_double4(xn, yn, zn, p.w);
-    if (LOG) pl.raw[tbase + u] = make_uint4(rn.v[0], rn.v[1], rn.v[2], (unsigned int)(int)p.w);
-  }
+  const int gs = blockIdx.x * PROPOSE_THREADS + threadIdx.x;
+  if (gs >= cs[ncell]) return;
+  const double4 p = pos[gs];
+  const long long c = local_cell(g, p.x, p.y, p.z);       // the cell the counting sort put it in
+  const int b = cs[c], n = cs[c + 1] - b;
+  int j = 0;
+  for (int k = 0; k < n; k++) j += pos[b + k].w < p.w;
+  const int iz = (int)(c % g.nz);
+  const long long r = c / g.nz;
+  const int iy = (int)(r % g.ny), l = (int)(r / g.ny);
+  const int gx = (g.gx0 + l >= g.nx) ? g.gx0 + l - g.nx : g.gx0 + l;
+  const long long gcell = ((long long)gx * g.ny + iy) * g.nz + iz;
+  // the reference's trial point (moves.c:52-57), apply_pbc (moves.c:215-226), then the cell test
+  const Philox4 rn = philox4x32_10((uint32_t)gcell, (HSMC_STREAM_MOVE << 24) | (uint32_t)j, a.sweep_lo, a.sweep_hi, a.key0, a.key1);
+  double xn = p.x + (hsmc_u01(rn.v[0]) - 0.5) * a.dr_max;
+  double yn = p.y + (hsmc_u01(rn.v[1]) - 0.5) * a.dr_max;
+  double zn = p.z + (hsmc_u01(rn.v[2]) - 0.5) * a.dr_max;
+  if (xn > g.Lx) xn -= g.Lx; else if (xn < 0.0) xn += g.Lx;
+  if (yn > g.Ly) yn -= g.Ly; else if (yn < 0.0) yn += g.Ly;
+  if (zn > g.Lz) zn -= g.Lz; else if (zn < 0.0) zn += g.Lz;
+  const bool act = axis_cell(xn, g.sx, g.iwx, g.nx) == gx && axis_cell(yn, g.sy, g.iwy, g.ny) == iy &&
+                   axis_cell(zn, g.sz, g.iwz, g.nz) == iz;
+  float4 nrel = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (act) nrel = make_rel(g, gx, iy, iz, xn, yn, zn);
+  const unsigned int code = (unsigned int)min(gs - b, 15) | (act ? TREC_ACT : 0u);
+  trec[b + j] = make_uint4(__float_as_uint(nrel.x), __float_as_uint(nrel.y), __float_as_uint(nrel.z), code);
+  prop[b + j] = make_double4(xn, yn, zn, p.w);
+  if (LOG) traw[b + j] = make_uint4(rn.v[0], rn.v[1], rn.v[2], (unsigned int)(int)p.w);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -390,28 +219,30 @@ __device__ __forceinline__ float lean_scan(const ulonglong2* __restrict__ s_xy, 
 // ---------------------------------------------------------------------------------------------------
 template <bool LOG>
 __global__ void __launch_bounds__(LEAN_THREADS, LEAN_MIN_CTAS)
-k_sweep_lean(SweepArgs a, BlockCfg bc, LeanPlan pl, const int* __restrict__ xoff, double4* pos, float4* rel,
-             const double4* __restrict__ prop, const int* __restrict__ cs, unsigned long long* __restrict__ cnt,
+k_sweep_lean(SweepArgs a, BlockCfg bc, const int* __restrict__ xoff, double4* pos, float4* rel,
+             const double4* __restrict__ prop, const uint4* __restrict__ trec, const uint4* __restrict__ traw,
+             const int* __restrict__ cs, unsigned long long* __restrict__ cnt,
              hsmc_gpu_trial* __restrict__ log, unsigned long long* __restrict__ nlog, long long logcap) {
   const Grid& g = a.g;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   ulonglong2* s_xy = reinterpret_cast<ulonglong2*>(smem_raw);                              // [cap/2] {x0,x1},{y0,y1}
   unsigned long long* s_z2 = reinterpret_cast<unsigned long long*>(s_xy + (bc.cap >> 1));   // [cap/2] {z0,z1}
   unsigned short* s_cz = reinterpret_cast<unsigned short*>(s_z2 + (bc.cap >> 1));           // [max_rows][cz_stride]
-  BlockRow* s_row = reinterpret_cast<BlockRow*>(s_cz + bc.max_rows * bc.cz_stride);         // [max_rows]
-  int* s_hdr = reinterpret_cast<int*>(s_row + bc.max_rows);                                 // [PLAN_HDR_INTS]
+  unsigned int* s_q = reinterpret_cast<unsigned int*>(s_cz + bc.max_rows * bc.cz_stride);   // [warps][32] trial items
   float* s_xyf = reinterpret_cast<float*>(s_xy);
   float* s_zf = reinterpret_cast<float*>(s_z2);
-  __shared__ __align__(8) uint64_t s_bar;
-  __shared__ int s_tick, s_done_idx;
+  __shared__ BlockRow s_row[LEAN_MAX_ROWS];
+  __shared__ int s_cnt[LEAN_MAX_ROWS + 1];
+  __shared__ int s_tick, s_done_idx, s_bad, s_bad2, s_need;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = LEAN_THREADS / 32;
   const int czs = bc.cz_stride;
+  const unsigned FULL = 0xffffffffu;
 
   // ---- which block (fused launches: ticket) -----------------------------------------------------------------
   const int hbz = bc.nbz >> 1, hby = bc.nby >> 1, hbx = bc.nbx >> 1;
   int ph = a.phase, bid = blockIdx.x;
-  if (tid == 0) mbar_init(&s_bar, 1);
+  if (tid == 0) { s_bad = 0; s_bad2 = 0; s_need = 0; }
   if (a.fuse > 1) {
     if (tid == 0) s_tick = (int)(atomicAdd(bc.ticket, 1u) - a.ticket_base);
     __syncthreads();
@@ -423,16 +254,32 @@ k_sweep_lean(SweepArgs a, BlockCfg bc, LeanPlan pl, const int* __restrict__ xoff
   const int bzi = 2 * (bid % hbz) + pcz;
   const int byi = 2 * ((bid / hbz) % hby) + pcy;
   const int bxi = 2 * (bid / (hbz * hby)) + pcx;
-  const int bl = (bxi * bc.nby + byi) * bc.nbz + bzi;
-  // the plan of this block is static data of an earlier kernel: fetch it while waiting for the neighbours
-  if (tid == 0) {
-    s_done_idx = bl;
-    const uint32_t b_hdr = PLAN_HDR_INTS * 4, b_row = (uint32_t)bc.max_rows * 16u, b_cz = (uint32_t)(bc.max_rows * czs) * 2u;
-    mbar_arrive_tx(&s_bar, b_hdr + b_row + b_cz);
-    tma_bulk_g2s(s_hdr, pl.hdr + (size_t)bl * PLAN_HDR_INTS, b_hdr, &s_bar);
-    tma_bulk_g2s(s_row, pl.row + (size_t)bl * bc.max_rows, b_row, &s_bar);
-    tma_bulk_g2s(s_cz, pl.cz + (size_t)bl * bc.max_rows * czs, b_cz, &s_bar);
+  const BlkGeom q = blk_geom(g, bc, xoff, bxi, byi, bzi);
+  const int nrows = q.nrows, nry = q.nry, lenz = q.lenz;
+  if (tid == 0) s_done_idx = (bxi * bc.nby + byi) * bc.nbz + bzi;
+
+  // ---- staging rows (static while cell membership is: no need to wait for the neighbours): one THREAD per row
+  //      (a row is some 25 cells: a short serial loop costs 30x fewer issue slots than a warp per row);
+  //      row-relative index of the first particle of every cell, row populations ---------------------------------
+  const float inv_nry = 1.0f / (float)nry;
+  for (int r = tid; r < nrows; r += LEAN_THREADS) {
+    const int rx = (int)(((float)r + 0.5f) * inv_nry), ry = r - rx * nry;       // (exact: r < 256, nry <= 16)
+    const int* row = cs + blk_global_row(g, q, rx, ry) * g.nz;
+    const int gbA = row[q.zs];
+    int gbB = 0, geA;
+    if (q.zwrap) { gbB = row[0]; geA = row[g.nz]; }
+    else geA = row[q.zs + lenz];
+    unsigned short* cz = s_cz + r * czs;
+    const int nA = min(lenz, g.nz - q.zs);          // cells zi <= nA read piece A
+#pragma unroll 4
+    for (int zi = 0; zi <= nA; zi++) cz[zi] = (unsigned short)(row[q.zs + zi] - gbA);
+    const int cA = geA - gbA;
+#pragma unroll 4
+    for (int zi = nA + 1; zi <= lenz; zi++) cz[zi] = (unsigned short)(cA + row[q.zs + zi - g.nz] - gbB);
+    s_row[r].gbA = gbA; s_row[r].gbB = gbB; s_row[r].cntA = cA;
+    s_cnt[r] = q.zwrap ? cA + (row[q.zs + lenz - g.nz] - gbB) : cA;
   }
+  // ---- fused launches: wait for the neighbouring blocks of earlier phases -----------------------------------------
   if (a.fuse > 1) {
     if (tid < 27 && tid != 13) {
       int nx = bxi + tid / 9 - 1, ny = byi + (tid / 3) % 3 - 1, nz = bzi + tid % 3 - 1;
@@ -459,32 +306,79 @@ k_sweep_lean(SweepArgs a, BlockCfg bc, LeanPlan pl, const int* __restrict__ xoff
       __threadfence();                     // acquire: everything those blocks wrote is visible from here on
     }
   }
-  __syncthreads();                          // (also: the mbarrier initialisation is visible to every waiter)
-  const BlkGeom q = blk_geom(g, bc, xoff, bxi, byi, bzi);
-  const int nrows = q.nrows, nry = q.nry, lenz = q.lenz;
-  mbar_wait_bounded(&s_bar, 0);
-  const int total = s_hdr[PLAN_TOTAL], pflags = s_hdr[PLAN_FLAGS];
-  const long long tbase = s_hdr[PLAN_TBASE];
+  __syncthreads();
+  if (tid < 32) {                               // exclusive scan of the row populations
+    int carry = 0;
+    for (int base = 0; base < nrows; base += 32) {
+      const int r = base + tid;
+      const int v = (r < nrows) ? s_cnt[r] : 0;
+      int inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(FULL, inc, o);
+        if (tid >= o) inc += t;
+      }
+      if (r < nrows) s_row[r].off = carry + inc - v;
+      carry += __shfl_sync(FULL, inc, 31);
+    }
+    if (tid == 0) {
+      s_cnt[nrows] = carry;
+      if (carry + LEAN_PAD > bc.cap) s_bad = 1;
+    }
+  }
+  __syncthreads();
+  const int total = s_cnt[nrows];
 
   int n_acc = 0, n_ov = 0, n_cell = 0;
-  if (!(pflags & PLAN_BAD) && !bc.force_global) {
+  const float wxf = (float)g.wx, wyf = (float)g.wy, wzf = (float)g.wz;
+  const float hxr = 0.5f * (float)q.nrx, hyr = 0.5f * (float)nry, hzr = 0.5f * (float)lenz;
+  if (!s_bad && !bc.force_global) {
+    // ---- staged indices of the cells; longest stencil row; trial records and proposals of the interior towards L2 ----
+    {
+      int need = 0;
+      bool deep_cell = false;
+      for (int r = tid; r < nrows; r += LEAN_THREADS) {
+        const int rx = (int)(((float)r + 0.5f) * inv_nry), ry = r - rx * nry;
+        const BlockRow rw = s_row[r];
+        unsigned short* cz = s_cz + r * czs;
+        const bool rint = rx >= 1 && rx <= q.ex && ry >= 1 && ry <= q.ey;
+        int vb = rw.off, v = (int)cz[1] + rw.off, vn = (int)cz[2] + rw.off;      // cells zi-1, zi, zi+1 (zi = 1)
+        cz[0] = (unsigned short)vb;
+        for (int zi = 1; zi <= q.ez; zi++) {
+          const int ve = (int)cz[zi + 2] + rw.off;                               // start of cell zi+2 = end of cell zi+1
+          cz[zi] = (unsigned short)v;
+          // entries a trial in cell zi scans in this row: from the pair-aligned start of cell zi-1 to the end of cell zi+1
+          need = max(need, ve - (vb & ~1));
+          deep_cell |= rint && vn - v > LEAN_MAX_OCC;
+          vb = v; v = vn; vn = ve;
+        }
+        cz[q.ez + 1] = (unsigned short)v;
+        cz[q.ez + 2] = (unsigned short)vn;
+        if (rint) {
+          // interior particles of the row: slots [first, first + m) of the (trial-ordered) tables
+          const int i1 = (int)cz[1] - rw.off, m = (int)cz[q.ez + 1] - (int)cz[1];
+          const int first = (i1 < rw.cntA) ? rw.gbA + i1 : rw.gbB + i1 - rw.cntA;
+          for (int k = 0; k < m; k += 8) prefetch_l2(trec + first + k);
+          for (int k = 0; k < m; k += 4) prefetch_l2(prop + first + k);
+        }
+      }
+      need = __reduce_max_sync(FULL, need);
+      if (lane == 0) atomicMax(&s_need, need);
+      if (__any_sync(FULL, deep_cell) && lane == 0) s_bad2 = 1;      // (s_bad itself must not change inside this branch)
+    }
     // ---- stage the fp32 shadow as block-relative coordinates fma(cell index - centre, edge, offset) -----------------
-    const float wxf = (float)g.wx, wyf = (float)g.wy, wzf = (float)g.wz;
-    const float hxr = 0.5f * (float)q.nrx, hyr = 0.5f * (float)nry, hzr = 0.5f * (float)lenz;
     {
       // each staged row is cut into P runs of particles, one (row, run) item per thread and round; a thread first
-      // issues all the loads of a batch, then converts them (the cell of a particle follows from the row's cell index)
+      // issues all the loads of a batch, then converts them (the shadow carries the z cell of its particle)
       const int P = (2 * nrows <= LEAN_THREADS) ? 2 : 1;
 #pragma unroll 1
       for (int idx = tid; idx < P * nrows; idx += LEAN_THREADS) {
         const int r = (P == 2) ? idx >> 1 : idx, piece = (P == 2) ? idx & 1 : 0;
         const BlockRow rw = s_row[r];
-        const int cntr = ((r + 1 < nrows) ? s_row[r + 1].off : total) - rw.off;
+        const int cntr = s_cnt[r];
         const int k0 = (cntr * piece) / P, k1 = (cntr * (piece + 1)) / P;
-        const int rx = r / nry, ry = r - rx * nry;
+        const int rx = (int)(((float)r + 0.5f) * inv_nry), ry = r - rx * nry;
         const float cxw = ((float)rx - hxr), cyw = ((float)ry - hyr);
-        const unsigned short* cz = s_cz + r * czs;
-        int zi = 0, nextb = cz[1];                       // cell of the particle being converted; start of the next cell
 #pragma unroll 1
         for (int kb = k0; kb < k1; kb += 8) {
           float4 v[8];
@@ -498,7 +392,8 @@ k_sweep_lean(SweepArgs a, BlockCfg bc, LeanPlan pl, const int* __restrict__ xoff
             const int k = kb + u;
             if (k < k1) {
               const int i = rw.off + k;
-              while (i >= nextb && zi < lenz - 1) { zi++; nextb = cz[zi + 1]; }
+              int zi = __float_as_int(v[u].w) - q.z0;                  // z cell of the particle inside the region
+              if (zi < 0) zi += g.nz; else if (zi >= g.nz) zi -= g.nz;
               float* xy = s_xyf + ((i >> 1) << 2) + (i & 1);
               xy[0] = __fmaf_rn(cxw, wxf, v[u].x);
               xy[2] = __fmaf_rn(cyw, wyf, v[u].y);
@@ -514,142 +409,201 @@ k_sweep_lean(SweepArgs a, BlockCfg bc, LeanPlan pl, const int* __restrict__ xoff
       }
     }
     __syncthreads();
-
+  }
+  if (!s_bad && !s_bad2 && !bc.force_global) {
     // ---- trials -----------------------------------------------------------------------------------------------
-    const unsigned FULL = 0xffffffffu;
     const float lo = 1.0f - a.eps, hi = 1.0f + a.eps;
-    const bool deep_rows = (pflags & PLAN_DEEP) != 0;
-    const int npairs = s_hdr[PLAN_NPAIRS];
-    int cbase = 0;
+    const int need = s_need;
+    const int npairs = min(LEAN_NP_MAX, max(LEAN_NP_MIN, (need + 1) >> 1));
+    const bool deep_rows = need > 2 * LEAN_NP_MAX;
+    const int parx = (g.gx0 + q.x0) & 1, pary = q.y0 & 1, parz = q.z0 & 1;   // parity of region cell (0,0,0); grids are even
+    unsigned int* my_q = s_q + warp * 32;
+    // ---- chunks: per colour, the interior cells of the colour (x slowest, z fastest) are cut into runs of at most 32
+    //      cells holding at most 32 trials; a run is one warp's work between two colour barriers (lane = trial, a
+    //      cell's trials in adjacent lanes).  One warp per colour finds the cuts.
+    unsigned short* s_cut = reinterpret_cast<unsigned short*>(s_q + NW * 32);       // [8][LEAN_MAX_CHUNKS + 1]
+    for (int col = warp; col < 8; col += NW) {
+      const int fx = 1 + ((parx + 1 + (col >> 2)) & 1), fy = 1 + ((pary + 1 + (col >> 1)) & 1), fz = 1 + ((parz + 1 + col) & 1);
+      const int nxc = (q.ex - fx + 2) >> 1, nyc = (q.ey - fy + 2) >> 1, nzc = (q.ez - fz + 2) >> 1;
+      const int ncell = nxc * nyc * nzc;
+      const float inz = 1.0f / (float)max(nzc, 1), iny = 1.0f / (float)max(nyc, 1);
+      unsigned short* cut = s_cut + col * (LEAN_MAX_CHUNKS + 1);
+      int at = 0, k = 0;
+      if (lane == 0) cut[0] = 0;
+      while (at < ncell && k < LEAN_MAX_CHUNKS) {
+        const int cq = at + lane;
+        int n = 0;
+        if (cq < ncell) {
+          const int t2 = (int)(((float)cq + 0.5f) * inz), izc = cq - t2 * nzc;      // (exact: cq < 4096, divisors <= 16)
+          const int ixc = (int)(((float)t2 + 0.5f) * iny), iyc = t2 - ixc * nyc;
+          const unsigned short* cz = s_cz + ((fx + 2 * ixc) * nry + fy + 2 * iyc) * czs + fz + 2 * izc;
+          n = (int)cz[1] - (int)cz[0];
+        }
+        int inc = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(FULL, inc, o);
+          if (lane >= o) inc += t;
+        }
+        at += __popc(__ballot_sync(FULL, cq < ncell && inc <= 32));
+        k++;
+        if (lane == 0) cut[k] = (unsigned short)at;
+      }
+      if (lane == 0) {
+        cut[LEAN_MAX_CHUNKS] = (unsigned short)k;
+        if (at < ncell) s_bad2 = 1;              // more chunks than the table holds: global-memory path
+      }
+    }
+    __syncthreads();
+    if (s_bad2) goto global_path;                // (block-uniform)
 #pragma unroll 1
     for (int col = 0; col < 8; col++) {
-      const int ntr = s_hdr[PLAN_NTR + col];
+      // interior cells of this colour: first index and count per axis
+      const int fx = 1 + ((parx + 1 + (col >> 2)) & 1), fy = 1 + ((pary + 1 + (col >> 1)) & 1), fz = 1 + ((parz + 1 + col) & 1);
+      const int nyc = (q.ey - fy + 2) >> 1, nzc = (q.ez - fz + 2) >> 1;
+      const float inz = 1.0f / (float)max(nzc, 1), iny = 1.0f / (float)max(nyc, 1);
+      const unsigned short* cut = s_cut + col * (LEAN_MAX_CHUNKS + 1);
+      const int nch = cut[LEAN_MAX_CHUNKS];
 #pragma unroll 1
-      for (int chunk = warp; chunk * 32 < ntr; chunk += NW) {
-        const int t = chunk * 32 + lane;
-        bool valid = t < ntr;
-        uint4 rec = make_uint4(0u, 0u, 0u, LEAN_INVALID);
-        if (valid) rec = __ldg(pl.trial + tbase + cbase + t);
-        // the next records of this warp (next chunk of this colour, else its first chunk of the next colour): towards L2
+      for (int kc = warp; kc < nch; kc += NW) {
+        // ---- this chunk's cells (lane = cell, z fastest) and their trials ----
+        const int c0 = cut[kc], c1 = cut[kc + 1];
+        const int cq = c0 + lane;
+        int ob = 0, n = 0, crx = 0, cry = 0, crz = 0;
+        if (cq < c1) {
+          const int t2 = (int)(((float)cq + 0.5f) * inz), izc = cq - t2 * nzc;
+          const int ixc = (int)(((float)t2 + 0.5f) * iny), iyc = t2 - ixc * nyc;
+          crx = fx + 2 * ixc; cry = fy + 2 * iyc; crz = fz + 2 * izc;
+          const unsigned short* cz = s_cz + (crx * nry + cry) * czs + crz;
+          ob = cz[0];
+          n = (int)cz[1] - ob;
+        }
+        int inc = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(FULL, inc, o);
+          if (lane >= o) inc += t;
+        }
+        const int T = __shfl_sync(FULL, inc, 31), start = inc - n;        // T <= 32 by construction
         {
-          const bool same = (chunk + NW) * 32 < ntr;
-          const long long nt = same ? (long long)cbase + t + NW * 32 : (long long)cbase + ((ntr + 31) & ~31) + warp * 32 + lane;
-          if (same || col < 7) prefetch_l1(pl.trial + tbase + nt);
-        }
-        const unsigned int code = rec.w;
-        valid = valid && code != LEAN_INVALID;
-        const bool act = valid && (code >> 31);
-        const int sel = code & 0xfff, rxc = (code >> 12) & 15, ryc = (code >> 16) & 15, rz = (code >> 20) & 31;
-        const int j = (code >> 25) & 7, n1 = (code >> 28) & 7;
-        // mates: the trials of a cell sit in adjacent lanes of one chunk (k_block_plan never lets a cell straddle)
-        const int nprev = valid ? j : 0;
-        const int nnext = valid ? n1 - j : 0;
-        if (act) {                                 // the proposal an accepted trial copies: towards L1 now
+          for (int j = 0; j < n; j++) my_q[start + j] = LEAN_ITEM(ob, crx, cry, crz, j, n - 1);
+          __syncwarp();
+          const bool valid = lane < T;
+          const unsigned int item = valid ? my_q[lane] : 0u;
+          __syncwarp();
+          const int cob = item & 0xfff, rxc = (item >> 12) & 15, ryc = (item >> 16) & 15, rz = (item >> 20) & 31;
+          const int j = (item >> 25) & 7, n1 = (item >> 28) & 7;
+          // mates of the same cell: all in this chunk, in adjacent lanes
+          const int nprev = valid ? j : 0;
+          const int nnext = valid ? n1 - j : 0;
+          // trial record: slot (cell start + j) of the rank-ordered tables
           const BlockRow rwc = s_row[rxc * nry + ryc];
-          const int ro = sel - rwc.off;
-          prefetch_l1(prop + ((ro < rwc.cntA) ? rwc.gbA + ro : rwc.gbB + ro - rwc.cntA));
-        }
-        // trial point, block-relative
-        const float tx = __fmaf_rn((float)rxc - hxr, wxf, __uint_as_float(rec.x));
-        const float ty = __fmaf_rn((float)ryc - hyr, wyf, __uint_as_float(rec.y));
-        const float tz = __fmaf_rn((float)rz - hzr, wzf, __uint_as_float(rec.z));
-        // every trial particle of the chunk is hidden while the chunk is scanned
-        float* mxy = s_xyf + ((sel >> 1) << 2) + (sel & 1);
-        float kx = 0.f, ky = 0.f, kz = 0.f;
-        if (valid) {
-          kx = mxy[0]; ky = mxy[2]; kz = s_zf[sel];
-          mxy[0] = LEAN_FAR; mxy[2] = LEAN_FAR; s_zf[sel] = LEAN_FAR;
-        }
-        __syncwarp();
-        float r2min = 3.0e38f;
-        if (act) {
-          const unsigned short* cp0 = s_cz + ((rxc - 1) * nry + ryc - 1) * czs + rz - 1;
-          if (npairs <= 3) r2min = lean_scan<3>(s_xy, s_z2, cp0, nry, czs, tx, ty, tz);
-          else if (npairs == 4) r2min = lean_scan<4>(s_xy, s_z2, cp0, nry, czs, tx, ty, tz);
-          else r2min = lean_scan<5>(s_xy, s_z2, cp0, nry, czs, tx, ty, tz);
-          if (deep_rows) {                         // some stencil row of this block is longer than the straight-line scan
-            const unsigned long long TX = f2_pack(tx, tx), TY = f2_pack(ty, ty), TZ = f2_pack(tz, tz);
+          const int ro = cob - rwc.off;
+          const int gcell0 = (ro < rwc.cntA) ? rwc.gbA + ro : rwc.gbB + ro - rwc.cntA;    // global slot of the cell's first particle
+          uint4 rec = make_uint4(0u, 0u, 0u, 0u);
+          if (valid) rec = __ldg(trec + gcell0 + j);
+          const bool act = valid && (rec.w & TREC_ACT);
+          const int koff = rec.w & 15;
+          const int sel = cob + koff;
+          // trial point, block-relative
+          const float tx = __fmaf_rn((float)rxc - hxr, wxf, __uint_as_float(rec.x));
+          const float ty = __fmaf_rn((float)ryc - hyr, wyf, __uint_as_float(rec.y));
+          const float tz = __fmaf_rn((float)rz - hzr, wzf, __uint_as_float(rec.z));
+          // every trial particle of the chunk is hidden while the chunk is scanned
+          float* mxy = s_xyf + ((sel >> 1) << 2) + (sel & 1);
+          float kx = 0.f, ky = 0.f, kz = 0.f;
+          if (valid) {
+            kx = mxy[0]; ky = mxy[2]; kz = s_zf[sel];
+            mxy[0] = LEAN_FAR; mxy[2] = LEAN_FAR; s_zf[sel] = LEAN_FAR;
+          }
+          __syncwarp();
+          float r2min = 3.0e38f;
+          if (act) {
+            const unsigned short* cp0 = s_cz + ((rxc - 1) * nry + ryc - 1) * czs + rz - 1;
+            if (npairs <= 3) r2min = lean_scan<3>(s_xy, s_z2, cp0, nry, czs, tx, ty, tz);
+            else if (npairs == 4) r2min = lean_scan<4>(s_xy, s_z2, cp0, nry, czs, tx, ty, tz);
+            else r2min = lean_scan<5>(s_xy, s_z2, cp0, nry, czs, tx, ty, tz);
+            if (deep_rows) {                         // some stencil row of this block is longer than the straight-line scan
+              const unsigned long long TX = f2_pack(tx, tx), TY = f2_pack(ty, ty), TZ = f2_pack(tz, tz);
 #pragma unroll 1
-            for (int r = 0; r < 9; r++) {
-              const unsigned short* cp = cp0 + ((r / 3) * nry + (r % 3)) * czs;
-              const int e = cp[3];
+              for (int r = 0; r < 9; r++) {
+                const unsigned short* cp = cp0 + ((r / 3) * nry + (r % 3)) * czs;
+                const int e = cp[3];
 #pragma unroll 1
-              for (int p = ((int)cp[0] >> 1) + LEAN_NP_MAX; 2 * p < e; p++) r2min = lean_pair(s_xy[p], s_z2[p], TX, TY, TZ, r2min);
+                for (int p = ((int)cp[0] >> 1) + LEAN_NP_MAX; 2 * p < e; p++) r2min = lean_pair(s_xy[p], s_z2[p], TX, TY, TZ, r2min);
+              }
             }
           }
-        }
-        // mates with a LATER trial in this chunk: still at their old positions
-        const int maxnext = __reduce_max_sync(FULL, nnext);
-        for (int s = 1; s <= maxnext; s++) {
-          const float qx = __shfl_down_sync(FULL, kx, s), qy = __shfl_down_sync(FULL, ky, s), qz = __shfl_down_sync(FULL, kz, s);
-          if (act && s <= nnext) {
-            const float ddx = tx - qx, ddy = ty - qy, ddz = tz - qz;
-            r2min = fminf(r2min, __fmaf_rn(ddz, ddz, __fmaf_rn(ddy, ddy, ddx * ddx)));
-          }
-        }
-        // verdicts in trial order: round s decides the trials with s earlier mates in the chunk; the later
-        // trials of those cells then see where the decided particle ended up
-        const int maxprev = __reduce_max_sync(FULL, nprev);
-        float fx = kx, fy = ky, fz = kz;              // where this lane's particle is after its own trial
-        int verdict = 2;
-#pragma unroll 1
-        for (int s = 0; s <= maxprev; s++) {
-          if (valid && nprev == s) {
-            if (act) {
-              const BlockRow rwc = s_row[rxc * nry + ryc];
-              const int ro = sel - rwc.off;
-              const int gs = (ro < rwc.cntA) ? rwc.gbA + ro : rwc.gbB + ro - rwc.cntA;
-              bool ov = r2min < lo;
-              if (!ov && r2min <= hi) {
-                const double4 pr = prop[gs];
-                ov = block_exact_rescan(pos, s_row, s_cz, czs, nry, rxc, ryc, rz, sel, pr.x, pr.y, pr.z, a.box);
-              }
-              if (ov) { verdict = 1; n_ov++; }
-              else {
-                verdict = 0; n_acc++;
-                fx = tx; fy = ty; fz = tz;
-                const double4 pr = prop[gs];
-                double* pd = reinterpret_cast<double*>(pos + gs);
-                *reinterpret_cast<double2*>(pd) = make_double2(pr.x, pr.y);
-                pd[2] = pr.z;
-                float* rl = reinterpret_cast<float*>(rel + gs);
-                *reinterpret_cast<float2*>(rl) = make_float2(__uint_as_float(rec.x), __uint_as_float(rec.y));
-                rl[2] = __uint_as_float(rec.z);
-              }
-            } else n_cell++;
-            mxy[0] = fx; mxy[2] = fy; s_zf[sel] = fz;
-          }
-          if (s < maxprev) {
-            __syncwarp();
-            const int src = (nprev > s) ? lane - (nprev - s) : lane;
-            const float qx = __shfl_sync(FULL, fx, src), qy = __shfl_sync(FULL, fy, src), qz = __shfl_sync(FULL, fz, src);
-            if (act && nprev > s) {
+          // mates with a LATER trial in this chunk: still at their old positions
+          const int maxnext = __reduce_max_sync(FULL, nnext);
+          for (int s = 1; s <= maxnext; s++) {
+            const float qx = __shfl_down_sync(FULL, kx, s), qy = __shfl_down_sync(FULL, ky, s), qz = __shfl_down_sync(FULL, kz, s);
+            if (act && s <= nnext) {
               const float ddx = tx - qx, ddy = ty - qy, ddz = tz - qz;
               r2min = fminf(r2min, __fmaf_rn(ddz, ddz, __fmaf_rn(ddy, ddy, ddx * ddx)));
             }
           }
-        }
-        if (LOG && valid) {
-          const uint4 rw4 = __ldg(pl.raw + tbase + cbase + t);
-          const int iy = q.y0 + ryc, iz = q.z0 + rz;
-          const int gxl = g.gx0 + q.x0 + rxc;
-          const int gx = (gxl >= g.nx) ? gxl - g.nx : gxl;
-          const long long gcell = ((long long)gx * g.ny + iy) * g.nz + iz;
-          const unsigned long long sl = atomicAdd(nlog, 1ull);
-          if ((long long)sl < logcap) {
-            hsmc_gpu_trial tr;
-            tr.seq = ((unsigned long long)(ph * 8 + col) << 56) | ((unsigned long long)gcell << 8) | (unsigned)j;
-            tr.id = (int)rw4.w; tr.verdict = verdict;
-            tr.raw[0] = rw4.x; tr.raw[1] = rw4.y; tr.raw[2] = rw4.z; tr.pad = 0;
-            log[sl] = tr;
+          // verdicts in trial order: round s decides the trials with s earlier mates in the chunk; the later
+          // trials of those cells then see where the decided particle ended up
+          const int maxprev = __reduce_max_sync(FULL, nprev);
+          float fx2 = kx, fy2 = ky, fz2 = kz;           // where this lane's particle is after its own trial
+          int verdict = 2;
+#pragma unroll 1
+          for (int s = 0; s <= maxprev; s++) {
+            if (valid && nprev == s) {
+              if (act) {
+                bool ov = r2min < lo;
+                if (!ov && r2min <= hi) {
+                  const double4 pr = prop[gcell0 + j];
+                  ov = block_exact_rescan(pos, s_row, s_cz, czs, nry, rxc, ryc, rz, sel, pr.x, pr.y, pr.z, a.box);
+                }
+                if (ov) { verdict = 1; n_ov++; }
+                else {
+                  verdict = 0; n_acc++;
+                  fx2 = tx; fy2 = ty; fz2 = tz;
+                  const double4 pr = prop[gcell0 + j];
+                  double* pd = reinterpret_cast<double*>(pos + gcell0 + koff);
+                  *reinterpret_cast<double2*>(pd) = make_double2(pr.x, pr.y);
+                  pd[2] = pr.z;
+                  float* rl = reinterpret_cast<float*>(rel + gcell0 + koff);
+                  *reinterpret_cast<float2*>(rl) = make_float2(__uint_as_float(rec.x), __uint_as_float(rec.y));
+                  rl[2] = __uint_as_float(rec.z);
+                }
+              } else n_cell++;
+              mxy[0] = fx2; mxy[2] = fy2; s_zf[sel] = fz2;
+            }
+            if (s < maxprev) {
+              __syncwarp();
+              const int src = (nprev > s) ? lane - (nprev - s) : lane;
+              const float qx = __shfl_sync(FULL, fx2, src), qy = __shfl_sync(FULL, fy2, src), qz = __shfl_sync(FULL, fz2, src);
+              if (act && nprev > s) {
+                const float ddx = tx - qx, ddy = ty - qy, ddz = tz - qz;
+                r2min = fminf(r2min, __fmaf_rn(ddz, ddz, __fmaf_rn(ddy, ddy, ddx * ddx)));
+              }
+            }
           }
+          if (LOG && valid) {
+            const uint4 rw4 = __ldg(traw + gcell0 + j);
+            const int iy = q.y0 + ryc, iz = q.z0 + rz;
+            const int gxl = g.gx0 + q.x0 + rxc;
+            const int gx = (gxl >= g.nx) ? gxl - g.nx : gxl;          // interior cells never wrap inside the block
+            const long long gcell = ((long long)gx * g.ny + iy) * g.nz + iz;
+            const unsigned long long sl = atomicAdd(nlog, 1ull);
+            if ((long long)sl < logcap) {
+              hsmc_gpu_trial tr;
+              tr.seq = ((unsigned long long)(ph * 8 + col) << 56) | ((unsigned long long)gcell << 8) | (unsigned)j;
+              tr.id = (int)rw4.w; tr.verdict = verdict;
+              tr.raw[0] = rw4.x; tr.raw[1] = rw4.y; tr.raw[2] = rw4.z; tr.pad = 0;
+              log[sl] = tr;
+            }
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
-      cbase += (ntr + 31) & ~31;
       __syncthreads();                       // colour barrier
     }
   } else {
+global_path:
     // ---- the block does not fit the staged scheme (unusually dense) or ablation: global-memory path,
     //      same order of updates ----------------------------------------------------------------------------------
     const int ncell_b = q.ex * q.ey * q.ez;
@@ -668,9 +622,9 @@ k_sweep_lean(SweepArgs a, BlockCfg bc, LeanPlan pl, const int* __restrict__ xoff
   }
 
   // ---- counters: warp reduce, then straight to the global counters ------------------------------------------
-  n_acc = __reduce_add_sync(0xffffffffu, n_acc);
-  n_ov = __reduce_add_sync(0xffffffffu, n_ov);
-  n_cell = __reduce_add_sync(0xffffffffu, n_cell);
+  n_acc = __reduce_add_sync(FULL, n_acc);
+  n_ov = __reduce_add_sync(FULL, n_ov);
+  n_cell = __reduce_add_sync(FULL, n_cell);
   if (lane == 0 && (n_acc | n_ov | n_cell)) {
     atomicAdd(&cnt[CNT_TRIALS], (unsigned long long)(n_acc + n_ov + n_cell));
     if (n_acc) atomicAdd(&cnt[CNT_ACC], (unsigned long long)n_acc);

@@ -9,6 +9,7 @@
 #include <time.h>
 
 #include "hs_sim.h"
+#include "hs_opt.h"
 
 static double now_s(void) {
   struct timespec t;
@@ -47,10 +48,6 @@ static opt_sample take_sample(hs_sim *s, int sweeps, bool npt) {
   return o;
 }
 
-static double secant(double x1, double y1, double x2, double y2, double target) {
-  return x2 - (y2 - target) * (x2 - x1) / (y2 - y1);
-}
-
 static void optimize(hs_sim *s, bool npt) {
   hs_input *in = &s->in;
   int per_sample = in->opt_sweeps / in->opt_samples;
@@ -63,21 +60,10 @@ static void optimize(hs_sim *s, bool npt) {
   if (npt) in->dv_max = (a.acc_vol > in->opt_vol_target) ? in->dv_max * 2 : in->dv_max / 2;
   opt_sample b = take_sample(s, per_sample, npt);
   for (int i = 0; i < in->opt_samples; i++) {
-    in->dr_max = secant(a.dr, a.acc_part, b.dr, b.acc_part, in->opt_part_target);
-    if (npt) in->dv_max = secant(a.dv, a.acc_vol, b.dv, b.acc_vol, in->opt_vol_target);
-    if (in->dr_max > 1.0) in->dr_max = 1.0;
-    else if (in->dr_max <= 0.0) {
-      in->dr_max = -in->dr_max;
-      if (in->dr_max > 1.0) in->dr_max = b.dr / 2;
-    }
-    if (npt && in->dv_max <= 0.0) {
-      in->dv_max = -in->dv_max;
-      if (in->dv_max > 0.1) in->dv_max = b.dv / 2;
-    }
-    /* the reference divides by (acc2 - acc1) unguarded and can emit NaN (SURVEY section 2,
-       optimizer hazard); keep the previous step in that case instead of poisoning the run */
-    if (!(in->dr_max == in->dr_max) || in->dr_max <= 0.0) in->dr_max = b.dr;
-    if (npt && (!(in->dv_max == in->dv_max) || in->dv_max <= 0.0)) in->dv_max = b.dv;
+    /* the reference's secant step with its clamps; a step that is not a positive finite number (two samples
+       with equal acceptance: the reference divides by zero, optimizer.c:45) keeps the previous one (hs_opt.h) */
+    in->dr_max = hs_opt_next_dr(a.dr, a.acc_part, b.dr, b.acc_part, in->opt_part_target);
+    if (npt) in->dv_max = hs_opt_next_dv(a.dv, a.acc_vol, b.dv, b.acc_vol, in->opt_vol_target);
     a = b;
     b = take_sample(s, per_sample, npt);
   }

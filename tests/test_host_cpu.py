@@ -330,3 +330,55 @@ def test_block_plan_of_the_benchmark_box(lib_built):
     p = G.plan_blocks(box, n)
     assert p["blocks"] == (54, 28, 10) and p["max_extent"] == (8, 8, 21) and p["ctas_per_phase"] == 1890
     assert p["xcuts"][0] == 0 and p["xcuts"][-1] == 420
+
+
+def test_optimizer_step_guard(tmp_path):
+    """the reference's secant step (optimizer.c:45-58, 115-139) divides by the difference of two
+    acceptance ratios unguarded; equal ratios give inf/NaN and poison the run.  hs_opt.h keeps the previous step
+    instead, and otherwise reproduces the reference's update (cap at 1.0, sign flip, halving) exactly."""
+    src = tmp_path / "t.c"
+    src.write_text(r'''
+#include <math.h>
+#include <stdio.h>
+#include "hs_opt.h"
+static double ref_dr(double x1, double y1, double x2, double y2, double t) {   /* optimizer.c:45-58 */
+  double v = x2 - (y2 - t) * (x2 - x1) / (y2 - y1);
+  if (v > 1.0) v = 1.0; else if (v <= 0.0) { v = -v; if (v > 1.0) v = x2 / 2; }
+  return v;
+}
+static double ref_dv(double x1, double y1, double x2, double y2, double t) {   /* optimizer.c:115-139 */
+  double v = x2 - (y2 - t) * (x2 - x1) / (y2 - y1);
+  if (v <= 0.0) { v = -v; if (v > 0.1) v = x2 / 2; }
+  return v;
+}
+int main(void) {
+  int bad = 0;
+  /* regular steps: identical to the reference's arithmetic */
+  double c[][5] = {{0.05, 0.8, 0.1, 0.6, 0.5}, {0.1, 0.6, 0.15, 0.45, 0.5}, {0.4, 0.52, 0.8, 0.3, 0.5},
+                   {0.2, 0.3, 0.1, 0.9, 0.5}, {0.001, 0.7, 0.002, 0.65, 0.5}, {0.9, 0.55, 1.0, 0.54, 0.5}};
+  for (int i = 0; i < 6; i++) {
+    if (hs_opt_next_dr(c[i][0], c[i][1], c[i][2], c[i][3], c[i][4]) != ref_dr(c[i][0], c[i][1], c[i][2], c[i][3], c[i][4])) bad |= 1;
+    if (hs_opt_next_dv(c[i][0], c[i][1], c[i][2], c[i][3], c[i][4]) != ref_dv(c[i][0], c[i][1], c[i][2], c[i][3], c[i][4])) bad |= 2;
+  }
+  /* equal acceptance ratios: the reference produces inf / NaN, the guard keeps the previous step */
+  if (isfinite(ref_dr(0.05, 0.5, 0.1, 0.5, 0.5))) bad |= 4;        /* 0/0 */
+  if (hs_opt_next_dr(0.05, 0.5, 0.1, 0.5, 0.5) != 0.1) bad |= 8;
+  if (hs_opt_next_dr(0.05, 0.7, 0.1, 0.7, 0.5) != 0.05) bad |= 16;   /* -inf: the reference's own clamp (sign flip, then x2/2) already yields a usable step */
+  if (hs_opt_next_dv(0.001, 0.3, 0.002, 0.3, 0.5) != 0.002) bad |= 32;
+  if (hs_opt_next_dv(0.001, 0.5, 0.002, 0.5, 0.5) != 0.002) bad |= 64;
+  /* a NaN sample (0 volume moves attempted: 0/0 acceptance) never reaches the step */
+  if (hs_opt_next_dv(0.001, NAN, 0.002, 0.4, 0.5) != 0.002) bad |= 128;
+  if (hs_opt_next_dr(0.05, 0.6, 0.1, NAN, 0.5) != 0.1) bad |= 256;
+  /* results are always usable steps */
+  for (double y1 = 0.0; y1 <= 1.0; y1 += 0.125) for (double y2 = 0.0; y2 <= 1.0; y2 += 0.125) {
+    double v = hs_opt_next_dr(0.05, y1, 0.1, y2, 0.5), w = hs_opt_next_dv(0.001, y1, 0.002, y2, 0.5);
+    if (!(v > 0.0 && v <= 1.0) || !(w > 0.0 && w < 1e300)) bad |= 512;
+  }
+  printf("%d\n", bad);
+  return bad != 0;
+}
+''')
+    exe = tmp_path / "t"
+    subprocess.run(["gcc", "-O2", "-std=gnu99", "-I", os.path.join(ROOT, "hsmc_b200", "host"), "-o", str(exe), str(src), "-lm"], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "0", r.stdout
