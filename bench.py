@@ -331,12 +331,24 @@ def widom_workload(args, rank, world, local_rank):
     rhos = [0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9]
     M = int(args.insertions)
     first, count = shard_range(M, rank, world)
-    handles = []
+    handles, prep = [], []
     for rho in rhos:
         box, conf = fcc_lattice(20, 20, 20, rho)
         h = hsmc_b200.HsmcGpu(conf.shape[0], box, seed=20261017, device=local_rank)      # same chain on every rank
         h.upload(conf)
-        h.sweep_nvt(400, min(0.5, 0.05 / rho ** 2))                                       # melt + equilibrate
+        # melt the fcc start and equilibrate: sweeps until the bond-order parameter q6 of the configuration has
+        # collapsed from its fcc value (0.57) to a fluid's (< 0.1), checked on cells wide enough for the first shell;
+        # every rank runs the same deterministic chain, so every rank holds the same fluid
+        dr_eq = min(0.5, 0.08 / rho ** 2)
+        q6, eq_sweeps = 1.0, 0
+        while q6 > 0.1 and eq_sweeps < args.widom_max_eq_sweeps:
+            h.sweep_nvt(2000, dr_eq)
+            eq_sweeps += 2000
+            with hsmc_b200.HsmcGpu(conf.shape[0], box, seed=1, device=local_rank, cell_min=1.5) as t:
+                t.upload(h.download())
+                q6 = t.order_parameter(6, 1.5)
+        h.sweep_nvt(2000, dr_eq)
+        prep.append({"rho": rho, "q6": q6, "equilibration_sweeps": eq_sweeps + 2000, "melted": bool(q6 <= 0.1)})
         info = h.info()
         nbar = conf.shape[0] / (info["cells"][0] * info["cells"][1] * info["cells"][2])
         handles.append((rho, h, nbar, torch.cuda.ExternalStream(h.stream_ptr(), device=torch.device("cuda", local_rank))))
@@ -394,6 +406,9 @@ def widom_workload(args, rank, world, local_rank):
                          "note": "no-reuse figure of SURVEY 8(d); the 1 MB table is cache-resident, so the kernel is "
                                  "bound by issue/latency, not HBM, and frac can exceed 1"},
             "mu_ex": {f"{r:.1f}": float(m) for r, m in zip(rhos, mu)},
+            "mu_ex_carnahan_starling": {f"{r:.1f}": float((8 * e - 9 * e * e + 3 * e ** 3) / (1 - e) ** 3)
+                                        for r, e in ((r, np.pi * r / 6) for r in rhos)},
+            "preparation": prep,
             "accepted_fraction": {f"{r:.1f}": float(f) for r, f in zip(rhos, frac_acc)},
         }
         args.emit(line)
@@ -574,6 +589,7 @@ def main():
                          "GPUs; c2 / c3: configs[1] / configs[2] run through the drop-in host driver on their input files "
                          "(the reference arm runs the reference executable on the identical file)")
     ap.add_argument("--insertions", type=float, default=1e8, help="--workload widom: insertions per sample and density")
+    ap.add_argument("--widom-max-eq-sweeps", type=int, default=200000, help="--workload widom: give up melting a density after this many sweeps (it is then flagged)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -77,7 +77,8 @@ struct BlockCfg {
   int mbx, mby, mbz;      // largest block extent per axis (cells)
   int cap;                // staged shadow capacity (float4 entries, pad included)
   int cs_stride;          // (unused)
-  int cz_stride;          // ushorts per staged CSR row (multiple of 8: rows are TMA destinations)
+  int cz_stride;          // ushorts per staged CSR row (multiple of 8)
+  int nslots;             // chunks (32 trial slots each) the block's trial table holds (< 256)
   int max_rows;           // (mbx+2)*(mby+2)
   int max_cells;          // mbx*mby*mbz
   int use_tma;
@@ -326,11 +327,11 @@ static void setup_blocks(hsmc_gpu* h) {
       slabs.push_back({x0, x1});
     }
   }
-  double capf = 1.08;
+  double capf = 1.12;        // (a block of a crystal can hold 10 % more than the mean: lattice planes beat against the cells)
   if (const char* e = getenv("HSMC_BLOCK_CAPF")) capf = atof(e);
   int want[3] = {0, 0, 0};
   if (const char* e = getenv("HSMC_BLOCK")) sscanf(e, "%d,%d,%d", &want[0], &want[1], &want[2]);
-  struct Shape { int bx, by, bz, mx, my, mz, cap; size_t smem; };
+  struct Shape { int bx, by, bz, mx, my, mz, cap, nslots; size_t smem; };
   auto eval = [&](int bx, int by, int bz, Shape& s) -> bool {
     // a block and its halo must not cover a cell twice: extent + 2 <= cells of the axis
     int mx = 0;
@@ -352,10 +353,14 @@ static void setup_blocks(hsmc_gpu* h) {
     if (cap > 4096) return false;
     int cz_stride = (mz + 3 + 7) & ~7;
     const size_t rows = (size_t)(mx + 2) * (my + 2);
-    size_t smem = (size_t)cap * 12 + rows * cz_stride * 2 + (LEAN_THREADS / 32) * 32 * 4 + 8 * (LEAN_MAX_CHUNKS + 1) * 2;
+    // trial table: chunks of at most 32 cells and 32 trials, handed out one by one; a chunk is cut at a cell boundary
+    // and balanced over the warps, so it holds ~27 trials on average; head-room for dense blocks
+    const double interior = (double)mx * my * mz;
+    const int nslots = std::min(250, (int)std::ceil(std::max(interior / 30.0, interior * std::max(nbar, 0.2) * 1.25 / 26.0)) + 16);
+    size_t smem = (size_t)cap * 12 + rows * cz_stride * 2 + (size_t)nslots * (64 + 4 + 1) + (size_t)cap / 8 + 8 * LEAN_COL_CHUNKS;
     smem = (smem + 15) & ~(size_t)15;
     if (smem > 100 * 1024) return false;
-    s = {bx, by, bz, mx, my, mz, cap, smem};
+    s = {bx, by, bz, mx, my, mz, cap, nslots, smem};
     return true;
   };
   Shape best{};
@@ -397,6 +402,7 @@ static void setup_blocks(hsmc_gpu* h) {
   b.cs_stride = 0; b.cz_stride = (best.mz + 3 + 7) & ~7;
   b.max_rows = (best.mx + 2) * (best.my + 2);
   b.max_cells = best.mx * best.my * best.mz;
+  b.nslots = best.nslots;
   b.use_tma = 0;
   b.force_global = (h->impl == IMPL_BLOCK_GLOBAL) ? 1 : 0;
   b.dbg = getenv("HSMC_BLOCK_DBG") ? atoi(getenv("HSMC_BLOCK_DBG")) : 0;
@@ -1406,6 +1412,18 @@ extern "C" int hsmc_gpu_profile_read(hsmc_gpu* h, double ms[HSMC_GPU_PROFILE_BUC
     ms[k] = h->prof_ms[k]; groups[k] = h->prof_n[k];
     h->prof_ms[k] = 0; h->prof_n[k] = 0;
   }
+  return 0;
+}
+
+// tuning aid (not part of the drop-in surface): the raw device counters; [4..6] count the blocks that left the
+// staged path of k_sweep_lean (staging capacity / a cell with more than 8 particles / trial-list capacity)
+extern "C" int hsmc_gpu_debug_counters(hsmc_gpu* h, uint64_t out[8]) {
+  if (!h || !out) return fail("null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  unsigned long long* hs = (unsigned long long*)h->h_stage;
+  CU(cudaMemcpyAsync(hs, h->d_cnt, sizeof(unsigned long long) * CNT_N, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  for (int k = 0; k < CNT_N; k++) out[k] = hs[k];
   return 0;
 }
 

@@ -12,7 +12,7 @@
 //    moves by its own trial) and on Philox(global cell, trial index, sweep).  k_propose, an element-wise throughput
 //    kernel (one thread per particle), generates them all: new position in double (moves.c:52-57, 215-226) into the
 //    idle half of the ping-pong master table, the cell test, and a 16-byte trial record {fp32 shadow of the new
-//    position, slot | accept-able}, both stored in TRIAL ORDER inside the cell's slot range (ascending particle id).
+//    position, slot | accept-able} stored in TRIAL ORDER inside the cell's slot range (ascending particle id).
 //    k_sweep_lean has no Philox and no double arithmetic on its hot path: 64 registers, 30 warps per SM.
 //  * The sweep kernel derives everything else itself: one warp per staged (x,y) row reads the row's CSR entries
 //    (lane = cell), a warp scan places the rows, the fp32 shadow is staged as block-relative coordinates in PAIRS
@@ -34,12 +34,12 @@
 #ifndef LEAN_MIN_CTAS
 #define LEAN_MIN_CTAS 5
 #endif
-#define LEAN_NP_MIN 3           // pair-records (2 entries each) scanned per stencil row in straight-line code:
-#define LEAN_NP_MAX 5           //   chosen per block from its longest stencil row; beyond MAX: deep loop
+#define LEAN_NP 4               // pair-records (2 entries each) per stencil row in straight-line code; longer rows: loop
 #define LEAN_PAD 12             // far-away entries after the last staged particle (covers the over-scan)
 #define LEAN_FAR 1.0e15f
 #define LEAN_MAX_OCC 8          // most particles per cell on the staged path (3-bit trial index)
-#define LEAN_MAX_ROWS 256       // (mbx+2)*(mby+2)
+#define LEAN_MAX_ROWS 144       // (mbx+2)*(mby+2): blocks of up to 10 x 10 cells across
+#define LEAN_COL_CHUNKS 32       // most chunks one cell colour of a block may need
 #define LEAN_MAX_CHUNKS 30       // chunks per cell colour of a block
 #define PROPOSE_THREADS 256
 
@@ -56,6 +56,7 @@ struct BlkGeom {
   int nrx, nry, lenz, nrows;
   int zs;                    // wrapped z of the region's first cell
   bool zwrap;
+  int bxi, byi, bzi;         // block index (k_sweep_lean)
 };
 
 __device__ __forceinline__ BlkGeom blk_geom(const Grid& g, const BlockCfg& bc, const int* __restrict__ xoff, int bxi,
@@ -86,12 +87,13 @@ __device__ __forceinline__ long long blk_global_row(const Grid& g, const BlkGeom
   return (long long)lx * g.ny + y;
 }
 
-// exact re-evaluation of a whole stencil from the master table (moves.c:157-212, 400-431)
-// (`pos` deliberately not const __restrict__: entries of this block were written earlier in this
-// launch by other threads of the CTA, so the loads must not take the non-coherent path)
-__device__ __noinline__ bool block_exact_rescan(const double4* pos, const BlockRow* s_row,
-                                                const unsigned short* s_cz, int cz_stride, int nry, int rxc,
-                                                int ryc, int rz, int sel, double xn, double yn, double zn,
+// exact re-evaluation of a whole stencil from the master table (moves.c:157-212, 400-431).  The block commits its
+// accepted moves to the master table at its end (one parallel pass): until then a particle of this block whose own
+// trial was accepted (bit set in s_pacc) is at its proposal, prop[slot].
+// (`pos` deliberately not const __restrict__: neighbouring blocks wrote it earlier in this launch)
+__device__ __noinline__ bool block_exact_rescan(const double4* pos, const double4* __restrict__ prop, const BlockRow* s_row,
+                                                const unsigned short* s_cz, const unsigned int* s_pacc, int cz_stride,
+                                                int nry, int rxc, int ryc, int rz, int sel, double xn, double yn, double zn,
                                                 const Box box) {
   for (int dx = -1; dx <= 1; dx++)
     for (int dy = -1; dy <= 1; dy++) {
@@ -103,7 +105,7 @@ __device__ __noinline__ bool block_exact_rescan(const double4* pos, const BlockR
         if (k == sel) continue;
         const int o = k - rw.off;
         const int gs = (o < rw.cntA) ? rw.gbA + o : rw.gbB + o - rw.cntA;
-        const double4 q = pos[gs];
+        const double4 q = ((s_pacc[k >> 5] >> (k & 31)) & 1u) ? prop[gs] : pos[gs];
         if (pair_r2(xn, yn, zn, q.x, q.y, q.z, box) < 1.0) return true;
       }
     }
@@ -112,7 +114,7 @@ __device__ __noinline__ bool block_exact_rescan(const double4* pos, const BlockR
 
 // ---------------------------------------------------------------------------------------------------
 // k_propose: one thread per resident particle.  Trial index j = number of particles of the same cell with a
-// smaller id; the proposal and the trial record are stored at slot (cell start + j), i.e. in trial order.
+// smaller id; the trial record is stored at slot (cell start + j), i.e. in trial order, the proposal at the particle's slot.
 // ---------------------------------------------------------------------------------------------------
 template <bool LOG>
 __global__ void __launch_bounds__(PROPOSE_THREADS)
@@ -145,7 +147,7 @@ k_propose(SweepArgs a, const double4* __restrict__ pos, const int* __restrict__ 
   if (act) nrel = make_rel(g, gx, iy, iz, xn, yn, zn);
   const unsigned int code = (unsigned int)min(gs - b, 15) | (act ? TREC_ACT : 0u);
   trec[b + j] = make_uint4(__float_as_uint(nrel.x), __float_as_uint(nrel.y), __float_as_uint(nrel.z), code);
-  prop[b + j] = make_double4(xn, yn, zn, p.w);
+  prop[gs] = make_double4(xn, yn, zn, p.w);
   if (LOG) traw[b + j] = make_uint4(rn.v[0], rn.v[1], rn.v[2], (unsigned int)(int)p.w);
 }
 
@@ -192,22 +194,58 @@ __device__ __forceinline__ float lean_pair(const ulonglong2 xy, const unsigned l
   return f_min3(r2min, lo, hi);
 }
 
-// the fp32 filter over the 27-cell stencil of one trial: nine (x,y) rows, NP pair-records each, read at fixed offsets
-// from the pair-aligned start of cell rz-1, unmasked (entries past the row's three cells are real particles farther
-// along -- true positions, so harmless -- or the far-away pad after the last staged particle)
-template <int NP>
-__device__ __forceinline__ float lean_scan(const ulonglong2* __restrict__ s_xy, const unsigned long long* __restrict__ s_z2,
-                                           const unsigned short* __restrict__ cp0, int nry, int czs, float tx, float ty,
-                                           float tz) {
+// The fp32 filter over the 27-cell stencil of one trial: nine (x,y) rows; in each, the three z-cells are one
+// contiguous staged range [b, e), read as pair-records from the pair-aligned start of cell rz-1.  A lane reads only the
+// records its own row needs (predicated loads: the kernel is bound by shared-memory wavefronts, and a row holds 2.7
+// particles on average but up to 8 when the lattice planes of a crystal beat against the cell grid), four in
+// straight-line code, the rare longer rows in a loop.  The entry before b in an odd-aligned first record and the one
+// after e in the last are real particles of the neighbouring cells (true positions: harmless) or the far-away pad.
+// (predicated loads in inline PTX: left to the compiler, every conditional record becomes a branch region of its own,
+//  which serialises the shared-memory latencies of a row)
+__device__ __forceinline__ void lds_pair_if(unsigned long long& x, unsigned long long& y, unsigned long long& z,
+                                            uint32_t a_xy, uint32_t a_z, int on) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %5, 0;\n\t@p ld.shared.v2.u64 {%0, %1}, [%3];\n\t@p ld.shared.u64 %2, [%4];\n\t}"
+               : "+l"(x), "+l"(y), "+l"(z) : "r"(a_xy), "r"(a_z), "r"(on));
+}
+
+__device__ __forceinline__ float lean_scan(uint32_t a_xy0, uint32_t a_z0, const unsigned short* __restrict__ cp0, int nry, int czs,
+                                           float tx, float ty, float tz) {
   const unsigned long long TX = f2_pack(tx, tx), TY = f2_pack(ty, ty), TZ = f2_pack(tz, tz);
   float r2min = 3.0e38f;
+  unsigned long long x0 = 0, y0 = 0, z0 = 0, x1 = 0, y1 = 0, z1 = 0;     // (a record not read keeps stale values: its minimum is not taken)
 #pragma unroll
   for (int r = 0; r < 9; r++) {
-    const int p0 = (int)cp0[((r / 3) * nry + (r % 3)) * czs] >> 1;
-    const ulonglong2* pxy = s_xy + p0;
-    const unsigned long long* pz = s_z2 + p0;
+    const unsigned short* cp = cp0 + ((r / 3) * nry + (r % 3)) * czs;
+    const int p0 = (int)cp[0] >> 1, e = cp[3];
+    const int np = (e + 1 - 2 * p0) >> 1;              // pair-records holding entries below e
+    const uint32_t axy = a_xy0 + 16u * (uint32_t)p0, az = a_z0 + 8u * (uint32_t)p0;
 #pragma unroll
-    for (int s = 0; s < NP; s++) r2min = lean_pair(pxy[s], pz[s], TX, TY, TZ, r2min);
+    for (int s0 = 0; s0 < LEAN_NP; s0 += 2) {
+      lds_pair_if(x0, y0, z0, axy + 16u * s0, az + 8u * s0, s0 < np);
+      lds_pair_if(x1, y1, z1, axy + 16u * (s0 + 1), az + 8u * (s0 + 1), s0 + 1 < np);
+      {
+        const unsigned long long dx = f2_sub(TX, x0), dy = f2_sub(TY, y0), dz = f2_sub(TZ, z0);
+        float lo, hi;
+        f2_unpack(f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx))), lo, hi);
+        if (s0 < np) r2min = f_min3(r2min, lo, hi);
+      }
+      {
+        const unsigned long long dx = f2_sub(TX, x1), dy = f2_sub(TY, y1), dz = f2_sub(TZ, z1);
+        float lo, hi;
+        f2_unpack(f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx))), lo, hi);
+        if (s0 + 1 < np) r2min = f_min3(r2min, lo, hi);
+      }
+    }
+    if (np > LEAN_NP) {
+#pragma unroll 1
+      for (int s = LEAN_NP; s < np; s++) {
+        lds_pair_if(x0, y0, z0, axy + 16u * s, az + 8u * s, 1);
+        const unsigned long long dx = f2_sub(TX, x0), dy = f2_sub(TY, y0), dz = f2_sub(TZ, z0);
+        float lo, hi;
+        f2_unpack(f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx))), lo, hi);
+        r2min = f_min3(r2min, lo, hi);
+      }
+    }
   }
   return r2min;
 }
@@ -228,35 +266,45 @@ k_sweep_lean(SweepArgs a, BlockCfg bc, const int* __restrict__ xoff, double4* po
   ulonglong2* s_xy = reinterpret_cast<ulonglong2*>(smem_raw);                              // [cap/2] {x0,x1},{y0,y1}
   unsigned long long* s_z2 = reinterpret_cast<unsigned long long*>(s_xy + (bc.cap >> 1));   // [cap/2] {z0,z1}
   unsigned short* s_cz = reinterpret_cast<unsigned short*>(s_z2 + (bc.cap >> 1));           // [max_rows][cz_stride]
-  unsigned int* s_q = reinterpret_cast<unsigned int*>(s_cz + bc.max_rows * bc.cz_stride);   // [warps][32] trial items
+  unsigned short* s_items = s_cz + bc.max_rows * bc.cz_stride;                              // [nslots][32] trial items: rx 4 | ry 4 | rz 5 | j 3
+  unsigned int* s_iacc = reinterpret_cast<unsigned int*>(s_items + bc.nslots * 32);         // [nslots] accepted trials of a chunk, one bit per lane
+  unsigned int* s_pacc = s_iacc + bc.nslots;                                                // [cap/32] staged particles whose trial was accepted
+  unsigned char* s_cht = reinterpret_cast<unsigned char*>(s_pacc + (bc.cap >> 5));          // [nslots] trials of each chunk
+  unsigned char* s_cslot = s_cht + bc.nslots;                                               // [8][LEAN_COL_CHUNKS] chunk slots of each colour
   float* s_xyf = reinterpret_cast<float*>(s_xy);
   float* s_zf = reinterpret_cast<float*>(s_z2);
   __shared__ BlockRow s_row[LEAN_MAX_ROWS];
   __shared__ int s_cnt[LEAN_MAX_ROWS + 1];
-  __shared__ int s_tick, s_done_idx, s_bad, s_bad2, s_need;
+  __shared__ int s_done_idx, s_bad, s_bad2, s_nch[8], s_ph, s_nslot;
+  __shared__ BlkGeom s_geom;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = LEAN_THREADS / 32;
   const int czs = bc.cz_stride;
   const unsigned FULL = 0xffffffffu;
 
   // ---- which block (fused launches: ticket) -----------------------------------------------------------------
-  const int hbz = bc.nbz >> 1, hby = bc.nby >> 1, hbx = bc.nbx >> 1;
-  int ph = a.phase, bid = blockIdx.x;
-  if (tid == 0) { s_bad = 0; s_bad2 = 0; s_need = 0; }
-  if (a.fuse > 1) {
-    if (tid == 0) s_tick = (int)(atomicAdd(bc.ticket, 1u) - a.ticket_base);
-    __syncthreads();
-    const int per = hbx * hby * hbz, t = s_tick;
-    ph = a.phase + t / per;
-    bid = t - (t / per) * per;
+  // (thread 0 alone does the index arithmetic -- a dozen integer divisions -- and shares the geometry)
+  if (tid == 0) {
+    const int hbz = bc.nbz >> 1, hby = bc.nby >> 1, hbx = bc.nbx >> 1;
+    int ph0 = a.phase, bid = blockIdx.x;
+    if (a.fuse > 1) {
+      const int per = hbx * hby * hbz, t = (int)(atomicAdd(bc.ticket, 1u) - a.ticket_base);
+      ph0 = a.phase + t / per;
+      bid = t - (t / per) * per;
+    }
+    const int bz0 = 2 * (bid % hbz) + (ph0 & 1);
+    const int by0 = 2 * ((bid / hbz) % hby) + ((ph0 >> 1) & 1);
+    const int bx0 = 2 * (bid / (hbz * hby)) + ((ph0 >> 2) & 1);
+    s_geom = blk_geom(g, bc, xoff, bx0, by0, bz0);
+    s_geom.bxi = bx0; s_geom.byi = by0; s_geom.bzi = bz0;
+    s_ph = ph0;
+    s_done_idx = (bx0 * bc.nby + by0) * bc.nbz + bz0;
+    s_bad = 0; s_bad2 = 0; s_nslot = 0;
   }
-  const int pcx = (ph >> 2) & 1, pcy = (ph >> 1) & 1, pcz = ph & 1;
-  const int bzi = 2 * (bid % hbz) + pcz;
-  const int byi = 2 * ((bid / hbz) % hby) + pcy;
-  const int bxi = 2 * (bid / (hbz * hby)) + pcx;
-  const BlkGeom q = blk_geom(g, bc, xoff, bxi, byi, bzi);
+  __syncthreads();
+  const BlkGeom q = s_geom;
+  const int ph = s_ph, bxi = q.bxi, byi = q.byi, bzi = q.bzi;
   const int nrows = q.nrows, nry = q.nry, lenz = q.lenz;
-  if (tid == 0) s_done_idx = (bxi * bc.nby + byi) * bc.nbz + bzi;
 
   // ---- staging rows (static while cell membership is: no need to wait for the neighbours): one THREAD per row
   //      (a row is some 25 cells: a short serial loop costs 30x fewer issue slots than a warp per row);
@@ -333,9 +381,8 @@ k_sweep_lean(SweepArgs a, BlockCfg bc, const int* __restrict__ xoff, double4* po
   const float wxf = (float)g.wx, wyf = (float)g.wy, wzf = (float)g.wz;
   const float hxr = 0.5f * (float)q.nrx, hyr = 0.5f * (float)nry, hzr = 0.5f * (float)lenz;
   if (!s_bad && !bc.force_global) {
-    // ---- staged indices of the cells; longest stencil row; trial records and proposals of the interior towards L2 ----
+    // ---- staged indices of the cells; trial records and proposals of the interior towards L2 ----
     {
-      int need = 0;
       bool deep_cell = false;
       for (int r = tid; r < nrows; r += LEAN_THREADS) {
         const int rx = (int)(((float)r + 0.5f) * inv_nry), ry = r - rx * nry;
@@ -347,8 +394,6 @@ k_sweep_lean(SweepArgs a, BlockCfg bc, const int* __restrict__ xoff, double4* po
         for (int zi = 1; zi <= q.ez; zi++) {
           const int ve = (int)cz[zi + 2] + rw.off;                               // start of cell zi+2 = end of cell zi+1
           cz[zi] = (unsigned short)v;
-          // entries a trial in cell zi scans in this row: from the pair-aligned start of cell zi-1 to the end of cell zi+1
-          need = max(need, ve - (vb & ~1));
           deep_cell |= rint && vn - v > LEAN_MAX_OCC;
           vb = v; v = vn; vn = ve;
         }
@@ -362,9 +407,7 @@ k_sweep_lean(SweepArgs a, BlockCfg bc, const int* __restrict__ xoff, double4* po
           for (int k = 0; k < m; k += 4) prefetch_l2(prop + first + k);
         }
       }
-      need = __reduce_max_sync(FULL, need);
-      if (lane == 0) atomicMax(&s_need, need);
-      if (__any_sync(FULL, deep_cell) && lane == 0) s_bad2 = 1;      // (s_bad itself must not change inside this branch)
+      if (__any_sync(FULL, deep_cell) && lane == 0) s_bad2 = 2;      // (s_bad itself must not change inside this branch)
     }
     // ---- stage the fp32 shadow as block-relative coordinates fma(cell index - centre, edge, offset) -----------------
     {
@@ -380,15 +423,15 @@ k_sweep_lean(SweepArgs a, BlockCfg bc, const int* __restrict__ xoff, double4* po
         const int rx = (int)(((float)r + 0.5f) * inv_nry), ry = r - rx * nry;
         const float cxw = ((float)rx - hxr), cyw = ((float)ry - hyr);
 #pragma unroll 1
-        for (int kb = k0; kb < k1; kb += 8) {
-          float4 v[8];
+        for (int kb = k0; kb < k1; kb += 4) {
+          float4 v[4];
 #pragma unroll
-          for (int u = 0; u < 8; u++) {
+          for (int u = 0; u < 4; u++) {
             const int k = kb + u;
             if (k < k1) v[u] = __ldcg(rel + ((k < rw.cntA) ? rw.gbA + k : rw.gbB + (k - rw.cntA)));   // L2: neighbours' blocks wrote these earlier in this launch
           }
 #pragma unroll
-          for (int u = 0; u < 8; u++) {
+          for (int u = 0; u < 4; u++) {
             const int k = kb + u;
             if (k < k1) {
               const int i = rw.off + k;
@@ -407,37 +450,44 @@ k_sweep_lean(SweepArgs a, BlockCfg bc, const int* __restrict__ xoff, double4* po
         float* xy = s_xyf + ((i >> 1) << 2) + (i & 1);
         xy[0] = LEAN_FAR; xy[2] = LEAN_FAR; s_zf[i] = LEAN_FAR;
       }
+      for (int i = tid; i < (bc.cap >> 5); i += LEAN_THREADS) s_pacc[i] = 0u;
+      for (int i = tid; i < bc.nslots; i += LEAN_THREADS) { s_iacc[i] = 0u; s_cht[i] = 0; }
     }
     __syncthreads();
   }
   if (!s_bad && !s_bad2 && !bc.force_global) {
     // ---- trials -----------------------------------------------------------------------------------------------
     const float lo = 1.0f - a.eps, hi = 1.0f + a.eps;
-    const int need = s_need;
-    const int npairs = min(LEAN_NP_MAX, max(LEAN_NP_MIN, (need + 1) >> 1));
-    const bool deep_rows = need > 2 * LEAN_NP_MAX;
     const int parx = (g.gx0 + q.x0) & 1, pary = q.y0 & 1, parz = q.z0 & 1;   // parity of region cell (0,0,0); grids are even
-    unsigned int* my_q = s_q + warp * 32;
     // ---- chunks: per colour, the interior cells of the colour (x slowest, z fastest) are cut into runs of at most 32
     //      cells holding at most 32 trials; a run is one warp's work between two colour barriers (lane = trial, a
-    //      cell's trials in adjacent lanes).  One warp per colour finds the cuts.
-    unsigned short* s_cut = reinterpret_cast<unsigned short*>(s_q + NW * 32);       // [8][LEAN_MAX_CHUNKS + 1]
+    //      cell's trials in adjacent lanes).  One warp per colour lists the trials of its chunks, once per block.
     for (int col = warp; col < 8; col += NW) {
       const int fx = 1 + ((parx + 1 + (col >> 2)) & 1), fy = 1 + ((pary + 1 + (col >> 1)) & 1), fz = 1 + ((parz + 1 + col) & 1);
       const int nxc = (q.ex - fx + 2) >> 1, nyc = (q.ey - fy + 2) >> 1, nzc = (q.ez - fz + 2) >> 1;
       const int ncell = nxc * nyc * nzc;
       const float inz = 1.0f / (float)max(nzc, 1), iny = 1.0f / (float)max(nyc, 1);
-      unsigned short* cut = s_cut + col * (LEAN_MAX_CHUNKS + 1);
+      const int tgt = 32;
       int at = 0, k = 0;
-      if (lane == 0) cut[0] = 0;
-      while (at < ncell && k < LEAN_MAX_CHUNKS) {
+      while (at < ncell) {
+        // a free chunk slot (any 32 consecutive trial slots of the block's table)
+        int slot = 0;
+        if (lane == 0) slot = atomicAdd(&s_nslot, 1);
+        slot = __shfl_sync(FULL, slot, 0);
+        if (slot >= bc.nslots || k >= LEAN_COL_CHUNKS) {          // table full: global-memory path
+          if (lane == 0) atomicOr(&s_bad2, 4);
+          break;
+        }
         const int cq = at + lane;
         int n = 0;
+        unsigned int cell = 0;
         if (cq < ncell) {
           const int t2 = (int)(((float)cq + 0.5f) * inz), izc = cq - t2 * nzc;      // (exact: cq < 4096, divisors <= 16)
           const int ixc = (int)(((float)t2 + 0.5f) * iny), iyc = t2 - ixc * nyc;
-          const unsigned short* cz = s_cz + ((fx + 2 * ixc) * nry + fy + 2 * iyc) * czs + fz + 2 * izc;
+          const int rx = fx + 2 * ixc, ry = fy + 2 * iyc, rz = fz + 2 * izc;
+          const unsigned short* cz = s_cz + (rx * nry + ry) * czs + rz;
           n = (int)cz[1] - (int)cz[0];
+          cell = ((unsigned)rx << 12) | ((unsigned)ry << 8) | ((unsigned)rz << 3);
         }
         int inc = n;
 #pragma unroll
@@ -445,162 +495,148 @@ k_sweep_lean(SweepArgs a, BlockCfg bc, const int* __restrict__ xoff, double4* po
           const int t = __shfl_up_sync(FULL, inc, o);
           if (lane >= o) inc += t;
         }
-        at += __popc(__ballot_sync(FULL, cq < ncell && inc <= 32));
+        const bool in = cq < ncell && inc <= tgt;
+        const unsigned m = __ballot_sync(FULL, in);
+        unsigned short* items = s_items + slot * 32;
+        if (in)
+          for (int j = 0; j < n; j++) items[inc - n + j] = (unsigned short)(cell | (unsigned)j);
+        const int ncl = __popc(m);                 // cells of this chunk (>= 1: a cell holds at most 8 trials)
+        if (lane == ncl - 1) s_cht[slot] = (unsigned char)inc;
+        if (lane == 0) s_cslot[col * LEAN_COL_CHUNKS + k] = (unsigned char)slot;
+        at += ncl;
         k++;
-        if (lane == 0) cut[k] = (unsigned short)at;
       }
-      if (lane == 0) {
-        cut[LEAN_MAX_CHUNKS] = (unsigned short)k;
-        if (at < ncell) s_bad2 = 1;              // more chunks than the table holds: global-memory path
-      }
+      if (lane == 0) s_nch[col] = k;
     }
     __syncthreads();
     if (s_bad2) goto global_path;                // (block-uniform)
 #pragma unroll 1
     for (int col = 0; col < 8; col++) {
-      // interior cells of this colour: first index and count per axis
-      const int fx = 1 + ((parx + 1 + (col >> 2)) & 1), fy = 1 + ((pary + 1 + (col >> 1)) & 1), fz = 1 + ((parz + 1 + col) & 1);
-      const int nyc = (q.ey - fy + 2) >> 1, nzc = (q.ez - fz + 2) >> 1;
-      const float inz = 1.0f / (float)max(nzc, 1), iny = 1.0f / (float)max(nyc, 1);
-      const unsigned short* cut = s_cut + col * (LEAN_MAX_CHUNKS + 1);
-      const int nch = cut[LEAN_MAX_CHUNKS];
+      const int nch = s_nch[col];
 #pragma unroll 1
       for (int kc = warp; kc < nch; kc += NW) {
-        // ---- this chunk's cells (lane = cell, z fastest) and their trials ----
-        const int c0 = cut[kc], c1 = cut[kc + 1];
-        const int cq = c0 + lane;
-        int ob = 0, n = 0, crx = 0, cry = 0, crz = 0;
-        if (cq < c1) {
-          const int t2 = (int)(((float)cq + 0.5f) * inz), izc = cq - t2 * nzc;
-          const int ixc = (int)(((float)t2 + 0.5f) * iny), iyc = t2 - ixc * nyc;
-          crx = fx + 2 * ixc; cry = fy + 2 * iyc; crz = fz + 2 * izc;
-          const unsigned short* cz = s_cz + (crx * nry + cry) * czs + crz;
-          ob = cz[0];
-          n = (int)cz[1] - ob;
+        const int slot = s_cslot[col * LEAN_COL_CHUNKS + kc];
+        const int T = s_cht[slot];
+        const bool valid = lane < T;
+        const unsigned int item = valid ? (unsigned int)s_items[slot * 32 + lane] : 0x1108u;    // (padding lanes: cell (1,1,1))
+        const int rxc = (item >> 12) & 15, ryc = (item >> 8) & 15, rz = (item >> 3) & 31, j = item & 7;
+        const unsigned short* czc = s_cz + (rxc * nry + ryc) * czs + rz;
+        const int cob = czc[0], n1 = (int)czc[1] - cob - 1;
+        // mates of the same cell: all in this chunk, in adjacent lanes
+        const int nprev = valid ? j : 0;
+        const int nnext = valid ? n1 - j : 0;
+        // trial record: slot (cell start + j) of the trial-ordered table
+        const BlockRow rwc = s_row[rxc * nry + ryc];
+        const int ro = cob - rwc.off;
+        const int gcell0 = (ro < rwc.cntA) ? rwc.gbA + ro : rwc.gbB + ro - rwc.cntA;    // global slot of the cell's first particle
+        uint4 rec = make_uint4(0u, 0u, 0u, 0u);
+        if (valid) rec = __ldg(trec + gcell0 + j);
+        const bool act = valid && (rec.w & TREC_ACT);
+        const int koff = rec.w & 15;
+        const int sel = cob + koff;
+        // trial point, block-relative
+        const float tx = __fmaf_rn((float)rxc - hxr, wxf, __uint_as_float(rec.x));
+        const float ty = __fmaf_rn((float)ryc - hyr, wyf, __uint_as_float(rec.y));
+        const float tz = __fmaf_rn((float)rz - hzr, wzf, __uint_as_float(rec.z));
+        // every trial particle of the chunk is hidden while the chunk is scanned
+        float* mxy = s_xyf + ((sel >> 1) << 2) + (sel & 1);
+        float kx = 0.f, ky = 0.f, kz = 0.f;
+        if (valid) {
+          kx = mxy[0]; ky = mxy[2]; kz = s_zf[sel];
+          mxy[0] = LEAN_FAR; mxy[2] = LEAN_FAR; s_zf[sel] = LEAN_FAR;
         }
-        int inc = n;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int t = __shfl_up_sync(FULL, inc, o);
-          if (lane >= o) inc += t;
+        __syncwarp();
+        float r2min = 3.0e38f;
+        if (act) {
+          const unsigned short* cp0 = s_cz + ((rxc - 1) * nry + ryc - 1) * czs + rz - 1;
+          r2min = lean_scan(smem_u32(s_xy), smem_u32(s_z2), cp0, nry, czs, tx, ty, tz);
         }
-        const int T = __shfl_sync(FULL, inc, 31), start = inc - n;        // T <= 32 by construction
-        {
-          for (int j = 0; j < n; j++) my_q[start + j] = LEAN_ITEM(ob, crx, cry, crz, j, n - 1);
-          __syncwarp();
-          const bool valid = lane < T;
-          const unsigned int item = valid ? my_q[lane] : 0u;
-          __syncwarp();
-          const int cob = item & 0xfff, rxc = (item >> 12) & 15, ryc = (item >> 16) & 15, rz = (item >> 20) & 31;
-          const int j = (item >> 25) & 7, n1 = (item >> 28) & 7;
-          // mates of the same cell: all in this chunk, in adjacent lanes
-          const int nprev = valid ? j : 0;
-          const int nnext = valid ? n1 - j : 0;
-          // trial record: slot (cell start + j) of the rank-ordered tables
-          const BlockRow rwc = s_row[rxc * nry + ryc];
-          const int ro = cob - rwc.off;
-          const int gcell0 = (ro < rwc.cntA) ? rwc.gbA + ro : rwc.gbB + ro - rwc.cntA;    // global slot of the cell's first particle
-          uint4 rec = make_uint4(0u, 0u, 0u, 0u);
-          if (valid) rec = __ldg(trec + gcell0 + j);
-          const bool act = valid && (rec.w & TREC_ACT);
-          const int koff = rec.w & 15;
-          const int sel = cob + koff;
-          // trial point, block-relative
-          const float tx = __fmaf_rn((float)rxc - hxr, wxf, __uint_as_float(rec.x));
-          const float ty = __fmaf_rn((float)ryc - hyr, wyf, __uint_as_float(rec.y));
-          const float tz = __fmaf_rn((float)rz - hzr, wzf, __uint_as_float(rec.z));
-          // every trial particle of the chunk is hidden while the chunk is scanned
-          float* mxy = s_xyf + ((sel >> 1) << 2) + (sel & 1);
-          float kx = 0.f, ky = 0.f, kz = 0.f;
-          if (valid) {
-            kx = mxy[0]; ky = mxy[2]; kz = s_zf[sel];
-            mxy[0] = LEAN_FAR; mxy[2] = LEAN_FAR; s_zf[sel] = LEAN_FAR;
+        // mates with a LATER trial in this chunk: still at their old positions
+        const int maxnext = __reduce_max_sync(FULL, nnext);
+        for (int s2 = 1; s2 <= maxnext; s2++) {
+          const float qx = __shfl_down_sync(FULL, kx, s2), qy = __shfl_down_sync(FULL, ky, s2), qz = __shfl_down_sync(FULL, kz, s2);
+          if (act && s2 <= nnext) {
+            const float ddx = tx - qx, ddy = ty - qy, ddz = tz - qz;
+            r2min = fminf(r2min, __fmaf_rn(ddz, ddz, __fmaf_rn(ddy, ddy, ddx * ddx)));
           }
-          __syncwarp();
-          float r2min = 3.0e38f;
-          if (act) {
-            const unsigned short* cp0 = s_cz + ((rxc - 1) * nry + ryc - 1) * czs + rz - 1;
-            if (npairs <= 3) r2min = lean_scan<3>(s_xy, s_z2, cp0, nry, czs, tx, ty, tz);
-            else if (npairs == 4) r2min = lean_scan<4>(s_xy, s_z2, cp0, nry, czs, tx, ty, tz);
-            else r2min = lean_scan<5>(s_xy, s_z2, cp0, nry, czs, tx, ty, tz);
-            if (deep_rows) {                         // some stencil row of this block is longer than the straight-line scan
-              const unsigned long long TX = f2_pack(tx, tx), TY = f2_pack(ty, ty), TZ = f2_pack(tz, tz);
+        }
+        // verdicts in trial order: round s decides the trials with s earlier mates in the chunk; the later
+        // trials of those cells then see where the decided particle ended up.  An accepted move updates the
+        // staged coordinates now; the master table follows at the end of the block.
+        const int maxprev = __reduce_max_sync(FULL, nprev);
+        float fx2 = kx, fy2 = ky, fz2 = kz;           // where this lane's particle is after its own trial
+        int verdict = 2;
+        bool accepted = false;
 #pragma unroll 1
-              for (int r = 0; r < 9; r++) {
-                const unsigned short* cp = cp0 + ((r / 3) * nry + (r % 3)) * czs;
-                const int e = cp[3];
-#pragma unroll 1
-                for (int p = ((int)cp[0] >> 1) + LEAN_NP_MAX; 2 * p < e; p++) r2min = lean_pair(s_xy[p], s_z2[p], TX, TY, TZ, r2min);
+        for (int s2 = 0; s2 <= maxprev; s2++) {
+          if (valid && nprev == s2) {
+            if (act) {
+              bool ov = r2min < lo;
+              if (!ov && r2min <= hi) {
+                const double4 pr = prop[gcell0 + koff];
+                ov = block_exact_rescan(pos, prop, s_row, s_cz, s_pacc, czs, nry, rxc, ryc, rz, sel, pr.x, pr.y, pr.z, a.box);
               }
-            }
+              if (ov) { verdict = 1; n_ov++; }
+              else {
+                verdict = 0; n_acc++;
+                accepted = true;
+                fx2 = tx; fy2 = ty; fz2 = tz;
+                atomicOr(&s_pacc[sel >> 5], 1u << (sel & 31));
+              }
+            } else n_cell++;
+            mxy[0] = fx2; mxy[2] = fy2; s_zf[sel] = fz2;
           }
-          // mates with a LATER trial in this chunk: still at their old positions
-          const int maxnext = __reduce_max_sync(FULL, nnext);
-          for (int s = 1; s <= maxnext; s++) {
-            const float qx = __shfl_down_sync(FULL, kx, s), qy = __shfl_down_sync(FULL, ky, s), qz = __shfl_down_sync(FULL, kz, s);
-            if (act && s <= nnext) {
+          if (s2 < maxprev) {
+            __syncwarp();
+            const int src = (nprev > s2) ? lane - (nprev - s2) : lane;
+            const float qx = __shfl_sync(FULL, fx2, src), qy = __shfl_sync(FULL, fy2, src), qz = __shfl_sync(FULL, fz2, src);
+            if (act && nprev > s2) {
               const float ddx = tx - qx, ddy = ty - qy, ddz = tz - qz;
               r2min = fminf(r2min, __fmaf_rn(ddz, ddz, __fmaf_rn(ddy, ddy, ddx * ddx)));
             }
           }
-          // verdicts in trial order: round s decides the trials with s earlier mates in the chunk; the later
-          // trials of those cells then see where the decided particle ended up
-          const int maxprev = __reduce_max_sync(FULL, nprev);
-          float fx2 = kx, fy2 = ky, fz2 = kz;           // where this lane's particle is after its own trial
-          int verdict = 2;
-#pragma unroll 1
-          for (int s = 0; s <= maxprev; s++) {
-            if (valid && nprev == s) {
-              if (act) {
-                bool ov = r2min < lo;
-                if (!ov && r2min <= hi) {
-                  const double4 pr = prop[gcell0 + j];
-                  ov = block_exact_rescan(pos, s_row, s_cz, czs, nry, rxc, ryc, rz, sel, pr.x, pr.y, pr.z, a.box);
-                }
-                if (ov) { verdict = 1; n_ov++; }
-                else {
-                  verdict = 0; n_acc++;
-                  fx2 = tx; fy2 = ty; fz2 = tz;
-                  const double4 pr = prop[gcell0 + j];
-                  double* pd = reinterpret_cast<double*>(pos + gcell0 + koff);
-                  *reinterpret_cast<double2*>(pd) = make_double2(pr.x, pr.y);
-                  pd[2] = pr.z;
-                  float* rl = reinterpret_cast<float*>(rel + gcell0 + koff);
-                  *reinterpret_cast<float2*>(rl) = make_float2(__uint_as_float(rec.x), __uint_as_float(rec.y));
-                  rl[2] = __uint_as_float(rec.z);
-                }
-              } else n_cell++;
-              mxy[0] = fx2; mxy[2] = fy2; s_zf[sel] = fz2;
-            }
-            if (s < maxprev) {
-              __syncwarp();
-              const int src = (nprev > s) ? lane - (nprev - s) : lane;
-              const float qx = __shfl_sync(FULL, fx2, src), qy = __shfl_sync(FULL, fy2, src), qz = __shfl_sync(FULL, fz2, src);
-              if (act && nprev > s) {
-                const float ddx = tx - qx, ddy = ty - qy, ddz = tz - qz;
-                r2min = fminf(r2min, __fmaf_rn(ddz, ddz, __fmaf_rn(ddy, ddy, ddx * ddx)));
-              }
-            }
-          }
-          if (LOG && valid) {
-            const uint4 rw4 = __ldg(traw + gcell0 + j);
-            const int iy = q.y0 + ryc, iz = q.z0 + rz;
-            const int gxl = g.gx0 + q.x0 + rxc;
-            const int gx = (gxl >= g.nx) ? gxl - g.nx : gxl;          // interior cells never wrap inside the block
-            const long long gcell = ((long long)gx * g.ny + iy) * g.nz + iz;
-            const unsigned long long sl = atomicAdd(nlog, 1ull);
-            if ((long long)sl < logcap) {
-              hsmc_gpu_trial tr;
-              tr.seq = ((unsigned long long)(ph * 8 + col) << 56) | ((unsigned long long)gcell << 8) | (unsigned)j;
-              tr.id = (int)rw4.w; tr.verdict = verdict;
-              tr.raw[0] = rw4.x; tr.raw[1] = rw4.y; tr.raw[2] = rw4.z; tr.pad = 0;
-              log[sl] = tr;
-            }
-          }
-          __syncwarp();
         }
+        const unsigned accm = __ballot_sync(FULL, accepted);
+        if (lane == 0) s_iacc[slot] = accm;
+        if (LOG && valid) {
+          const uint4 rw4 = __ldg(traw + gcell0 + j);
+          const int iy = q.y0 + ryc, iz = q.z0 + rz;
+          const int gxl = g.gx0 + q.x0 + rxc;
+          const int gx = (gxl >= g.nx) ? gxl - g.nx : gxl;          // interior cells never wrap inside the block
+          const long long gcell = ((long long)gx * g.ny + iy) * g.nz + iz;
+          const unsigned long long sl = atomicAdd(nlog, 1ull);
+          if ((long long)sl < logcap) {
+            hsmc_gpu_trial tr;
+            tr.seq = ((unsigned long long)(ph * 8 + col) << 56) | ((unsigned long long)gcell << 8) | (unsigned)j;
+            tr.id = (int)rw4.w; tr.verdict = verdict;
+            tr.raw[0] = rw4.x; tr.raw[1] = rw4.y; tr.raw[2] = rw4.z; tr.pad = 0;
+            log[sl] = tr;
+          }
+        }
+        __syncwarp();
       }
       __syncthreads();                       // colour barrier
+    }
+    // ---- commit: the accepted moves of the block go to the master table and its shadow, all at once ----------------
+#pragma unroll 1
+    for (int idx = tid; idx < min(s_nslot, bc.nslots) * 32; idx += LEAN_THREADS) {
+      const int slot = idx >> 5, l = idx & 31;
+      if (!((s_iacc[slot] >> l) & 1u)) continue;          // (zeroed with the staging: chunks that never ran hold no bits)
+      const unsigned int item = s_items[idx];
+      const int rxc = (item >> 12) & 15, ryc = (item >> 8) & 15, rz = (item >> 3) & 31, j = item & 7;
+      const int cob = s_cz[(rxc * nry + ryc) * czs + rz];
+      const BlockRow rwc = s_row[rxc * nry + ryc];
+      const int ro = cob - rwc.off;
+      const int gcell0 = (ro < rwc.cntA) ? rwc.gbA + ro : rwc.gbB + ro - rwc.cntA;
+      const uint4 rec = __ldg(trec + gcell0 + j);
+      const int gs = gcell0 + (int)(rec.w & 15);
+      const double4 pr = prop[gs];
+      double* pd = reinterpret_cast<double*>(pos + gs);
+      *reinterpret_cast<double2*>(pd) = make_double2(pr.x, pr.y);
+      pd[2] = pr.z;
+      float* rl = reinterpret_cast<float*>(rel + gs);
+      *reinterpret_cast<float2*>(rl) = make_float2(__uint_as_float(rec.x), __uint_as_float(rec.y));
+      rl[2] = __uint_as_float(rec.z);
     }
   } else {
 global_path:
@@ -621,6 +657,8 @@ global_path:
     }
   }
 
+  // (tuning aid: how many blocks left the staged path, and why -- hsmc_gpu_debug_counters)
+  if (tid == 0 && (s_bad | s_bad2) && !bc.force_global) atomicAdd(&cnt[4 + (s_bad ? 0 : (s_bad2 & 2) ? 1 : 2)], 1ull);
   // ---- counters: warp reduce, then straight to the global counters ------------------------------------------
   n_acc = __reduce_add_sync(FULL, n_acc);
   n_ov = __reduce_add_sync(FULL, n_ov);

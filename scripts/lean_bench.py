@@ -35,6 +35,15 @@ for impl in ([a.impl, 5] if a.check else [a.impl]):
     print(f"impl {impl} lib {os.path.basename(os.environ.get('HSMC_GPU_LIB', 'default'))} block {os.environ.get('HSMC_BLOCK', '-')}: "
           f"{N * a.sweeps / dt:.3e} moves/s wall | per sweep ms: " +
           " ".join(f"{k} {v[0] / a.sweeps:.3f}" for k, v in p.items()) + f" | acc {c[1] / c[0]:.3f} min_r2 {h.min_dist2():.6f}", flush=True)
+    try:
+        import ctypes
+        raw = (ctypes.c_uint64 * 8)()
+        h.L.hsmc_gpu_debug_counters.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        h.L.hsmc_gpu_debug_counters(h.h, raw)
+        if raw[4] or raw[5] or raw[6]:
+            print(f"   blocks off the staged path: capacity {raw[4]} deep cell {raw[5]} trial lists {raw[6]}", flush=True)
+    except Exception as e:
+        print("   (no debug counters:", e, ")")
     if a.check:
         outs.append(h.download())
     h.close()

@@ -189,7 +189,7 @@ def test_kernel_variants_produce_the_same_chain(hs, oracle_built, block, monkeyp
     assert cnts[0][0] == 12 * N
 
 
-@pytest.mark.parametrize("block", [None, "2,2,2", "3,2,4", "8,8,24", "14,14,6"])      # the last: 256 staging rows per block
+@pytest.mark.parametrize("block", [None, "2,2,2", "3,2,4", "8,8,24", "10,10,6"])      # the last: 144 staging rows per block
 @pytest.mark.parametrize("impl", [0, 5], ids=["staged", "global"])
 def test_fused_phase_launch_is_the_same_chain(hs, oracle_built, block, impl, monkeypatch):
     """All eight block phases in ONE launch, ordered by per-block completion flags, against eight
