@@ -273,9 +273,10 @@ def secondary_observables(h, stream, N, nbar, peak, device):
     ms = _timed(stream, lambda: h.presst_flags(sf))
     entry("presst_flags", "particles/s", N, ms, 32.0 * (14.0 * nbar + 1.0),
           "hsmc_gpu_presst_flags, 20 compressions in one pass (k_overlap_scaled)")
-    ms = _timed(stream, lambda: h.contact_counts(0.002, 1))
+    dr_c = min(0.002, 0.9 * (min(h.info()["cell_size"]) - 1.0))       # one bin that still fits the cell edge
+    ms = _timed(stream, lambda: h.contact_counts(dr_c, 1))
     entry("contact_counts", "particles/s", N, ms, 32.0 * (14.0 * nbar + 1.0),
-          "hsmc_gpu_contact_counts(dr=0.002, bins up to the cell edge) (k_contact_hist)")
+          f"hsmc_gpu_contact_counts(dr={dr_c:.5f}, one bin below the cell edge) (k_contact_hist)")
 
     # RDF on the C2 shape
     box2, conf2 = fcc_lattice(20, 20, 20, RHO)

@@ -368,11 +368,12 @@ static void setup_blocks(hsmc_gpu* h) {
   if (want[0] > 0 && want[1] > 0 && want[2] > 0) have = eval(want[0], want[1], want[2], best);
   if (!have) {
     // Measured on B200 (profiles/): the cost per trial is flat once a CTA holds >= ~1000 trials and
-    // four CTAs fit an SM; smaller blocks pay the fixed prologue more often, larger ones lose
-    // residency.  Score = (fraction of the 4 x 148 CTA slots a phase can fill) x (prologue
-    // amortisation) x (residency), ties to the larger block.
+    // five CTAs fit an SM; smaller blocks pay the fixed prologue more often, larger ones lose
+    // residency (8x8x23 cells: four CTAs per SM, 12 % slower per trial than 8x8x21 with five).
+    // Score = (fraction of the 5 x 148 CTA slots a phase can fill) x (prologue amortisation) x
+    // (residency), ties to the larger block.
     double best_score = -1.0;
-    const int cand_xy[] = {2, 3, 4, 5, 6, 8}, cand_z[] = {2, 4, 6, 8, 10, 12, 16, 20, 24, 28};
+    const int cand_xy[] = {2, 3, 4, 5, 6, 8}, cand_z[] = {2, 4, 6, 8, 10, 12, 16, 18, 20, 22, 24, 28};
     for (int bx : cand_xy) for (int by : cand_xy) for (int bz : cand_z) {
       Shape s;
       if (!eval(bx, by, bz, s)) continue;
@@ -384,15 +385,15 @@ static void setup_blocks(hsmc_gpu* h) {
         ctas = (Wv > 1) ? std::max(ctas, c) : ctas + c;
       }
       ctas *= (long long)(even_blocks(g.ny, by) / 2) * (even_blocks(g.nz, bz) / 2);
-      // (the round-1 kernel staged 16 bytes per particle plus its trial slots; its measure of residency is kept:
-      //  the block shape is part of the chain's definition)
-      const int per_sm = (int)std::min<size_t>(4, (size_t)(227 * 1024) / ((size_t)s.cap * 16 + 16 * 1024));
+      // CTAs of k_sweep_lean per SM: dynamic + static shared memory + the 1 KB the hardware reserves per CTA; the
+      // register file holds five 192-thread CTAs of 64 registers
+      const int per_sm = (int)std::min<size_t>(5, (size_t)(227 * 1024) / (s.smem + sizeof(BlockRow) * LEAN_MAX_ROWS + 4 * LEAN_MAX_ROWS + 1200));
       if (per_sm < 1) continue;
       const double interior = (double)s.mx * s.my * s.mz;
       // below two waves of CTA slots the ragged last wave costs a whole CTA latency
       const double waves = (double)ctas / (148.0 * per_sm);
       const double fill = waves < 2.0 ? waves / std::ceil(waves) : 1.0;
-      const double score = fill * (interior / (interior + 400.0)) * (per_sm / 4.0) + 1e-9 * interior;
+      const double score = fill * (interior / (interior + 400.0)) * (per_sm / 5.0) + 1e-9 * interior;
       if (score > best_score) { best_score = score; best = s; have = true; }
     }
   }

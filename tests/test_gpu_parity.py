@@ -98,7 +98,8 @@ def test_accepted_volume_move_rescales_like_the_reference(hs, path, oracle_built
     g = dict(np.load(path))
     box = np.array(g["box"][:3], dtype=np.float64)
     N = g["conf"].shape[0]
-    for sf in (1.0 + 3.0e-4, pow(1.0 - 1.0e-3, 1.0 / 3.0), 1.13):
+    sf_big = (np.floor(box[0]) + 2.5) / box[0]          # enough to change the number of (even) cells per axis
+    for sf in (1.0 + 3.0e-4, pow(1.0 - 1.0e-3, 1.0 / 3.0), sf_big):
         p = oracle_built.Port(g["conf"], g["box"], neigh_dr=1.0, max_part=16)
         new_box = np.array([box[0] * sf, box[1] * sf, box[2] * sf])      # moves.c:129-131 order: edge * sf
         with _gpu(hs, g) as h:
@@ -108,7 +109,7 @@ def test_accepted_volume_move_rescales_like_the_reference(hs, path, oracle_built
             out = h.download()
             assert np.array_equal(out, p.get_conf()), f"sf={sf}"
             assert np.allclose(h.info()["box"], new_box, rtol=0, atol=0)
-            if sf == 1.13:
+            if sf == sf_big:
                 assert h.info()["cells"] != cells0
             # the rebuilt device cell list answers like the oracle on the rescaled configuration
             rng = np.random.default_rng(5)
