@@ -9,8 +9,10 @@
 // host-side orchestration and the ABI entry points ("new kernel" table):
 //   cell_list.cuh      K1  k_cell_count / k_scan_* / k_cell_scatter   cell_list_new (cell_list.c:142-175)
 //   sweep_generic.cuh  K2  k_sweep_phase (global memory)  part_move + check_overlap (moves.c:27-80,157-212)
-//   sweep_lean.cuh     K2  k_propose + k_sweep_lean       the default: all proposals of a sweep up front, block-resident
-//                                                         fp32x2 stencil filter, fused block phases
+//   sweep_lean.cuh     K2  k_propose + k_sweep_lean       all proposals of a sweep up front; block-resident fp32x2 stencil
+//                                                         filter, fused block phases (the sweep of small systems)
+//   sweep_gather.cuh   K2  k_sweep_gather                 one thread per trial, one launch per (colour, trial index): the
+//                                                         sweep of large systems
 //   observables.cuh    K3  k_overlap_scaled   vol_move / presst verdict   (moves.c:106-112)
 //                      K4  k_widom            widom_insertion             (compute_widom_chem_pot.c:44-71)
 //                      K5  k_rdf_pairs        rdf_hist_compute            (compute_rdf.c:110-128)
@@ -91,11 +93,20 @@ struct BlockCfg {
 // per-row staging record: global slots of the row's one or two pieces, staged offset
 struct BlockRow { int gbA, gbB, cntA, off; };
 
+// trial lists of k_sweep_gather (sweep_gather.cuh), filled by k_propose
+struct GatherLists {
+  int* list;                    // [GATHER_LISTS][stride] local cell indices
+  int* count;                   // [GATHER_LISTS]
+  long long stride;
+};
+
 // cfg.sweep_impl: low byte = kernel variant, next byte = virtual world of the x block partition
-// 0 default (k_propose + k_sweep_lean); 1 one thread per cell from global memory, one launch per CELL colour
-// (a different, equally valid update order); 3 the default with the filter's error band forced to zero (negative
-// control of the parity tests); 5 the default's update order evaluated all in double from global memory
-enum { IMPL_LEAN = 0, IMPL_CELL_GLOBAL = 1, IMPL_EPS0 = 3, IMPL_BLOCK_GLOBAL = 5 };
+// 0 (= 8) default: k_propose + k_sweep_lean (block-resident, one launch per sweep).  7: k_propose + k_sweep_gather (one
+// thread per trial, one launch per cell colour and trial index; measured slower, kept as the second implementation
+// of its chain).  Reference evaluations of the same two update orders, all in double from global memory: 5 the
+// block order (the chain of 0), 1 one thread per cell, one launch per cell colour (the chain of 7).  3: the default
+// with the filter's error band forced to zero (negative control of the parity tests).
+enum { IMPL_AUTO = 0, IMPL_CELL_GLOBAL = 1, IMPL_EPS0 = 3, IMPL_BLOCK_GLOBAL = 5, IMPL_GATHER = 7, IMPL_LEAN = 8 };
 
 struct hsmc_gpu {
   hsmc_gpu_config cfg;
@@ -151,6 +162,8 @@ struct hsmc_gpu {
   bool blk_ok = false;                   // the block-resident kernel runs the sweeps
   uint4* trec = nullptr;                 // [cap] trial records of the current sweep, trial order inside each cell (k_propose)
   uint4* traw = nullptr;                 // [cap] logged sweeps only: {raw draws, id}
+  bool gather = false;                   // the sweeps run k_sweep_gather (else k_sweep_lean if blk_ok, else k_sweep_phase)
+  GatherLists glists = {nullptr, nullptr, 0};
   float blk_eps = 0.f;
   std::vector<int> xoff;                 // x block boundaries (local layers), blk.nbx + 1 entries
   int* d_xoff = nullptr;
@@ -195,6 +208,7 @@ static inline int nblk(int64_t n, int t) { return (int)((n + t - 1) / t); }
 #include "async_copy.cuh"
 #include "sweep_generic.cuh"
 #include "sweep_lean.cuh"
+#include "sweep_gather.cuh"
 
 #include "observables.cuh"
 #include "slab.cuh"
@@ -428,7 +442,7 @@ static void setup_blocks(hsmc_gpu* h) {
   for (int k = 0; k < 3; k++) sum += 2.0 * half_ulp(mag[k]) + 2.0 * wv[k] * ldexp(1.0, -24) + 2.0 * wv[k] * ldexp(1.0, -25);
   double r2err = 2.0 * 1.01 * sum + 8.0 * ldexp(1.0, -24);
   h->blk_eps = (float)(2.0 * r2err);
-  h->blk_ok = (h->impl == IMPL_LEAN || h->impl == IMPL_EPS0 || h->impl == IMPL_BLOCK_GLOBAL);
+  h->blk_ok = (h->impl == IMPL_AUTO || h->impl == IMPL_LEAN || h->impl == IMPL_EPS0 || h->impl == IMPL_BLOCK_GLOBAL);
   if (getenv("HSMC_DEBUG_TILES"))
     fprintf(stderr, "[hsmc_gpu] rank %d: blocks %dx%dx%d of up to %dx%dx%d cells, %d CTAs/phase, cap %d, smem %zu B, eps %.3g\n",
             h->cfg.rank, b.nbx, b.nby, b.nbz, b.mbx, b.mby, b.mbz, (b.nbx / 2) * (b.nby / 2) * (b.nbz / 2), b.cap,
@@ -625,7 +639,7 @@ extern "C" int hsmc_gpu_destroy(hsmc_gpu* h) {
   void* ptrs[] = {h->pos[0], h->pos[1], h->rel, h->key, h->rnk, h->cell_count, h->cell_start, h->bsum, h->d_cnt,
                   h->d_scratch, h->d_slot_of_id, h->d_io, h->send_l, h->send_r, h->recv_l, h->recv_r,
                   h->d_halo_cnt, h->d_sfargs, h->d_log, h->key_halo, h->rnk_halo, h->d_lay,
-                  h->d_xoff, h->d_fuse, h->trec, h->traw};
+                  h->d_xoff, h->d_fuse, h->trec, h->traw, h->glists.list, h->glists.count};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -654,7 +668,8 @@ extern "C" int hsmc_gpu_create(hsmc_gpu** out, const hsmc_gpu_config* cfg, int64
   h->cfg = *cfg;
   h->impl = cfg->sweep_impl & 0xff;
   h->xpart_world = (cfg->sweep_impl >> 8) & 0xff;
-  if (h->impl != IMPL_LEAN && h->impl != IMPL_CELL_GLOBAL && h->impl != IMPL_EPS0 && h->impl != IMPL_BLOCK_GLOBAL) {
+  if (h->impl != IMPL_AUTO && h->impl != IMPL_LEAN && h->impl != IMPL_GATHER && h->impl != IMPL_CELL_GLOBAL &&
+      h->impl != IMPL_EPS0 && h->impl != IMPL_BLOCK_GLOBAL) {
     delete h;
     return fail("unknown sweep_impl variant");
   }
@@ -923,6 +938,16 @@ static int do_regrid(hsmc_gpu* h) {
 static int ensure_trial_tables(hsmc_gpu* h, bool logged) {
   if (!h->trec) CU(cudaMalloc(&h->trec, sizeof(uint4) * (size_t)h->cap));
   if (logged && !h->traw) CU(cudaMalloc(&h->traw, sizeof(uint4) * (size_t)h->cap));
+  if (h->gather) {
+    // a list holds at most one entry per cell of its colour
+    const long long need = (long long)(h->g.own_hi - h->g.own_lo) * h->g.ny * h->g.nz / 8 + 1024;
+    if (need > h->glists.stride) {
+      if (h->glists.list) cudaFree(h->glists.list);
+      h->glists.stride = need + need / 8;
+      CU(cudaMalloc(&h->glists.list, sizeof(int) * (size_t)GATHER_LISTS * (size_t)h->glists.stride));
+    }
+    if (!h->glists.count) CU(cudaMalloc(&h->glists.count, sizeof(int) * GATHER_LISTS));
+  }
   return 0;
 }
 
@@ -974,23 +999,46 @@ static int sweep_once(hsmc_gpu* h, double dr_max, bool logged) {
   }
   a.fuse = fuse; a.epoch = 0; a.ticket_base = 0;
   a.cx = a.cy = a.cz = a.phase = 0;
-  if (h->blk_ok) {
+  h->gather = h->impl == IMPL_GATHER;
+  if (h->gather) a.eps = 1.0e-5f * (float)std::max(1.0, std::max(g.wx, std::max(g.wy, g.wz)));
+  if (h->blk_ok || h->gather) {
     // all proposals of the sweep, element-wise (they only depend on the particles' own positions at this point)
     ProfSpan span(h, 3);
     TRY(ensure_trial_tables(h, logged));
+    int* lists = h->gather ? h->glists.list : nullptr;
+    if (h->gather) CU(cudaMemsetAsync(h->glists.count, 0, sizeof(int) * GATHER_LISTS, h->st));
     if (logged)
       k_propose<true><<<nblk(h->cap, PROPOSE_THREADS), PROPOSE_THREADS, 0, h->st>>>(a, h->pos[h->cur], h->cell_start, h->ncell,
-                                                                                   h->pos[h->cur ^ 1], h->trec, h->traw);
+                                                                                   h->pos[h->cur ^ 1], h->trec, h->traw, lists,
+                                                                                   h->glists.count, h->glists.stride);
     else
       k_propose<false><<<nblk(h->cap, PROPOSE_THREADS), PROPOSE_THREADS, 0, h->st>>>(a, h->pos[h->cur], h->cell_start, h->ncell,
-                                                                                    h->pos[h->cur ^ 1], h->trec, nullptr);
+                                                                                    h->pos[h->cur ^ 1], h->trec, nullptr, lists,
+                                                                                    h->glists.count, h->glists.stride);
     h->launches++;
   }
+  if (h->gather) fuse = 1;
   for (int ph = 0; ph < 8; ph++) {
     a.cx = (ph >> 2) & 1; a.cy = (ph >> 1) & 1; a.cz = ph & 1; a.phase = ph;
     if (fuse <= 1 || ph % fuse == 0) {     // else: launched together with phase ph - ph % fuse
     ProfSpan span(h, 0);
-    if (h->blk_ok) {
+    if (h->gather) {
+      // cell colour ph: first, second, third trial of every cell, then the cells holding more (4 launches)
+      const long long cells_c = (long long)((g.own_hi - g.own_lo) / 2) * (g.ny / 2) * (g.nz / 2);
+      for (int jj = 0; jj < 4; jj++) {
+        // (second and later trials: fewer than a third of the cells have them)
+        const int nb = (int)std::min<long long>(148LL * 8, std::max<long long>(1, nblk(jj == 0 ? cells_c : cells_c / 3, GATHER_THREADS)));
+        if (logged)
+          k_sweep_gather<true><<<nb, GATHER_THREADS, 0, h->st>>>(a, h->glists, ph, jj, h->pos[h->cur], h->rel, h->pos[h->cur ^ 1], h->trec,
+                                                                 h->traw, h->cell_start, h->d_cnt, h->d_log, h->d_scratch,
+                                                                 (long long)h->cap_log);
+        else
+          k_sweep_gather<false><<<nb, GATHER_THREADS, 0, h->st>>>(a, h->glists, ph, jj, h->pos[h->cur], h->rel, h->pos[h->cur ^ 1], h->trec,
+                                                                  nullptr, h->cell_start, h->d_cnt, nullptr, nullptr, 0);
+        h->launches++;
+      }
+      h->launches--;
+    } else if (h->blk_ok) {
       // block phase ph (or phases ph .. ph+fuse-1): all blocks of block-index parity (cx,cy,cz);
       // each CTA runs the eight cell colours of its block
       const int nb = (h->blk.nbx / 2) * (h->blk.nby / 2) * (h->blk.nbz / 2) * fuse;

@@ -42,6 +42,7 @@
 #define LEAN_COL_CHUNKS 32       // most chunks one cell colour of a block may need
 #define LEAN_MAX_CHUNKS 30       // chunks per cell colour of a block
 #define PROPOSE_THREADS 256
+#define GATHER_LISTS_N 32        // trial lists of k_sweep_gather: 8 colours x {first, second, third trial, cells with more}
 
 // trial record code: slot of the particle inside its cell (4 bits) | bit 4: the trial stays inside its cell
 #define TREC_ACT 16u
@@ -119,10 +120,15 @@ __device__ __noinline__ bool block_exact_rescan(const double4* pos, const double
 template <bool LOG>
 __global__ void __launch_bounds__(PROPOSE_THREADS)
 k_propose(SweepArgs a, const double4* __restrict__ pos, const int* __restrict__ cs, long long ncell,
-          double4* __restrict__ prop, uint4* __restrict__ trec, uint4* __restrict__ traw) {
+          double4* __restrict__ prop, uint4* __restrict__ trec, uint4* __restrict__ traw, int* __restrict__ lists,
+          int* __restrict__ lcount, long long lstride) {
   const Grid& g = a.g;
-  const int gs = blockIdx.x * PROPOSE_THREADS + threadIdx.x;
-  if (gs >= cs[ncell]) return;
+  int gs = blockIdx.x * PROPOSE_THREADS + threadIdx.x;
+  const bool live = gs < cs[ncell];
+  if (!live) {
+    if (!lists) return;
+    gs = 0;                      // (keeps the CTA's barriers of the list building; nothing is written for this thread)
+  }
   const double4 p = pos[gs];
   const long long c = local_cell(g, p.x, p.y, p.z);       // the cell the counting sort put it in
   const int b = cs[c], n = cs[c + 1] - b;
@@ -146,9 +152,30 @@ k_propose(SweepArgs a, const double4* __restrict__ pos, const int* __restrict__ 
   float4 nrel = make_float4(0.f, 0.f, 0.f, 0.f);
   if (act) nrel = make_rel(g, gx, iy, iz, xn, yn, zn);
   const unsigned int code = (unsigned int)min(gs - b, 15) | (act ? TREC_ACT : 0u);
-  trec[b + j] = make_uint4(__float_as_uint(nrel.x), __float_as_uint(nrel.y), __float_as_uint(nrel.z), code);
-  prop[gs] = make_double4(xn, yn, zn, p.w);
-  if (LOG) traw[b + j] = make_uint4(rn.v[0], rn.v[1], rn.v[2], (unsigned int)(int)p.w);
+  if (live) {
+    trec[b + j] = make_uint4(__float_as_uint(nrel.x), __float_as_uint(nrel.y), __float_as_uint(nrel.z), code);
+    prop[gs] = make_double4(xn, yn, zn, p.w);
+    if (LOG) traw[b + j] = make_uint4(rn.v[0], rn.v[1], rn.v[2], (unsigned int)(int)p.w);
+  }
+  // k_sweep_gather: per cell colour, the cells holding a first / second / third trial and those holding more
+  // (owned cells only).  The 32 list counters are bumped once per CTA: ranks inside the CTA come from shared-memory
+  // counters, then one global atomic per list reserves the CTA's range.
+  if (lists) {
+    __shared__ int s_n[GATHER_LISTS_N], s_base[GATHER_LISTS_N];
+    if (threadIdx.x < GATHER_LISTS_N) s_n[threadIdx.x] = 0;
+    __syncthreads();
+    const bool mine = live && j <= 3 && l >= g.own_lo && l < g.own_hi;
+    const int li = ((((gx & 1) << 2) | ((iy & 1) << 1) | (iz & 1)) << 2) | (j & 3);
+    int rank = 0;
+    if (mine) rank = atomicAdd(&s_n[li], 1);
+    __syncthreads();
+    if (threadIdx.x < GATHER_LISTS_N && s_n[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&lcount[threadIdx.x], s_n[threadIdx.x]);
+    __syncthreads();
+    if (mine) {
+      const int at = s_base[li] + rank;
+      if (at < lstride) lists[(long long)li * lstride + at] = (l << 20) | (iy << 10) | iz;     // (fewer than 1024 cells per axis and rank)
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------

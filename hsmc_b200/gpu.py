@@ -155,9 +155,9 @@ class HsmcGpu:
 
     def __init__(self, n_particles, box, seed=0, device=0, rank=0, world=1, nccl_id=None, cell_min=1.0,
                  regrid_interval=1, sweep_impl=0, xpart_world=0):
-        # sweep_impl: 0 default (k_propose + k_sweep_lean), 5 the same chain evaluated all in double
-        # from global memory, 3 the default with the fp32 error band forced to zero (negative
-        # control); 1: one launch per cell colour from global memory (a different update order).  xpart_world: a single-GPU run uses the x block
+        # sweep_impl: 0 default (k_sweep_gather for N >= 2e6, k_sweep_lean below); 7 / 8 force them.
+        # 1 / 5: the same two chains evaluated all in double from global memory; 3: the lean kernel
+        # with the fp32 error band forced to zero (negative control).  xpart_world: a single-GPU run uses the x block
         # partition of a run on that many slabs (bitwise identity checks).
         sweep_impl = int(sweep_impl) | (int(xpart_world) << 8)
         self.L = load_library()

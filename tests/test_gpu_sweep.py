@@ -33,7 +33,7 @@ def _replay(checker, log, dr_max):
     return keep, acc
 
 
-@pytest.mark.parametrize("impl", [0, 5, 1], ids=["lean", "block_global", "cell_global"])
+@pytest.mark.parametrize("impl", [0, 8, 5, 7, 1], ids=["auto", "lean", "block_global", "gather", "cell_global"])
 @pytest.mark.parametrize("path", GOLDEN_FILES, ids=IDS)
 def test_every_trial_verdict_replays_through_oracle(hs, path, impl, oracle_built):
     g = dict(np.load(path))
@@ -171,7 +171,7 @@ def test_kernel_variants_produce_the_same_chain(hs, oracle_built, block, monkeyp
     wrapped regions and ragged blocks -- and running the default twice gives the same bits.  (The
     one-launch-per-cell-colour kernel, sweep_impl 1, orders the updates differently and is a
     different -- equally valid -- chain.)"""
-    impls = (0, 5, 0)
+    impls = (8, 5, 8)
     if block is not None:
         monkeypatch.setenv("HSMC_BLOCK", block)
     box, conf = oracle_built.Port.lattice(2, 14, 9, 11, 0.85)
@@ -189,8 +189,36 @@ def test_kernel_variants_produce_the_same_chain(hs, oracle_built, block, monkeyp
     assert cnts[0][0] == 12 * N
 
 
+def test_gather_kernel_is_the_cell_colour_chain(hs, oracle_built):
+    """k_sweep_gather (one thread per trial, one launch per cell colour and trial index, fp32 filter over the shadow
+    table + exact re-check) against the one-launch-per-colour all-double reference kernel (sweep_impl 1): the same
+    Markov chain, bit for bit -- on a box with wrapped columns, boundary cells and cells holding several particles."""
+    box, conf = oracle_built.Port.lattice(2, 14, 9, 11, 0.85)
+    N = conf.shape[0]
+    outs, cnts = [], []
+    for impl in (7, 1, 7):
+        with hs.HsmcGpu(N, box[:3], seed=77, sweep_impl=impl) as h:
+            h.upload(conf)
+            h.sweep_nvt(12, 0.15)
+            outs.append(h.download())
+            cnts.append(h.counters())
+            assert h.min_dist2() >= 1.0
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    assert np.array_equal(cnts[0], cnts[1]) and cnts[0][0] == 12 * N
+    # denser cells (cell edge 1.3: up to five particles per cell, the tail launch runs)
+    box, conf = oracle_built.Port.lattice(2, 9, 9, 9, 0.95)
+    N = conf.shape[0]
+    outs = []
+    for impl in (7, 1):
+        with hs.HsmcGpu(N, box[:3], seed=5, sweep_impl=impl, cell_min=1.3) as h:
+            h.upload(conf)
+            h.sweep_nvt(10, 0.05)
+            outs.append(h.download())
+    assert np.array_equal(outs[0], outs[1])
+
+
 @pytest.mark.parametrize("block", [None, "2,2,2", "3,2,4", "8,8,24", "10,10,6"])      # the last: 144 staging rows per block
-@pytest.mark.parametrize("impl", [0, 5], ids=["staged", "global"])
+@pytest.mark.parametrize("impl", [8, 5], ids=["staged", "global"])
 def test_fused_phase_launch_is_the_same_chain(hs, oracle_built, block, impl, monkeypatch):
     """All eight block phases in ONE launch, ordered by per-block completion flags, against eight
     separate launches (HSMC_FUSE=0): identical coordinates and counters.  Small blocks give
@@ -269,7 +297,7 @@ def test_fp32_filter_without_error_band_is_caught(hs, oracle_built):
     box, conf, dr = _near_contact_system(oracle_built)
     N = conf.shape[0]
     p = oracle_built.Port(conf, box, neigh_dr=1.0, max_part=12)
-    with hs.HsmcGpu(N, box[:3], seed=8, sweep_impl=3) as h:
+    with hs.HsmcGpu(N, box[:3], seed=8, sweep_impl=3) as h:      # (3 = the block-resident kernel with eps = 0)
         h.upload(conf)
         mismatch = False
         for _ in range(8):
