@@ -137,6 +137,7 @@ struct hsmc_gpu {
   void* h_stage = nullptr;               // pinned staging for small results
   double* d_io = nullptr;                // staging for upload/download
   int64_t cap_io = 0;
+  bool io_packed = false;                // d_io holds the current table by id (hsmc_gpu_pack_table)
   uint64_t sweeps_done = 0;
   uint64_t launches = 0, nccl_calls = 0;
   int64_t vol_cnt[3] = {0, 0, 0};
@@ -829,6 +830,7 @@ extern "C" int hsmc_gpu_sync(hsmc_gpu* h) {
 
 extern "C" int hsmc_gpu_upload(hsmc_gpu* h, const double* rows, int64_t n_rows) {
   if (!h || !rows) return fail("null argument");
+  h->io_packed = false;
   CU(cudaSetDevice(h->cfg.device));
   if (h->cfg.world == 1 && n_rows != h->N) return fail("upload: n_rows must equal the particle count");
   if (n_rows < 0 || n_rows > h->N) return fail("upload: bad row count");
@@ -851,8 +853,39 @@ extern "C" int hsmc_gpu_download(hsmc_gpu* h, double* conf) {
   k_pack_by_id<<<nblk(h->N, 256), 256, 0, h->st>>>(h->pos[h->cur], 0, (int)h->N, h->d_io);
   h->launches++;
   CU(cudaGetLastError());
+  h->io_packed = true;
   CU(cudaMemcpyAsync(conf, h->d_io, sizeof(double) * 4 * (size_t)h->N, cudaMemcpyDeviceToHost, h->st));
   CU(cudaStreamSynchronize(h->st));
+  return 0;
+}
+
+extern "C" int hsmc_gpu_pack_table(hsmc_gpu* h) {
+  if (!h) return fail("null handle");
+  if (!h->have_conf) return fail("download: no configuration uploaded");
+  if (h->cfg.world != 1) return fail("pack_table: full-table download needs world == 1; use download_owned");
+  CU(cudaSetDevice(h->cfg.device));
+  TRY(ensure_io(h, h->N));
+  k_pack_by_id<<<nblk(h->N, 256), 256, 0, h->st>>>(h->pos[h->cur], 0, (int)h->N, h->d_io);
+  h->launches++;
+  CU(cudaGetLastError());
+  h->io_packed = true;
+  return 0;
+}
+
+extern "C" int hsmc_gpu_fetch_rows(hsmc_gpu* h, int64_t first_row, int64_t n_rows, double* rows) {
+  if (!h || !rows) return fail("null argument");
+  if (!h->io_packed) return fail("fetch_rows: call pack_table first (and again after the configuration changed)");
+  if (first_row < 0 || n_rows < 0 || first_row + n_rows > h->N) return fail("fetch_rows: row range out of bounds");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaMemcpyAsync(rows, h->d_io + 4 * first_row, sizeof(double) * 4 * (size_t)n_rows, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  return 0;
+}
+
+extern "C" int hsmc_gpu_pin_host(void* ptr, size_t bytes, int pin) {
+  if (!ptr) return fail("null argument");
+  if (pin) CU(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+  else CU(cudaHostUnregister(ptr));
   return 0;
 }
 
@@ -863,6 +896,7 @@ extern "C" int hsmc_gpu_download_owned(hsmc_gpu* h, double* rows, int64_t capaci
   TRY(sync_layout(h));
   if (capacity_rows < h->n_owned) return fail("download_owned: buffer too small");
   TRY(ensure_io(h, std::max<int64_t>(h->n_owned, 1)));
+  h->io_packed = false;
   if (h->n_owned > 0) {
     k_pack_rows<<<nblk(h->n_owned, 256), 256, 0, h->st>>>(h->pos[h->cur], (int)h->own_first, (int)h->n_owned, h->d_io);
     h->launches++;
@@ -952,6 +986,7 @@ static int ensure_trial_tables(hsmc_gpu* h, bool logged) {
 }
 
 static int sweep_once(hsmc_gpu* h, double dr_max, bool logged) {
+  h->io_packed = false;
   if (h->since_regrid % h->cfg.regrid_interval == 0) TRY(do_regrid(h));
   h->since_regrid++;
   Grid& g = h->g;
@@ -1191,6 +1226,7 @@ extern "C" int hsmc_gpu_presst_flags(hsmc_gpu* h, const double* sf, int nn, int*
 
 extern "C" int hsmc_gpu_rescale(hsmc_gpu* h, double sf, const double new_box[3]) {
   if (!h || !new_box) return fail("null argument");
+  h->io_packed = false;
   if (!h->have_conf) return fail("no configuration uploaded");
   CU(cudaSetDevice(h->cfg.device));
   if (h->cfg.world > 1) {

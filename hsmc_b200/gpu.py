@@ -19,7 +19,7 @@ NCCL_ID_BYTES = 128
 ABI_SYMBOLS = [
     "hsmc_gpu_last_error", "hsmc_gpu_device_count", "hsmc_gpu_nccl_id", "hsmc_gpu_create",
     "hsmc_gpu_destroy", "hsmc_gpu_ipc_export", "hsmc_gpu_ipc_attach", "hsmc_gpu_get_info", "hsmc_gpu_plan", "hsmc_gpu_plan_blocks", "hsmc_gpu_stream", "hsmc_gpu_sync", "hsmc_gpu_upload",
-    "hsmc_gpu_download", "hsmc_gpu_download_owned", "hsmc_gpu_sweep_nvt", "hsmc_gpu_overlap_scaled",
+    "hsmc_gpu_download", "hsmc_gpu_download_owned", "hsmc_gpu_pack_table", "hsmc_gpu_fetch_rows", "hsmc_gpu_pin_host", "hsmc_gpu_sweep_nvt", "hsmc_gpu_overlap_scaled",
     "hsmc_gpu_rescale", "hsmc_gpu_widom", "hsmc_gpu_rdf_counts", "hsmc_gpu_rdf_counts_part", "hsmc_gpu_contact_counts",
     "hsmc_gpu_presst_flags", "hsmc_gpu_order_parameter", "hsmc_gpu_counters", "hsmc_gpu_reset_counters", "hsmc_gpu_add_vol_move",
     "hsmc_gpu_cell_rejects", "hsmc_gpu_profile", "hsmc_gpu_profile_read", "hsmc_gpu_set_sweep_counter", "hsmc_gpu_trial_verdicts",
@@ -90,6 +90,9 @@ def load_library():
     L.hsmc_gpu_upload.argtypes = [vp, vp, C.c_int64]
     L.hsmc_gpu_download.argtypes = [vp, vp]
     L.hsmc_gpu_download_owned.argtypes = [vp, vp, C.c_int64, C.POINTER(C.c_int64)]
+    L.hsmc_gpu_pack_table.argtypes = [vp]
+    L.hsmc_gpu_fetch_rows.argtypes = [vp, C.c_int64, C.c_int64, vp]
+    L.hsmc_gpu_pin_host.argtypes = [vp, C.c_size_t, C.c_int]
     L.hsmc_gpu_sweep_nvt.argtypes = [vp, C.c_int, C.c_double]
     L.hsmc_gpu_overlap_scaled.argtypes = [vp, C.c_double, ip]
     L.hsmc_gpu_rescale.argtypes = [vp, C.c_double, dp]
@@ -242,6 +245,15 @@ class HsmcGpu:
         n = C.c_int64(0)
         self._ck(self.L.hsmc_gpu_download_owned(self.h, _ptr(out), out.shape[0], C.byref(n)))
         return out[: n.value]
+
+    def pack_table(self):
+        self._ck(self.L.hsmc_gpu_pack_table(self.h))
+
+    def fetch_rows(self, first, n, out=None):
+        if out is None:
+            out = np.empty((n, 4))
+        self._ck(self.L.hsmc_gpu_fetch_rows(self.h, C.c_int64(first), C.c_int64(n), _ptr(out)))
+        return out
 
     def download_owned_ptr(self, ptr, cap):
         n = C.c_int64(0)

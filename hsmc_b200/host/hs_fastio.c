@@ -81,6 +81,7 @@ typedef struct {
   const char *header;
   size_t header_len;
   chunk_out *out;
+  int avail;              /* rows [0, avail) of conf are valid (streaming source; n when the table is complete) */
   int next;               /* next chunk to hand out */
   int written;            /* chunks already written by the main thread */
   int failed;
@@ -151,6 +152,10 @@ static void *worker(void *arg) {
       pthread_cond_wait(&J->cv_room, &J->mu);            /* do not run far ahead of the writer */
     if (J->failed || J->next >= J->nchunks) { pthread_mutex_unlock(&J->mu); break; }
     const int c = J->next++;
+    {                                                      /* streaming source: wait for the rows of this chunk */
+      const int r1 = ((c + 1) * ROWS_PER_CHUNK < J->n) ? (c + 1) * ROWS_PER_CHUNK : J->n;
+      while (!J->failed && J->avail < r1) pthread_cond_wait(&J->cv_done, &J->mu);
+    }
     pthread_mutex_unlock(&J->mu);
 
     chunk_out *o = &J->out[c % J->window];
@@ -172,8 +177,34 @@ static void *worker(void *arg) {
   return NULL;
 }
 
+/* producer of a streamed snapshot: fetches consecutive slices of the table and publishes how far it got */
+typedef struct { job *J; hs_fastio_fetch_fn fetch; void *ctx; int slice; } feeder;
+
+static void *feed(void *arg) {
+  feeder *F = arg;
+  job *J = F->J;
+  for (int r0 = 0; r0 < J->n; r0 += F->slice) {
+    const int m = (r0 + F->slice < J->n) ? F->slice : J->n - r0;
+    const int rc = F->fetch(F->ctx, r0, m);
+    pthread_mutex_lock(&J->mu);
+    if (rc) J->failed = 1; else J->avail = r0 + m;
+    pthread_cond_broadcast(&J->cv_done);
+    pthread_cond_broadcast(&J->cv_room);
+    const int stop = J->failed;
+    pthread_mutex_unlock(&J->mu);
+    if (stop) break;
+  }
+  return NULL;
+}
+
 int hs_fastio_write_config(const char *name, int append, int sweep, int n, const double box[3],
                            const double (*conf)[4], int threads) {
+  return hs_fastio_write_config_stream(name, append, sweep, n, box, conf, threads, NULL, NULL, 0);
+}
+
+int hs_fastio_write_config_stream(const char *name, int append, int sweep, int n, const double box[3],
+                                  const double (*conf)[4], int threads, hs_fastio_fetch_fn fetch, void *ctx,
+                                  int slice_rows) {
   if (n < 0) { errno = EINVAL; return -1; }
   const char *env = getenv("HSMC_IO_THREADS");
   if (env && atoi(env) > 0) threads = atoi(env);
@@ -196,6 +227,7 @@ int hs_fastio_write_config(const char *name, int append, int sweep, int n, const
   job J;
   memset(&J, 0, sizeof(J));
   J.conf = conf; J.n = n; J.level = level; J.strategy = strategy;
+  J.avail = fetch ? 0 : n;
   J.header = header; J.header_len = (size_t)hl;
   J.nchunks = n == 0 ? 1 : (n + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK;
   if (threads > J.nchunks) threads = J.nchunks;
@@ -215,6 +247,18 @@ int hs_fastio_write_config(const char *name, int append, int sweep, int n, const
       if (pthread_create(&tid[started], NULL, worker, &J)) break;
   int rc = 0;
   if (started == 0) { rc = -1; J.failed = 1; }
+  feeder F = {&J, fetch, ctx, slice_rows > 0 ? slice_rows : (1 << 20)};
+  pthread_t feed_tid;
+  int feeding = 0;
+  if (fetch && rc == 0) {
+    if (pthread_create(&feed_tid, NULL, feed, &F)) {     /* no thread: fetch everything here, then go on as usual */
+      if (fetch(ctx, 0, n)) { rc = -1; J.failed = 1; }
+      pthread_mutex_lock(&J.mu);
+      J.avail = n;
+      pthread_cond_broadcast(&J.cv_done);
+      pthread_mutex_unlock(&J.mu);
+    } else feeding = 1;
+  }
 
   /* ordered writer */
   for (int c = 0; c < J.nchunks && rc == 0; c++) {
@@ -236,7 +280,11 @@ int hs_fastio_write_config(const char *name, int append, int sweep, int n, const
   if (rc) J.failed = 1;
   pthread_cond_broadcast(&J.cv_room);
   pthread_mutex_unlock(&J.mu);
+  pthread_mutex_lock(&J.mu);
+  pthread_cond_broadcast(&J.cv_done);                      /* (workers waiting for rows see `failed`) */
+  pthread_mutex_unlock(&J.mu);
   for (int t = 0; t < started; t++) pthread_join(tid[t], NULL);
+  if (feeding) pthread_join(feed_tid, NULL);
   for (int c = 0; c < J.window; c++) free(J.out[c].gz);
   free(tid);
   free(J.out);

@@ -24,4 +24,13 @@ int hs_fmt_f8(char *out, double x);
 int hs_fastio_write_config(const char *name, int append, int sweep, int n, const double box[3],
                            const double (*conf)[4], int threads);
 
+/* The same writer fed piecewise: `fetch(ctx, first_row, n_rows)` must fill conf[first_row .. first_row + n_rows)
+   (rows in id order) and return 0; it is called from a producer thread for consecutive slices of `slice_rows` rows
+   while the workers format and deflate the rows that have already arrived -- the device-to-host copy of a large
+   table overlaps its compression.  After the call conf holds the whole table. */
+typedef int (*hs_fastio_fetch_fn)(void *ctx, long long first_row, long long n_rows);
+int hs_fastio_write_config_stream(const char *name, int append, int sweep, int n, const double box[3],
+                                  const double (*conf)[4], int threads, hs_fastio_fetch_fn fetch, void *ctx,
+                                  int slice_rows);
+
 #endif

@@ -160,10 +160,15 @@ void hs_gpu_open(hs_sim *s) {
     }
   }
   hs_gpu_check(hsmc_gpu_set_sweep_counter(s->gpu, s->philox_sweeps));
+  /* a large table is page-locked so that uploads and (sliced) snapshot downloads run at full PCIe speed and
+     asynchronously; failing to lock it only makes them slower */
+  if (s->mp.world == 1 && s->part.NN >= (1 << 18) && !s->conf_pinned)
+    s->conf_pinned = hsmc_gpu_pin_host(s->conf, (size_t)s->part.NN * sizeof(*s->conf), 1) == 0;
   hs_gpu_push(s);
 }
 
 void hs_gpu_close(hs_sim *s) {
+  if (s->conf_pinned) { hsmc_gpu_pin_host(s->conf, 0, 0); s->conf_pinned = false; }
   if (s->gpu_rep) hsmc_gpu_destroy(s->gpu_rep);
   s->gpu_rep = NULL;
   if (s->gpu) hsmc_gpu_destroy(s->gpu);
@@ -260,6 +265,13 @@ void hs_read_restart(hs_sim *s, const char *name) {
 }
 
 /* ---- configuration snapshots: io_config.c:134-191 ----------------------------------- */
+/* one slice of the id-ordered table from the device into the host mirror (called from the writer's producer thread) */
+static int fetch_slice(void *ctx, long long first, long long n) {
+  hs_sim *s = ctx;
+  if (hsmc_gpu_fetch_rows(s->gpu, first, n, &s->conf[first][0])) { s->fetch_failed = true; return -1; }
+  return 0;
+}
+
 void hs_write_config(hs_sim *s, int sweep) {
   const hs_input *in = &s->in;
   if (!s->config_checked) {
@@ -270,7 +282,10 @@ void hs_write_config(hs_sim *s, int sweep) {
   char name[32];
   snprintf(name, sizeof(name), "config_%06d.dat.gz", s->config_file_id);
   const int append = s->config_samples_in_file != 0;
-  hs_gpu_pull(s);
+  /* one GPU, mirror stale: the table comes over in slices while the slices that have arrived are being formatted and
+     deflated (hs_fastio.c); otherwise (slabs, serial writer, mirror already current) the whole table first */
+  const int stream = s->mp.world == 1 && !s->mirror_current && !getenv("HSMC_IO_SERIAL") && !getenv("HSMC_IO_NO_STREAM");
+  if (!stream) hs_gpu_pull(s);
   if (!HS_ROOT(s)) {
     /* keep the file counters in step with rank 0 */
   } else if (getenv("HSMC_IO_SERIAL")) {
@@ -287,7 +302,16 @@ void hs_write_config(hs_sim *s, int sweep) {
   } else {
     /* same bytes after decompression, formatted and deflated chunk-parallel (hs_fastio.c) */
     const double b3[3] = {s->box.lx, s->box.ly, s->box.lz};
-    if (hs_fastio_write_config(name, append, sweep, s->part.NN, b3, (const double (*)[4])s->conf, 0)) {
+    int rc;
+    if (stream) {
+      hs_gpu_check(hsmc_gpu_pack_table(s->gpu));
+      rc = hs_fastio_write_config_stream(name, append, sweep, s->part.NN, b3, (const double (*)[4])s->conf, 0, fetch_slice, s,
+                                         1 << 20);
+      if (s->fetch_failed) hs_gpu_check(1);
+      s->mirror_current = rc == 0;
+    } else
+      rc = hs_fastio_write_config(name, append, sweep, s->part.NN, b3, (const double (*)[4])s->conf, 0);
+    if (rc) {
       perror("Error while creating configuration file");
       exit(EXIT_FAILURE);
     }

@@ -45,6 +45,8 @@ typedef struct hs_sim {
   hs_pinfo part;
   double (*conf)[4];
   bool mirror_current;     /* host mirror == device state */
+  bool conf_pinned;        /* the table is page-locked (hs_gpu_open) */
+  bool fetch_failed;       /* a slice of a streamed snapshot did not arrive (hs_write_config) */
   hs_rng rng;
   hsmc_gpu *gpu;
   hs_mp mp;                /* process-per-GPU plumbing (`-g K`); world 1 = the plain serial driver */

@@ -130,6 +130,18 @@ int hsmc_gpu_download(hsmc_gpu *h, double *conf /* n_particles x 4 */);
 /* Owned rows of this rank, cell-ordered, {id,x,y,z}; any world size. */
 int hsmc_gpu_download_owned(hsmc_gpu *h, double *rows, int64_t capacity_rows, int64_t *n_rows);
 
+/* The same table as hsmc_gpu_download, piecewise, for writers that work while the copy goes on (write_config,
+   io_config.c:134-191: formatting + deflate of rows [0, k) overlaps the transfer of rows [k, ...)).
+   pack_table orders the table by id on the device once (the device copy of what download would return);
+   fetch_rows copies rows [first_row, first_row + n_rows) of it to the host and returns when they have arrived.
+   The packed copy is valid until the next call that changes the configuration.  world == 1. */
+int hsmc_gpu_pack_table(hsmc_gpu *h);
+int hsmc_gpu_fetch_rows(hsmc_gpu *h, int64_t first_row, int64_t n_rows, double *rows);
+
+/* Page-lock (or release: pin = 0) a host buffer the caller owns -- the particle table part_conf of
+   sim_info.c:99 -- so that uploads and downloads run at the full host-link rate.  Optional; failure is not fatal. */
+int hsmc_gpu_pin_host(void *ptr, size_t bytes, int pin);
+
 /* Replaces n_sweeps x sweep_nvt() (nvt.c:201-209): each sweep = N single-particle
    trial displacements (moves.c:27-80) executed as 8 checkerboard colour phases.
    dr_max is passed every call because the optimizer mutates it (optimizer.c:34-48). */

@@ -106,6 +106,51 @@ def test_chunking_and_thread_count_do_not_change_the_bytes(fastio, tmp_path, n):
         assert gzip.open(p).read() == want
 
 
+FETCH = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_longlong, C.c_longlong)
+
+
+@pytest.mark.parametrize("n,slice_rows", [(0, 1000), (1, 1000), (100_003, 7001), (100_003, 1 << 20), (250_000, 32768)])
+def test_streamed_table_gives_the_same_bytes(fastio, tmp_path, n, slice_rows):
+    """hs_fastio_write_config_stream: the table arrives slice by slice (on the GPU: D2H copies of the id-ordered
+    table, hs_sim.c:hs_write_config) while earlier slices are formatted and deflated; a chunk never reads rows
+    that have not arrived -- the destination starts as NaN, which would show in the text."""
+    import time
+    fastio.hs_fastio_write_config_stream.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double),
+                                                     C.c_void_p, C.c_int, FETCH, C.c_void_p, C.c_int]
+    rng = np.random.default_rng(n + slice_rows)
+    src = np.empty((n, 4))
+    src[:, 0] = rng.permutation(n)
+    src[:, 1:] = rng.random((n, 3)) * 97.3
+    dst = np.full((n, 4), np.nan)
+    calls = []
+
+    def fetch(ctx, first, m):
+        time.sleep(0.002)                       # the writer threads are ahead of the producer
+        dst[first:first + m] = src[first:first + m]
+        calls.append((first, m))
+        return 0
+
+    box = (97.3, 97.3, 97.3)
+    b = (C.c_double * 3)(*box)
+    p = str(tmp_path / "s.gz")
+    rc = fastio.hs_fastio_write_config_stream(os.fsencode(p), 0, 3, n, b, C.c_void_p(dst.ctypes.data), 4, FETCH(fetch), None,
+                                              slice_rows)
+    assert rc == 0
+    assert gzip.open(p).read() == _expected(3, box, src)
+    assert calls == [(f, min(slice_rows, n - f)) for f in range(0, n, slice_rows)]
+
+
+def test_streamed_table_fetch_failure_is_reported(fastio, tmp_path):
+    fastio.hs_fastio_write_config_stream.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double),
+                                                     C.c_void_p, C.c_int, FETCH, C.c_void_p, C.c_int]
+    n = 200_000
+    dst = np.zeros((n, 4))
+    b = (C.c_double * 3)(1.0, 1.0, 1.0)
+    rc = fastio.hs_fastio_write_config_stream(os.fsencode(str(tmp_path / "f.gz")), 0, 0, n, b, C.c_void_p(dst.ctypes.data), 4,
+                                              FETCH(lambda ctx, first, m: -1 if first else 0), None, 50_000)
+    assert rc != 0
+
+
 def test_unwritable_path_reports_failure(fastio, tmp_path):
     conf = np.zeros((4, 4))
     b = (C.c_double * 3)(1.0, 1.0, 1.0)

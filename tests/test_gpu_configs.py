@@ -122,6 +122,48 @@ def test_config3_npt_108000():
     assert 100 < vol_moves < 250                                  # about one per sweep
 
 
+CONFIG_SNAP = """# N = 1,048,576: two snapshots of a GPU-evolved configuration
+rho 0.9
+cells_x 64
+cells_y 64
+cells_z 64
+type 2
+neigh_list 1.0 1
+dr_max 0.1
+opt 0 100 10 0.5 0.5
+seed 3
+config_write 5 100
+sweep_eq 4
+sweep_stat 10
+out 5
+"""
+
+
+def test_streamed_snapshot_equals_the_whole_table_path():
+    """hs_write_config on one GPU: the id-ordered table is fetched in slices (hsmc_gpu_pack_table +
+    hsmc_gpu_fetch_rows) while earlier slices are being formatted and deflated.  Same chain, same bytes as the
+    path that downloads the whole table first and as the serial gzprintf writer (the reference's own loop,
+    io_config.c:134-191); and what was written is the configuration the device holds."""
+    import gzip
+    d1, _ = _run(CONFIG_SNAP)
+    d2, _ = _run(CONFIG_SNAP, env={"HSMC_IO_NO_STREAM": "1"})
+    d3, _ = _run(CONFIG_SNAP, env={"HSMC_IO_SERIAL": "1"})
+    names = sorted(f for f in os.listdir(d1) if f.startswith("config_"))
+    assert names and names == sorted(f for f in os.listdir(d2) if f.startswith("config_"))
+    for f in names:
+        a = gzip.open(os.path.join(d1, f)).read()
+        assert a == gzip.open(os.path.join(d2, f)).read() == gzip.open(os.path.join(d3, f)).read()
+        parts = a.split(b"# Sweep number\n")[1:]
+        assert len(parts) == 2                                      # sweeps 5 and 10 appended to one file
+        for part in parts:
+            rows = np.loadtxt(part.split(b"# Configuration\n")[1].decode().splitlines())
+            assert rows.shape == (4 * 64 ** 3, 4) and np.array_equal(rows[:, 0], np.arange(rows.shape[0]))
+            assert np.all((rows[:, 1:] >= 0) & (rows[:, 1:] <= 64 * (4 / 0.9) ** (1 / 3) + 1e-6))
+        first = np.loadtxt(parts[0].split(b"# Configuration\n")[1].decode().splitlines())
+        second = np.loadtxt(parts[1].split(b"# Configuration\n")[1].decode().splitlines())
+        assert 0.3 < np.mean(np.any(first[:, 1:] != second[:, 1:], axis=1)) <= 1.0     # the chain moved in between
+
+
 def test_restart_round_trip():
     d, log = _run(CONFIG1)
     rs = sorted(f for f in os.listdir(d) if f.startswith("restart_"))
