@@ -337,19 +337,26 @@ def widom_workload(args, rank, world, local_rank):
         box, conf = fcc_lattice(20, 20, 20, rho)
         h = hsmc_b200.HsmcGpu(conf.shape[0], box, seed=20261017, device=local_rank)      # same chain on every rank
         h.upload(conf)
-        # melt the fcc start and equilibrate: sweeps until the bond-order parameter q6 of the configuration has
-        # collapsed from its fcc value (0.57) to a fluid's (< 0.1), checked on cells wide enough for the first shell;
-        # every rank runs the same deterministic chain, so every rank holds the same fluid
+        # melt the fcc start and equilibrate: sweeps until the Bragg peaks of the start lattice are gone -- the
+        # structure factor S(G)/N = |sum_j exp(i G r_j)|^2 / N^2 at the {111} and {200} reciprocal vectors of the
+        # 20^3 fcc cells is ~0.8 for the crystal and O(1/N) for a fluid (the reference's q_l is an average of
+        # per-particle values and stays near 0.35 in a dense fluid, so it cannot tell).  Every rank runs the same
+        # deterministic chain, so every rank holds the same fluid
         dr_eq = min(0.5, 0.08 / rho ** 2)
-        q6, eq_sweeps = 1.0, 0
-        while q6 > 0.1 and eq_sweeps < args.widom_max_eq_sweeps:
-            h.sweep_nvt(2000, dr_eq)
-            eq_sweeps += 2000
-            with hsmc_b200.HsmcGpu(conf.shape[0], box, seed=1, device=local_rank, cell_min=1.5) as t:
-                t.upload(h.download())
-                q6 = t.order_parameter(6, 1.5)
+        gvecs = 2.0 * np.pi * 20.0 / np.asarray(box[:3]) * np.array(
+            [[1, 1, 1], [-1, 1, 1], [1, -1, 1], [1, 1, -1], [2, 0, 0], [0, 2, 0], [0, 0, 2]], dtype=np.float64)
+
+        def bragg(rows):
+            ph = rows[:, 1:4] @ gvecs.T
+            return float(np.max(np.cos(ph).sum(axis=0) ** 2 + np.sin(ph).sum(axis=0) ** 2) / rows.shape[0] ** 2)
+
+        sg, eq_sweeps = 1.0, 0
+        while sg > 0.005 and eq_sweeps < args.widom_max_eq_sweeps:
+            h.sweep_nvt(1000, dr_eq)
+            eq_sweeps += 1000
+            sg = bragg(h.download())
         h.sweep_nvt(2000, dr_eq)
-        prep.append({"rho": rho, "q6": q6, "equilibration_sweeps": eq_sweeps + 2000, "melted": bool(q6 <= 0.1)})
+        prep.append({"rho": rho, "bragg_peak_S_over_N": sg, "equilibration_sweeps": eq_sweeps + 2000, "melted": bool(sg <= 0.005)})
         info = h.info()
         nbar = conf.shape[0] / (info["cells"][0] * info["cells"][1] * info["cells"][2])
         handles.append((rho, h, nbar, torch.cuda.ExternalStream(h.stream_ptr(), device=torch.device("cuda", local_rank))))
@@ -590,7 +597,7 @@ def main():
                          "GPUs; c2 / c3: configs[1] / configs[2] run through the drop-in host driver on their input files "
                          "(the reference arm runs the reference executable on the identical file)")
     ap.add_argument("--insertions", type=float, default=1e8, help="--workload widom: insertions per sample and density")
-    ap.add_argument("--widom-max-eq-sweeps", type=int, default=200000, help="--workload widom: give up melting a density after this many sweeps (it is then flagged)")
+    ap.add_argument("--widom-max-eq-sweeps", type=int, default=60000, help="--workload widom: give up melting a density after this many sweeps (it is then flagged)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

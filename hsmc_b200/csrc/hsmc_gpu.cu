@@ -402,13 +402,13 @@ static void setup_blocks(hsmc_gpu* h) {
       ctas *= (long long)(even_blocks(g.ny, by) / 2) * (even_blocks(g.nz, bz) / 2);
       // CTAs of k_sweep_lean per SM: dynamic + static shared memory + the 1 KB the hardware reserves per CTA; the
       // register file holds five 192-thread CTAs of 64 registers
-      const int per_sm = (int)std::min<size_t>(5, (size_t)(227 * 1024) / (s.smem + sizeof(BlockRow) * LEAN_MAX_ROWS + 4 * LEAN_MAX_ROWS + 1200));
+      const int per_sm = (int)std::min<size_t>(LEAN_MIN_CTAS, (size_t)(227 * 1024) / (s.smem + sizeof(BlockRow) * LEAN_MAX_ROWS + 4 * LEAN_MAX_ROWS + 1200));
       if (per_sm < 1) continue;
       const double interior = (double)s.mx * s.my * s.mz;
       // below two waves of CTA slots the ragged last wave costs a whole CTA latency
-      const double waves = (double)ctas / (148.0 * per_sm);
+      const double waves = (double)ctas / (148.0 * per_sm);   // (register file: LEAN_MIN_CTAS CTAs of LEAN_THREADS threads)
       const double fill = waves < 2.0 ? waves / std::ceil(waves) : 1.0;
-      const double score = fill * (interior / (interior + 400.0)) * (per_sm / 5.0) + 1e-9 * interior;
+      const double score = fill * (interior / (interior + 400.0)) * (per_sm / (double)LEAN_MIN_CTAS) + 1e-9 * interior;
       if (score > best_score) { best_score = score; best = s; have = true; }
     }
   }
@@ -1151,6 +1151,12 @@ extern "C" int hsmc_gpu_sweep_nvt_logged(hsmc_gpu* h, double dr_max, hsmc_gpu_tr
   return 0;
 }
 
+// HSMC_OBS_DOUBLE=1: the all-double pair kernels (thread per cell) instead of the fp32-prefiltered ones -- cross-check
+static bool obs_all_double() {
+  const char* e = getenv("HSMC_OBS_DOUBLE");          // (read per call: tests switch it inside one process)
+  return e && atoi(e) != 0;
+}
+
 // ---- scaled overlap verdicts -----------------------------------------------------
 static int overlap_flags(hsmc_gpu* h, const double* sf, int nn, int* flags_out) {
   if (nn < 1 || nn > MAX_SF) return fail("scaled overlap: number of scale factors must be in [1, 64]");
@@ -1183,9 +1189,16 @@ static int overlap_flags(hsmc_gpu* h, const double* sf, int nn, int* flags_out) 
   if (wide)
     k_overlap_scaled_wide<<<nblk(total, 128), 128, 0, h->st>>>(g, make_box(g.Lx, g.Ly, g.Lz, 1.0), (const SfArgs*)h->d_sfargs,
                                                                 h->pos[h->cur], h->cell_start, 2, d_flags);
-  else
+  else if (obs_all_double())
     k_overlap_scaled<<<nblk(total, 128), 128, 0, h->st>>>(g, make_box(g.Lx, g.Ly, g.Lz, 1.0), (const SfArgs*)h->d_sfargs,
                                                            h->pos[h->cur], h->cell_start, d_flags);
+  else {
+    TRY(sync_layout(h));
+    if (h->n_owned > 0)
+      k_overlap_scaled_f32<<<nblk(h->n_owned, 256), 256, 0, h->st>>>(g, make_box(g.Lx, g.Ly, g.Lz, 1.0), (const SfArgs*)h->d_sfargs,
+                                                                    h->pos[h->cur], h->rel, h->cell_start, (int)h->own_first,
+                                                                    (int)h->n_owned, d_flags);
+  }
   h->launches++;
   CU(cudaGetLastError());
   if (h->cfg.world > 1) {
@@ -1335,8 +1348,16 @@ extern "C" int hsmc_gpu_contact_counts(hsmc_gpu* h, double dr_bin, int nn, uint6
     return fail("The size of the cells in the neighbor list does not allow a correct calculation of the pressure, increase neigh_list");
   CU(cudaMemsetAsync(h->d_scratch, 0, sizeof(unsigned long long) * nn, h->st));
   long long total = (long long)(g.own_hi - g.own_lo) * g.ny * g.nz;
-  k_contact_hist<<<nblk(total, 128), 128, 0, h->st>>>(g, make_box(g.Lx, g.Ly, g.Lz, 1.0), h->pos[h->cur],
-                                                       h->cell_start, rmax, dr_bin, nn, h->d_scratch);
+  if (obs_all_double())
+    k_contact_hist<<<nblk(total, 128), 128, 0, h->st>>>(g, make_box(g.Lx, g.Ly, g.Lz, 1.0), h->pos[h->cur],
+                                                         h->cell_start, rmax, dr_bin, nn, h->d_scratch);
+  else {
+    TRY(sync_layout(h));
+    if (h->n_owned > 0)
+      k_contact_hist_f32<<<nblk(h->n_owned, 256), 256, 0, h->st>>>(g, make_box(g.Lx, g.Ly, g.Lz, 1.0), h->pos[h->cur], h->rel,
+                                                                  h->cell_start, (int)h->own_first, (int)h->n_owned, rmax,
+                                                                  dr_bin, nn, h->d_scratch);
+  }
   h->launches++;
   CU(cudaGetLastError());
   if (h->cfg.world > 1) {

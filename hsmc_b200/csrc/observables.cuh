@@ -86,6 +86,89 @@ k_overlap_scaled_wide(Grid g, Box ubox, const SfArgs* __restrict__ sa, const dou
 }
 
 // ----------------------------------------------------------------------------------
+// Near pairs through the fp32 shadow (K3 / K6, default): one thread per owned particle slot walks the forward half
+// of its 27-cell stencil in the 16-byte shadow table (cell-relative offsets, z cell in .w) and computes r^2 in fp32
+// from offsets + (cell difference) * edge; only pairs whose fp32 r^2 is below the caller's threshold (exact
+// threshold + a margin far above the fp32 error: offsets are at most 1.5 cell edges, so r^2 near the threshold carries
+// an error below ~2e-5 * max(1, edge)^2) are handed to f(k), which evaluates them from the master table in the
+// reference's double arithmetic.  The pair set and the arithmetic behind every verdict / bin are those of the
+// all-double kernels above; the filter only drops pairs that are certainly far.  Every unordered pair is visited once:
+// inside the own cell from the lower slot, between cells from the cell that is lexicographically first (stencil_half's
+// rule, so slabs see a pair across a face once, from the lower-x rank).
+// ----------------------------------------------------------------------------------
+template <class F>
+__device__ __forceinline__ void near_pairs_f32(const Grid& g, const float4* __restrict__ rel, const int* __restrict__ cs,
+                                               int s, int l, int iy, int iz, float thr, F f) {
+  const float4 me = rel[s];
+  const float wxf = (float)g.wx, wyf = (float)g.wy, wzf = (float)g.wz;
+  auto test = [&](int k, float ox, float oy, float oz) {
+    const float4 q = rel[k];
+    const float dx = (q.x + ox) - me.x, dy = (q.y + oy) - me.y, dz = (q.z + oz) - me.z;
+    if (__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx)) < thr) f(k);
+  };
+  {
+    // row (0,0): the later slots of the own cell, then the +z neighbour cell
+    const long long rb = ((long long)l * g.ny + iy) * g.nz;
+    const int m = cs[rb + iz + 1];
+    for (int k = s + 1; k < m; k++) test(k, 0.f, 0.f, 0.f);
+    int b2 = m, e2;
+    if (iz + 1 < g.nz) e2 = cs[rb + iz + 2];
+    else { b2 = cs[rb]; e2 = cs[rb + 1]; }
+    for (int k = b2; k < e2; k++) test(k, 0.f, 0.f, wzf);
+  }
+#pragma unroll 1
+  for (int r = 0; r < 4; r++) {            // rows (0,+1), (+1,-1), (+1,0), (+1,+1): three cells each
+    const int dx = r == 0 ? 0 : 1, dy = r == 0 ? 1 : r - 2;
+    int ll = l + dx;
+    if (g.wrap_x && ll >= g.nlx) ll -= g.nlx;
+    int yy = iy + dy;
+    if (yy < 0) yy += g.ny; else if (yy >= g.ny) yy -= g.ny;
+    const long long rb = ((long long)ll * g.ny + yy) * g.nz;
+    const float ox = (float)dx * wxf, oy = (float)dy * wyf;
+    auto range = [&](int b, int e) {
+      for (int k = b; k < e; k++) {
+        const float4 q = rel[k];
+        int dzc = __float_as_int(q.w) - iz;
+        if (dzc > 1) dzc -= g.nz; else if (dzc < -1) dzc += g.nz;
+        const float ddx = (q.x + ox) - me.x, ddy = (q.y + oy) - me.y, ddz = (q.z + (float)dzc * wzf) - me.z;
+        if (__fmaf_rn(ddz, ddz, __fmaf_rn(ddy, ddy, ddx * ddx)) < thr) f(k);
+      }
+    };
+    const int zlo = iz - 1, zhi = iz + 1;
+    if (zlo >= 0 && zhi < g.nz) range(cs[rb + zlo], cs[rb + zhi + 1]);
+    else if (zlo < 0) { range(cs[rb + g.nz - 1], cs[rb + g.nz]); range(cs[rb], cs[rb + 2]); }
+    else { range(cs[rb + g.nz - 2], cs[rb + g.nz]); range(cs[rb], cs[rb + 1]); }
+  }
+}
+
+// margin of the fp32 pre-test (see above)
+__host__ __device__ inline float near_pairs_margin(const Grid& g) {
+  const double w = fmax(1.0, fmax(g.wx, fmax(g.wy, g.wz)));
+  return (float)(1.0e-4 + 2.0e-5 * w * w);
+}
+
+__global__ void __launch_bounds__(256)
+k_overlap_scaled_f32(Grid g, Box ubox, const SfArgs* __restrict__ sa, const double4* __restrict__ pos,
+                     const float4* __restrict__ rel, const int* __restrict__ cs, int first, int n, int* __restrict__ flags) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int nsf = sa->n;
+  if (nsf == 1 && flags[0]) return;   // verdict already known
+  const int s = first + t;
+  const double4 p = pos[s];
+  const long long c = local_cell(g, p.x, p.y, p.z);
+  const int iz = (int)(c % g.nz);
+  const long long r = c / g.nz;
+  const double r2_skip = sa->r2_skip;
+  near_pairs_f32(g, rel, cs, s, (int)(r / g.ny), (int)(r % g.ny), iz, (float)r2_skip + near_pairs_margin(g), [&](int k) {
+    const double4 q = pos[k];
+    if (pair_r2(p.x, p.y, p.z, q.x, q.y, q.z, ubox) > r2_skip) return;
+    for (int m = 0; m < nsf; m++)
+      if (pair_r2_scaled(p.x, p.y, p.z, q.x, q.y, q.z, sa->sf[m], sa->box[m]) < 1.0) flags[m] = 1;
+  });
+}
+
+// ----------------------------------------------------------------------------------
 // K4: Widom insertions.  One thread per insertion point; the point is
 // r = u * L (compute_widom_chem_pot.c:73-80) with u from Philox(sample, index).
 // ----------------------------------------------------------------------------------
@@ -249,6 +332,39 @@ k_contact_hist(Grid g, Box box, const double4* __restrict__ pos, const int* __re
         return false;
       });
     }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < nn; k += blockDim.x)
+    if (sh[k]) atomicAdd(&hist[k], (unsigned long long)sh[k]);
+}
+
+// K6 through the fp32 shadow (default; see near_pairs_f32): same pairs, same bins
+__global__ void __launch_bounds__(256)
+k_contact_hist_f32(Grid g, Box box, const double4* __restrict__ pos, const float4* __restrict__ rel,
+                   const int* __restrict__ cs, int first, int n, double rmax, double dr_bin, int nn,
+                   unsigned long long* __restrict__ hist) {
+  __shared__ unsigned int sh[CONTACT_MAX_BINS];
+  for (int k = threadIdx.x; k < nn; k += blockDim.x) sh[k] = 0;
+  __syncthreads();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) {
+    const int s = first + t;
+    const double4 p = pos[s];
+    const long long c = local_cell(g, p.x, p.y, p.z);
+    const int iz = (int)(c % g.nz);
+    const long long r = c / g.nz;
+    const double r2_pre = rmax * rmax * (1.0 + 1e-9);
+    near_pairs_f32(g, rel, cs, s, (int)(r / g.ny), (int)(r % g.ny), iz, (float)r2_pre + near_pairs_margin(g), [&](int k) {
+      const double4 q = pos[k];
+      const double r2 = pair_r2(p.x, p.y, p.z, q.x, q.y, q.z, box);
+      if (r2 < r2_pre) {
+        const double dr = sqrt(r2);
+        if (dr < rmax) {
+          const int bin = (int)((dr - 1.0) / dr_bin);
+          if (bin >= 0 && bin < nn) atomicAdd(&sh[bin], 1u);
+        }
+      }
+    });
   }
   __syncthreads();
   for (int k = threadIdx.x; k < nn; k += blockDim.x)

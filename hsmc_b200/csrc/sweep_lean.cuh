@@ -34,6 +34,9 @@
 #ifndef LEAN_MIN_CTAS
 #define LEAN_MIN_CTAS 5
 #endif
+#ifndef LEAN_STAGE_B
+#define LEAN_STAGE_B 4          // shadow entries a staging thread requests before converting them
+#endif
 #define LEAN_NP 4               // pair-records (2 entries each) per stencil row in straight-line code; longer rows: loop
 #define LEAN_PAD 12             // far-away entries after the last staged particle (covers the over-scan)
 #define LEAN_FAR 1.0e15f
@@ -450,15 +453,15 @@ k_sweep_lean(SweepArgs a, BlockCfg bc, const int* __restrict__ xoff, double4* po
         const int rx = (int)(((float)r + 0.5f) * inv_nry), ry = r - rx * nry;
         const float cxw = ((float)rx - hxr), cyw = ((float)ry - hyr);
 #pragma unroll 1
-        for (int kb = k0; kb < k1; kb += 4) {
-          float4 v[4];
+        for (int kb = k0; kb < k1; kb += LEAN_STAGE_B) {
+          float4 v[LEAN_STAGE_B];
 #pragma unroll
-          for (int u = 0; u < 4; u++) {
+          for (int u = 0; u < LEAN_STAGE_B; u++) {
             const int k = kb + u;
             if (k < k1) v[u] = __ldcg(rel + ((k < rw.cntA) ? rw.gbA + k : rw.gbB + (k - rw.cntA)));   // L2: neighbours' blocks wrote these earlier in this launch
           }
 #pragma unroll
-          for (int u = 0; u < 4; u++) {
+          for (int u = 0; u < LEAN_STAGE_B; u++) {
             const int k = kb + u;
             if (k < k1) {
               const int i = rw.off + k;

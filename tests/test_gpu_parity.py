@@ -205,6 +205,33 @@ def test_contact_counts(hs, path, oracle_built):
         assert np.array_equal(h.contact_counts(0.002, nn), full[:nn])
 
 
+@pytest.mark.parametrize("cells,rho,cell_min", [((12, 10, 8), 0.9, 1.0), ((9, 9, 9), 0.6, 1.3), ((24, 24, 24), 0.94, 1.0)])
+def test_prefiltered_pair_kernels_equal_the_all_double_ones(hs, monkeypatch, cells, rho, cell_min):
+    """K3 / K6 walk the fp32 shadow table first (thread per particle) and evaluate in double only what the filter
+    lets through; HSMC_OBS_DOUBLE=1 selects the all-double thread-per-cell kernels.  Same verdicts for a ladder of
+    compressions that straddles the closest pair, same contact histogram, on configurations evolved on shifted
+    grids (offsets of particles in the cell that straddles the periodic edge included)."""
+    import bench
+    box, conf = bench.fcc_lattice(*cells, rho)
+    with hs.HsmcGpu(conf.shape[0], box, seed=5, cell_min=cell_min) as h:
+        h.upload(conf)
+        for rounds in range(3):
+            h.sweep_nvt(7, 0.1)
+            rmin = float(np.sqrt(h.min_dist2()))
+            w = min(h.info()["cell_size"])
+            lo = max(1.0 / w, 0.98 / rmin) + 1e-9
+            sfs = np.concatenate([np.linspace(lo, 1.0 / rmin, 9), [np.nextafter(1.0 / rmin, 0), np.nextafter(1.0 / rmin, 2), 1.0]])
+            nn, dr = 20, min(0.002, 0.9 * (w - 1.0) / 20)
+            res = {}
+            for mode in ("0", "1"):
+                monkeypatch.setenv("HSMC_OBS_DOUBLE", mode)
+                res[mode] = (h.presst_flags(sfs), [h.overlap_scaled(float(x)) for x in sfs[-4:]], h.contact_counts(dr, nn))
+            assert np.array_equal(res["0"][0], res["1"][0]) and res["0"][1] == res["1"][1]
+            assert np.array_equal(res["0"][2], res["1"][2])
+            assert res["0"][0].any() and not res["0"][0].all()          # the ladder straddles the closest pair
+            assert res["0"][2].sum() > 0
+
+
 def test_random_fluid_against_oracle(hs, oracle_built):
     """Seeded non-lattice input: dilute random configuration, larger box, ragged cells."""
     rng = np.random.default_rng(11)
