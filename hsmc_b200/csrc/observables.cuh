@@ -151,21 +151,38 @@ __global__ void __launch_bounds__(256)
 k_overlap_scaled_f32(Grid g, Box ubox, const SfArgs* __restrict__ sa, const double4* __restrict__ pos,
                      const float4* __restrict__ rel, const int* __restrict__ cs, int first, int n, int* __restrict__ flags) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n) return;
   const int nsf = sa->n;
-  if (nsf == 1 && flags[0]) return;   // verdict already known
-  const int s = first + t;
-  const double4 p = pos[s];
-  const long long c = local_cell(g, p.x, p.y, p.z);
-  const int iz = (int)(c % g.nz);
-  const long long r = c / g.nz;
   const double r2_skip = sa->r2_skip;
-  near_pairs_f32(g, rel, cs, s, (int)(r / g.ny), (int)(r % g.ny), iz, (float)r2_skip + near_pairs_margin(g), [&](int k) {
-    const double4 q = pos[k];
-    if (pair_r2(p.x, p.y, p.z, q.x, q.y, q.z, ubox) > r2_skip) return;
-    for (int m = 0; m < nsf; m++)
+  const int s = first + min(t, n - 1);
+  // pairs that pass the filter are not evaluated where they are found (a lane with one such pair would hold its
+  // warp for nsf serial evaluations): each lane keeps up to four, and the warp then evaluates them together, one
+  // scale factor per lane
+  int c0 = -1, c1 = -1, c2 = -1, c3 = -1;
+  if (t < n && !(nsf == 1 && flags[0])) {                    // (one factor: verdict already known -> nothing to do)
+    const double4 p = pos[s];
+    const long long c = local_cell(g, p.x, p.y, p.z);
+    const int iz = (int)(c % g.nz);
+    const long long r = c / g.nz;
+    near_pairs_f32(g, rel, cs, s, (int)(r / g.ny), (int)(r % g.ny), iz, (float)r2_skip + near_pairs_margin(g), [&](int k) {
+      if (c3 < 0) { c3 = c2; c2 = c1; c1 = c0; c0 = k; return; }
+      const double4 q = pos[k];                               // a fifth one: here and now
+      if (pair_r2(p.x, p.y, p.z, q.x, q.y, q.z, ubox) > r2_skip) return;
+      for (int m = 0; m < nsf; m++)
+        if (pair_r2_scaled(p.x, p.y, p.z, q.x, q.y, q.z, sa->sf[m], sa->box[m]) < 1.0) flags[m] = 1;
+    });
+  }
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    const unsigned have = __ballot_sync(0xffffffffu, c0 >= 0);
+    if (!have) break;
+    const int src = __ffs(have) - 1;
+    const int k = __shfl_sync(0xffffffffu, c0, src), si = __shfl_sync(0xffffffffu, s, src);
+    if (lane == src) { c0 = c1; c1 = c2; c2 = c3; c3 = -1; }
+    const double4 p = pos[si], q = pos[k];
+    if (pair_r2(p.x, p.y, p.z, q.x, q.y, q.z, ubox) > r2_skip) continue;
+    for (int m = lane; m < nsf; m += 32)
       if (pair_r2_scaled(p.x, p.y, p.z, q.x, q.y, q.z, sa->sf[m], sa->box[m]) < 1.0) flags[m] = 1;
-  });
+  }
 }
 
 // ----------------------------------------------------------------------------------

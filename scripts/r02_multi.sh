@@ -9,6 +9,12 @@ timeout 900 python -m pytest tests/test_gpu_multi.py -q --tb=short -k "${N}-" 2>
 if [ "$N" = "2" ]; then
   timeout 600 python -m pytest tests/test_gpu_configs.py -q --tb=short -k "two_gpus" 2>&1 | tail -8 >> gpurun_out/r02_multi${N}_pytest.log; tail -3 gpurun_out/r02_multi${N}_pytest.log
 fi
+# the identity check itself, with its per-quantity report (what the tests above assert on)
+for P2P in 1 0; do
+  HSMC_CHECK_CELLS=$([ "$N" = "2" ] && echo 24,10,12 || echo 40,10,12) HSMC_CHECK_P2P=$P2P timeout 600 python -m torch.distributed.run --nnodes=1 \
+    --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29620 + P2P)) tests/multi_gpu_check.py 2>/dev/null | grep -v "^\*\|OMP_NUM" >> gpurun_out/r02_multi_gpu_check_world${N}.txt
+done
+tail -4 gpurun_out/r02_multi_gpu_check_world${N}.txt
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29611 \
   bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r02_bench_n${N}.json 2> gpurun_out/r02_bench_n${N}.err
 tail -c 1500 gpurun_out/r02_bench_n${N}.json; tail -3 gpurun_out/r02_bench_n${N}.err
