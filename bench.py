@@ -841,7 +841,7 @@ def main():
     if traffic and world == 1 and os.environ.get("HSMC_FUSE", "1") != "0":
         # dram__bytes of one launch of the same kernel from the committed ncu capture; marked stale when the capture
         # is of another kernel than the one timed here
-        if traffic.get("kernel", "") == kname.split(" ")[0]:
+        if traffic.get("kernel", "") == kname.split(" ")[0] and traffic.get("N", N) == N:
             roofline["traffic"] = traffic.get("dram_bytes_per_launch")
             roofline["traffic_source"] = traffic.get("source")
         else:

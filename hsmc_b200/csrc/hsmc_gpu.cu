@@ -401,7 +401,7 @@ static void setup_blocks(hsmc_gpu* h) {
       }
       ctas *= (long long)(even_blocks(g.ny, by) / 2) * (even_blocks(g.nz, bz) / 2);
       // CTAs of k_sweep_lean per SM: dynamic + static shared memory + the 1 KB the hardware reserves per CTA; the
-      // register file holds five 192-thread CTAs of 64 registers
+      // register file holds LEAN_MIN_CTAS CTAs of LEAN_THREADS threads at 64 registers
       const int per_sm = (int)std::min<size_t>(LEAN_MIN_CTAS, (size_t)(227 * 1024) / (s.smem + sizeof(BlockRow) * LEAN_MAX_ROWS + 4 * LEAN_MAX_ROWS + 1200));
       if (per_sm < 1) continue;
       const double interior = (double)s.mx * s.my * s.mz;

@@ -13,7 +13,7 @@
 //    kernel (one thread per particle), generates them all: new position in double (moves.c:52-57, 215-226) into the
 //    idle half of the ping-pong master table, the cell test, and a 16-byte trial record {fp32 shadow of the new
 //    position, slot | accept-able} stored in TRIAL ORDER inside the cell's slot range (ascending particle id).
-//    k_sweep_lean has no Philox and no double arithmetic on its hot path: 64 registers, 30 warps per SM.
+//    k_sweep_lean has no Philox and no double arithmetic on its hot path: 64 registers, 32 warps per SM.
 //  * The sweep kernel derives everything else itself: one warp per staged (x,y) row reads the row's CSR entries
 //    (lane = cell), a warp scan places the rows, the fp32 shadow is staged as block-relative coordinates in PAIRS
 //    {x0,x1,y0,y1} + {z0,z1}, so the stencil filter runs on packed fp32x2 instructions (FADD2 / FMUL2 / FFMA2 +
@@ -28,11 +28,13 @@
 // ordered with warp shuffles: a later trial sees its earlier mates at the positions their own trials left them in.
 #pragma once
 
+// 256 threads x 4 CTAs per SM (64 registers): 2.02 ms per sweep at the benchmark against 2.09 for 192 x 5, 2.04 for
+// 128 x 7 and 224 x 4, 2.18 for 320 x 3 (profiles/r02_variants_rejected.txt); the block shape follows (setup_blocks)
 #ifndef LEAN_THREADS
-#define LEAN_THREADS 192
+#define LEAN_THREADS 256
 #endif
 #ifndef LEAN_MIN_CTAS
-#define LEAN_MIN_CTAS 5
+#define LEAN_MIN_CTAS 4
 #endif
 #ifndef LEAN_STAGE_B
 #define LEAN_STAGE_B 4          // shadow entries a staging thread requests before converting them
@@ -357,6 +359,7 @@ k_sweep_lean(SweepArgs a, BlockCfg bc, const int* __restrict__ xoff, double4* po
     s_row[r].gbA = gbA; s_row[r].gbB = gbB; s_row[r].cntA = cA;
     s_cnt[r] = q.zwrap ? cA + (row[q.zs + lenz - g.nz] - gbB) : cA;
   }
+  for (int i = tid; i < bc.nslots; i += LEAN_THREADS) s_cht[i] = 0;
   // ---- fused launches: wait for the neighbouring blocks of earlier phases -----------------------------------------
   if (a.fuse > 1) {
     if (tid < 27 && tid != 13) {
@@ -404,6 +407,59 @@ k_sweep_lean(SweepArgs a, BlockCfg bc, const int* __restrict__ xoff, double4* po
       if (carry + LEAN_PAD > bc.cap) s_bad = 1;
     }
   }
+  const int parx = (g.gx0 + q.x0) & 1, pary = q.y0 & 1, parz = q.z0 & 1;   // parity of region cell (0,0,0); grids are even
+  if (!bc.force_global) {
+  // ---- chunks (same barrier interval as the row scan: they only need the row-relative cell indices): per colour, the interior cells of the colour (x slowest, z fastest) are cut into runs of at most 32
+  //      cells holding at most 32 trials; a run is one warp's work between two colour barriers (lane = trial, a
+  //      cell's trials in adjacent lanes).  One warp per colour lists the trials of its chunks, once per block.
+  for (int col = warp; col < 8; col += NW) {
+    const int fx = 1 + ((parx + 1 + (col >> 2)) & 1), fy = 1 + ((pary + 1 + (col >> 1)) & 1), fz = 1 + ((parz + 1 + col) & 1);
+    const int nxc = (q.ex - fx + 2) >> 1, nyc = (q.ey - fy + 2) >> 1, nzc = (q.ez - fz + 2) >> 1;
+    const int ncell = nxc * nyc * nzc;
+    const float inz = 1.0f / (float)max(nzc, 1), iny = 1.0f / (float)max(nyc, 1);
+    const int tgt = 32;
+    int at = 0, k = 0;
+    while (at < ncell) {
+      // a free chunk slot (any 32 consecutive trial slots of the block's table)
+      int slot = 0;
+      if (lane == 0) slot = atomicAdd(&s_nslot, 1);
+      slot = __shfl_sync(FULL, slot, 0);
+      if (slot >= bc.nslots || k >= LEAN_COL_CHUNKS) {          // table full: global-memory path
+        if (lane == 0) atomicOr(&s_bad2, 4);
+        break;
+      }
+      const int cq = at + lane;
+      int n = 0;
+      unsigned int cell = 0;
+      if (cq < ncell) {
+        const int t2 = (int)(((float)cq + 0.5f) * inz), izc = cq - t2 * nzc;      // (exact: cq < 4096, divisors <= 16)
+        const int ixc = (int)(((float)t2 + 0.5f) * iny), iyc = t2 - ixc * nyc;
+        const int rx = fx + 2 * ixc, ry = fy + 2 * iyc, rz = fz + 2 * izc;
+        const unsigned short* cz = s_cz + (rx * nry + ry) * czs + rz;
+        n = (int)cz[1] - (int)cz[0];
+        cell = ((unsigned)rx << 12) | ((unsigned)ry << 8) | ((unsigned)rz << 3);
+        if (n > LEAN_MAX_OCC) { n = 0; atomicOr(&s_bad2, 2); }        // unusually full cell: the block takes the global-memory path
+      }
+      int inc = n;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += t;
+      }
+      const bool in = cq < ncell && inc <= tgt;
+      const unsigned m = __ballot_sync(FULL, in);
+      unsigned short* items = s_items + slot * 32;
+      if (in)
+        for (int j = 0; j < n; j++) items[inc - n + j] = (unsigned short)(cell | (unsigned)j);
+      const int ncl = __popc(m);                 // cells of this chunk (>= 1: a cell holds at most 8 trials)
+      if (lane == ncl - 1) s_cht[slot] = (unsigned char)inc;
+      if (lane == 0) s_cslot[col * LEAN_COL_CHUNKS + k] = (unsigned char)slot;
+      at += ncl;
+      k++;
+    }
+    if (lane == 0) s_nch[col] = k;
+  }
+  }
   __syncthreads();
   const int total = s_cnt[nrows];
 
@@ -413,7 +469,6 @@ k_sweep_lean(SweepArgs a, BlockCfg bc, const int* __restrict__ xoff, double4* po
   if (!s_bad && !bc.force_global) {
     // ---- staged indices of the cells; trial records and proposals of the interior towards L2 ----
     {
-      bool deep_cell = false;
       for (int r = tid; r < nrows; r += LEAN_THREADS) {
         const int rx = (int)(((float)r + 0.5f) * inv_nry), ry = r - rx * nry;
         const BlockRow rw = s_row[r];
@@ -424,7 +479,6 @@ k_sweep_lean(SweepArgs a, BlockCfg bc, const int* __restrict__ xoff, double4* po
         for (int zi = 1; zi <= q.ez; zi++) {
           const int ve = (int)cz[zi + 2] + rw.off;                               // start of cell zi+2 = end of cell zi+1
           cz[zi] = (unsigned short)v;
-          deep_cell |= rint && vn - v > LEAN_MAX_OCC;
           vb = v; v = vn; vn = ve;
         }
         cz[q.ez + 1] = (unsigned short)v;
@@ -437,7 +491,6 @@ k_sweep_lean(SweepArgs a, BlockCfg bc, const int* __restrict__ xoff, double4* po
           for (int k = 0; k < m; k += 4) prefetch_l2(prop + first + k);
         }
       }
-      if (__any_sync(FULL, deep_cell) && lane == 0) s_bad2 = 2;      // (s_bad itself must not change inside this branch)
     }
     // ---- stage the fp32 shadow as block-relative coordinates fma(cell index - centre, edge, offset) -----------------
     {
@@ -481,64 +534,13 @@ k_sweep_lean(SweepArgs a, BlockCfg bc, const int* __restrict__ xoff, double4* po
         xy[0] = LEAN_FAR; xy[2] = LEAN_FAR; s_zf[i] = LEAN_FAR;
       }
       for (int i = tid; i < (bc.cap >> 5); i += LEAN_THREADS) s_pacc[i] = 0u;
-      for (int i = tid; i < bc.nslots; i += LEAN_THREADS) { s_iacc[i] = 0u; s_cht[i] = 0; }
+      for (int i = tid; i < bc.nslots; i += LEAN_THREADS) s_iacc[i] = 0u;
     }
     __syncthreads();
   }
   if (!s_bad && !s_bad2 && !bc.force_global) {
     // ---- trials -----------------------------------------------------------------------------------------------
     const float lo = 1.0f - a.eps, hi = 1.0f + a.eps;
-    const int parx = (g.gx0 + q.x0) & 1, pary = q.y0 & 1, parz = q.z0 & 1;   // parity of region cell (0,0,0); grids are even
-    // ---- chunks: per colour, the interior cells of the colour (x slowest, z fastest) are cut into runs of at most 32
-    //      cells holding at most 32 trials; a run is one warp's work between two colour barriers (lane = trial, a
-    //      cell's trials in adjacent lanes).  One warp per colour lists the trials of its chunks, once per block.
-    for (int col = warp; col < 8; col += NW) {
-      const int fx = 1 + ((parx + 1 + (col >> 2)) & 1), fy = 1 + ((pary + 1 + (col >> 1)) & 1), fz = 1 + ((parz + 1 + col) & 1);
-      const int nxc = (q.ex - fx + 2) >> 1, nyc = (q.ey - fy + 2) >> 1, nzc = (q.ez - fz + 2) >> 1;
-      const int ncell = nxc * nyc * nzc;
-      const float inz = 1.0f / (float)max(nzc, 1), iny = 1.0f / (float)max(nyc, 1);
-      const int tgt = 32;
-      int at = 0, k = 0;
-      while (at < ncell) {
-        // a free chunk slot (any 32 consecutive trial slots of the block's table)
-        int slot = 0;
-        if (lane == 0) slot = atomicAdd(&s_nslot, 1);
-        slot = __shfl_sync(FULL, slot, 0);
-        if (slot >= bc.nslots || k >= LEAN_COL_CHUNKS) {          // table full: global-memory path
-          if (lane == 0) atomicOr(&s_bad2, 4);
-          break;
-        }
-        const int cq = at + lane;
-        int n = 0;
-        unsigned int cell = 0;
-        if (cq < ncell) {
-          const int t2 = (int)(((float)cq + 0.5f) * inz), izc = cq - t2 * nzc;      // (exact: cq < 4096, divisors <= 16)
-          const int ixc = (int)(((float)t2 + 0.5f) * iny), iyc = t2 - ixc * nyc;
-          const int rx = fx + 2 * ixc, ry = fy + 2 * iyc, rz = fz + 2 * izc;
-          const unsigned short* cz = s_cz + (rx * nry + ry) * czs + rz;
-          n = (int)cz[1] - (int)cz[0];
-          cell = ((unsigned)rx << 12) | ((unsigned)ry << 8) | ((unsigned)rz << 3);
-        }
-        int inc = n;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int t = __shfl_up_sync(FULL, inc, o);
-          if (lane >= o) inc += t;
-        }
-        const bool in = cq < ncell && inc <= tgt;
-        const unsigned m = __ballot_sync(FULL, in);
-        unsigned short* items = s_items + slot * 32;
-        if (in)
-          for (int j = 0; j < n; j++) items[inc - n + j] = (unsigned short)(cell | (unsigned)j);
-        const int ncl = __popc(m);                 // cells of this chunk (>= 1: a cell holds at most 8 trials)
-        if (lane == ncl - 1) s_cht[slot] = (unsigned char)inc;
-        if (lane == 0) s_cslot[col * LEAN_COL_CHUNKS + k] = (unsigned char)slot;
-        at += ncl;
-        k++;
-      }
-      if (lane == 0) s_nch[col] = k;
-    }
-    __syncthreads();
     if (s_bad2) goto global_path;                // (block-uniform)
 #pragma unroll 1
     for (int col = 0; col < 8; col++) {
