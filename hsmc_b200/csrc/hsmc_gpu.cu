@@ -88,6 +88,7 @@ struct BlockCfg {
   int dbg;                // timing ablations (env HSMC_BLOCK_DBG), 0 in production
   unsigned int* ticket;   // fused launches: CTA ticket counter (never reset; SweepArgs::ticket_base)
   unsigned int* done;     // fused launches: [nbx][nby][nbz] epoch of the launch that last finished the block
+  unsigned long long* stamps;   // tuning aid (HSMC_BLOCK_STAMPS=1): [0..23] clock cycles summed per stage of a block, [31] blocks
 };
 
 // per-row staging record: global slots of the row's one or two pieces, staged offset
@@ -98,6 +99,21 @@ struct GatherLists {
   int* list;                    // [GATHER_LISTS][stride] local cell indices
   int* count;                   // [GATHER_LISTS]
   long long stride;
+};
+
+// Slab runs over NVLink windows: the right ghost layer is delivered INSIDE the sweep launch.  The blocks of a rank's
+// first owned layer (block column 0, phases 0-3) store that layer's cells straight into the left neighbour's right
+// ghost layer (same cells, same slot order: both are kept id-sorted) and then raise a per-(y,z)-block flag in the
+// neighbour's window; the neighbour's last block column (phases 4-7), the only reader of that ghost layer, waits for
+// the nine flags around it.  So all eight block phases of a slab are ONE launch, with no halo exchange in between.
+struct SlabLink {
+  double4* peer_pos[2];                 // left neighbour's master table (both halves), nullptr = link off
+  float4* peer_rel;
+  unsigned int* peer_done;              // left neighbour's window: [nby][nbz] number of the last sweep that block finished
+  const volatile unsigned int* info;    // my window: {right-ghost base slot, rebuild number, current half} of the LEFT neighbour
+  const volatile unsigned int* my_done; // my window: the same flags, raised by the right neighbour
+  unsigned int seq;                     // this sweep (same count on every rank)
+  unsigned int rebuild;                 // the rebuild the layout must come from
 };
 
 // cfg.sweep_impl: low byte = kernel variant, next byte = virtual world of the x block partition
@@ -156,6 +172,9 @@ struct hsmc_gpu {
   unsigned char* win = nullptr;          // my receive window: [flags | A_l x2 | A_r x2 | B | C]
   unsigned char *win_left = nullptr, *win_right = nullptr;   // neighbours' windows, mapped
   bool p2p = false;
+  bool pos_in_win = false;               // pos[*] / rel live inside the window allocation (slab runs)
+  size_t peer_off[4] = {0, 0, 0, 0};     // left neighbour's window: offsets of its block flags, pos[0], pos[1], rel
+  uint32_t seqG = 0, seqR = 0;           // sweeps with the in-kernel ghost delivery / slab rebuilds so far (same on every rank)
   uint32_t seqA = 0, seqB = 0, seqC = 0; // exchanges issued so far (same on every rank)             // left ghost layer not refreshed since the last odd-x phases
   void* d_sfargs = nullptr;
   BlockCfg blk;
@@ -174,6 +193,7 @@ struct hsmc_gpu {
   int fuse_mode = -1;                  // -1: not decided yet; 0 off (HSMC_FUSE=0); 1 on
   int64_t cap_xoff = 0;
   bool xoff_dirty = true;
+  unsigned long long* d_stamps = nullptr;   // HSMC_BLOCK_STAMPS
   hsmc_gpu_trial* d_log = nullptr;
   int64_t cap_log = 0;
   // optional event timing
@@ -422,6 +442,12 @@ static void setup_blocks(hsmc_gpu* h) {
   b.use_tma = 0;
   b.force_global = (h->impl == IMPL_BLOCK_GLOBAL) ? 1 : 0;
   b.dbg = getenv("HSMC_BLOCK_DBG") ? atoi(getenv("HSMC_BLOCK_DBG")) : 0;
+  b.stamps = nullptr;
+  if (getenv("HSMC_BLOCK_STAMPS") && atoi(getenv("HSMC_BLOCK_STAMPS"))) {
+    if (!h->d_stamps && cudaMalloc(&h->d_stamps, sizeof(unsigned long long) * 32) == cudaSuccess)
+      cudaMemset(h->d_stamps, 0, sizeof(unsigned long long) * 32);
+    b.stamps = h->d_stamps;
+  }
   h->xoff.clear();
   for (auto& sl : slabs) {
     int n = sl.second - sl.first, nb = even_blocks(n, best.bx);
@@ -456,7 +482,18 @@ static inline size_t win_off_A(const hsmc_gpu* h, int from_right, int parity) {
 }
 static inline size_t win_off_B(const hsmc_gpu* h) { return 256 + (size_t)4 * h->cap_halo * sizeof(double4); }
 static inline size_t win_off_C(const hsmc_gpu* h) { return win_off_B(h) + (size_t)(h->cap_halo / 2) * sizeof(double4); }
-static inline size_t win_bytes(const hsmc_gpu* h) { return win_off_C(h) + (size_t)(h->cap_halo / 2) * sizeof(double4); }
+// ... followed by the block flags of the in-kernel ghost delivery and, so that a neighbour can store into them, the
+// master table and its shadow themselves.  Header: uint32 0-3 message flags, 8-10 SlabLink::info; byte 64: four
+// uint64 offsets {block flags, pos[0], pos[1], rel} (cap differs from rank to rank, so a neighbour reads them here)
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+static inline size_t win_off_gdone(const hsmc_gpu* h) { return align256(win_off_C(h) + (size_t)(h->cap_halo / 2) * sizeof(double4)); }
+static inline size_t win_gdone_n(const hsmc_gpu* h) { return (size_t)(h->g.ny / 2) * (size_t)(h->g.nz / 2) + 64; }
+static inline size_t win_off_pos(const hsmc_gpu* h, int k) {
+  return align256(win_off_gdone(h) + win_gdone_n(h) * sizeof(unsigned int)) + (size_t)k * align256(sizeof(double4) * (size_t)h->cap);
+}
+static inline size_t win_off_rel(const hsmc_gpu* h) { return win_off_pos(h, 2); }
+static inline size_t win_bytes(const hsmc_gpu* h) { return win_off_rel(h) + align256(sizeof(float4) * (size_t)h->cap); }
+enum { WIN_INFO = 8, WIN_OFFSETS_BYTE = 64 };
 static inline volatile uint32_t* win_flag(unsigned char* w, int k) { return reinterpret_cast<volatile uint32_t*>(w) + k; }
 enum { FLAG_A_FROM_LEFT = 0, FLAG_A_FROM_RIGHT = 1, FLAG_B = 2, FLAG_C = 3 };
 
@@ -547,7 +584,11 @@ static int rebuild(hsmc_gpu* h, const double4* src, int64_t n_in, int rows_layou
   long long per = (long long)g.ny * g.nz;
   k_sort_cells_by_id<<<dim3(nblk(2 * per, 128), 2), 128, 0, h->st>>>(g, dst, h->rel, h->cell_start, 0, 1);
   h->launches++;
-  k_gather_layout<<<1, 32, 0, h->st>>>(g, h->cell_start, h->d_halo_cnt, h->d_lay);
+  // (+ for the in-kernel ghost delivery: where my right ghost layer starts, in which half, after which rebuild -- into
+  //  the window of the rank that writes it, my right neighbour)
+  h->seqR++;
+  k_gather_layout<<<1, 32, 0, h->st>>>(g, h->cell_start, h->d_halo_cnt, h->d_lay,
+                                       h->p2p ? win_flag(h->win_right, WIN_INFO) : nullptr, h->seqR, h->cur ^ 1);
   h->launches++;
   CU(cudaGetLastError());
   h->cur ^= 1;
@@ -600,10 +641,7 @@ extern "C" int hsmc_gpu_ipc_export(hsmc_gpu* h, void* out_blob) {
   if (!h || !out_blob) return fail("null argument");
   if (h->cfg.world < 2) return fail("ipc_export: only meaningful with world > 1");
   CU(cudaSetDevice(h->cfg.device));
-  if (!h->win) {
-    CU(cudaMalloc(&h->win, win_bytes(h)));
-    CU(cudaMemset(h->win, 0, win_bytes(h)));
-  }
+  if (!h->win) return fail("ipc_export: no window (internal)");
   cudaIpcMemHandle_t mh;
   CU(cudaIpcGetMemHandle(&mh, h->win));
   static_assert(sizeof(cudaIpcMemHandle_t) == HSMC_GPU_IPC_BYTES, "ipc handle size");
@@ -625,6 +663,9 @@ extern "C" int hsmc_gpu_ipc_attach(hsmc_gpu* h, const void* left_blob, const voi
   else CU(cudaIpcOpenMemHandle(&pr, mr, cudaIpcMemLazyEnablePeerAccess));
   h->win_left = (unsigned char*)pl;
   h->win_right = (unsigned char*)pr;
+  unsigned long long offs[4];
+  CU(cudaMemcpy(offs, h->win_left + WIN_OFFSETS_BYTE, sizeof(offs), cudaMemcpyDeviceToHost));
+  for (int k = 0; k < 4; k++) h->peer_off[k] = (size_t)offs[k];
   h->p2p = true;
   return 0;
 }
@@ -637,10 +678,11 @@ extern "C" int hsmc_gpu_destroy(hsmc_gpu* h) {
   if (h->win_right && h->win_right != h->win_left) cudaIpcCloseMemHandle(h->win_right);
   if (h->win) cudaFree(h->win);
   if (h->comm) ncclCommDestroy(h->comm);
+  if (h->pos_in_win) h->pos[0] = h->pos[1] = nullptr, h->rel = nullptr;      // part of the window, freed above
   void* ptrs[] = {h->pos[0], h->pos[1], h->rel, h->key, h->rnk, h->cell_count, h->cell_start, h->bsum, h->d_cnt,
                   h->d_scratch, h->d_slot_of_id, h->d_io, h->send_l, h->send_r, h->recv_l, h->recv_r,
                   h->d_halo_cnt, h->d_sfargs, h->d_log, h->key_halo, h->rnk_halo, h->d_lay,
-                  h->d_xoff, h->d_fuse, h->trec, h->traw, h->glists.list, h->glists.count};
+                  h->d_xoff, h->d_fuse, h->trec, h->traw, h->glists.list, h->glists.count, h->d_stamps};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -706,9 +748,22 @@ extern "C" int hsmc_gpu_create(hsmc_gpu** out, const hsmc_gpu_config* cfg, int64
     // a cell layer of a crystal can hold 1.6x the mean (lattice planes beat against the cell grid)
     h->cap_halo = (int64_t)(2 * lay_frac * h->N * 2.5) + 4096;
   }
-  CUD(cudaMalloc(&h->pos[0], sizeof(double4) * (size_t)h->cap));
-  CUD(cudaMalloc(&h->pos[1], sizeof(double4) * (size_t)h->cap));
-  CUD(cudaMalloc(&h->rel, sizeof(float4) * (size_t)h->cap));
+  if (W == 1) {
+    CUD(cudaMalloc(&h->pos[0], sizeof(double4) * (size_t)h->cap));
+    CUD(cudaMalloc(&h->pos[1], sizeof(double4) * (size_t)h->cap));
+    CUD(cudaMalloc(&h->rel, sizeof(float4) * (size_t)h->cap));
+  } else {
+    // one allocation = the NVLink window (hsmc_gpu_ipc_export hands out its handle): message areas, block flags,
+    // and the tables a neighbour stores its boundary layer into
+    CUD(cudaMalloc(&h->win, win_bytes(h)));
+    CUD(cudaMemset(h->win, 0, win_off_pos(h, 0)));
+    h->pos[0] = reinterpret_cast<double4*>(h->win + win_off_pos(h, 0));
+    h->pos[1] = reinterpret_cast<double4*>(h->win + win_off_pos(h, 1));
+    h->rel = reinterpret_cast<float4*>(h->win + win_off_rel(h));
+    h->pos_in_win = true;
+    const unsigned long long offs[4] = {win_off_gdone(h), win_off_pos(h, 0), win_off_pos(h, 1), win_off_rel(h)};
+    CUD(cudaMemcpy(h->win + WIN_OFFSETS_BYTE, offs, sizeof(offs), cudaMemcpyHostToDevice));
+  }
   if (h->cap_halo) {
     CUD(cudaMalloc(&h->key_halo, sizeof(int) * (size_t)(2 * h->cap_halo)));
     CUD(cudaMalloc(&h->rnk_halo, sizeof(int) * (size_t)(2 * h->cap_halo)));
@@ -1016,9 +1071,17 @@ static int sweep_once(hsmc_gpu* h, double dr_max, bool logged) {
   // CTAs order themselves by per-block completion flags (see k_sweep_block): all eight on a single
   // GPU, 0-3 and 4-7 in slab mode.  HSMC_FUSE=0 launches the phases one by one (same chain).
   int fuse = 1;
+  bool link = false;
   if (h->blk_ok) {
     if (h->fuse_mode < 0) { const char* e = getenv("HSMC_FUSE"); h->fuse_mode = (e && atoi(e) == 0) ? 0 : 1; }
     if (h->fuse_mode == 1 && h->blk.dbg == 0) fuse = (h->cfg.world > 1) ? 4 : 8;
+    // slabs over NVLink windows: the right ghost layer arrives inside the launch (SlabLink), so all eight phases fuse.
+    // (needs a rebuild before every sweep: the ghost layout is published by the rebuild.  HSMC_SLAB_LINK=0: two launches
+    //  with the boundary-layer exchange in between, as over NCCL)
+    if (fuse == 4 && h->p2p && h->cfg.regrid_interval == 1 && h->impl != IMPL_GATHER) {
+      static const bool off = getenv("HSMC_SLAB_LINK") && atoi(getenv("HSMC_SLAB_LINK")) == 0;
+      if (!off) { fuse = 8; link = true; }
+    }
     if (fuse > 1) {
       const int64_t need = 64 + (int64_t)h->blk.nbx * h->blk.nby * h->blk.nbz;
       if (need > h->cap_fuse) {
@@ -1031,6 +1094,18 @@ static int sweep_once(hsmc_gpu* h, double dr_max, bool logged) {
       h->blk.ticket = h->d_fuse;
       h->blk.done = h->d_fuse + 64;
     }
+  }
+  SlabLink sl;
+  memset(&sl, 0, sizeof(sl));
+  if (link) {
+    sl.peer_pos[0] = reinterpret_cast<double4*>(h->win_left + h->peer_off[1]);
+    sl.peer_pos[1] = reinterpret_cast<double4*>(h->win_left + h->peer_off[2]);
+    sl.peer_rel = reinterpret_cast<float4*>(h->win_left + h->peer_off[3]);
+    sl.peer_done = reinterpret_cast<unsigned int*>(h->win_left + h->peer_off[0]);
+    sl.info = win_flag(h->win, WIN_INFO);
+    sl.my_done = reinterpret_cast<const volatile unsigned int*>(h->win + win_off_gdone(h));
+    sl.seq = ++h->seqG;
+    sl.rebuild = h->seqR;
   }
   a.fuse = fuse; a.epoch = 0; a.ticket_base = 0;
   a.cx = a.cy = a.cz = a.phase = 0;
@@ -1084,11 +1159,11 @@ static int sweep_once(hsmc_gpu* h, double dr_max, bool logged) {
         h->fuse_tickets += (unsigned int)nb;
       }
       if (logged)
-        k_sweep_lean<true><<<nb, LEAN_THREADS, h->blk_smem, h->st>>>(a, h->blk, h->d_xoff, h->pos[h->cur], h->rel, h->pos[h->cur ^ 1],
+        k_sweep_lean<true><<<nb, LEAN_THREADS, h->blk_smem, h->st>>>(a, h->blk, sl, h->d_xoff, h->pos[h->cur], h->rel, h->pos[h->cur ^ 1],
                                                                      h->trec, h->traw, h->cell_start, h->d_cnt, h->d_log,
                                                                      h->d_scratch, (long long)h->cap_log);
       else
-        k_sweep_lean<false><<<nb, LEAN_THREADS, h->blk_smem, h->st>>>(a, h->blk, h->d_xoff, h->pos[h->cur], h->rel, h->pos[h->cur ^ 1],
+        k_sweep_lean<false><<<nb, LEAN_THREADS, h->blk_smem, h->st>>>(a, h->blk, sl, h->d_xoff, h->pos[h->cur], h->rel, h->pos[h->cur ^ 1],
                                                                       h->trec, nullptr, h->cell_start, h->d_cnt, nullptr, nullptr, 0);
     } else if (logged)
       k_sweep_phase<true><<<nblk(total, T), T, 0, h->st>>>(a, h->pos[h->cur], h->rel, h->cell_start, h->d_cnt, h->d_log,
@@ -1101,7 +1176,7 @@ static int sweep_once(hsmc_gpu* h, double dr_max, bool logged) {
     if (h->cfg.world > 1) {
       // ghosts of parity cx are read only by phases of the other parity: one refresh
       // after the last phase of each parity is enough
-      if (ph == 3) TRY(halo_refresh(h, 0));
+      if (ph == 3 && !link) TRY(halo_refresh(h, 0));        // (link: delivered inside the launch)
       // the odd-parity boundary layer is read next by phases 0-3 of the FOLLOWING sweep; when
       // that sweep regrids first, its exchange rebuilds the ghost layers anyway, so the refresh
       // is deferred until somebody needs current ghosts (observables, end of the call)
@@ -1530,6 +1605,20 @@ extern "C" int hsmc_gpu_debug_counters(hsmc_gpu* h, uint64_t out[8]) {
   CU(cudaMemcpyAsync(hs, h->d_cnt, sizeof(unsigned long long) * CNT_N, cudaMemcpyDeviceToHost, h->st));
   CU(cudaStreamSynchronize(h->st));
   for (int k = 0; k < CNT_N; k++) out[k] = hs[k];
+  return 0;
+}
+
+// tuning aid: clock cycles per stage of k_sweep_lean summed over blocks (HSMC_BLOCK_STAMPS=1), [31] = blocks; read + reset
+extern "C" int hsmc_gpu_debug_stamps(hsmc_gpu* h, uint64_t out[32]) {
+  if (!h || !out) return fail("null argument");
+  memset(out, 0, sizeof(uint64_t) * 32);
+  if (!h->d_stamps) return 0;
+  CU(cudaSetDevice(h->cfg.device));
+  unsigned long long* hs = (unsigned long long*)h->h_stage;
+  CU(cudaMemcpyAsync(hs, h->d_stamps, sizeof(unsigned long long) * 32, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaMemsetAsync(h->d_stamps, 0, sizeof(unsigned long long) * 32, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  for (int k = 0; k < 32; k++) out[k] = hs[k];
   return 0;
 }
 

@@ -201,9 +201,19 @@ __global__ void k_rel_layer(Grid g, const double4* __restrict__ pos, float4* __r
 
 // slab mode: the six layer offsets and the error flags in one staging vector (one D2H copy)
 __global__ void k_gather_layout(Grid g, const int* __restrict__ cs, const int* __restrict__ halo_cnt,
-                                int* __restrict__ out) {
+                                int* __restrict__ out, volatile uint32_t* peer_info, uint32_t rebuild, int half) {
   long long per = (long long)g.ny * g.nz;
   int k = threadIdx.x;
+  if (k == 9 && peer_info) {
+    // SlabLink::info of the right neighbour: base slot of my right ghost layer, the half of the ping-pong table that
+    // holds it, and -- last, behind a fence -- the number of the rebuild this comes from (everything this stream did
+    // before, the rebuilt tables included, is then visible to whoever sees the number)
+    peer_info[0] = (uint32_t)cs[(long long)(g.nlx - 1) * per];
+    peer_info[2] = (uint32_t)half;
+    __threadfence_system();
+    peer_info[1] = rebuild;
+    __threadfence_system();
+  }
   if (k < 6) {
     long long offs = (k == 0) ? 0 : (k == 1) ? per : (k == 2) ? 2 * per : (k == 3) ? (long long)(g.nlx - 2) * per
                    : (k == 4) ? (long long)(g.nlx - 1) * per : (long long)g.nlx * per;

@@ -36,10 +36,10 @@
 #ifndef LEAN_MIN_CTAS
 #define LEAN_MIN_CTAS 4
 #endif
-#ifndef LEAN_STAGE_B
-#define LEAN_STAGE_B 4          // shadow entries a staging thread requests before converting them
+#ifndef LEAN_NP
+#define LEAN_NP 3               // pair-records (2 entries each) per stencil row in straight-line code; longer rows: loop
+                                // (3: -3 % against 4 at the benchmark, rows of three cells hold 2.7 particles; 2: -2 %)
 #endif
-#define LEAN_NP 4               // pair-records (2 entries each) per stencil row in straight-line code; longer rows: loop
 #define LEAN_PAD 12             // far-away entries after the last staged particle (covers the over-scan)
 #define LEAN_FAR 1.0e15f
 #define LEAN_MAX_OCC 8          // most particles per cell on the staged path (3-bit trial index)
@@ -252,20 +252,19 @@ __device__ __forceinline__ float lean_scan(uint32_t a_xy0, uint32_t a_z0, const 
     const int np = (e + 1 - 2 * p0) >> 1;              // pair-records holding entries below e
     const uint32_t axy = a_xy0 + 16u * (uint32_t)p0, az = a_z0 + 8u * (uint32_t)p0;
 #pragma unroll
-    for (int s0 = 0; s0 < LEAN_NP; s0 += 2) {
-      lds_pair_if(x0, y0, z0, axy + 16u * s0, az + 8u * s0, s0 < np);
-      lds_pair_if(x1, y1, z1, axy + 16u * (s0 + 1), az + 8u * (s0 + 1), s0 + 1 < np);
-      {
+    for (int s0 = 0; s0 < LEAN_NP; s0++) {               // (two register sets in turn, so that a load can run ahead)
+      if (s0 & 1) {
+        lds_pair_if(x1, y1, z1, axy + 16u * s0, az + 8u * s0, s0 < np);
+        const unsigned long long dx = f2_sub(TX, x1), dy = f2_sub(TY, y1), dz = f2_sub(TZ, z1);
+        float lo, hi;
+        f2_unpack(f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx))), lo, hi);
+        if (s0 < np) r2min = f_min3(r2min, lo, hi);
+      } else {
+        lds_pair_if(x0, y0, z0, axy + 16u * s0, az + 8u * s0, s0 < np);
         const unsigned long long dx = f2_sub(TX, x0), dy = f2_sub(TY, y0), dz = f2_sub(TZ, z0);
         float lo, hi;
         f2_unpack(f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx))), lo, hi);
         if (s0 < np) r2min = f_min3(r2min, lo, hi);
-      }
-      {
-        const unsigned long long dx = f2_sub(TX, x1), dy = f2_sub(TY, y1), dz = f2_sub(TZ, z1);
-        float lo, hi;
-        f2_unpack(f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx))), lo, hi);
-        if (s0 + 1 < np) r2min = f_min3(r2min, lo, hi);
       }
     }
     if (np > LEAN_NP) {
@@ -289,7 +288,7 @@ __device__ __forceinline__ float lean_scan(uint32_t a_xy0, uint32_t a_z0, const 
 // ---------------------------------------------------------------------------------------------------
 template <bool LOG>
 __global__ void __launch_bounds__(LEAN_THREADS, LEAN_MIN_CTAS)
-k_sweep_lean(SweepArgs a, BlockCfg bc, const int* __restrict__ xoff, double4* pos, float4* rel,
+k_sweep_lean(SweepArgs a, BlockCfg bc, SlabLink sl, const int* __restrict__ xoff, double4* pos, float4* rel,
              const double4* __restrict__ prop, const uint4* __restrict__ trec, const uint4* __restrict__ traw,
              const int* __restrict__ cs, unsigned long long* __restrict__ cnt,
              hsmc_gpu_trial* __restrict__ log, unsigned long long* __restrict__ nlog, long long logcap) {
@@ -307,8 +306,11 @@ k_sweep_lean(SweepArgs a, BlockCfg bc, const int* __restrict__ xoff, double4* po
   float* s_zf = reinterpret_cast<float*>(s_z2);
   __shared__ BlockRow s_row[LEAN_MAX_ROWS];
   __shared__ int s_cnt[LEAN_MAX_ROWS + 1];
-  __shared__ int s_done_idx, s_bad, s_bad2, s_nch[8], s_ph, s_nslot;
+  __shared__ int s_done_idx, s_bad, s_bad2, s_nch[8], s_ph, s_nslot, s_next_row;
   __shared__ BlkGeom s_geom;
+  __shared__ long long s_t[24];                 // tuning aid (bc.stamps): clock at the stage boundaries, thread 0
+#define LEAN_STAMP(i) do { if (bc.stamps && threadIdx.x == 0) s_t[i] = clock64(); } while (0)
+  LEAN_STAMP(0);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = LEAN_THREADS / 32;
   const int czs = bc.cz_stride;
@@ -331,9 +333,10 @@ k_sweep_lean(SweepArgs a, BlockCfg bc, const int* __restrict__ xoff, double4* po
     s_geom.bxi = bx0; s_geom.byi = by0; s_geom.bzi = bz0;
     s_ph = ph0;
     s_done_idx = (bx0 * bc.nby + by0) * bc.nbz + bz0;
-    s_bad = 0; s_bad2 = 0; s_nslot = 0;
+    s_bad = 0; s_bad2 = 0; s_nslot = 0; s_next_row = 0;
   }
   __syncthreads();
+  LEAN_STAMP(1);
   const BlkGeom q = s_geom;
   const int ph = s_ph, bxi = q.bxi, byi = q.byi, bzi = q.bzi;
   const int nrows = q.nrows, nry = q.nry, lenz = q.lenz;
@@ -357,7 +360,12 @@ k_sweep_lean(SweepArgs a, BlockCfg bc, const int* __restrict__ xoff, double4* po
 #pragma unroll 4
     for (int zi = nA + 1; zi <= lenz; zi++) cz[zi] = (unsigned short)(cA + row[q.zs + zi - g.nz] - gbB);
     s_row[r].gbA = gbA; s_row[r].gbB = gbB; s_row[r].cntA = cA;
-    s_cnt[r] = q.zwrap ? cA + (row[q.zs + lenz - g.nz] - gbB) : cA;
+    const int cntr = q.zwrap ? cA + (row[q.zs + lenz - g.nz] - gbB) : cA;
+    s_cnt[r] = cntr;
+    // the row's shadow entries towards L2 now; they are staged two barriers later (a neighbour that is still writing
+    // some of them writes into L2 as well)
+    for (int k = 0; k < cA; k += 8) prefetch_l2(rel + gbA + k);
+    for (int k = 0; k < cntr - cA; k += 8) prefetch_l2(rel + gbB + k);
   }
   for (int i = tid; i < bc.nslots; i += LEAN_THREADS) s_cht[i] = 0;
   // ---- fused launches: wait for the neighbouring blocks of earlier phases -----------------------------------------
@@ -386,8 +394,30 @@ k_sweep_lean(SweepArgs a, BlockCfg bc, const int* __restrict__ xoff, double4* po
       }
       __threadfence();                     // acquire: everything those blocks wrote is visible from here on
     }
+    // slab with in-kernel ghost delivery: the last block column (odd, phases 4-7) is the only reader of the right ghost
+    // layer; the right neighbour's first-column blocks behind the nine (y,z) blocks around this one must have stored
+    // their cells of this sweep (SlabLink)
+    if (sl.my_done && bxi == bc.nbx - 1 && tid >= 32 && tid < 41) {
+      const int k = tid - 32;
+      int ny = byi + k / 3 - 1, nz = bzi + k % 3 - 1;
+      if (ny < 0) ny += bc.nby; else if (ny >= bc.nby) ny -= bc.nby;
+      if (nz < 0) nz += bc.nbz; else if (nz >= bc.nbz) nz -= bc.nbz;
+      const volatile unsigned int* f = sl.my_done + ny * bc.nbz + nz;
+      unsigned long long t0 = 0;
+      unsigned int spins = 0;
+      while ((int)(*f - sl.seq) < 0) {
+        __nanosleep(100);
+        if ((++spins & 4095u) == 0) {
+          const unsigned long long t = hsmc_globaltimer_ns();
+          if (t0 == 0) t0 = t;
+          else if (t - t0 > 60ull * 1000000000ull) __trap();
+        }
+      }
+      __threadfence_system();
+    }
   }
   __syncthreads();
+  LEAN_STAMP(2);
   if (tid < 32) {                               // exclusive scan of the row populations
     int carry = 0;
     for (int base = 0; base < nrows; base += 32) {
@@ -461,6 +491,7 @@ k_sweep_lean(SweepArgs a, BlockCfg bc, const int* __restrict__ xoff, double4* po
   }
   }
   __syncthreads();
+  LEAN_STAMP(3);
   const int total = s_cnt[nrows];
 
   int n_acc = 0, n_ov = 0, n_cell = 0;
@@ -492,42 +523,30 @@ k_sweep_lean(SweepArgs a, BlockCfg bc, const int* __restrict__ xoff, double4* po
         }
       }
     }
+    LEAN_STAMP(14);
     // ---- stage the fp32 shadow as block-relative coordinates fma(cell index - centre, edge, offset) -----------------
     {
-      // each staged row is cut into P runs of particles, one (row, run) item per thread and round; a thread first
-      // issues all the loads of a batch, then converts them (the shadow carries the z cell of its particle)
-      const int P = (2 * nrows <= LEAN_THREADS) ? 2 : 1;
+      // one WARP per staged row, lane = particle of the row (a row holds ~26 particles): coalesced 16-byte loads of the
+      // shadow (it carries the z cell of its particle), already on their way to L2 since the row pass.  (Measured: more
+      // rows in flight per warp, rows handed out on request, or a thread per row piece are all slower.)
 #pragma unroll 1
-      for (int idx = tid; idx < P * nrows; idx += LEAN_THREADS) {
-        const int r = (P == 2) ? idx >> 1 : idx, piece = (P == 2) ? idx & 1 : 0;
+      for (int r = warp; r < nrows; r += NW) {
         const BlockRow rw = s_row[r];
         const int cntr = s_cnt[r];
-        const int k0 = (cntr * piece) / P, k1 = (cntr * (piece + 1)) / P;
         const int rx = (int)(((float)r + 0.5f) * inv_nry), ry = r - rx * nry;
-        const float cxw = ((float)rx - hxr), cyw = ((float)ry - hyr);
-#pragma unroll 1
-        for (int kb = k0; kb < k1; kb += LEAN_STAGE_B) {
-          float4 v[LEAN_STAGE_B];
-#pragma unroll
-          for (int u = 0; u < LEAN_STAGE_B; u++) {
-            const int k = kb + u;
-            if (k < k1) v[u] = __ldcg(rel + ((k < rw.cntA) ? rw.gbA + k : rw.gbB + (k - rw.cntA)));   // L2: neighbours' blocks wrote these earlier in this launch
-          }
-#pragma unroll
-          for (int u = 0; u < LEAN_STAGE_B; u++) {
-            const int k = kb + u;
-            if (k < k1) {
-              const int i = rw.off + k;
-              int zi = __float_as_int(v[u].w) - q.z0;                  // z cell of the particle inside the region
-              if (zi < 0) zi += g.nz; else if (zi >= g.nz) zi -= g.nz;
-              float* xy = s_xyf + ((i >> 1) << 2) + (i & 1);
-              xy[0] = __fmaf_rn(cxw, wxf, v[u].x);
-              xy[2] = __fmaf_rn(cyw, wyf, v[u].y);
-              s_zf[i] = __fmaf_rn((float)zi - hzr, wzf, v[u].z);
-            }
-          }
+        const float cxw = (float)rx - hxr, cyw = (float)ry - hyr;
+        for (int k = lane; k < cntr; k += 32) {
+          const float4 w = __ldcg(rel + ((k < rw.cntA) ? rw.gbA + k : rw.gbB + (k - rw.cntA)));   // L2: neighbours' blocks wrote these earlier in this launch
+          const int i = rw.off + k;
+          int zi = __float_as_int(w.w) - q.z0;                    // z cell of the particle inside the region
+          if (zi < 0) zi += g.nz; else if (zi >= g.nz) zi -= g.nz;
+          float* xy = s_xyf + ((i >> 1) << 2) + (i & 1);
+          xy[0] = __fmaf_rn(cxw, wxf, w.x);
+          xy[2] = __fmaf_rn(cyw, wyf, w.y);
+          s_zf[i] = __fmaf_rn((float)zi - hzr, wzf, w.z);
         }
       }
+      LEAN_STAMP(15);
       if (tid < LEAN_PAD) {
         const int i = total + tid;
         float* xy = s_xyf + ((i >> 1) << 2) + (i & 1);
@@ -541,6 +560,7 @@ k_sweep_lean(SweepArgs a, BlockCfg bc, const int* __restrict__ xoff, double4* po
   if (!s_bad && !s_bad2 && !bc.force_global) {
     // ---- trials -----------------------------------------------------------------------------------------------
     const float lo = 1.0f - a.eps, hi = 1.0f + a.eps;
+    LEAN_STAMP(4);
     if (s_bad2) goto global_path;                // (block-uniform)
 #pragma unroll 1
     for (int col = 0; col < 8; col++) {
@@ -648,27 +668,53 @@ k_sweep_lean(SweepArgs a, BlockCfg bc, const int* __restrict__ xoff, double4* po
         __syncwarp();
       }
       __syncthreads();                       // colour barrier
+      LEAN_STAMP(5 + col);
     }
-    // ---- commit: the accepted moves of the block go to the master table and its shadow, all at once ----------------
+    // ---- commit: the accepted moves of the block go to the master table and its shadow; two items per thread and round,
+    //      the loads of both (trial record, then proposal) issued before either is stored -----------------------------
+    {
+      const int nidx = min(s_nslot, bc.nslots) * 32;
 #pragma unroll 1
-    for (int idx = tid; idx < min(s_nslot, bc.nslots) * 32; idx += LEAN_THREADS) {
-      const int slot = idx >> 5, l = idx & 31;
-      if (!((s_iacc[slot] >> l) & 1u)) continue;          // (zeroed with the staging: chunks that never ran hold no bits)
-      const unsigned int item = s_items[idx];
-      const int rxc = (item >> 12) & 15, ryc = (item >> 8) & 15, rz = (item >> 3) & 31, j = item & 7;
-      const int cob = s_cz[(rxc * nry + ryc) * czs + rz];
-      const BlockRow rwc = s_row[rxc * nry + ryc];
-      const int ro = cob - rwc.off;
-      const int gcell0 = (ro < rwc.cntA) ? rwc.gbA + ro : rwc.gbB + ro - rwc.cntA;
-      const uint4 rec = __ldg(trec + gcell0 + j);
-      const int gs = gcell0 + (int)(rec.w & 15);
-      const double4 pr = prop[gs];
-      double* pd = reinterpret_cast<double*>(pos + gs);
-      *reinterpret_cast<double2*>(pd) = make_double2(pr.x, pr.y);
-      pd[2] = pr.z;
-      float* rl = reinterpret_cast<float*>(rel + gs);
-      *reinterpret_cast<float2*>(rl) = make_float2(__uint_as_float(rec.x), __uint_as_float(rec.y));
-      rl[2] = __uint_as_float(rec.z);
+      for (int idx = tid; idx < nidx; idx += 2 * LEAN_THREADS) {
+        int g0[2];
+        uint4 rec[2];
+        double2 pxy[2];
+        double pz[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          const int id2 = idx + u * LEAN_THREADS;
+          g0[u] = -1;
+          if (id2 < nidx && ((s_iacc[id2 >> 5] >> (id2 & 31)) & 1u)) {
+            const unsigned int item = s_items[id2];
+            const int rxc = (item >> 12) & 15, ryc = (item >> 8) & 15, rz = (item >> 3) & 31;
+            const int cob = s_cz[(rxc * nry + ryc) * czs + rz];
+            const BlockRow rwc = s_row[rxc * nry + ryc];
+            const int ro = cob - rwc.off;
+            g0[u] = (ro < rwc.cntA) ? rwc.gbA + ro : rwc.gbB + ro - rwc.cntA;
+            rec[u] = __ldg(trec + g0[u] + (int)(item & 7u));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          if (g0[u] >= 0) {
+            g0[u] += (int)(rec[u].w & 15);
+            const double* pp = reinterpret_cast<const double*>(prop + g0[u]);
+            pxy[u] = *reinterpret_cast<const double2*>(pp);
+            pz[u] = pp[2];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          if (g0[u] >= 0) {
+            double* pd = reinterpret_cast<double*>(pos + g0[u]);
+            *reinterpret_cast<double2*>(pd) = pxy[u];
+            pd[2] = pz[u];
+            float* rl = reinterpret_cast<float*>(rel + g0[u]);
+            *reinterpret_cast<float2*>(rl) = make_float2(__uint_as_float(rec[u].x), __uint_as_float(rec[u].y));
+            rl[2] = __uint_as_float(rec[u].z);
+          }
+        }
+      }
     }
   } else {
 global_path:
@@ -689,6 +735,7 @@ global_path:
     }
   }
 
+  LEAN_STAMP(13);
   // (tuning aid: how many blocks left the staged path, and why -- hsmc_gpu_debug_counters)
   if (tid == 0 && (s_bad | s_bad2) && !bc.force_global) atomicAdd(&cnt[4 + (s_bad ? 0 : (s_bad2 & 2) ? 1 : 2)], 1ull);
   // ---- counters: warp reduce, then straight to the global counters ------------------------------------------
@@ -701,12 +748,52 @@ global_path:
     if (n_ov) atomicAdd(&cnt[CNT_REJ_OVERLAP], (unsigned long long)n_ov);
     if (n_cell) atomicAdd(&cnt[CNT_REJ_CELL], (unsigned long long)n_cell);
   }
+  const bool deliver = sl.peer_rel != nullptr && bxi == 0;
+  if (deliver) {
+    // ---- slab: this block's cells of the first owned layer go to the left neighbour's right ghost layer, slot for
+    //      slot (SlabLink); the neighbour has published where that layer starts after its rebuild ------------------
+    __syncthreads();                                   // the commit above is complete
+    unsigned long long t0 = 0;
+    unsigned int spins = 0;
+    while ((int)(sl.info[1] - sl.rebuild) < 0) {
+      __nanosleep(100);
+      if ((++spins & 4095u) == 0) {
+        const unsigned long long t = hsmc_globaltimer_ns();
+        if (t0 == 0) t0 = t;
+        else if (t - t0 > 60ull * 1000000000ull) __trap();
+      }
+    }
+    __threadfence_system();
+    const long long per = (long long)g.ny * g.nz;
+    const int shift = (int)sl.info[0] - cs[(long long)g.own_lo * per];
+    double4* ppos = sl.peer_pos[sl.info[2] & 1u];
+    for (int y = warp; y < q.ey; y += NW) {
+      const long long c0 = (long long)g.own_lo * per + (long long)(q.ya + y) * g.nz + q.za;
+      const int e = cs[c0 + q.ez];
+      for (int k = cs[c0] + lane; k < e; k += 32) {
+        ppos[k + shift] = pos[k];
+        sl.peer_rel[k + shift] = rel[k];
+      }
+    }
+  }
   if (a.fuse > 1) {
     // every thread's stores to pos / rel precede the barrier; thread 0 then publishes the block
     __syncthreads();
     if (tid == 0) {
+      if (deliver) {
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned int*>(sl.peer_done + byi * bc.nbz + bzi) = sl.seq;
+      }
       __threadfence();
       st_release_gpu(bc.done + s_done_idx, a.epoch);
     }
+  }
+  if (bc.stamps && tid == 0 && !s_bad && !s_bad2) {
+    const long long t14 = clock64();
+    for (int i = 0; i < 13; i++) atomicAdd(bc.stamps + i, (unsigned long long)(s_t[i + 1] - s_t[i]));
+    atomicAdd(bc.stamps + 13, (unsigned long long)(t14 - s_t[13]));
+    atomicAdd(bc.stamps + 14, (unsigned long long)(s_t[14] - s_t[3]));       // warp 0: cell index pass + prefetches
+    atomicAdd(bc.stamps + 15, (unsigned long long)(s_t[15] - s_t[14]));      // warp 0: its staging rows
+    atomicAdd(bc.stamps + 31, 1ull);
   }
 }

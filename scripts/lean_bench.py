@@ -44,6 +44,18 @@ for impl in ([a.impl, 5] if a.check else [a.impl]):
             print(f"   blocks off the staged path: capacity {raw[4]} deep cell {raw[5]} trial lists {raw[6]}", flush=True)
     except Exception as e:
         print("   (no debug counters:", e, ")")
+    try:
+        st = (ctypes.c_uint64 * 32)()
+        h.L.hsmc_gpu_debug_stamps.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        h.L.hsmc_gpu_debug_stamps(h.h, st)
+        if st[31]:
+            names = ["geometry", "rows+flag wait", "row scan+chunks", "cell index+staging"] + [f"colour {c}" for c in range(8)] + ["commit", "counters+publish"]
+            tot = sum(st[i] for i in range(14))
+            print(f"   cycles per block (thread 0's clock, {st[31]} blocks, {tot / st[31]:.0f} total): " +
+                  ", ".join(f"{n} {st[i] / st[31]:.0f}" for i, n in enumerate(names)) +
+                  f" | warp 0 inside staging: cell index pass {st[14] / st[31]:.0f}, its rows {st[15] / st[31]:.0f}", flush=True)
+    except Exception as e:
+        print("   (no stamps:", e, ")")
     if a.check:
         outs.append(h.download())
     h.close()

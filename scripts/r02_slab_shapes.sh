@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 : > gpurun_out/r02_slab_shapes.txt
 port=29700
-for shape in auto 6,8,27 6,8,14 4,8,14 4,6,14 4,4,14 4,4,27 3,4,14 6,6,10 4,4,8; do
+for shape in ${SHAPES:-auto 8,8,27 6,8,27 8,8,19 6,8,19 8,8,14 6,8,14 4,8,14 6,8,10}; do
   port=$((port+1))
   if [ "$shape" = "auto" ]; then unset HSMC_BLOCK; else export HSMC_BLOCK=$shape; fi
   HSMC_DEBUG_TILES=1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port $port \

@@ -328,8 +328,12 @@ def test_block_plan_of_the_benchmark_box(lib_built):
     from hsmc_b200 import gpu as G
     box, n = _fcc_box(256, 128, 128, 0.9)
     p = G.plan_blocks(box, n)
-    assert p["blocks"] == (54, 28, 10) and p["max_extent"] == (8, 8, 21) and p["ctas_per_phase"] == 1890
+    # 256 threads x 4 CTAs per SM leave 56 KB of shared memory per CTA: 8 x 8 x 27-cell blocks
+    assert p["blocks"] == (54, 28, 8) and p["max_extent"] == (8, 8, 27) and p["ctas_per_phase"] == 1512
     assert p["xcuts"][0] == 0 and p["xcuts"][-1] == 420
+    box, n = _fcc_box(162, 162, 162, 0.9)               # bench.py's default box
+    p = G.plan_blocks(box, n)
+    assert p["blocks"] == (34, 34, 10) and p["max_extent"] == (8, 8, 27) and p["smem_bytes"] <= 56 * 1024
 
 
 def test_optimizer_step_guard(tmp_path):
