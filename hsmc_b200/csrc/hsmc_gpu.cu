@@ -1075,12 +1075,14 @@ static int sweep_once(hsmc_gpu* h, double dr_max, bool logged) {
   if (h->blk_ok) {
     if (h->fuse_mode < 0) { const char* e = getenv("HSMC_FUSE"); h->fuse_mode = (e && atoi(e) == 0) ? 0 : 1; }
     if (h->fuse_mode == 1 && h->blk.dbg == 0) fuse = (h->cfg.world > 1) ? 4 : 8;
-    // slabs over NVLink windows: the right ghost layer arrives inside the launch (SlabLink), so all eight phases fuse.
-    // (needs a rebuild before every sweep: the ghost layout is published by the rebuild.  HSMC_SLAB_LINK=0: two launches
-    //  with the boundary-layer exchange in between, as over NCCL)
+    // slabs over NVLink windows, HSMC_SLAB_LINK=1: the right ghost layer arrives inside the launch (SlabLink), so all
+    // eight phases fuse into one launch per sweep (needs a rebuild before every sweep: the ghost layout is published by
+    // the rebuild).  Same chain, tested at 2 and 8 GPUs; NOT the default: measured at 8 GPUs it is 2 % slower than two
+    // launches with the boundary-layer message in between (profiles/r02_bench_n8*.json) -- a slab's sweep is a chain of
+    // eight block latencies either way.
     if (fuse == 4 && h->p2p && h->cfg.regrid_interval == 1 && h->impl != IMPL_GATHER) {
-      static const bool off = getenv("HSMC_SLAB_LINK") && atoi(getenv("HSMC_SLAB_LINK")) == 0;
-      if (!off) { fuse = 8; link = true; }
+      const char* e = getenv("HSMC_SLAB_LINK");
+      if (e && atoi(e) == 1) { fuse = 8; link = true; }
     }
     if (fuse > 1) {
       const int64_t need = 64 + (int64_t)h->blk.nbx * h->blk.nby * h->blk.nbz;

@@ -13,7 +13,7 @@ if [[ "$PARTS" == *ncu* ]]; then
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_sweep_lean -s 1 -c 1 -f -o /tmp/r02_lean python scripts/profile_all.py > /dev/null 2>&1
   python profiles/ncu_summary.py /tmp/r02_lean.ncu-rep > gpurun_out/r02_ncu_k_sweep_lean.txt 2>&1
   python profiles/ncu_source_hot.py /tmp/r02_lean.ncu-rep 60 > gpurun_out/r02_ncu_k_sweep_lean_source.txt 2>&1
-  python profiles/ncu_source_regions.py /tmp/r02_lean.ncu-rep "{'prologue+cz rows+flag wait':(296,384),'row scan':(385,405),'cell index pass+prefetch':(406,438),'staging':(439,482),'chunk build':(483,539),'trial decode+record':(540,576),'stencil scan':(180,284),'scan call+mates':(577,588),'verdict rounds':(589,626),'log+colour barrier':(627,646),'commit':(647,668),'global path+epilogue':(669,720)}" > gpurun_out/r02_ncu_k_sweep_lean_regions.txt 2>&1
+  python profiles/ncu_source_regions.py /tmp/r02_lean.ncu-rep "{'prologue+geometry':(300,343),'CSR rows+shadow prefetch+flag wait':(344,420),'row scan':(421,441),'chunk build':(442,494),'cell index pass+prefetch':(495,526),'staging':(527,560),'trial decode+record':(561,603),'stencil scan':(180,290),'scan call+mates':(604,614),'verdict rounds':(615,652),'log+colour barrier':(653,672),'commit':(673,719),'global path+epilogue+ghost delivery':(720,800)}" > gpurun_out/r02_ncu_k_sweep_lean_regions.txt 2>&1
   sz=$(stat -c %s /tmp/r02_lean.ncu-rep 2>/dev/null || echo 0); if [ "$sz" -gt 0 ] && [ "$sz" -lt 25000000 ]; then cp /tmp/r02_lean.ncu-rep gpurun_out/; fi
   grep -E "^###|gpu__time_duration" gpurun_out/r02_ncu_all_kernels.txt | paste - - | awk '{print $2, $(NF-1), $NF}' | sort | uniq -c | sort -rn | head -30
   cat gpurun_out/r02_ncu_k_sweep_lean_regions.txt
