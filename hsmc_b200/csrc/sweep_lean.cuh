@@ -14,13 +14,15 @@
 //    idle half of the ping-pong master table, the cell test, and a 16-byte trial record {fp32 shadow of the new
 //    position, slot | accept-able} stored in TRIAL ORDER inside the cell's slot range (ascending particle id).
 //    k_sweep_lean has no Philox and no double arithmetic on its hot path: 64 registers, 32 warps per SM.
-//  * The sweep kernel derives everything else itself: one warp per staged (x,y) row reads the row's CSR entries
-//    (lane = cell), a warp scan places the rows, the fp32 shadow is staged as block-relative coordinates in PAIRS
+//  * The sweep kernel derives everything else itself: one thread per staged (x,y) row reads the row's CSR entries, a
+//    warp scan places the rows, one warp per row stages the fp32 shadow as block-relative coordinates in PAIRS
 //    {x0,x1,y0,y1} + {z0,z1}, so the stencil filter runs on packed fp32x2 instructions (FADD2 / FMUL2 / FFMA2 +
 //    FMNMX3: 7 math instructions and two loads per two neighbours instead of 14 + 2).
-//  * Per cell colour each warp owns a contiguous group of the colour's cells (lane = cell, z fastest, so that the
-//    stencil rows of neighbouring lanes start at nearby shared-memory addresses); the cells' trials are compacted with
-//    a warp scan into lane-slots.  The trials of one cell are always handled by one warp, in order.
+//  * Per cell colour one warp cuts the colour's cells (z fastest, so that the stencil rows of neighbouring lanes start at
+//    nearby shared-memory addresses) into chunks of at most 32 cells and 32 trials; a chunk is one warp's work between
+//    two colour barriers, lane = trial.  The trials of one cell are always in one chunk, in adjacent lanes, in order.
+//  * Where the time goes (profiles/r02_block_stamps.txt, r02_ncu_k_sweep_lean*.txt): the kernel is bound by the
+//    latency of a block's dependent stages, not by arithmetic; DESIGN.md section 5 lists what was measured and dropped.
 //
 // Exactness is unchanged: the fp32 minimum r^2 is a filter with a rigorous error bound eps (setup_blocks); min < 1 - eps
 // is a certain overlap, min > 1 + eps a certain miss, anything in between is re-evaluated from the master table with
