@@ -1,4 +1,4 @@
-"""Host-side model of the fused block-phase launch (hsmc_b200/csrc/sweep_block.cuh, "which block"):
+"""Host-side model of the fused block-phase launch (hsmc_b200/csrc/sweep_lean.cuh, "which block"):
 tickets enumerate (phase, block) in phase order, a CTA waits for the neighbouring blocks of EARLIER
 phases of the launch, then runs and publishes its flag.  The model replays the kernel's index arithmetic
 with a bounded number of resident CTAs and random CTA durations and checks the two claims DESIGN.md
@@ -99,3 +99,83 @@ def test_fused_launch_drains_and_respects_phase_order(shape, resident, mode):
                 d = [min((b1[k] - b2[k]) % n, (b2[k] - b1[k]) % n) if (k or wrap_x) else abs(b1[k] - b2[k])
                      for k, n in enumerate((nbx, nby, nbz))]
                 assert max(d) >= 2 or b1 == b2, (b1, b2)
+
+
+def _simulate_linked_slabs(world, nbx, nby, nbz, resident, seed, stagger):
+    """HSMC_SLAB_LINK=1 (SlabLink in sweep_lean.cuh): every rank runs all eight phases of its slab as one launch with its
+    own ticket counter and its own CTA slots; a block of the LAST column (odd x parity, phases 4-7) also waits for the
+    nine first-column blocks around it on the right neighbour's GPU -- their flags arrive over NVLink."""
+    rng = random.Random(seed)
+    per = (nbx // 2) * (nby // 2) * (nbz // 2)
+    total = per * 8
+    done = [set() for _ in range(world)]
+    started, finished_at = {}, {}
+    running = []                                   # heap of (finish time, rank, block)
+    waiting = [[] for _ in range(world)]
+    in_flight = [0] * world
+    next_ticket = [0] * world
+    launch_at = [rng.uniform(0.0, stagger) for _ in range(world)]     # the ranks do not start together
+    now = 0.0
+
+    def deps_of(r, b, ph):
+        local = {(r, nb) for nb in _deps(b, ph, nbx, nby, nbz, 0, False)}
+        if b[0] == nbx - 1:
+            rr = (r + 1) % world
+            local |= {(rr, (0, (b[1] + dy) % nby, (b[2] + dz) % nbz)) for dy in (-1, 0, 1) for dz in (-1, 0, 1)}
+        return local
+
+    n_done = 0
+    while n_done < total * world:
+        progressed = False
+        for r in range(world):
+            if now < launch_at[r]:
+                continue
+            while in_flight[r] + len(waiting[r]) < resident and next_ticket[r] < total:
+                ph, b = _blocks_of_ticket(next_ticket[r], nbx, nby, nbz, 0)
+                next_ticket[r] += 1
+                waiting[r].append((b, ph, deps_of(r, b, ph)))
+            still = []
+            for b, ph, deps in waiting[r]:
+                if all(nb in done[rr] for rr, nb in deps):
+                    started[(r, b)] = (now, ph)
+                    heapq.heappush(running, (now + rng.uniform(0.5, 1.5), r, b))
+                    in_flight[r] += 1
+                    progressed = True
+                else:
+                    still.append((b, ph, deps))
+            waiting[r] = still
+        if running:
+            now, r, b = heapq.heappop(running)
+            done[r].add(b)
+            finished_at[(r, b)] = now
+            in_flight[r] -= 1
+            n_done += 1
+        else:
+            pending = [t for t in launch_at if t > now]
+            assert pending or progressed, "deadlock: every resident CTA on every rank is waiting"
+            if pending and not progressed:
+                now = min(pending)
+    return started, finished_at
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("shape", [(2, 2, 2), (2, 4, 6), (4, 6, 4)])
+@pytest.mark.parametrize("resident", [1, 3, 64])
+def test_linked_slab_launches_drain_and_respect_the_order_across_ranks(world, shape, resident):
+    nbx, nby, nbz = shape
+    started, finished_at = _simulate_linked_slabs(world, nbx, nby, nbz, resident, seed=world * 100 + resident, stagger=5.0)
+    per = (nbx // 2) * (nby // 2) * (nbz // 2)
+    assert len(finished_at) == world * per * 8
+    for (r, b), (t0, ph) in started.items():
+        for nb in _deps(b, ph, nbx, nby, nbz, 0, False):
+            assert finished_at[(r, nb)] <= t0
+        if b[0] == nbx - 1:
+            # the right neighbour's first-column blocks around this one (phases 0-3 there) had finished: their boundary
+            # layer was in this rank's ghost slots before the block staged it
+            rr = (r + 1) % world
+            for dy in (-1, 0, 1):
+                for dz in (-1, 0, 1):
+                    assert finished_at[(rr, (0, (b[1] + dy) % nby, (b[2] + dz) % nbz))] <= t0
+        if b[0] == 0:
+            # ... and a first-column block never waits for anything on another rank (no cycle is possible)
+            assert ph < 4
