@@ -38,6 +38,10 @@
 #ifndef LEAN_MIN_CTAS
 #define LEAN_MIN_CTAS 4
 #endif
+#ifndef LEAN_COMMIT_B
+#define LEAN_COMMIT_B 2         // items a thread commits per round (the loads of all of them before any store);
+                                // measured at the benchmark: 1 -> 1.80, 2 -> 1.71, 3 -> 1.73, 4 -> 1.76 ms per sweep
+#endif
 #ifndef LEAN_NP
 #define LEAN_NP 3               // pair-records (2 entries each) per stencil row in straight-line code; longer rows: loop
                                 // (3: -3 % against 4 at the benchmark, rows of three cells hold 2.7 particles; 2: -2 %)
@@ -677,13 +681,13 @@ k_sweep_lean(SweepArgs a, BlockCfg bc, SlabLink sl, const int* __restrict__ xoff
     {
       const int nidx = min(s_nslot, bc.nslots) * 32;
 #pragma unroll 1
-      for (int idx = tid; idx < nidx; idx += 2 * LEAN_THREADS) {
-        int g0[2];
-        uint4 rec[2];
-        double2 pxy[2];
-        double pz[2];
+      for (int idx = tid; idx < nidx; idx += LEAN_COMMIT_B * LEAN_THREADS) {
+        int g0[LEAN_COMMIT_B];
+        uint4 rec[LEAN_COMMIT_B];
+        double2 pxy[LEAN_COMMIT_B];
+        double pz[LEAN_COMMIT_B];
 #pragma unroll
-        for (int u = 0; u < 2; u++) {
+        for (int u = 0; u < LEAN_COMMIT_B; u++) {
           const int id2 = idx + u * LEAN_THREADS;
           g0[u] = -1;
           if (id2 < nidx && ((s_iacc[id2 >> 5] >> (id2 & 31)) & 1u)) {
@@ -697,7 +701,7 @@ k_sweep_lean(SweepArgs a, BlockCfg bc, SlabLink sl, const int* __restrict__ xoff
           }
         }
 #pragma unroll
-        for (int u = 0; u < 2; u++) {
+        for (int u = 0; u < LEAN_COMMIT_B; u++) {
           if (g0[u] >= 0) {
             g0[u] += (int)(rec[u].w & 15);
             const double* pp = reinterpret_cast<const double*>(prop + g0[u]);
@@ -706,7 +710,7 @@ k_sweep_lean(SweepArgs a, BlockCfg bc, SlabLink sl, const int* __restrict__ xoff
           }
         }
 #pragma unroll
-        for (int u = 0; u < 2; u++) {
+        for (int u = 0; u < LEAN_COMMIT_B; u++) {
           if (g0[u] >= 0) {
             double* pd = reinterpret_cast<double*>(pos + g0[u]);
             *reinterpret_cast<double2*>(pd) = pxy[u];
