@@ -504,7 +504,7 @@ k_sweep_lean(SweepArgs a, BlockCfg bc, SlabLink sl, const int* __restrict__ xoff
   const float wxf = (float)g.wx, wyf = (float)g.wy, wzf = (float)g.wz;
   const float hxr = 0.5f * (float)q.nrx, hyr = 0.5f * (float)nry, hzr = 0.5f * (float)lenz;
   if (!s_bad && !bc.force_global) {
-    // ---- staged indices of the cells; trial records and proposals of the interior towards L2 ----
+    // ---- staged indices of the cells; trial records of the interior towards L2 ----
     {
       for (int r = tid; r < nrows; r += LEAN_THREADS) {
         const int rx = (int)(((float)r + 0.5f) * inv_nry), ry = r - rx * nry;
@@ -524,8 +524,7 @@ k_sweep_lean(SweepArgs a, BlockCfg bc, SlabLink sl, const int* __restrict__ xoff
           // interior particles of the row: slots [first, first + m) of the (trial-ordered) tables
           const int i1 = (int)cz[1] - rw.off, m = (int)cz[q.ez + 1] - (int)cz[1];
           const int first = (i1 < rw.cntA) ? rw.gbA + i1 : rw.gbB + i1 - rw.cntA;
-          for (int k = 0; k < m; k += 8) prefetch_l2(trec + first + k);
-          for (int k = 0; k < m; k += 4) prefetch_l2(prop + first + k);
+          for (int k = 0; k < m; k += 8) prefetch_l2(trec + first + k);      // (the proposals are not prefetched: measured, no gain)
         }
       }
     }
@@ -685,7 +684,7 @@ k_sweep_lean(SweepArgs a, BlockCfg bc, SlabLink sl, const int* __restrict__ xoff
         int g0[LEAN_COMMIT_B];
         uint4 rec[LEAN_COMMIT_B];
         double2 pxy[LEAN_COMMIT_B];
-        double pz[LEAN_COMMIT_B];
+        double2 pzw[LEAN_COMMIT_B];
 #pragma unroll
         for (int u = 0; u < LEAN_COMMIT_B; u++) {
           const int id2 = idx + u * LEAN_THREADS;
@@ -706,7 +705,7 @@ k_sweep_lean(SweepArgs a, BlockCfg bc, SlabLink sl, const int* __restrict__ xoff
             g0[u] += (int)(rec[u].w & 15);
             const double* pp = reinterpret_cast<const double*>(prop + g0[u]);
             pxy[u] = *reinterpret_cast<const double2*>(pp);
-            pz[u] = pp[2];
+            pzw[u] = *reinterpret_cast<const double2*>(pp + 2);
           }
         }
 #pragma unroll
@@ -714,7 +713,7 @@ k_sweep_lean(SweepArgs a, BlockCfg bc, SlabLink sl, const int* __restrict__ xoff
           if (g0[u] >= 0) {
             double* pd = reinterpret_cast<double*>(pos + g0[u]);
             *reinterpret_cast<double2*>(pd) = pxy[u];
-            pd[2] = pz[u];
+            *reinterpret_cast<double2*>(pd + 2) = pzw[u];          // (the whole 32-byte sector {x,y,z,id}: nothing to read-fill on eviction)
             float* rl = reinterpret_cast<float*>(rel + g0[u]);
             *reinterpret_cast<float2*>(rl) = make_float2(__uint_as_float(rec[u].x), __uint_as_float(rec[u].y));
             rl[2] = __uint_as_float(rec[u].z);
